@@ -1,0 +1,152 @@
+/*
+ * lsq_b200.h — C ABI of the B200-native LSQ hot path (liblsq_b200.so).
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, and returns an int status
+ * (0 = ok, non-zero = error; text via lsq_last_error()) — except the two linscan symbols, which keep
+ * the reference's `void` signatures byte for byte so that src/linscan/Linscan.jl works unchanged.
+ * Citations `file:line` are relative to the reference repository (una-dinosauria/local-search-quantization).
+ *
+ * Array conventions = the bytes Julia's ccall passes for its column-major arrays:
+ *   X  (d-by-n  Matrix{Float32})      -> const float*   [n][d]
+ *   B  (m-by-n  Matrix{Int16})        -> const int16_t* [n][m]   1-BASED codes, as everywhere in Julia
+ *   C  (cat(3, C...), d-by-h-by-m)    -> const float*   [m][h][d]
+ *   uint8 codes (UInt8(B-1))          -> const uint8_t* [n][m]   0-based (linscan, device API)
+ * h must be 256 and m <= 16 on the encode path (the reference GPU path hard-codes both,
+ * src/encodings/cuda/cudautils.cu:38,57,94,155,245).
+ *
+ * Host-pointer functions (lsq_*) copy to the device, run, copy back, and are what the Julia overlay
+ * binds.  Device-pointer functions (lsq_dev_*) take device buffers and a CUDA stream and never touch
+ * the host; the host-pointer functions are thin wrappers over them.  There is no CPU fallback: with no
+ * usable GPU every compute entry point returns LSQ_ERR_CUDA.
+ */
+#ifndef LSQ_B200_H_
+#define LSQ_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSQ_OK 0
+#define LSQ_ERR_ARG 1   /* invalid argument (m > 16, h != 256, npert > m, ...) */
+#define LSQ_ERR_CUDA 2  /* CUDA runtime / no device */
+#define LSQ_ERR_LIMIT 3 /* documented capacity limit exceeded */
+
+/* ---- runtime (replaces CudaUtilsModule.init / finit, cudaUtilsModule.jl:37-43, and the
+ *      CuDevice(0)/CuContext of encode_icm_cuda.jl:59-64) ------------------------------------------ */
+int lsq_init(int device);
+int lsq_finalize(void);
+const char* lsq_last_error(void);
+int lsq_device_count(void);
+const char* lsq_version(void);
+
+/* ---- a10: splitarray (utils.jl:152-177): part p of nparts over 0..n-1 -> [lo, hi) ------------- */
+int lsq_splitarray(int64_t n, int nparts, int p, int64_t* lo, int64_t* hi);
+
+/* ---- canonical schedule (replaces randperm/sample/rand of encode_icm.jl:46-64 and the curand
+ *      setup_kernel/perturb of cudautils.cu:14-80): Philox4x32-10 keyed by seed, counter = (global
+ *      vector index, ILS iteration); independent of sharding ------------------------------------- */
+int lsq_make_to_look(uint64_t seed, uint32_t ils_iter, int m, int randord, int32_t* to_look);
+int lsq_make_perturb(uint64_t seed, uint32_t ils_iter, uint64_t g0, int64_t n, int m, int h, int npert,
+                     uint8_t* slots /*[n][npert]*/, int16_t* vals /*[n][npert] 0-based*/);
+
+/* ---- a3 get_unaries (utils.jl:94-122): U[m][n][h] = -2*C_i'*X + ||c||^2 ------------------------ */
+int lsq_get_unaries(const float* X, int d, int64_t n, const float* C, int m, int h, float* U);
+/* ---- a4 get_binaries (utils.jl:125-144): G[ncbi][h][h] (G[idx][b][a] = 2<C_i[:,a],C_j[:,b]>, i<j),
+ *      cbi[ncbi][2] 1-based pairs like the reference's `cbi` -------------------------------------- */
+int lsq_get_binaries(const float* C, int d, int m, int h, float* G, int32_t* cbi);
+/* ---- a5 veccost / qerror / reconstruct (utils.jl:225-254, 257-285, 203-223) ------------------- */
+int lsq_veccost(const float* X, int d, int64_t n, const int16_t* B, const float* C, int m, int h,
+                float* cost);
+int lsq_qerror(const float* X, int d, int64_t n, const int16_t* B, const float* C, int m, int h,
+               float* out);
+int lsq_reconstruct(const int16_t* B, int64_t n, const float* C, int d, int m, int h, float* CB);
+
+/* ---- a1/a2 encoding_icm (encode_icm.jl:131-189): ONE ILS iteration.  newB may alias oldB.
+ *      g0 = global index of X's first vector (0 unless the caller shards). ----------------------- */
+int lsq_encoding_icm(const float* X, int d, int64_t n, const int16_t* oldB, int16_t* newB,
+                     const float* C, int m, int h, int niter, int randord, int npert, uint64_t seed,
+                     uint32_t ils_iter, uint64_t g0, int verbose);
+/* same, explicit schedule: to_look[m] 0-based; slots[n][npert] 0-based ascending; vals[n][npert]
+ * 0-based new codes.  This is the entry point the parity tests drive. */
+int lsq_encoding_icm_sched(const float* X, int d, int64_t n, const int16_t* oldB, int16_t* newB,
+                           const float* C, int m, int h, int niter, const int32_t* to_look, int npert,
+                           const uint8_t* slots, const int16_t* vals, int verbose);
+
+/* ---- a6 encode_icm_cuda (encode_icm_cuda.jl:253-296): all ILS iterations in one call; snapshots of
+ *      the codes and objective at the iteration counts in ilsiters[nr].  Bs: [nr][n][m] 1-based.
+ *      nsplits only bounds device memory (as in the reference); results do not depend on it. -------- */
+int lsq_encode_icm_cuda(const float* RX, int d, int64_t n, const int16_t* B, const float* C, int m,
+                        int h, const int64_t* ilsiters, int nr, int icmiter, int npert, int randord,
+                        int nsplits, uint64_t seed, uint64_t g0, int16_t* Bs, float* objs, int verbose);
+
+/* ---- a7 update_codebooks (codebook_update.jl:52-86): Cout[m][h][d] = min-norm least-squares
+ *      codebooks for fixed codes.  method: "lsqr" or "lsmr" (anything else -> LSQ_ERR_ARG, as the
+ *      reference's error at :59). --------------------------------------------------------------- */
+int lsq_update_codebooks(const float* X, int d, int64_t n, const int16_t* B, int m, int h, float* Cout,
+                         const char* method, int verbose);
+
+/* ---- a8 linscan_lsq: EXACT reference symbol + signature (linscan_aqd_pairwise_byte.cpp:97-104;
+ *      bound at Linscan.jl:63-69).  idx is 1-based; rows ascending by (distance, id). ------------- */
+void linscan_aqd_query_extra_byte(float* dists, int* idx, unsigned char* codes, float* queries,
+                                  float* codebooks, float* dbnorms, int nqueries, int ncodes, int m,
+                                  int h, int d, int nn);
+/* ---- a9 linscan_pq / linscan_opq: EXACT reference symbol + signature (linscan_aqd.cpp:107-113;
+ *      bound at Linscan.jl:19-23).  res is 0-based (Julia adds 1, Linscan.jl:25). ----------------- */
+void linscan_aqd_query(float* dists, unsigned int* res, unsigned char* codes, float* centers,
+                       float* queries, int N, unsigned int NQ, int B, int K, int dim1codes,
+                       int dim1queries, int subdim);
+/* status-returning twins of the two above (same arguments) */
+int lsq_linscan_lsq(float* dists, int* idx, const unsigned char* codes, const float* queries,
+                    const float* codebooks, const float* dbnorms, int nqueries, int ncodes, int m, int h,
+                    int d, int nn);
+int lsq_linscan_pq(float* dists, unsigned int* res, const unsigned char* codes, const float* centers,
+                   const float* queries, int N, unsigned int NQ, int B, int K, int dim1codes,
+                   int dim1queries, int subdim);
+
+/* ---- f2 quantize_norms (utils.jl:6-31): out[n] 1-based index of the nearest norm-codebook entry - */
+int lsq_quantize_norms(const int16_t* B, int64_t n, const float* C, int d, int m, int h,
+                       const float* cbnorms, int hn, int16_t* out);
+
+/* =====================================================================================================
+ * Device-pointer API.  All pointers are device pointers; `stream` is a cudaStream_t (0 = legacy
+ * default stream).  Codes are uint8 0-based [n][m].  Nothing here synchronises the host.
+ * =================================================================================================== */
+/* bytes of table storage for m codebooks: T[m][m][256][256] floats (both orientations materialised,
+ * cf. binaries + binaries_t, encode_icm.jl:25-28) */
+int64_t lsq_dev_tables_bytes(int m);
+/* T[j][k][b][a] = 2<C_j[:,a], C_k[:,b]> for j != k */
+int lsq_dev_build_tables(const float* dC, int d, int m, float* dT, void* stream);
+/* U[m][n][256] */
+int lsq_dev_build_unaries(const float* dX, int d, int64_t n, const float* dC, int m, float* dU,
+                          void* stream);
+int lsq_dev_veccost(const float* dX, int d, int64_t n, const uint8_t* dcodes, const float* dC, int m,
+                    float* dcost, void* stream);
+/* `niters` ILS iterations, numbered ils_iter0 .. ils_iter0+niters-1, in ONE launch.
+ *   orders   : HOST int8 [niters][m] visit orders (travel in the kernel parameter block)
+ *   dslots/dvals: explicit perturbations [niters][n][npert] (uint8 / uint8) or NULL -> Philox(seed)
+ *   dcodes   : in/out accepted codes; dcost: in/out cost of dcodes (must be valid on entry)
+ *   dsnap    : NULL or uint8 [nsnap][n][m]; dsnapcost: NULL or float [nsnap][n];
+ *              snap_of_iter (HOST int32[niters], -1 = none) says which snapshot slot receives the
+ *              accepted codes (and their costs) after each iteration. */
+int lsq_dev_icm_ils(const float* dX, int d, int64_t n, const float* dC, int m, const float* dU,
+                    const float* dT, uint8_t* dcodes, float* dcost, int icmiter, int npert,
+                    const int8_t* orders, const uint8_t* dslots, const uint8_t* dvals, uint64_t seed,
+                    uint32_t ils_iter0, int niters, uint64_t g0, uint8_t* dsnap, float* dsnapcost,
+                    const int32_t* snap_of_iter, void* stream);
+/* codebook-update statistics of one shard: Gram[mh][mh] += co-occurrence counts (float64),
+ * Rhs[mh][d] += per-code sums of X (float64).  Sum over shards (ncclAllReduce), then solve. */
+int lsq_dev_cb_stats(const float* dX, int d, int64_t n, const uint8_t* dcodes, int m, double* dGram,
+                     double* dRhs, void* stream);
+/* min-norm solve of Gram * K = Rhs by conjugate gradients from K0 = 0; dCout float [m][256][d]. */
+int lsq_dev_cb_solve(const double* dGram, const double* dRhs, int m, int d, float* dCout, int max_iter,
+                     double tol, int* iters_out, void* stream);
+/* ADC scan with device buffers: lut_kind 0 = LSQ (-2<q,c>, + dbnorms, 1-based ids), 1 = PQ. */
+int lsq_dev_linscan(const uint8_t* dcodes, int64_t n, int m, const float* dqueries, int nq, int d,
+                    const float* dcodebooks, const float* dbnorms, int lut_kind, int subdim, int nn,
+                    float* ddists, int32_t* dids, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSQ_B200_H_ */

@@ -1,0 +1,316 @@
+"""Host-side mirror of the reference API over the C ABI (include/lsq_b200.h).  See package docstring."""
+import ctypes as ct
+import os
+
+import numpy as np
+
+__all__ = [
+    "LsqError", "lib", "lib_path", "have_library", "init", "finalize", "device_count", "version",
+    "splitarray", "make_to_look", "make_perturb", "get_unaries", "get_binaries", "veccost", "qerror",
+    "reconstruct", "quantize_norms", "encoding_icm", "encoding_icm_sched", "encode_icm_cuda",
+    "update_codebooks", "linscan_lsq", "linscan_pq", "linscan_opq", "eval_recall", "randinit",
+    "EXPORTED_SYMBOLS",
+]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liblsq_b200.so")
+_lib = None
+
+# every symbol include/lsq_b200.h declares (tests check the .so exports exactly these)
+EXPORTED_SYMBOLS = [
+    "lsq_init", "lsq_finalize", "lsq_last_error", "lsq_device_count", "lsq_version", "lsq_splitarray",
+    "lsq_make_to_look", "lsq_make_perturb", "lsq_get_unaries", "lsq_get_binaries", "lsq_veccost",
+    "lsq_qerror", "lsq_reconstruct", "lsq_encoding_icm", "lsq_encoding_icm_sched", "lsq_encode_icm_cuda",
+    "lsq_update_codebooks", "linscan_aqd_query_extra_byte", "linscan_aqd_query", "lsq_linscan_lsq",
+    "lsq_linscan_pq", "lsq_quantize_norms", "lsq_dev_tables_bytes", "lsq_dev_build_tables",
+    "lsq_dev_build_unaries", "lsq_dev_veccost", "lsq_dev_icm_ils", "lsq_dev_cb_stats", "lsq_dev_cb_solve",
+    "lsq_dev_linscan",
+]
+
+
+class LsqError(RuntimeError):
+    """Raised for every non-zero status of the C ABI (and when the library itself is missing)."""
+
+    def __init__(self, code, msg):
+        super().__init__(f"lsq_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def have_library():
+    return os.path.exists(_LIB_PATH)
+
+
+def lib():
+    """The loaded CDLL.  Fails loudly when the CUDA library has not been built: no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise LsqError(-1, f"{_LIB_PATH} is missing: build it with "
+                               f"`python local-search-quantization_b200/build.py` (there is no CPU fallback)")
+        L = ct.CDLL(_LIB_PATH)
+        L.lsq_last_error.restype = ct.c_char_p
+        L.lsq_version.restype = ct.c_char_p
+        L.lsq_dev_tables_bytes.restype = ct.c_int64
+        L.linscan_aqd_query_extra_byte.restype = None
+        L.linscan_aqd_query.restype = None
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise LsqError(rc, lib().lsq_last_error().decode())
+
+
+def _p(a):
+    return a.ctypes.data_as(ct.c_void_p) if a is not None else None
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _codebooks(C):
+    """Vector{Matrix} (list of m arrays (h, d)) or an (m, h, d) array -> (m, h, d) float32."""
+    if isinstance(C, (list, tuple)):
+        C = np.stack([np.asarray(c, np.float32) for c in C])
+    C = _f32(C)
+    if C.ndim != 3:
+        raise ValueError("C must be m codebooks of shape (h, d)")
+    return C
+
+
+def _codes16(B, n=None):
+    B = np.asarray(B)
+    if B.dtype != np.int16:
+        raise TypeError("B must be a Matrix{Int16} (numpy int16, 1-based)")
+    return np.ascontiguousarray(B)
+
+
+def init(device=0):
+    """CudaUtilsModule.init (cudaUtilsModule.jl:41-43) equivalent."""
+    _check(lib().lsq_init(int(device)))
+
+
+def finalize():
+    """CudaUtilsModule.finit (cudaUtilsModule.jl:37-39) equivalent."""
+    _check(lib().lsq_finalize())
+
+
+def device_count():
+    return int(lib().lsq_device_count())
+
+
+def version():
+    return lib().lsq_version().decode()
+
+
+def splitarray(n, nparts):
+    """utils.jl:152-177 over the range 0..n-1 -> list of (lo, hi) half-open parts."""
+    lo, hi = ct.c_int64(), ct.c_int64()
+    out = []
+    for p in range(nparts):
+        _check(lib().lsq_splitarray(ct.c_int64(n), int(nparts), p, ct.byref(lo), ct.byref(hi)))
+        out.append((lo.value, hi.value))
+    return out
+
+
+def randinit(n, m, h, rng=None):
+    """initializations.jl:2-8: uniform 1..h Int16 codes, (n, m)."""
+    rng = np.random.default_rng() if rng is None else rng
+    return rng.integers(1, h + 1, size=(n, m)).astype(np.int16)
+
+
+def make_to_look(seed, ils_iter, m, randord):
+    out = np.zeros(m, np.int32)
+    _check(lib().lsq_make_to_look(ct.c_uint64(seed), ct.c_uint32(ils_iter), int(m), int(bool(randord)), _p(out)))
+    return out
+
+
+def make_perturb(seed, ils_iter, g0, n, m, h, npert):
+    slots = np.zeros((n, npert), np.uint8)
+    vals = np.zeros((n, npert), np.int16)
+    _check(lib().lsq_make_perturb(ct.c_uint64(seed), ct.c_uint32(ils_iter), ct.c_uint64(g0), ct.c_int64(n),
+                                  int(m), int(h), int(npert), _p(slots), _p(vals)))
+    return slots, vals
+
+
+def get_unaries(X, C, V=False):
+    """utils.jl:94-122 -> (m, n, h) float32."""
+    X, C = _f32(X), _codebooks(C)
+    n, d = X.shape
+    m, h, _ = C.shape
+    U = np.empty((m, n, h), np.float32)
+    _check(lib().lsq_get_unaries(_p(X), d, ct.c_int64(n), _p(C), m, h, _p(U)))
+    return U
+
+
+def get_binaries(C):
+    """utils.jl:125-144 -> (binaries (ncbi, h, h) with [idx][b][a], cbi (ncbi, 2) 1-based)."""
+    C = _codebooks(C)
+    m, h, d = C.shape
+    ncbi = m * (m - 1) // 2
+    G = np.empty((max(ncbi, 1), h, h), np.float32)
+    cbi = np.zeros((max(ncbi, 1), 2), np.int32)
+    _check(lib().lsq_get_binaries(_p(C), d, m, h, _p(G), _p(cbi)))
+    return G[:ncbi], cbi[:ncbi]
+
+
+def veccost(X, B, C):
+    """utils.jl:225-254 -> (n,) float32."""
+    X, C, B = _f32(X), _codebooks(C), _codes16(B)
+    n, d = X.shape
+    m, h, _ = C.shape
+    out = np.empty(n, np.float32)
+    _check(lib().lsq_veccost(_p(X), d, ct.c_int64(n), _p(B), _p(C), m, h, _p(out)))
+    return out
+
+
+def qerror(X, B, C):
+    """utils.jl:257-285 -> float."""
+    X, C, B = _f32(X), _codebooks(C), _codes16(B)
+    n, d = X.shape
+    m, h, _ = C.shape
+    out = ct.c_float()
+    _check(lib().lsq_qerror(_p(X), d, ct.c_int64(n), _p(B), _p(C), m, h, ct.byref(out)))
+    return float(out.value)
+
+
+def reconstruct(B, C):
+    """utils.jl:203-223 -> (n, d) float32."""
+    C, B = _codebooks(C), _codes16(B)
+    n, m = B.shape
+    _, h, d = C.shape
+    out = np.empty((n, d), np.float32)
+    _check(lib().lsq_reconstruct(_p(B), ct.c_int64(n), _p(C), d, m, h, _p(out)))
+    return out
+
+
+def quantize_norms(B, C, cbnorms):
+    """utils.jl:6-31 -> (n,) int16, 1-based."""
+    C, B, cbnorms = _codebooks(C), _codes16(B), _f32(cbnorms)
+    n, m = B.shape
+    _, h, d = C.shape
+    out = np.empty(n, np.int16)
+    _check(lib().lsq_quantize_norms(_p(B), ct.c_int64(n), _p(C), d, m, h, _p(cbnorms), len(cbnorms), _p(out)))
+    return out
+
+
+def encoding_icm(X, oldB, C, niter, randord, npert, V=False, *, seed=0, ils_iter=0, g0=0):
+    """encode_icm.jl:131-189: one ILS iteration; returns the new (n, m) int16 1-based codes.
+
+    The reference draws its schedule from Julia's global RNG; here it is Philox(seed, ils_iter, global
+    vector index), so callers that loop (`for i = 1:ilsiter`, LSQ.jl:45-48) should pass ils_iter=i.
+    """
+    X, C, oldB = _f32(X), _codebooks(C), _codes16(oldB)
+    n, d = X.shape
+    m, h, _ = C.shape
+    if oldB.shape != (n, m):
+        raise ValueError("oldB must be (n, m)")
+    newB = np.empty_like(oldB)
+    _check(lib().lsq_encoding_icm(_p(X), d, ct.c_int64(n), _p(oldB), _p(newB), _p(C), m, h, int(niter),
+                                  int(bool(randord)), int(npert), ct.c_uint64(seed), ct.c_uint32(ils_iter),
+                                  ct.c_uint64(g0), int(bool(V))))
+    return newB
+
+
+def encoding_icm_sched(X, oldB, C, niter, to_look, slots, vals, V=False):
+    """encoding_icm with an explicit schedule (0-based to_look / slots / vals) — the parity entry."""
+    X, C, oldB = _f32(X), _codebooks(C), _codes16(oldB)
+    n, d = X.shape
+    m, h, _ = C.shape
+    to_look = np.ascontiguousarray(to_look, np.int32)
+    slots = np.ascontiguousarray(slots, np.uint8).reshape(n, -1)
+    vals = np.ascontiguousarray(vals, np.int16).reshape(n, -1)
+    npert = slots.shape[1]
+    newB = np.empty_like(oldB)
+    _check(lib().lsq_encoding_icm_sched(_p(X), d, ct.c_int64(n), _p(oldB), _p(newB), _p(C), m, h, int(niter),
+                                        _p(to_look), npert, _p(slots), _p(vals), int(bool(V))))
+    return newB
+
+
+def encode_icm_cuda(RX, B, C, ilsiters, icmiter, npert, randord, nsplits=2, V=False, *, seed=0, g0=0):
+    """encode_icm_cuda.jl:253-296 -> (Bs: list of (n, m) int16, objs: (nr,) float32)."""
+    RX, C, B = _f32(RX), _codebooks(C), _codes16(B)
+    n, d = RX.shape
+    m, h, _ = C.shape
+    its = np.ascontiguousarray(ilsiters, np.int64)
+    nr = len(its)
+    Bs = np.zeros((nr, n, m), np.int16)
+    objs = np.zeros(nr, np.float32)
+    _check(lib().lsq_encode_icm_cuda(_p(RX), d, ct.c_int64(n), _p(B), _p(C), m, h, _p(its), nr, int(icmiter),
+                                     int(npert), int(bool(randord)), int(nsplits), ct.c_uint64(seed),
+                                     ct.c_uint64(g0), _p(Bs), _p(objs), int(bool(V))))
+    return [Bs[r] for r in range(nr)], objs
+
+
+def update_codebooks(X, B, h, V=False, codebook_upd_method="lsqr"):
+    """codebook_update.jl:52-86 -> (m, h, d) float32."""
+    if codebook_upd_method not in ("lsmr", "lsqr"):
+        raise LsqError(1, "Codebook update method unknown")  # codebook_update.jl:59
+    X, B = _f32(X), _codes16(B)
+    n, d = X.shape
+    m = B.shape[1]
+    C = np.empty((m, h, d), np.float32)
+    _check(lib().lsq_update_codebooks(_p(X), d, ct.c_int64(n), _p(B), m, int(h), _p(C),
+                                      codebook_upd_method.encode(), int(bool(V))))
+    return C
+
+
+def linscan_lsq(B, X, C, dbnorms, R, k=10000):
+    """Linscan.jl:46-73.  B (n, m) uint8 0-based; X (nq, d) queries; R (d, d) rotation (RX = R'X).
+    Returns (dists (nq, k) float32, idx (nq, k) int32 1-based)."""
+    B = np.ascontiguousarray(B)
+    if B.dtype != np.uint8:
+        raise TypeError("B must be Matrix{UInt8}")
+    C = _codebooks(C)
+    RX = _f32(_f32(X) @ _f32(R))
+    dbnorms = _f32(dbnorms)
+    n, m = B.shape
+    nq, d = RX.shape
+    h = C.shape[1]
+    dists = np.zeros((nq, k), np.float32)
+    res = np.zeros((nq, k), np.int32)
+    _check(lib().lsq_linscan_lsq(_p(dists), _p(res), _p(B), _p(RX), _p(C), _p(dbnorms), nq, n, m, h, d, int(k)))
+    return dists, res
+
+
+def linscan_pq(B, X, C, b, k=10000):
+    """Linscan.jl:5-27.  C: m codebooks (h, d/m).  Returns (dists, ids 1-based like `res .+= 1`)."""
+    B = np.ascontiguousarray(B)
+    if B.dtype != np.uint8:
+        raise TypeError("B must be Matrix{UInt8}")
+    C = _codebooks(C)
+    X = _f32(X)
+    n, m = B.shape
+    nq, d = X.shape
+    dists = np.zeros((nq, k), np.float32)
+    res = np.zeros((nq, k), np.uint32)
+    _check(lib().lsq_linscan_pq(_p(dists), _p(res), _p(B), _p(C), _p(X), n, ct.c_uint32(nq), int(b), int(k), m, d,
+                                d // m))
+    res += 1
+    return dists, res
+
+
+def linscan_opq(B, X, C, b, R, k=10000):
+    """Linscan.jl:30-43: rotate the queries, then linscan_pq."""
+    return linscan_pq(B, _f32(_f32(X) @ _f32(R)), C, b, k)
+
+
+def eval_recall(ids_gnd, ids_predicted, k):
+    """Linscan.jl:76-117 -> recall@i for i = 1..k (fractions).  ids_predicted is (nq, >=k)."""
+    ids_gnd = np.asarray(ids_gnd).reshape(-1)
+    ids_predicted = np.asarray(ids_predicted)
+    nquery = ids_predicted.shape[0]
+    assert nquery == len(ids_gnd)
+    nn_ranks = np.full(nquery, k + 1, np.int64)
+    for i in range(nquery):
+        pos = np.nonzero(ids_predicted[i, :k] == ids_gnd[i])[0]
+        if len(pos) == 1:
+            nn_ranks[i] = pos[0] + 1
+    nn_ranks.sort()
+    return np.searchsorted(nn_ranks, np.arange(1, k + 1), side="right") / nquery

@@ -1,0 +1,524 @@
+// capi.cu — the extern "C" boundary (include/lsq_b200.h): argument checks, host<->device staging, and
+// the orchestration of the kernels.  No compute happens on the host; without a GPU every compute call
+// fails with LSQ_ERR_CUDA.
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "icm.cuh"
+#include "linscan.cuh"
+#include "cbupdate.cuh"
+
+namespace lsq {
+
+static thread_local std::string g_err;
+static std::mutex g_mu;
+static int g_device = -1;
+static cudaStream_t g_stream = nullptr;
+
+void set_error(const std::string& msg) { g_err = msg; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+  g_err = buf;
+  cudaGetLastError();  // clear sticky-free errors
+  return LSQ_ERR_CUDA;
+}
+
+// lazily bind a device + private stream for the host-pointer API
+static int ensure_init() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_device >= 0) {
+    LSQ_CUDA(cudaSetDevice(g_device));
+    return LSQ_OK;
+  }
+  int cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess || cnt == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available: liblsq_b200 has no CPU fallback");
+    return LSQ_ERR_CUDA;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  LSQ_CUDA(cudaSetDevice(dev));
+  LSQ_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  g_device = dev;
+  return LSQ_OK;
+}
+
+int host_ctx(cudaStream_t* st) {
+  LSQ_TRY(ensure_init());
+  *st = g_stream;
+  return LSQ_OK;
+}
+
+static int check_encode_args(int d, int64_t n, int m, int h, int niter, int npert) {
+  LSQ_CHECK_ARG(d >= 1, "d must be >= 1");
+  LSQ_CHECK_ARG(n >= 0, "n must be >= 0");
+  LSQ_CHECK_ARG(m >= 1 && m <= LSQ_MAXM, "m must be in 1..16 (cudautils.cu:38)");
+  LSQ_CHECK_ARG(h == LSQ_H, "h must be 256 (cudautils.cu:245)");
+  LSQ_CHECK_ARG(niter >= 0, "niter must be >= 0");
+  LSQ_CHECK_ARG(npert >= 0 && npert <= m, "npert must be in 0..m (sample without replacement, encode_icm.jl:58)");
+  return LSQ_OK;
+}
+
+// Number of vectors whose unaries (m KB each) fit comfortably in free device memory.
+static int64_t unary_chunk_capacity(int m, int d) {
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
+  const double budget = 0.6 * (double)free_b;
+  const double per_vec = (double)m * LSQ_H * 4 + (double)d * 4 + 64;
+  int64_t cap = (int64_t)(budget / per_vec);
+  return cap < 1024 ? 1024 : cap;
+}
+
+// upload Int16 1-based codes and convert to uint8 0-based on the device
+static int upload_codes(const int16_t* hB, int64_t count, uint8_t* d8, cudaStream_t st) {
+  DevBuf<int16_t> d16;
+  DevBuf<int> derr;
+  LSQ_CUDA(d16.alloc(count));
+  LSQ_CUDA(derr.alloc(1));
+  LSQ_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), st));
+  LSQ_CUDA(cudaMemcpyAsync(d16.p, hB, count * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+  LSQ_TRY(launch_codes_i16_to_u8(d16.p, d8, count, derr.p, st));
+  int herr = 0;
+  LSQ_CUDA(cudaMemcpyAsync(&herr, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LSQ_CUDA(cudaStreamSynchronize(st));
+  LSQ_CHECK_ARG(herr == 0, "codes must be 1-based in 1..256");
+  return LSQ_OK;
+}
+
+static int download_codes(const uint8_t* d8, int64_t count, int16_t* hB, cudaStream_t st) {
+  DevBuf<int16_t> d16;
+  LSQ_CUDA(d16.alloc(count));
+  LSQ_TRY(launch_codes_u8_to_i16(d8, d16.p, count, st));
+  LSQ_CUDA(cudaMemcpyAsync(hB, d16.p, count * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+  LSQ_CUDA(cudaStreamSynchronize(st));
+  return LSQ_OK;
+}
+
+// The shared driver of lsq_encoding_icm[_sched] and lsq_encode_icm_cuda: uploads, builds tables,
+// walks the base set in memory-bounded chunks, runs `total_iters` ILS iterations per chunk.
+struct EncodeJob {
+  const float* X; int d; int64_t n;
+  const int16_t* B_in;
+  const float* C; int m;
+  int icmiter, npert, randord;
+  uint64_t seed, g0; uint32_t ils_iter0; int total_iters;
+  // explicit schedule (single iteration only) or null
+  const int32_t* to_look; const uint8_t* slots; const int16_t* vals;
+  // outputs
+  int16_t* B_out;                 // final codes (may be null)
+  const int64_t* ilsiters; int nr; int16_t* Bs; float* objs;  // snapshots (may be null/0)
+  int nsplits; int verbose;
+};
+
+static int run_encode_job(const EncodeJob& J) {
+  LSQ_TRY(ensure_init());
+  cudaStream_t st = g_stream;
+  const int d = J.d, m = J.m;
+  const int64_t n = J.n;
+
+  DevBuf<float> dC, dnorms, dT;
+  LSQ_CUDA(dC.alloc((size_t)m * LSQ_H * d));
+  LSQ_CUDA(dnorms.alloc((size_t)m * LSQ_H));
+  LSQ_CUDA(dT.alloc((size_t)m * m * LSQ_H * LSQ_H));
+  LSQ_CUDA(cudaMemcpyAsync(dC.p, J.C, (size_t)m * LSQ_H * d * sizeof(float), cudaMemcpyHostToDevice, st));
+  LSQ_TRY(build_norms(dC.p, d, m, dnorms.p, st));
+  LSQ_TRY(build_tables(dC.p, d, m, dT.p, st));
+
+  // snapshot map: ILS iteration i (1-based) -> first r with ilsiters[r] == i (encode_icm_cuda.jl:211-213)
+  std::vector<int> snap_of(J.total_iters, -1);
+  for (int i = 1; i <= J.total_iters; i++)
+    for (int r = 0; r < J.nr; r++)
+      if (J.ilsiters[r] == i) { snap_of[i - 1] = r; break; }
+  std::vector<double> obj_sum(J.nr > 0 ? J.nr : 1, 0.0);
+  std::vector<char> obj_set(J.nr > 0 ? J.nr : 1, 0);
+
+  // chunking: at least nsplits splitarray parts (encode_icm_cuda.jl:272), more if memory demands
+  int64_t cap = unary_chunk_capacity(m, d);
+  int nparts = J.nsplits > 1 ? J.nsplits : 1;
+  while (ceil_div(n, nparts) > cap) nparts++;
+  if (n == 0) nparts = 1;
+  const int64_t maxchunk = ceil_div(n, nparts) + 1;
+
+  DevBuf<float> dX, dU, dcost, dsnapcost;
+  DevBuf<uint8_t> dcodes, dsnap, dslots, dvals;
+  DevBuf<double> dsum;
+  LSQ_CUDA(dX.alloc((size_t)maxchunk * d));
+  LSQ_CUDA(dU.alloc((size_t)maxchunk * m * LSQ_H));
+  LSQ_CUDA(dcost.alloc(maxchunk));
+  LSQ_CUDA(dcodes.alloc((size_t)maxchunk * m));
+  LSQ_CUDA(dsum.alloc(1025));
+  if (J.nr > 0) {
+    LSQ_CUDA(dsnap.alloc((size_t)J.nr * maxchunk * m));
+    LSQ_CUDA(dsnapcost.alloc((size_t)J.nr * maxchunk));
+  }
+
+  for (int part = 0; part < nparts; part++) {
+    int64_t lo, hi;
+    lsq_splitarray(n, nparts, part, &lo, &hi);
+    const int64_t nc = hi - lo;
+    if (nc <= 0) continue;
+    LSQ_CUDA(cudaMemcpyAsync(dX.p, J.X + (size_t)lo * d, (size_t)nc * d * sizeof(float), cudaMemcpyHostToDevice, st));
+    LSQ_TRY(upload_codes(J.B_in + (size_t)lo * m, nc * m, dcodes.p, st));
+    LSQ_TRY(build_unaries(dX.p, d, nc, dC.p, m, dnorms.p, dU.p, st));
+    LSQ_TRY(launch_veccost(dX.p, d, nc, dcodes.p, dC.p, m, dcost.p, st));
+    if (J.nr > 0) LSQ_CUDA(cudaMemsetAsync(dsnap.p, 0, (size_t)J.nr * nc * m, st));
+
+    if (J.slots != nullptr && J.npert > 0) {
+      // explicit perturbations: [n][npert] uint8 slots, int16 0-based values -> uint8
+      std::vector<uint8_t> v8((size_t)nc * J.npert);
+      for (size_t i = 0; i < v8.size(); i++) {
+        const int16_t x = J.vals[(size_t)lo * J.npert + i];
+        LSQ_CHECK_ARG(x >= 0 && x < LSQ_H, "perturbation values must be 0-based in 0..255");
+        LSQ_CHECK_ARG(J.slots[(size_t)lo * J.npert + i] < m, "perturbation slots must be < m");
+        v8[i] = (uint8_t)x;
+      }
+      LSQ_CUDA(dslots.alloc(v8.size()));
+      LSQ_CUDA(dvals.alloc(v8.size()));
+      LSQ_CUDA(cudaMemcpyAsync(dslots.p, J.slots + (size_t)lo * J.npert, v8.size(), cudaMemcpyHostToDevice, st));
+      LSQ_CUDA(cudaMemcpyAsync(dvals.p, v8.data(), v8.size(), cudaMemcpyHostToDevice, st));
+      LSQ_CUDA(cudaStreamSynchronize(st));
+    }
+
+    for (int it0 = 0; it0 < J.total_iters; it0 += ICM_MAX_ITERS_PER_LAUNCH) {
+      const int nit = std::min(ICM_MAX_ITERS_PER_LAUNCH, J.total_iters - it0);
+      IcmParams p;
+      memset(&p, 0, sizeof(p));
+      p.X = dX.p; p.C = dC.p; p.U = dU.p; p.T = dT.p;
+      p.codes = dcodes.p; p.cost = dcost.p;
+      p.slots = (J.slots && J.npert > 0) ? dslots.p : nullptr;
+      p.vals = (J.slots && J.npert > 0) ? dvals.p : nullptr;
+      p.snap = J.nr > 0 ? dsnap.p : nullptr;
+      p.snapcost = J.nr > 0 ? dsnapcost.p : nullptr;
+      p.n = nc; p.seed = J.seed; p.g0 = J.g0 + (uint64_t)lo;
+      p.ils_iter0 = J.ils_iter0 + (uint32_t)it0;
+      p.d = d; p.m = m; p.icmiter = J.icmiter; p.npert = J.npert; p.niters = nit;
+      for (int i = 0; i < nit; i++) {
+        p.snap_of_iter[i] = (int16_t)snap_of[it0 + i];
+        int32_t order[LSQ_MAXM];
+        if (J.to_look) memcpy(order, J.to_look, sizeof(int32_t) * m);
+        else make_to_look_host(J.seed, J.ils_iter0 + (uint32_t)(it0 + i), m, J.randord, order);
+        for (int k = 0; k < m; k++) p.orders[i][k] = (int8_t)order[k];
+      }
+      LSQ_TRY(launch_icm_warp(p, st));
+    }
+
+    if (J.B_out) LSQ_TRY(download_codes(dcodes.p, nc * m, J.B_out + (size_t)lo * m, st));
+    for (int r = 0; r < J.nr; r++) {
+      bool used = false;
+      for (int i = 0; i < J.total_iters; i++) used |= (snap_of[i] == r);
+      if (!used) continue;
+      LSQ_TRY(download_codes(dsnap.p + (size_t)r * nc * m, nc * m, J.Bs + ((size_t)r * n + lo) * m, st));
+      LSQ_TRY(launch_sum_f32_to_f64(dsnapcost.p + (size_t)r * nc, nc, dsum.p, st));
+      double s = 0.0;
+      LSQ_CUDA(cudaMemcpyAsync(&s, dsum.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+      LSQ_CUDA(cudaStreamSynchronize(st));
+      obj_sum[r] += s;
+      obj_set[r] = 1;
+    }
+    if (J.verbose) fprintf(stderr, "[lsq_b200] encoded part %d/%d (%lld vectors)\n", part + 1, nparts, (long long)nc);
+  }
+  LSQ_CUDA(cudaStreamSynchronize(st));
+  for (int r = 0; r < J.nr; r++)
+    if (J.objs) J.objs[r] = obj_set[r] ? (float)(obj_sum[r] / (double)(n ? n : 1)) : 0.0f;
+  return LSQ_OK;
+}
+
+}  // namespace lsq
+
+using namespace lsq;
+
+extern "C" {
+
+int lsq_init(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess || cnt == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available: liblsq_b200 has no CPU fallback");
+    return LSQ_ERR_CUDA;
+  }
+  LSQ_CHECK_ARG(device >= 0 && device < cnt, "device index out of range");
+  LSQ_CUDA(cudaSetDevice(device));
+  if (g_stream && g_device != device) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
+  if (!g_stream) LSQ_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  g_device = device;
+  return LSQ_OK;
+}
+
+int lsq_finalize(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_stream) { cudaStreamSynchronize(g_stream); cudaStreamDestroy(g_stream); g_stream = nullptr; }
+  g_device = -1;
+  return LSQ_OK;
+}
+
+const char* lsq_last_error(void) { return g_err.c_str(); }
+
+int lsq_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return cnt;
+}
+
+const char* lsq_version(void) { return "lsq_b200 0.1 (sm_100a)"; }
+
+int lsq_splitarray(int64_t n, int nparts, int p, int64_t* lo, int64_t* hi) {
+  LSQ_CHECK_ARG(nparts >= 1 && p >= 0 && p < nparts && n >= 0, "splitarray: need 0 <= p < nparts, n >= 0");
+  const int64_t per = n / nparts, xtra = n % nparts;
+  if (p < xtra) { *lo = p * (per + 1); *hi = *lo + per + 1; }
+  else { *lo = xtra * (per + 1) + (p - xtra) * per; *hi = *lo + per; }
+  return LSQ_OK;
+}
+
+int lsq_make_to_look(uint64_t seed, uint32_t ils_iter, int m, int randord, int32_t* to_look) {
+  LSQ_CHECK_ARG(m >= 1 && m <= LSQ_MAXM, "m must be in 1..16");
+  make_to_look_host(seed, ils_iter, m, randord, to_look);
+  return LSQ_OK;
+}
+
+int lsq_make_perturb(uint64_t seed, uint32_t ils_iter, uint64_t g0, int64_t n, int m, int h, int npert,
+                     uint8_t* slots, int16_t* vals) {
+  LSQ_CHECK_ARG(m >= 1 && m <= LSQ_MAXM, "m must be in 1..16");
+  LSQ_CHECK_ARG(npert >= 0 && npert <= m, "npert must be in 0..m");
+  LSQ_CHECK_ARG(h >= 1 && h <= 256, "h must be in 1..256");
+  for (int64_t v = 0; v < n; v++) {
+    uint8_t s[LSQ_MAXM], x[LSQ_MAXM];
+    make_perturb_one(seed, ils_iter, g0 + (uint64_t)v, m, h, npert, s, x);
+    for (int i = 0; i < npert; i++) { slots[v * npert + i] = s[i]; vals[v * npert + i] = x[i]; }
+  }
+  return LSQ_OK;
+}
+
+int lsq_get_unaries(const float* X, int d, int64_t n, const float* C, int m, int h, float* U) {
+  LSQ_TRY(check_encode_args(d, n, m, h, 0, 0));
+  LSQ_TRY(ensure_init());
+  cudaStream_t st = g_stream;
+  DevBuf<float> dX, dC, dn, dU;
+  LSQ_CUDA(dX.alloc((size_t)n * d));
+  LSQ_CUDA(dC.alloc((size_t)m * h * d));
+  LSQ_CUDA(dn.alloc((size_t)m * h));
+  LSQ_CUDA(dU.alloc((size_t)m * n * h));
+  LSQ_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)n * d * 4, cudaMemcpyHostToDevice, st));
+  LSQ_CUDA(cudaMemcpyAsync(dC.p, C, (size_t)m * h * d * 4, cudaMemcpyHostToDevice, st));
+  LSQ_TRY(build_norms(dC.p, d, m, dn.p, st));
+  LSQ_TRY(build_unaries(dX.p, d, n, dC.p, m, dn.p, dU.p, st));
+  LSQ_CUDA(cudaMemcpyAsync(U, dU.p, (size_t)m * n * h * 4, cudaMemcpyDeviceToHost, st));
+  LSQ_CUDA(cudaStreamSynchronize(st));
+  return LSQ_OK;
+}
+
+int lsq_get_binaries(const float* C, int d, int m, int h, float* G, int32_t* cbi) {
+  LSQ_TRY(check_encode_args(d, 0, m, h, 0, 0));
+  LSQ_TRY(ensure_init());
+  cudaStream_t st = g_stream;
+  DevBuf<float> dC, dT;
+  LSQ_CUDA(dC.alloc((size_t)m * h * d));
+  LSQ_CUDA(dT.alloc((size_t)m * m * h * h));
+  LSQ_CUDA(cudaMemcpyAsync(dC.p, C, (size_t)m * h * d * 4, cudaMemcpyHostToDevice, st));
+  LSQ_TRY(build_tables(dC.p, d, m, dT.p, st));
+  int idx = 0;
+  for (int i = 0; i < m; i++)
+    for (int j = i + 1; j < m; j++, idx++) {
+      cbi[2 * idx] = i + 1; cbi[2 * idx + 1] = j + 1;
+      // binaries[idx][b][a] = 2<C_i[:,a], C_j[:,b]> = T[i][j][b][a]
+      LSQ_CUDA(cudaMemcpyAsync(G + (size_t)idx * h * h, dT.p + (size_t)(i * m + j) * h * h, (size_t)h * h * 4,
+                               cudaMemcpyDeviceToHost, st));
+    }
+  LSQ_CUDA(cudaStreamSynchronize(st));
+  return LSQ_OK;
+}
+
+static int cost_common(const float* X, int d, int64_t n, const int16_t* B, const float* C, int m, int h,
+                       float* cost, float* mean_out) {
+  LSQ_TRY(check_encode_args(d, n, m, h, 0, 0));
+  LSQ_TRY(ensure_init());
+  cudaStream_t st = g_stream;
+  DevBuf<float> dX, dC, dcost;
+  DevBuf<uint8_t> dcodes;
+  DevBuf<double> dsum;
+  LSQ_CUDA(dX.alloc((size_t)n * d));
+  LSQ_CUDA(dC.alloc((size_t)m * h * d));
+  LSQ_CUDA(dcost.alloc(n));
+  LSQ_CUDA(dcodes.alloc((size_t)n * m));
+  LSQ_CUDA(dsum.alloc(1025));
+  LSQ_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)n * d * 4, cudaMemcpyHostToDevice, st));
+  LSQ_CUDA(cudaMemcpyAsync(dC.p, C, (size_t)m * h * d * 4, cudaMemcpyHostToDevice, st));
+  LSQ_TRY(upload_codes(B, n * m, dcodes.p, st));
+  LSQ_TRY(launch_veccost(dX.p, d, n, dcodes.p, dC.p, m, dcost.p, st));
+  if (cost) LSQ_CUDA(cudaMemcpyAsync(cost, dcost.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  if (mean_out) {
+    LSQ_TRY(launch_sum_f32_to_f64(dcost.p, n, dsum.p, st));
+    double s = 0;
+    LSQ_CUDA(cudaMemcpyAsync(&s, dsum.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    LSQ_CUDA(cudaStreamSynchronize(st));
+    *mean_out = (float)(n ? s / (double)n : 0.0);
+  }
+  LSQ_CUDA(cudaStreamSynchronize(st));
+  return LSQ_OK;
+}
+
+int lsq_veccost(const float* X, int d, int64_t n, const int16_t* B, const float* C, int m, int h, float* cost) {
+  return cost_common(X, d, n, B, C, m, h, cost, nullptr);
+}
+
+int lsq_qerror(const float* X, int d, int64_t n, const int16_t* B, const float* C, int m, int h, float* out) {
+  return cost_common(X, d, n, B, C, m, h, nullptr, out);
+}
+
+int lsq_reconstruct(const int16_t* B, int64_t n, const float* C, int d, int m, int h, float* CB) {
+  LSQ_TRY(check_encode_args(d, n, m, h, 0, 0));
+  LSQ_TRY(ensure_init());
+  cudaStream_t st = g_stream;
+  DevBuf<float> dC, dCB;
+  DevBuf<uint8_t> dcodes;
+  LSQ_CUDA(dC.alloc((size_t)m * h * d));
+  LSQ_CUDA(dCB.alloc((size_t)n * d));
+  LSQ_CUDA(dcodes.alloc((size_t)n * m));
+  LSQ_CUDA(cudaMemcpyAsync(dC.p, C, (size_t)m * h * d * 4, cudaMemcpyHostToDevice, st));
+  LSQ_TRY(upload_codes(B, n * m, dcodes.p, st));
+  LSQ_TRY(launch_reconstruct(dcodes.p, n, dC.p, d, m, dCB.p, st));
+  LSQ_CUDA(cudaMemcpyAsync(CB, dCB.p, (size_t)n * d * 4, cudaMemcpyDeviceToHost, st));
+  LSQ_CUDA(cudaStreamSynchronize(st));
+  return LSQ_OK;
+}
+
+int lsq_quantize_norms(const int16_t* B, int64_t n, const float* C, int d, int m, int h, const float* cbnorms,
+                       int hn, int16_t* out) {
+  LSQ_TRY(check_encode_args(d, n, m, h, 0, 0));
+  LSQ_CHECK_ARG(hn >= 1, "norm codebook must be non-empty");
+  LSQ_TRY(ensure_init());
+  cudaStream_t st = g_stream;
+  DevBuf<float> dC, dcb;
+  DevBuf<uint8_t> dcodes;
+  DevBuf<int16_t> dout;
+  LSQ_CUDA(dC.alloc((size_t)m * h * d));
+  LSQ_CUDA(dcb.alloc(hn));
+  LSQ_CUDA(dcodes.alloc((size_t)n * m));
+  LSQ_CUDA(dout.alloc(n));
+  LSQ_CUDA(cudaMemcpyAsync(dC.p, C, (size_t)m * h * d * 4, cudaMemcpyHostToDevice, st));
+  LSQ_CUDA(cudaMemcpyAsync(dcb.p, cbnorms, (size_t)hn * 4, cudaMemcpyHostToDevice, st));
+  LSQ_TRY(upload_codes(B, n * m, dcodes.p, st));
+  LSQ_TRY(launch_quantize_norms(dcodes.p, n, dC.p, d, m, dcb.p, hn, dout.p, st));
+  LSQ_CUDA(cudaMemcpyAsync(out, dout.p, (size_t)n * 2, cudaMemcpyDeviceToHost, st));
+  LSQ_CUDA(cudaStreamSynchronize(st));
+  return LSQ_OK;
+}
+
+int lsq_encoding_icm(const float* X, int d, int64_t n, const int16_t* oldB, int16_t* newB, const float* C,
+                     int m, int h, int niter, int randord, int npert, uint64_t seed, uint32_t ils_iter,
+                     uint64_t g0, int verbose) {
+  LSQ_TRY(check_encode_args(d, n, m, h, niter, npert));
+  EncodeJob J;
+  memset(&J, 0, sizeof(J));
+  J.X = X; J.d = d; J.n = n; J.B_in = oldB; J.C = C; J.m = m;
+  J.icmiter = niter; J.npert = npert; J.randord = randord;
+  J.seed = seed; J.g0 = g0; J.ils_iter0 = ils_iter; J.total_iters = 1;
+  J.B_out = newB; J.nsplits = 1; J.verbose = verbose;
+  return run_encode_job(J);
+}
+
+int lsq_encoding_icm_sched(const float* X, int d, int64_t n, const int16_t* oldB, int16_t* newB,
+                           const float* C, int m, int h, int niter, const int32_t* to_look, int npert,
+                           const uint8_t* slots, const int16_t* vals, int verbose) {
+  LSQ_TRY(check_encode_args(d, n, m, h, niter, npert));
+  LSQ_CHECK_ARG(to_look != nullptr, "to_look is required");
+  LSQ_CHECK_ARG(npert == 0 || (slots != nullptr && vals != nullptr), "slots/vals are required when npert > 0");
+  uint32_t seen = 0;
+  for (int i = 0; i < m; i++) {
+    LSQ_CHECK_ARG(to_look[i] >= 0 && to_look[i] < m, "to_look must be a 0-based permutation of 0..m-1");
+    seen |= 1u << to_look[i];
+  }
+  LSQ_CHECK_ARG(seen == (m == 32 ? 0xFFFFFFFFu : ((1u << m) - 1)), "to_look must be a permutation");
+  EncodeJob J;
+  memset(&J, 0, sizeof(J));
+  J.X = X; J.d = d; J.n = n; J.B_in = oldB; J.C = C; J.m = m;
+  J.icmiter = niter; J.npert = npert; J.randord = 0;
+  J.total_iters = 1; J.to_look = to_look; J.slots = slots; J.vals = vals;
+  J.B_out = newB; J.nsplits = 1; J.verbose = verbose;
+  return run_encode_job(J);
+}
+
+int lsq_encode_icm_cuda(const float* RX, int d, int64_t n, const int16_t* B, const float* C, int m, int h,
+                        const int64_t* ilsiters, int nr, int icmiter, int npert, int randord, int nsplits,
+                        uint64_t seed, uint64_t g0, int16_t* Bs, float* objs, int verbose) {
+  LSQ_TRY(check_encode_args(d, n, m, h, icmiter, npert));
+  LSQ_CHECK_ARG(nr >= 1 && ilsiters != nullptr, "ilsiters must hold at least one iteration count");
+  LSQ_CHECK_ARG(nr < 32767, "too many snapshots");
+  LSQ_CHECK_ARG(nsplits >= 1, "nsplits must be >= 1");
+  int64_t maxit = 0;
+  for (int r = 0; r < nr; r++) maxit = std::max(maxit, ilsiters[r]);
+  LSQ_CHECK_ARG(maxit >= 0 && maxit < (1 << 30), "ilsiters out of range");
+  EncodeJob J;
+  memset(&J, 0, sizeof(J));
+  J.X = RX; J.d = d; J.n = n; J.B_in = B; J.C = C; J.m = m;
+  J.icmiter = icmiter; J.npert = npert; J.randord = randord;
+  J.seed = seed; J.g0 = g0; J.ils_iter0 = 0; J.total_iters = (int)maxit;
+  J.ilsiters = ilsiters; J.nr = nr; J.Bs = Bs; J.objs = objs;
+  J.nsplits = nsplits; J.verbose = verbose;
+  if (Bs) memset(Bs, 0, (size_t)nr * n * m * sizeof(int16_t));
+  return run_encode_job(J);
+}
+
+// ---- device-pointer API ----------------------------------------------------------------------
+int64_t lsq_dev_tables_bytes(int m) { return (int64_t)m * m * LSQ_H * LSQ_H * (int64_t)sizeof(float); }
+
+int lsq_dev_build_tables(const float* dC, int d, int m, float* dT, void* stream) {
+  LSQ_TRY(check_encode_args(d, 0, m, LSQ_H, 0, 0));
+  return build_tables(dC, d, m, dT, (cudaStream_t)stream);
+}
+
+int lsq_dev_build_unaries(const float* dX, int d, int64_t n, const float* dC, int m, float* dU, void* stream) {
+  LSQ_TRY(check_encode_args(d, n, m, LSQ_H, 0, 0));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* dn = nullptr;
+  LSQ_CUDA(cudaMallocAsync((void**)&dn, (size_t)m * LSQ_H * sizeof(float), st));
+  int rc = build_norms(dC, d, m, dn, st);
+  if (rc == LSQ_OK) rc = build_unaries(dX, d, n, dC, m, dn, dU, st);
+  cudaFreeAsync(dn, st);
+  return rc;
+}
+
+int lsq_dev_veccost(const float* dX, int d, int64_t n, const uint8_t* dcodes, const float* dC, int m,
+                    float* dcost, void* stream) {
+  LSQ_TRY(check_encode_args(d, n, m, LSQ_H, 0, 0));
+  return launch_veccost(dX, d, n, dcodes, dC, m, dcost, (cudaStream_t)stream);
+}
+
+int lsq_dev_icm_ils(const float* dX, int d, int64_t n, const float* dC, int m, const float* dU, const float* dT,
+                    uint8_t* dcodes, float* dcost, int icmiter, int npert, const int8_t* orders,
+                    const uint8_t* dslots, const uint8_t* dvals, uint64_t seed, uint32_t ils_iter0, int niters,
+                    uint64_t g0, uint8_t* dsnap, float* dsnapcost, const int32_t* snap_of_iter, void* stream) {
+  LSQ_TRY(check_encode_args(d, n, m, LSQ_H, icmiter, npert));
+  LSQ_CHECK_ARG(niters >= 0 && orders != nullptr, "orders (host int8 [niters][m]) is required");
+  for (int it0 = 0; it0 < niters; it0 += ICM_MAX_ITERS_PER_LAUNCH) {
+    const int nit = std::min(ICM_MAX_ITERS_PER_LAUNCH, niters - it0);
+    IcmParams p;
+    memset(&p, 0, sizeof(p));
+    p.X = dX; p.C = dC; p.U = dU; p.T = dT; p.codes = dcodes; p.cost = dcost;
+    p.slots = dslots ? dslots + (size_t)it0 * n * npert : nullptr;
+    p.vals = dvals ? dvals + (size_t)it0 * n * npert : nullptr;
+    p.snap = dsnap; p.snapcost = dsnapcost;
+    p.n = n; p.seed = seed; p.g0 = g0; p.ils_iter0 = ils_iter0 + (uint32_t)it0;
+    p.d = d; p.m = m; p.icmiter = icmiter; p.npert = npert; p.niters = nit;
+    for (int i = 0; i < nit; i++) {
+      p.snap_of_iter[i] = (dsnap && snap_of_iter) ? (int16_t)snap_of_iter[it0 + i] : (int16_t)-1;
+      for (int k = 0; k < m; k++) {
+        const int8_t o = orders[(size_t)(it0 + i) * m + k];
+        LSQ_CHECK_ARG(o >= 0 && o < m, "orders entries must be in 0..m-1");
+        p.orders[i][k] = o;
+      }
+    }
+    LSQ_TRY(launch_icm_warp(p, (cudaStream_t)stream));
+  }
+  return LSQ_OK;
+}
+
+}  // extern "C"

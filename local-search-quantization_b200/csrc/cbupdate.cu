@@ -1,0 +1,290 @@
+// cbupdate.cu — update_codebooks (codebook_update.jl:52-86) in normal-equation form.
+//
+// The reference solves min_K ||X - K*onehot(B)'||_F with d independent LSQR runs on the n-by-(m*h)
+// one-hot matrix A (updatecb!, codebook_update.jl:8-46; sparsify_codes, utils.jl:50-69).  LSQR from
+// x0 = 0 is, analytically, conjugate gradients on the normal equations A'A k = A'x and converges to
+// the minimum-norm least-squares solution.  Here:
+//   cb_stats : ONE pass over the shard: Gram = A'A (integer co-occurrence counts, exact) and
+//              Rhs = A'X' (float64 sums).  HBM-bound: reads 4d + m bytes per vector.  These two
+//              matrices are the only thing a multi-GPU run has to all-reduce (one collective per outer
+//              iteration); everything after is independent of n.
+//   cb_solve : CG on Gram*K = Rhs from K0 = 0 in float64 for all d right-hand sides in lock-step
+//              (per-column step sizes), i.e. the same Krylov iteration LSQR performs, run to a far
+//              tighter tolerance than LSQR's sqrt(eps(Float32)).  Unused codes stay exactly zero, as
+//              in the reference (Appendix A.13 of SURVEY.md).
+#include "cbupdate.cuh"
+#include "icm.cuh"
+
+#include <algorithm>
+
+#include <vector>
+
+namespace lsq {
+
+__global__ void __launch_bounds__(256) cb_stats_kernel(const float* __restrict__ X, int d, int64_t n,
+                                                       const uint8_t* __restrict__ codes, int m,
+                                                       int* __restrict__ cnt, double* __restrict__ rhs) {
+  const int lane = threadIdx.x & 31;
+  const int mh = m * LSQ_H;
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t v = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); v < n; v += nwarps) {
+    const int mycode = (lane < m) ? (int)codes[v * m + lane] : 0;
+    // co-occurrence counts: all ordered pairs (i, j), including i == j (the diagonal = code counts)
+    for (int p0 = 0; p0 < m * m; p0 += 32) {
+      const int p = p0 + lane;
+      const int i = (p < m * m) ? p / m : 0, j = (p < m * m) ? p % m : 0;
+      const int bi = __shfl_sync(0xFFFFFFFFu, mycode, i);
+      const int bj = __shfl_sync(0xFFFFFFFFu, mycode, j);
+      if (p < m * m) atomicAdd(&cnt[(size_t)(i * LSQ_H + bi) * mh + (j * LSQ_H + bj)], 1);
+    }
+    // per-code sums of x
+    const float* x = X + (size_t)v * d;
+    for (int i = 0; i < m; i++) {
+      const int row = i * LSQ_H + __shfl_sync(0xFFFFFFFFu, mycode, i);
+      double* dst = rhs + (size_t)row * d;
+      for (int t = lane; t < d; t += 32) atomicAdd(dst + t, (double)__ldg(x + t));
+    }
+  }
+}
+
+__global__ void add_counts_kernel(const int* __restrict__ cnt, double* __restrict__ gram, int64_t count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) gram[i] += (double)cnt[i];
+}
+
+int cb_stats(const float* dX, int d, int64_t n, const uint8_t* dcodes, int m, double* dGram, double* dRhs,
+             cudaStream_t st) {
+  if (n == 0) return LSQ_OK;
+  const int64_t mh = (int64_t)m * LSQ_H;
+  int* dcnt = nullptr;
+  LSQ_CUDA(cudaMallocAsync((void**)&dcnt, (size_t)mh * mh * sizeof(int), st));
+  LSQ_CUDA(cudaMemsetAsync(dcnt, 0, (size_t)mh * mh * sizeof(int), st));
+  const int64_t blocks = std::min<int64_t>(ceil_div(n, 8), (int64_t)LSQ_NUM_SMS_HINT * 8);
+  cb_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(dX, d, n, dcodes, m, dcnt, dRhs);
+  add_counts_kernel<<<(unsigned)ceil_div(mh * mh, 256), 256, 0, st>>>(dcnt, dGram, mh * mh);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(dcnt, st);
+  LSQ_CUDA(e);
+  return LSQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CG.  Work vectors are stored column-major per right-hand side: V[c][r], c < d, r < mh.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_256(double v, double* sm) {
+  const int tid = threadIdx.x;
+  sm[tid] = v;
+  __syncthreads();
+  for (int s = 128; s >= 1; s >>= 1) {
+    if (tid < s) sm[tid] += sm[tid + s];
+    __syncthreads();
+  }
+  const double out = sm[0];
+  __syncthreads();
+  return out;
+}
+
+__global__ void __launch_bounds__(256) cg_init_kernel(const double* __restrict__ rhs, int mh, int d,
+                                                      double* __restrict__ Xt, double* __restrict__ Rt,
+                                                      double* __restrict__ Pt, double* __restrict__ rs,
+                                                      double* __restrict__ rs0, int* __restrict__ done) {
+  __shared__ double sm[256];
+  const int c = blockIdx.x;
+  double acc = 0.0;
+  for (int r = threadIdx.x; r < mh; r += 256) {
+    const double v = rhs[(size_t)r * d + c];
+    Xt[(size_t)c * mh + r] = 0.0;
+    Rt[(size_t)c * mh + r] = v;
+    Pt[(size_t)c * mh + r] = v;
+    acc += v * v;
+  }
+  const double tot = block_sum_256(acc, sm);
+  if (threadIdx.x == 0) { rs[c] = tot; rs0[c] = tot; done[c] = (tot == 0.0) ? 1 : 0; }
+}
+
+// APt[c][r] = sum_k Pt[c][k] * G[k][r]   (G symmetric).  Tile 32 (c) x 64 (r), K step 16.
+__global__ void __launch_bounds__(256) cg_gemm_kernel(const double* __restrict__ G, const double* __restrict__ Pt,
+                                                      int mh, int d, double* __restrict__ APt) {
+  __shared__ double Ps[16][32 + 1];
+  __shared__ double Gs[16][64];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // tx: 4 r's, ty: 2 c's
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
+  double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  for (int k0 = 0; k0 < mh; k0 += 16) {
+    {  // Pt tile: 32 c x 16 k
+      const int cc = tid >> 4, kk = tid & 15;
+      for (int h = 0; h < 2; h++) {
+        const int c = c0 + cc + 16 * h;
+        Ps[kk][cc + 16 * h] = (c < d) ? Pt[(size_t)c * mh + k0 + kk] : 0.0;
+      }
+      // G tile: 16 k x 64 r
+      for (int e = tid; e < 16 * 64; e += 256) {
+        const int kk2 = e >> 6, rr = e & 63;
+        Gs[kk2][rr] = G[(size_t)(k0 + kk2) * mh + r0 + rr];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; kk++) {
+      const double p0 = Ps[kk][ty * 2], p1 = Ps[kk][ty * 2 + 1];
+      const double g0 = Gs[kk][tx * 4], g1 = Gs[kk][tx * 4 + 1], g2 = Gs[kk][tx * 4 + 2], g3 = Gs[kk][tx * 4 + 3];
+      acc[0][0] = fma(p0, g0, acc[0][0]); acc[0][1] = fma(p0, g1, acc[0][1]);
+      acc[0][2] = fma(p0, g2, acc[0][2]); acc[0][3] = fma(p0, g3, acc[0][3]);
+      acc[1][0] = fma(p1, g0, acc[1][0]); acc[1][1] = fma(p1, g1, acc[1][1]);
+      acc[1][2] = fma(p1, g2, acc[1][2]); acc[1][3] = fma(p1, g3, acc[1][3]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const int c = c0 + ty * 2 + i;
+    if (c >= d) continue;
+#pragma unroll
+    for (int j = 0; j < 4; j++) APt[(size_t)c * mh + r0 + tx * 4 + j] = acc[i][j];
+  }
+}
+
+// one CTA per right-hand side: step sizes, updates, convergence flag
+__global__ void __launch_bounds__(256) cg_step_kernel(int mh, double tol2, double* __restrict__ Xt,
+                                                      double* __restrict__ Rt, double* __restrict__ Pt,
+                                                      const double* __restrict__ APt, double* __restrict__ rs,
+                                                      const double* __restrict__ rs0, int* __restrict__ done) {
+  __shared__ double sm[256];
+  const int c = blockIdx.x;
+  if (done[c]) return;
+  double* x = Xt + (size_t)c * mh;
+  double* r = Rt + (size_t)c * mh;
+  double* p = Pt + (size_t)c * mh;
+  const double* ap = APt + (size_t)c * mh;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < mh; i += 256) acc += p[i] * ap[i];
+  const double pAp = block_sum_256(acc, sm);
+  if (!(pAp > 0.0)) {
+    if (threadIdx.x == 0) done[c] = 1;
+    return;
+  }
+  const double rsold = rs[c];
+  const double alpha = rsold / pAp;
+  acc = 0.0;
+  for (int i = threadIdx.x; i < mh; i += 256) {
+    x[i] += alpha * p[i];
+    const double rn = r[i] - alpha * ap[i];
+    r[i] = rn;
+    acc += rn * rn;
+  }
+  const double rsnew = block_sum_256(acc, sm);
+  const double beta = rsnew / rsold;
+  for (int i = threadIdx.x; i < mh; i += 256) p[i] = r[i] + beta * p[i];
+  if (threadIdx.x == 0) {
+    rs[c] = rsnew;
+    if (rsnew <= tol2 * rs0[c]) done[c] = 1;
+  }
+}
+
+__global__ void cg_finish_kernel(const double* __restrict__ Xt, int mh, int d, float* __restrict__ Cout) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)mh * d) return;
+  const int r = (int)(e / d), c = (int)(e % d);
+  Cout[e] = (float)Xt[(size_t)c * mh + r];  // K2vec (utils.jl:72-87): C[i][:, b] = K[:, i*h + b]
+}
+
+int cb_solve(const double* dGram, const double* dRhs, int m, int d, float* dCout, int max_iter, double tol,
+             int* iters_out, cudaStream_t st) {
+  const int mh = m * LSQ_H;
+  if (max_iter <= 0) max_iter = 4 * mh;
+  if (!(tol > 0.0)) tol = 1e-9;
+  DevBuf<double> Xt, Rt, Pt, APt, rs, rs0;
+  DevBuf<int> done;
+  LSQ_CUDA(Xt.alloc((size_t)mh * d));
+  LSQ_CUDA(Rt.alloc((size_t)mh * d));
+  LSQ_CUDA(Pt.alloc((size_t)mh * d));
+  LSQ_CUDA(APt.alloc((size_t)mh * d));
+  LSQ_CUDA(rs.alloc(d));
+  LSQ_CUDA(rs0.alloc(d));
+  LSQ_CUDA(done.alloc(d));
+  cg_init_kernel<<<d, 256, 0, st>>>(dRhs, mh, d, Xt.p, Rt.p, Pt.p, rs.p, rs0.p, done.p);
+  LSQ_CUDA(cudaGetLastError());
+  std::vector<int> hdone(d);
+  dim3 ggrid(mh / 64, (unsigned)ceil_div(d, 32), 1);
+  int it = 0;
+  for (; it < max_iter; it++) {
+    cg_gemm_kernel<<<ggrid, 256, 0, st>>>(dGram, Pt.p, mh, d, APt.p);
+    cg_step_kernel<<<d, 256, 0, st>>>(mh, tol * tol, Xt.p, Rt.p, Pt.p, APt.p, rs.p, rs0.p, done.p);
+    if ((it & 15) == 15) {
+      LSQ_CUDA(cudaMemcpyAsync(hdone.data(), done.p, (size_t)d * sizeof(int), cudaMemcpyDeviceToHost, st));
+      LSQ_CUDA(cudaStreamSynchronize(st));
+      bool all = true;
+      for (int c = 0; c < d; c++) all &= (hdone[c] != 0);
+      if (all) { it++; break; }
+    }
+  }
+  LSQ_CUDA(cudaGetLastError());
+  cg_finish_kernel<<<(unsigned)ceil_div((int64_t)mh * d, 256), 256, 0, st>>>(Xt.p, mh, d, dCout);
+  LSQ_CUDA(cudaGetLastError());
+  LSQ_CUDA(cudaStreamSynchronize(st));
+  if (iters_out) *iters_out = it;
+  return LSQ_OK;
+}
+
+}  // namespace lsq
+
+using namespace lsq;
+
+extern "C" {
+
+int lsq_dev_cb_stats(const float* dX, int d, int64_t n, const uint8_t* dcodes, int m, double* dGram, double* dRhs,
+                     void* stream) {
+  LSQ_CHECK_ARG(m >= 1 && m <= LSQ_MAXM && d >= 1 && n >= 0, "cb_stats: bad sizes");
+  return cb_stats(dX, d, n, dcodes, m, dGram, dRhs, (cudaStream_t)stream);
+}
+
+int lsq_dev_cb_solve(const double* dGram, const double* dRhs, int m, int d, float* dCout, int max_iter, double tol,
+                     int* iters_out, void* stream) {
+  LSQ_CHECK_ARG(m >= 1 && m <= LSQ_MAXM && d >= 1, "cb_solve: bad sizes");
+  return cb_solve(dGram, dRhs, m, d, dCout, max_iter, tol, iters_out, (cudaStream_t)stream);
+}
+
+int lsq_update_codebooks(const float* X, int d, int64_t n, const int16_t* B, int m, int h, float* Cout,
+                         const char* method, int verbose) {
+  // "Codebook update method unknown" (codebook_update.jl:59)
+  LSQ_CHECK_ARG(method != nullptr && (strcmp(method, "lsqr") == 0 || strcmp(method, "lsmr") == 0),
+                "Codebook update method unknown");
+  LSQ_CHECK_ARG(m >= 1 && m <= LSQ_MAXM, "m must be in 1..16");
+  LSQ_CHECK_ARG(h == LSQ_H, "h must be 256");
+  LSQ_CHECK_ARG(d >= 1 && n >= 0, "bad sizes");
+  cudaStream_t st;
+  LSQ_TRY(host_ctx(&st));
+  const int64_t mh = (int64_t)m * h;
+  DevBuf<float> dX, dC;
+  DevBuf<int16_t> d16;
+  DevBuf<uint8_t> dcodes;
+  DevBuf<double> dG, dR;
+  DevBuf<int> derr;
+  LSQ_CUDA(dX.alloc((size_t)n * d));
+  LSQ_CUDA(dC.alloc((size_t)mh * d));
+  LSQ_CUDA(d16.alloc((size_t)n * m));
+  LSQ_CUDA(dcodes.alloc((size_t)n * m));
+  LSQ_CUDA(dG.alloc((size_t)mh * mh));
+  LSQ_CUDA(dR.alloc((size_t)mh * d));
+  LSQ_CUDA(derr.alloc(1));
+  LSQ_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), st));
+  LSQ_CUDA(cudaMemsetAsync(dG.p, 0, (size_t)mh * mh * sizeof(double), st));
+  LSQ_CUDA(cudaMemsetAsync(dR.p, 0, (size_t)mh * d * sizeof(double), st));
+  LSQ_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)n * d * 4, cudaMemcpyHostToDevice, st));
+  LSQ_CUDA(cudaMemcpyAsync(d16.p, B, (size_t)n * m * 2, cudaMemcpyHostToDevice, st));
+  LSQ_TRY(launch_codes_i16_to_u8(d16.p, dcodes.p, n * m, derr.p, st));
+  int herr = 0;
+  LSQ_CUDA(cudaMemcpyAsync(&herr, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LSQ_CUDA(cudaStreamSynchronize(st));
+  LSQ_CHECK_ARG(herr == 0, "codes must be 1-based in 1..256");
+  LSQ_TRY(cb_stats(dX.p, d, n, dcodes.p, m, dG.p, dR.p, st));
+  int iters = 0;
+  LSQ_TRY(cb_solve(dG.p, dR.p, m, d, dC.p, 0, 0.0, &iters, st));
+  if (verbose) fprintf(stderr, "[lsq_b200] codebook update: CG converged in %d iterations\n", iters);
+  LSQ_CUDA(cudaMemcpyAsync(Cout, dC.p, (size_t)mh * d * 4, cudaMemcpyDeviceToHost, st));
+  LSQ_CUDA(cudaStreamSynchronize(st));
+  return LSQ_OK;
+}
+
+}  // extern "C"

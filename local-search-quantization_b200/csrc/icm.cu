@@ -1,0 +1,312 @@
+// icm.cu — ICM / ILS encoding kernels (encode_icm_fully! encode_icm.jl:4-127, encoding_icm :131-189,
+// the ILS loop of encode_icm_cuda_single encode_icm_cuda.jl:124-222, replacing perturb / veccost2 /
+// condition_icm3 of cuda/cudautils.cu).
+//
+// Kernel `icm_ils_warp_kernel` — one warp per database vector, ALL requested ILS iterations in one
+// launch (vectors never interact, Appendix A.1 of SURVEY.md), codes and costs live in registers:
+//   perturb (Philox or explicit)  ->  icmiter sweeps over the m nodes in the iteration's visit order
+//   ->  veccost of the new codes  ->  keep iff strictly better (encode_icm.jl:183-186).
+// A node visit streams the vector's 1 KB unary row from HBM (2 x LDG.128 per lane, fully coalesced),
+// adds the m-1 conditioning columns T[j][k][code_k][:] (1 KB each, L2-resident tables) in ascending k
+// with separate fp32 adds (the reference's order, encode_icm.jl:84-101), and takes the first strict
+// minimum of the 256 candidates: 8 candidates per lane in ascending order, then a shuffle-xor
+// lexicographic (value, index) reduction.  Lane l owns candidates 4l..4l+3 and 128+4l..128+4l+3.
+#include "icm.cuh"
+
+namespace lsq {
+
+template <int M>
+__device__ __forceinline__ uint32_t get_code(uint64_t lo, uint64_t hi, int k) {
+  return (M <= 8 || k < 8) ? (uint32_t)(lo >> (8 * (k & 7))) & 0xFFu : (uint32_t)(hi >> (8 * (k & 7))) & 0xFFu;
+}
+
+template <int M>
+__device__ __forceinline__ void set_code(uint64_t& lo, uint64_t& hi, int j, uint32_t val) {
+  const int sh = 8 * (j & 7);
+  if (M <= 8 || j < 8) lo = (lo & ~(0xFFull << sh)) | ((uint64_t)val << sh);
+  else hi = (hi & ~(0xFFull << sh)) | ((uint64_t)val << sh);
+}
+
+// veccost of one vector by one warp (utils.jl:225-254, canonical reduction order (2) of the oracle)
+template <int M>
+__device__ __forceinline__ float warp_veccost(const float* __restrict__ x, const float* __restrict__ C, int d,
+                                              uint64_t lo, uint64_t hi, int lane) {
+  float p = 0.0f;
+  for (int t = lane; t < d; t += 32) {
+    float r = 0.0f;
+#pragma unroll
+    for (int k = 0; k < M; k++)
+      r = __fadd_rn(r, __ldg(C + ((size_t)k * LSQ_H + get_code<M>(lo, hi, k)) * d + t));
+    const float df = __fsub_rn(r, __ldg(x + t));
+    p = __fadd_rn(p, __fmul_rn(df, df));
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) p = __fadd_rn(p, __shfl_xor_sync(0xFFFFFFFFu, p, off));
+  return p;
+}
+
+__device__ __forceinline__ void add4(float4& a, const float4 g) {
+  a.x = __fadd_rn(a.x, g.x); a.y = __fadd_rn(a.y, g.y); a.z = __fadd_rn(a.z, g.z); a.w = __fadd_rn(a.w, g.w);
+}
+
+template <int M>
+__global__ void __launch_bounds__(256) icm_ils_warp_kernel(const __grid_constant__ IcmParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); v < p.n; v += nwarps) {
+    uint64_t lo = 0, hi = 0;
+    {
+      const uint8_t* cp = p.codes + v * M;
+#pragma unroll
+      for (int k = 0; k < M; k++) set_code<M>(lo, hi, k, cp[k]);
+    }
+    float prev = p.cost[v];
+    const float* xv = p.X + (size_t)v * p.d;
+
+    for (int it = 0; it < p.niters; it++) {
+      uint64_t wlo = lo, whi = hi;
+      // ---- perturbation (encode_icm.jl:56-70) ----
+      if (p.slots != nullptr) {
+        const size_t base = ((size_t)it * p.n + v) * p.npert;
+        for (int i = 0; i < p.npert; i++) set_code<M>(wlo, whi, p.slots[base + i], p.vals[base + i]);
+      } else if (p.npert > 0) {
+        uint8_t s[LSQ_MAXM], x[LSQ_MAXM];
+        make_perturb_one(p.seed, p.ils_iter0 + it, p.g0 + (uint64_t)v, M, LSQ_H, p.npert, s, x);
+        for (int i = 0; i < p.npert; i++) set_code<M>(wlo, whi, s[i], x[i]);
+      }
+      // ---- block-ICM sweeps (encode_icm.jl:72-125) ----
+      for (int sweep = 0; sweep < p.icmiter; sweep++) {
+        for (int jj = 0; jj < M; jj++) {
+          const int j = p.orders[it][jj];
+          const float4* up = reinterpret_cast<const float4*>(p.U + ((size_t)j * p.n + v) * LSQ_H);
+          float4 a0 = __ldg(up + lane);
+          float4 a1 = __ldg(up + 32 + lane);
+          const float* tj = p.T + (size_t)j * M * LSQ_H * LSQ_H;
+#pragma unroll
+          for (int k = 0; k < M; k++) {
+            if (k == j) continue;
+            const float4* tp =
+                reinterpret_cast<const float4*>(tj + ((size_t)k * LSQ_H + get_code<M>(wlo, whi, k)) * LSQ_H);
+            const float4 g0 = __ldg(tp + lane);
+            const float4 g1 = __ldg(tp + 32 + lane);
+            add4(a0, g0);
+            add4(a1, g1);
+          }
+          // first strict minimum (encode_icm.jl:105-119)
+          float best = a0.x;
+          int bi = 4 * lane;
+          if (a0.y < best) { best = a0.y; bi = 4 * lane + 1; }
+          if (a0.z < best) { best = a0.z; bi = 4 * lane + 2; }
+          if (a0.w < best) { best = a0.w; bi = 4 * lane + 3; }
+          if (a1.x < best) { best = a1.x; bi = 128 + 4 * lane; }
+          if (a1.y < best) { best = a1.y; bi = 128 + 4 * lane + 1; }
+          if (a1.z < best) { best = a1.z; bi = 128 + 4 * lane + 2; }
+          if (a1.w < best) { best = a1.w; bi = 128 + 4 * lane + 3; }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xFFFFFFFFu, best, off);
+            const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, off);
+            if (ov < best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+          }
+          set_code<M>(wlo, whi, j, (uint32_t)bi);
+        }
+      }
+      // ---- accept iff strictly better (encode_icm.jl:178-186) ----
+      const float newc = warp_veccost<M>(xv, p.C, p.d, wlo, whi, lane);
+      if (newc < prev) { prev = newc; lo = wlo; hi = whi; }
+      const int sn = p.snap_of_iter[it];
+      if (sn >= 0) {
+        if (lane < M) p.snap[((size_t)sn * p.n + v) * M + lane] = (uint8_t)get_code<M>(lo, hi, lane);
+        if (lane == 0 && p.snapcost != nullptr) p.snapcost[(size_t)sn * p.n + v] = prev;
+      }
+    }
+    if (lane < M) p.codes[v * M + lane] = (uint8_t)get_code<M>(lo, hi, lane);
+    if (lane == 0) p.cost[v] = prev;
+  }
+}
+
+template <int M>
+static int launch_icm_warp_m(const IcmParams& p, cudaStream_t st) {
+  int dev = 0, sms = LSQ_NUM_SMS_HINT;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t blocks_needed = ceil_div(p.n, 8);
+  const int64_t cap = (int64_t)sms * 8;
+  const unsigned grid = (unsigned)(blocks_needed < cap ? blocks_needed : cap);
+  icm_ils_warp_kernel<M><<<grid, 256, 0, st>>>(p);
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
+}
+
+int launch_icm_warp(const IcmParams& p, cudaStream_t st) {
+  if (p.n == 0 || p.niters == 0) return LSQ_OK;
+  switch (p.m) {
+#define LSQ_CASE(MM) case MM: return launch_icm_warp_m<MM>(p, st);
+    LSQ_CASE(1) LSQ_CASE(2) LSQ_CASE(3) LSQ_CASE(4) LSQ_CASE(5) LSQ_CASE(6) LSQ_CASE(7) LSQ_CASE(8)
+    LSQ_CASE(9) LSQ_CASE(10) LSQ_CASE(11) LSQ_CASE(12) LSQ_CASE(13) LSQ_CASE(14) LSQ_CASE(15) LSQ_CASE(16)
+#undef LSQ_CASE
+  }
+  set_error("m must be in 1..16");
+  return LSQ_ERR_ARG;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stand-alone cost / decode kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) veccost_kernel(const float* __restrict__ X, int d, int64_t n,
+                                                      const uint8_t* __restrict__ codes,
+                                                      const float* __restrict__ C, int m,
+                                                      float* __restrict__ cost) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t v = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); v < n; v += nwarps) {
+    const uint8_t* cp = codes + v * m;
+    float p = 0.0f;
+    for (int t = lane; t < d; t += 32) {
+      float r = 0.0f;
+      for (int k = 0; k < m; k++) r = __fadd_rn(r, __ldg(C + ((size_t)k * LSQ_H + cp[k]) * d + t));
+      const float df = __fsub_rn(r, __ldg(X + (size_t)v * d + t));
+      p = __fadd_rn(p, __fmul_rn(df, df));
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) p = __fadd_rn(p, __shfl_xor_sync(0xFFFFFFFFu, p, off));
+    if (lane == 0) cost[v] = p;
+  }
+}
+
+static unsigned warp_grid(int64_t n) {
+  const int64_t b = ceil_div(n, 8);
+  const int64_t cap = (int64_t)LSQ_NUM_SMS_HINT * 16;
+  return (unsigned)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+int launch_veccost(const float* dX, int d, int64_t n, const uint8_t* dcodes, const float* dC, int m,
+                   float* dcost, cudaStream_t st) {
+  if (n == 0) return LSQ_OK;
+  veccost_kernel<<<warp_grid(n), 256, 0, st>>>(dX, d, n, dcodes, dC, m, dcost);
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
+}
+
+// reconstruct (utils.jl:203-223): CB[v][t] = ((0 + C_0[b_0][t]) + C_1[b_1][t]) + ...
+__global__ void __launch_bounds__(256) reconstruct_kernel(const uint8_t* __restrict__ codes, int64_t n,
+                                                          const float* __restrict__ C, int d, int m,
+                                                          float* __restrict__ CB) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * 8;
+  for (int64_t v = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); v < n; v += nwarps) {
+    const uint8_t* cp = codes + v * m;
+    for (int t = lane; t < d; t += 32) {
+      float r = 0.0f;
+      for (int k = 0; k < m; k++) r = __fadd_rn(r, __ldg(C + ((size_t)k * LSQ_H + cp[k]) * d + t));
+      CB[(size_t)v * d + t] = r;
+    }
+  }
+}
+
+int launch_reconstruct(const uint8_t* dcodes, int64_t n, const float* dC, int d, int m, float* dCB,
+                       cudaStream_t st) {
+  if (n == 0) return LSQ_OK;
+  reconstruct_kernel<<<warp_grid(n), 256, 0, st>>>(dcodes, n, dC, d, m, dCB);
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
+}
+
+// deterministic float64 sum of a float32 vector: fixed 1024-block partials, then one block.
+__global__ void __launch_bounds__(256) sum_partial_kernel(const float* __restrict__ v, int64_t n,
+                                                          double* __restrict__ partial) {
+  __shared__ double sm[256];
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * per;
+  const int64_t hi = (lo + per < n) ? lo + per : n;
+  double acc = 0.0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) acc += (double)v[i];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s >= 1; s >>= 1) {
+    if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sm[0];
+}
+
+__global__ void sum_final_kernel(const double* __restrict__ partial, int np, double* __restrict__ out) {
+  __shared__ double sm[1024];
+  sm[threadIdx.x] = ((int)threadIdx.x < np) ? partial[threadIdx.x] : 0.0;
+  __syncthreads();
+  for (int s = 512; s >= 1; s >>= 1) {
+    if ((int)threadIdx.x < s) sm[threadIdx.x] += sm[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = sm[0];
+}
+
+// dout: [1 + 1024] doubles; dout[0] receives the sum, the rest is scratch
+int launch_sum_f32_to_f64(const float* dv, int64_t n, double* dout, cudaStream_t st) {
+  sum_partial_kernel<<<1024, 256, 0, st>>>(dv, n, dout + 1);
+  sum_final_kernel<<<1, 1024, 0, st>>>(dout + 1, 1024, dout);
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
+}
+
+// quantize_norms (utils.jl:6-31): one thread per vector, sequential arithmetic as in the oracle.
+__global__ void __launch_bounds__(128) quantize_norms_kernel(const uint8_t* __restrict__ codes, int64_t n,
+                                                             const float* __restrict__ C, int d, int m,
+                                                             const float* __restrict__ cbnorms, int hn,
+                                                             int16_t* __restrict__ out1) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const uint8_t* cp = codes + v * m;
+  float nrm = 0.0f;
+  for (int t = 0; t < d; t++) {
+    float r = 0.0f;
+    for (int k = 0; k < m; k++) r = __fadd_rn(r, __ldg(C + ((size_t)k * LSQ_H + cp[k]) * d + t));
+    nrm = __fadd_rn(nrm, __fmul_rn(r, r));
+  }
+  float e0 = __fsub_rn(nrm, cbnorms[0]);
+  float best = __fmul_rn(e0, e0);
+  int bi = 0;
+  for (int j = 1; j < hn; j++) {
+    const float e = __fsub_rn(nrm, cbnorms[j]);
+    const float dd = __fmul_rn(e, e);
+    if (dd < best) { best = dd; bi = j; }
+  }
+  out1[v] = (int16_t)(bi + 1);
+}
+
+int launch_quantize_norms(const uint8_t* dcodes, int64_t n, const float* dC, int d, int m,
+                          const float* dcbnorms, int hn, int16_t* dout1, cudaStream_t st) {
+  if (n == 0) return LSQ_OK;
+  quantize_norms_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(dcodes, n, dC, d, m, dcbnorms, hn, dout1);
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
+}
+
+// Int16 1-based (Julia) <-> uint8 0-based (device); out-of-range codes raise *derr.
+__global__ void i16_to_u8_kernel(const int16_t* __restrict__ s, uint8_t* __restrict__ o, int64_t count,
+                                 int* __restrict__ derr) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int c = (int)s[i] - 1;
+  if (c < 0 || c >= LSQ_H) { *derr = 1; o[i] = 0; }
+  else o[i] = (uint8_t)c;
+}
+__global__ void u8_to_i16_kernel(const uint8_t* __restrict__ s, int16_t* __restrict__ o, int64_t count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) o[i] = (int16_t)((int)s[i] + 1);
+}
+
+int launch_codes_i16_to_u8(const int16_t* d16, uint8_t* d8, int64_t count, int* derr, cudaStream_t st) {
+  if (count == 0) return LSQ_OK;
+  i16_to_u8_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(d16, d8, count, derr);
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
+}
+int launch_codes_u8_to_i16(const uint8_t* d8, int16_t* d16, int64_t count, cudaStream_t st) {
+  if (count == 0) return LSQ_OK;
+  u8_to_i16_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(d8, d16, count);
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
+}
+
+}  // namespace lsq

@@ -1,0 +1,615 @@
+// linscan.cu — ADC lookup-table linear scan with exact top-k (replaces src/linscan/cpp/
+// linscan_aqd_pairwise_byte.cpp:14-93 and linscan_aqd.cpp:37-102).
+//
+// Bit-exactness contract (checked against the reference's own .so in tests/):
+//   LUT   LSQ: t -= (2*q[k])*c[k], k ascending, separate mul/sub   (linscan_aqd_pairwise_byte.cpp:42-48)
+//         PQ : t += sqr(c[s]-q[s]),  s ascending                   (linscan_aqd.cpp:66-74)
+//   dist  ((0 + LUT_0[c0]) + LUT_1[c1]) + ... (+ dbnorm), fp32 adds in that order       (:69-73 / :84-86)
+//   top-k ascending by (distance, id), the order std::partial_sort gives pair<float,int> (:81 / :91)
+//
+// Data flow on the GPU:
+//   1. lut_kernel      LUT tiles, query-fastest: lut[tile][k*256+c][QT]  (QT queries per tile)
+//   2. scan_kernel     one CTA = one query tile x one slice of the base set.  The tile's whole LUT
+//                      (m*256*QT floats, up to 224 KB) is staged in shared memory by TMA bulk copies.
+//                      Lane = query: for a base vector all lanes read the SAME (k, code) row, so every
+//                      shared-memory wavefront is 32 consecutive floats — conflict-free by
+//                      construction, 32 lookups per wavefront.  Code rows are loaded once per 32 base
+//                      vectors (one row per lane) and broadcast by warp shuffles.
+//   3. exact top-k     a strided sample of the base set gives each query a threshold tau that bounds
+//                      its nn-th distance from above (checked, never assumed: a query whose candidate
+//                      count ends up < nn or > capacity is re-run on the exhaustive path); the main
+//                      pass appends only candidates with dist <= tau; a per-query CTA then sorts the
+//                      64-bit keys (ordered(dist) << 32 | id) in shared memory (bitonic), or, when the
+//                      candidate list is longer than the sorter, radix-selects the nn-th key first.
+#include "linscan.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <vector>
+
+namespace lsq {
+
+constexpr int SCAN_THREADS = 512;
+constexpr int LUT_SMEM_BUDGET = 229376;  // 224 KB of the 227 KB per-CTA limit
+constexpr int SAMPLE_MAX = 16384;
+constexpr int SORT_CAP = LINSCAN_MAX_NN;  // keys the shared-memory bitonic sorter holds (128 KB)
+
+enum { MODE_SAMPLE = 0, MODE_MAIN = 1, MODE_ALL = 2 };
+enum { ST_OK = 0, ST_REDO = 1 };
+
+__host__ __device__ constexpr int tile_queries(int m) {
+  return (LUT_SMEM_BUDGET / (m * LSQ_H * 4)) < 32 ? (LUT_SMEM_BUDGET / (m * LSQ_H * 4)) : 32;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1. LUT construction.  block (32, 8): x = query lane within the tile, y*8.. = 64 table rows.
+// ------------------------------------------------------------------------------------------------
+constexpr int LUT_KC = 64;
+constexpr int LUT_JPT = 8;
+
+template <int KIND>
+__global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ queries, int nq, int qstride,
+                                                  const float* __restrict__ cb, int m, int kd, int QT,
+                                                  float* __restrict__ lut) {
+  __shared__ float qs[LUT_KC][33];
+  const int lane = threadIdx.x, ty = threadIdx.y;
+  const int tile = blockIdx.x;
+  const int jblock = blockIdx.y * (8 * LUT_JPT);
+  const int q0 = tile * QT;
+  const int qoff = (KIND == LUT_PQ) ? (jblock / LSQ_H) * kd : 0;
+  float acc[LUT_JPT];
+#pragma unroll
+  for (int i = 0; i < LUT_JPT; i++) acc[i] = 0.0f;
+
+  for (int k0 = 0; k0 < kd; k0 += LUT_KC) {
+    const int kc = (kd - k0 < LUT_KC) ? (kd - k0) : LUT_KC;
+    __syncthreads();
+    for (int e = ty * 32 + lane; e < 32 * LUT_KC; e += 256) {
+      const int qq = e / LUT_KC, kk = e % LUT_KC;
+      float v = 0.0f;
+      if (qq < QT && q0 + qq < nq && kk < kc) v = queries[(size_t)(q0 + qq) * qstride + qoff + k0 + kk];
+      qs[kk][qq] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < LUT_JPT; i++) {
+      const int j = jblock + ty * LUT_JPT + i;
+      const float* c = cb + (size_t)j * kd + k0;
+      float t = acc[i];
+      for (int kk = 0; kk < kc; kk++) {
+        const float cv = __ldg(c + kk);
+        const float qv = qs[kk][lane];
+        if (KIND == LUT_LSQ) {
+          t = __fsub_rn(t, __fmul_rn(__fmul_rn(2.0f, qv), cv));
+        } else {
+          const float df = __fsub_rn(cv, qv);
+          t = __fadd_rn(t, __fmul_rn(df, df));
+        }
+      }
+      acc[i] = t;
+    }
+  }
+  if (lane < QT) {
+#pragma unroll
+    for (int i = 0; i < LUT_JPT; i++) {
+      const int j = jblock + ty * LUT_JPT + i;
+      lut[((size_t)tile * m * LSQ_H + j) * QT + lane] = acc[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. scan
+// ------------------------------------------------------------------------------------------------
+struct ScanParams {
+  const uint8_t* codes;      // [n][m]
+  const float* norms;        // [n] or nullptr
+  const float* lut;          // tiles
+  const float* tau;          // [ntiles*32] thresholds (MODE_MAIN)
+  unsigned long long* cand;  // [nq][cap] keys
+  int* cnt;                  // [nq]
+  uint32_t* sbuf;            // MODE_SAMPLE: [(tile*count + t)*32 + lane] ordered distances
+  int64_t stride, count;     // base index of step t = t*stride, t < count
+  int64_t cap;
+  int nq, mode, id_base;
+};
+
+template <int M>
+__global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_constant__ ScanParams p) {
+  constexpr int QT = tile_queries(M);
+  constexpr uint32_t LUT_BYTES = (uint32_t)M * LSQ_H * QT * 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* lut = reinterpret_cast<float*>(smem_raw);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + LUT_BYTES);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int W = SCAN_THREADS / 32;
+  const int tile = blockIdx.x;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) bulk_load_issue(lut, p.lut + (size_t)tile * (LUT_BYTES / 4), LUT_BYTES, bar);
+
+  const int q = tile * QT + lane;
+  const bool qvalid = (lane < QT) && (q < p.nq);
+  float tau = INFINITY;
+  if (p.mode == MODE_MAIN && qvalid) tau = p.tau[tile * 32 + lane];
+
+  // slice of the step range handled by this CTA (multiple of 32 steps)
+  int64_t per = (p.count + gridDim.y - 1) / gridDim.y;
+  per = (per + 31) & ~(int64_t)31;
+  const int64_t t_begin = (int64_t)blockIdx.y * per;
+  const int64_t t_end = (t_begin + per < p.count) ? (t_begin + per) : p.count;
+
+  mbar_wait(bar, 0);
+
+  for (int64_t c0 = t_begin + (int64_t)warp * 32; c0 < t_end; c0 += (int64_t)W * 32) {
+    // lane l fetches the code row (and norm) of step c0 + l
+    uint64_t lo = 0, hi = 0;
+    float nrm = 0.0f;
+    {
+      const int64_t t = c0 + lane;
+      if (t < t_end) {
+        const int64_t i = t * p.stride;
+        const uint8_t* cp = p.codes + i * M;
+        if (M == 8) {
+          lo = *reinterpret_cast<const uint64_t*>(cp);
+        } else if (M == 16) {
+          const uint2 a = *reinterpret_cast<const uint2*>(cp);
+          const uint2 b = *reinterpret_cast<const uint2*>(cp + 8);
+          lo = ((uint64_t)a.y << 32) | a.x;
+          hi = ((uint64_t)b.y << 32) | b.x;
+        } else {
+#pragma unroll
+          for (int k = 0; k < M; k++) {
+            const uint64_t c = cp[k];
+            if (k < 8) lo |= c << (8 * k);
+            else hi |= c << (8 * (k - 8));
+          }
+        }
+        if (p.norms != nullptr) nrm = p.norms[i];
+      }
+    }
+#pragma unroll 4
+    for (int b = 0; b < 32; b++) {
+      const uint64_t clo = __shfl_sync(0xFFFFFFFFu, lo, b);
+      const uint64_t chi = (M > 8) ? __shfl_sync(0xFFFFFFFFu, hi, b) : 0ull;
+      const float nb = __shfl_sync(0xFFFFFFFFu, nrm, b);
+      float dist = 0.0f;
+#pragma unroll
+      for (int k = 0; k < M; k++) {
+        const uint32_t c = (k < 8) ? ((uint32_t)(clo >> (8 * k)) & 0xFFu) : ((uint32_t)(chi >> (8 * (k - 8))) & 0xFFu);
+        dist = __fadd_rn(dist, lut[(k * LSQ_H + c) * QT + lane]);
+      }
+      if (p.norms != nullptr) dist = __fadd_rn(dist, nb);
+      const int64_t t = c0 + b;
+      if (qvalid && t < t_end) {
+        if (p.mode == MODE_SAMPLE) {
+          p.sbuf[((size_t)tile * p.count + t) * 32 + lane] = float_to_ordered(dist);
+        } else {
+          const uint32_t id = (uint32_t)(t * p.stride + p.id_base);
+          const unsigned long long key = ((unsigned long long)float_to_ordered(dist) << 32) | id;
+          if (p.mode == MODE_ALL) {
+            p.cand[(size_t)q * p.cap + t] = key;
+          } else if (dist <= tau) {
+            const int pos = atomicAdd(&p.cnt[q], 1);
+            if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = key;
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3a. per-query threshold: the r-th smallest (1-based) of the tile's sample, lane = query.
+//     MSB-first radix select, 4 passes of 8 bits over the ordered-uint distances.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) threshold_kernel(const uint32_t* __restrict__ sbuf, int64_t s, int r,
+                                                         float* __restrict__ tau) {
+  __shared__ int hist[32][257];
+  __shared__ uint32_t prefix[32];
+  __shared__ int rank[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tile = blockIdx.x;
+  if (tid < 32) { prefix[tid] = 0; rank[tid] = r; }
+  for (int pass = 0; pass < 4; pass++) {
+    const int shift = 24 - 8 * pass;
+    const uint32_t pmask = (pass == 0) ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int e = tid; e < 32 * 257; e += 1024) (&hist[0][0])[e] = 0;
+    __syncthreads();
+    const uint32_t pre = prefix[lane];
+    for (int64_t t = warp; t < s; t += 32) {
+      const uint32_t v = sbuf[((size_t)tile * s + t) * 32 + lane];
+      if ((v & pmask) == pre) atomicAdd(&hist[lane][(v >> shift) & 0xFFu], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      int rr = rank[tid], dsel = 255;
+      for (int b = 0; b < 256; b++) {
+        const int c = hist[tid][b];
+        if (rr <= c) { dsel = b; break; }
+        rr -= c;
+      }
+      rank[tid] = rr;
+      prefix[tid] |= (uint32_t)dsel << shift;
+    }
+    __syncthreads();
+  }
+  if (tid < 32) tau[tile * 32 + tid] = ordered_to_float(prefix[tid]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3b. per-query exact top-nn over its candidate keys
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bitonic_sort_smem(unsigned long long* keys, int N, int tid, int nthreads) {
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < N; i += nthreads) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = keys[i], b = keys[ixj];
+          const bool up = ((i & k) == 0);
+          if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(1024) topk_kernel(const unsigned long long* __restrict__ cand, int64_t cap,
+                                                    const int* __restrict__ cnt, int64_t fixed_count, int nn,
+                                                    const int* __restrict__ scatter, float* __restrict__ dists,
+                                                    int32_t* __restrict__ ids, int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned long long keys[];  // SORT_CAP keys
+  __shared__ int hist[256];
+  __shared__ unsigned long long sh_prefix;
+  __shared__ int sh_rank, sh_fill;
+  const int tid = threadIdx.x;
+  const int q = blockIdx.x;
+  const int64_t c = (fixed_count >= 0) ? fixed_count : (int64_t)cnt[q];
+  const int qo = scatter ? scatter[q] : q;
+  if (c < nn || c > cap) {
+    if (tid == 0) status[q] = ST_REDO;
+    return;
+  }
+  if (tid == 0) status[q] = ST_OK;
+  const unsigned long long* src = cand + (size_t)q * cap;
+  int N;
+  if (c <= SORT_CAP) {
+    N = 2;
+    while (N < c) N <<= 1;
+    for (int i = tid; i < N; i += 1024) keys[i] = (i < c) ? src[i] : ~0ull;
+    __syncthreads();
+  } else {
+    // radix-select the nn-th smallest key (keys are unique: the id is part of the key)
+    if (tid == 0) { sh_prefix = 0ull; sh_rank = nn; }
+    for (int pass = 0; pass < 8; pass++) {
+      const int shift = 56 - 8 * pass;
+      const unsigned long long pmask = (pass == 0) ? 0ull : (~0ull << (shift + 8));
+      if (tid < 256) hist[tid] = 0;
+      __syncthreads();
+      const unsigned long long pre = sh_prefix;
+      for (int64_t i = tid; i < c; i += 1024) {
+        const unsigned long long v = src[i];
+        if ((v & pmask) == pre) atomicAdd(&hist[(int)((v >> shift) & 0xFFull)], 1);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int rr = sh_rank, dsel = 255;
+        for (int b = 0; b < 256; b++) {
+          const int h = hist[b];
+          if (rr <= h) { dsel = b; break; }
+          rr -= h;
+        }
+        sh_rank = rr;
+        sh_prefix = pre | ((unsigned long long)dsel << shift);
+      }
+      __syncthreads();
+    }
+    const unsigned long long kth = sh_prefix;
+    if (tid == 0) sh_fill = 0;
+    N = 2;
+    while (N < nn) N <<= 1;
+    for (int i = tid; i < N; i += 1024) keys[i] = ~0ull;
+    __syncthreads();
+    for (int64_t i = tid; i < c; i += 1024) {
+      const unsigned long long v = src[i];
+      if (v <= kth) keys[atomicAdd(&sh_fill, 1)] = v;
+    }
+    __syncthreads();
+  }
+  bitonic_sort_smem(keys, N, tid, 1024);
+  for (int j = tid; j < nn; j += 1024) {
+    const unsigned long long k = keys[j];
+    dists[(size_t)qo * nn + j] = ordered_to_float((uint32_t)(k >> 32));
+    ids[(size_t)qo * nn + j] = (int32_t)(uint32_t)(k & 0xFFFFFFFFull);
+  }
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ rows, int nrows, int d,
+                                   float* __restrict__ dst) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)nrows * d) return;
+  const int r = (int)(e / d), k = (int)(e % d);
+  dst[e] = src[(size_t)rows[r] * d + k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------------
+template <int M>
+static int launch_scan_m(const ScanParams& p, int ntiles, int nsplit, cudaStream_t st) {
+  constexpr int QT = tile_queries(M);
+  constexpr size_t smem = (size_t)M * LSQ_H * QT * 4 + 16;
+  static bool configured = false;
+  if (!configured) {
+    LSQ_CUDA(cudaFuncSetAttribute(scan_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid(ntiles, nsplit, 1);
+  scan_kernel<M><<<grid, SCAN_THREADS, smem, st>>>(p);
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
+}
+
+static int launch_scan(int m, const ScanParams& p, int ntiles, cudaStream_t st) {
+  // enough CTAs to fill the machine a few times over, but slices of at least 4096 steps
+  int nsplit = (int)ceil_div(4 * LSQ_NUM_SMS_HINT, ntiles);
+  const int64_t max_split = std::max<int64_t>(1, p.count / 4096);
+  if (nsplit > max_split) nsplit = (int)max_split;
+  if (nsplit < 1) nsplit = 1;
+  switch (m) {
+#define LSQ_CASE(MM) case MM: return launch_scan_m<MM>(p, ntiles, nsplit, st);
+    LSQ_CASE(1) LSQ_CASE(2) LSQ_CASE(3) LSQ_CASE(4) LSQ_CASE(5) LSQ_CASE(6) LSQ_CASE(7) LSQ_CASE(8)
+    LSQ_CASE(9) LSQ_CASE(10) LSQ_CASE(11) LSQ_CASE(12) LSQ_CASE(13) LSQ_CASE(14) LSQ_CASE(15) LSQ_CASE(16)
+#undef LSQ_CASE
+  }
+  set_error("linscan: m must be in 1..16");
+  return LSQ_ERR_ARG;
+}
+
+static int launch_lut(int lut_kind, const float* dq, int nq, int qstride, const float* dcb, int m, int kd, int QT,
+                      float* dlut, cudaStream_t st) {
+  const int ntiles = (int)ceil_div(nq, QT);
+  dim3 grid(ntiles, m * LSQ_H / (8 * LUT_JPT), 1), block(32, 8, 1);
+  if (lut_kind == LUT_LSQ) lut_kernel<LUT_LSQ><<<grid, block, 0, st>>>(dq, nq, qstride, dcb, m, kd, QT, dlut);
+  else lut_kernel<LUT_PQ><<<grid, block, 0, st>>>(dq, nq, qstride, dcb, m, kd, QT, dlut);
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
+}
+
+static int configure_topk() {
+  static bool configured = false;
+  if (!configured) {
+    LSQ_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_CAP * 8));
+    configured = true;
+  }
+  return LSQ_OK;
+}
+
+struct ScanCtx {
+  const uint8_t* dcodes; int64_t n; int m;
+  const float* dcb; const float* dnorms;
+  int lut_kind, kd, qstride, nn, id_base;
+  float* ddists; int32_t* dids;
+  cudaStream_t st;
+};
+
+// exhaustive path: every base vector becomes a candidate.  `dq` holds nqc query rows (stride qstride);
+// results go to output row scatter[i] (device int array) or i.
+static int scan_exhaustive(const ScanCtx& S, const float* dq, int nqc, const int* dscatter) {
+  const int QT = tile_queries(S.m);
+  // batch so that the candidate buffer stays <= 1 GiB
+  int64_t batch = ((int64_t)1 << 27) / std::max<int64_t>(S.n, 1);
+  batch = std::max<int64_t>(1, std::min<int64_t>(batch, nqc));
+  batch = ceil_div(batch, QT) * QT;  // whole tiles
+  DevBuf<unsigned long long> dcand;
+  DevBuf<float> dlut;
+  DevBuf<int> dstatus;
+  LSQ_CUDA(dcand.alloc((size_t)batch * S.n));
+  LSQ_CUDA(dlut.alloc((size_t)ceil_div(batch, QT) * S.m * LSQ_H * QT));
+  LSQ_CUDA(dstatus.alloc(batch));
+  LSQ_TRY(configure_topk());
+  for (int64_t q0 = 0; q0 < nqc; q0 += batch) {
+    const int nb = (int)std::min<int64_t>(batch, nqc - q0);
+    const int ntiles = (int)ceil_div(nb, QT);
+    LSQ_TRY(launch_lut(S.lut_kind, dq + (size_t)q0 * S.qstride, nb, S.qstride, S.dcb, S.m, S.kd, QT, dlut.p, S.st));
+    ScanParams p;
+    memset(&p, 0, sizeof(p));
+    p.codes = S.dcodes; p.norms = S.dnorms; p.lut = dlut.p; p.cand = dcand.p;
+    p.stride = 1; p.count = S.n; p.cap = S.n; p.nq = nb; p.mode = MODE_ALL; p.id_base = S.id_base;
+    LSQ_TRY(launch_scan(S.m, p, ntiles, S.st));
+    // outputs of this batch: rows q0.. (or scattered)
+    if (dscatter) {
+      topk_kernel<<<nb, 1024, SORT_CAP * 8, S.st>>>(dcand.p, S.n, nullptr, S.n, S.nn, dscatter + q0, S.ddists,
+                                                     S.dids, dstatus.p);
+    } else {
+      topk_kernel<<<nb, 1024, SORT_CAP * 8, S.st>>>(dcand.p, S.n, nullptr, S.n, S.nn, nullptr,
+                                                     S.ddists + (size_t)q0 * S.nn, S.dids + (size_t)q0 * S.nn,
+                                                     dstatus.p);
+    }
+    LSQ_CUDA(cudaGetLastError());
+  }
+  LSQ_CUDA(cudaStreamSynchronize(S.st));
+  return LSQ_OK;
+}
+
+int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dqueries, int nq, int d,
+                   const float* dcodebooks, const float* dbnorms, int lut_kind, int subdim, int nn,
+                   float* ddists, int32_t* dids, cudaStream_t st) {
+  LSQ_CHECK_ARG(m >= 1 && m <= LSQ_MAXM, "linscan: m must be in 1..16");
+  LSQ_CHECK_ARG(nq >= 0 && n >= 0 && d >= 1, "linscan: bad sizes");
+  LSQ_CHECK_ARG(n < ((int64_t)1 << 31) - 1, "linscan: n must fit an int32 id");
+  LSQ_CHECK_ARG(nn >= 0 && nn <= n, "linscan: need 0 <= nn <= ncodes");
+  if (nn > LINSCAN_MAX_NN) {
+    set_error("linscan: nn > 16384 exceeds the top-k sorter capacity");
+    return LSQ_ERR_LIMIT;
+  }
+  if (lut_kind == LUT_PQ) LSQ_CHECK_ARG(subdim >= 1 && (int64_t)subdim * m <= d, "linscan_pq: subdim*m must be <= d");
+  if (nq == 0 || nn == 0) return LSQ_OK;
+
+  ScanCtx S;
+  S.dcodes = dcodes; S.n = n; S.m = m; S.dcb = dcodebooks;
+  S.dnorms = (lut_kind == LUT_LSQ) ? dbnorms : nullptr;
+  S.lut_kind = lut_kind; S.kd = (lut_kind == LUT_LSQ) ? d : subdim; S.qstride = d; S.nn = nn;
+  S.id_base = (lut_kind == LUT_LSQ) ? 1 : 0;
+  S.ddists = ddists; S.dids = dids; S.st = st;
+
+  // sampling plan
+  const int64_t s = std::min<int64_t>(SAMPLE_MAX, n);
+  const int64_t stride = n / s;
+  const double mu = (double)nn * (double)s / (double)n;
+  const int64_t r = (int64_t)ceil(mu + 6.0 * sqrt(mu) + 8.0);
+  const double expected = (double)r * (double)n / (double)s;
+  int64_t cap = SORT_CAP;
+  while ((double)cap < 2.0 * expected) cap <<= 1;
+  if (n <= SORT_CAP || r >= s || cap >= n) return scan_exhaustive(S, dqueries, nq, nullptr);
+
+  const int QT = tile_queries(m);
+  LSQ_TRY(configure_topk());
+  // query batches so that candidates + sample stay within ~4 GiB
+  int64_t qbatch = ((int64_t)1 << 32) / (cap * 8 + s * 4);
+  qbatch = std::max<int64_t>(QT, std::min<int64_t>(qbatch, nq));
+  qbatch = ceil_div(qbatch, QT) * QT;
+  const int max_tiles = (int)ceil_div(qbatch, QT);
+
+  DevBuf<float> dlut, dtau;
+  DevBuf<uint32_t> dsbuf;
+  DevBuf<unsigned long long> dcand;
+  DevBuf<int> dcnt, dstatus;
+  LSQ_CUDA(dlut.alloc((size_t)max_tiles * m * LSQ_H * QT));
+  LSQ_CUDA(dtau.alloc((size_t)max_tiles * 32));
+  LSQ_CUDA(dsbuf.alloc((size_t)max_tiles * s * 32));
+  LSQ_CUDA(dcand.alloc((size_t)qbatch * cap));
+  LSQ_CUDA(dcnt.alloc(qbatch));
+  LSQ_CUDA(dstatus.alloc(qbatch));
+  std::vector<int> hstatus(qbatch), redo;
+
+  for (int64_t q0 = 0; q0 < nq; q0 += qbatch) {
+    const int nb = (int)std::min<int64_t>(qbatch, nq - q0);
+    const int ntiles = (int)ceil_div(nb, QT);
+    const float* dq = dqueries + (size_t)q0 * d;
+    LSQ_TRY(launch_lut(lut_kind, dq, nb, d, dcodebooks, m, S.kd, QT, dlut.p, st));
+    ScanParams p;
+    memset(&p, 0, sizeof(p));
+    p.codes = dcodes; p.norms = S.dnorms; p.lut = dlut.p; p.tau = dtau.p; p.cand = dcand.p; p.cnt = dcnt.p;
+    p.sbuf = dsbuf.p; p.cap = cap; p.nq = nb; p.id_base = S.id_base;
+    // sample pass -> thresholds
+    p.mode = MODE_SAMPLE; p.stride = stride; p.count = s;
+    LSQ_TRY(launch_scan(m, p, ntiles, st));
+    threshold_kernel<<<ntiles, 1024, 0, st>>>(dsbuf.p, s, (int)r, dtau.p);
+    LSQ_CUDA(cudaGetLastError());
+    // main pass
+    LSQ_CUDA(cudaMemsetAsync(dcnt.p, 0, (size_t)nb * sizeof(int), st));
+    p.mode = MODE_MAIN; p.stride = 1; p.count = n;
+    LSQ_TRY(launch_scan(m, p, ntiles, st));
+    topk_kernel<<<nb, 1024, SORT_CAP * 8, st>>>(dcand.p, cap, dcnt.p, -1, nn, nullptr, ddists + (size_t)q0 * nn,
+                                                 dids + (size_t)q0 * nn, dstatus.p);
+    LSQ_CUDA(cudaGetLastError());
+    LSQ_CUDA(cudaMemcpyAsync(hstatus.data(), dstatus.p, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, st));
+    LSQ_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < nb; i++)
+      if (hstatus[i] != ST_OK) redo.push_back((int)(q0 + i));
+  }
+
+  if (!redo.empty()) {
+    // thresholds that missed (or overflowed): exhaustive re-run of just those queries
+    const int nr = (int)redo.size();
+    DevBuf<int> drows;
+    DevBuf<float> dqsel;
+    LSQ_CUDA(drows.alloc(nr));
+    LSQ_CUDA(dqsel.alloc((size_t)nr * d));
+    LSQ_CUDA(cudaMemcpyAsync(drows.p, redo.data(), (size_t)nr * sizeof(int), cudaMemcpyHostToDevice, st));
+    gather_rows_kernel<<<(unsigned)ceil_div((int64_t)nr * d, 256), 256, 0, st>>>(dqueries, drows.p, nr, d, dqsel.p);
+    LSQ_CUDA(cudaGetLastError());
+    LSQ_TRY(scan_exhaustive(S, dqsel.p, nr, drows.p));
+  }
+  return LSQ_OK;
+}
+
+// host-pointer front end shared by the four exported symbols
+static int linscan_host(float* dists, int32_t* ids, const unsigned char* codes, const float* queries,
+                        const float* codebooks, size_t cb_floats, const float* dbnorms, int nq, int64_t n, int m,
+                        int d, int lut_kind, int subdim, int nn) {
+  LSQ_CHECK_ARG(m >= 1 && m <= LSQ_MAXM, "linscan: m must be in 1..16");
+  LSQ_CHECK_ARG(nq >= 0 && n >= 0 && d >= 1 && nn >= 0, "linscan: bad sizes");
+  cudaStream_t st;
+  LSQ_TRY(host_ctx(&st));
+  DevBuf<uint8_t> dcodes;
+  DevBuf<float> dq, dcb, dnorm, dd;
+  DevBuf<int32_t> di;
+  LSQ_CUDA(dcodes.alloc((size_t)n * m));
+  LSQ_CUDA(dq.alloc((size_t)nq * d));
+  LSQ_CUDA(dcb.alloc(cb_floats));
+  LSQ_CUDA(dd.alloc((size_t)nq * nn));
+  LSQ_CUDA(di.alloc((size_t)nq * nn));
+  LSQ_CUDA(cudaMemcpyAsync(dcodes.p, codes, (size_t)n * m, cudaMemcpyHostToDevice, st));
+  LSQ_CUDA(cudaMemcpyAsync(dq.p, queries, (size_t)nq * d * 4, cudaMemcpyHostToDevice, st));
+  LSQ_CUDA(cudaMemcpyAsync(dcb.p, codebooks, cb_floats * 4, cudaMemcpyHostToDevice, st));
+  if (lut_kind == LUT_LSQ) {
+    LSQ_CUDA(dnorm.alloc(n));
+    LSQ_CUDA(cudaMemcpyAsync(dnorm.p, dbnorms, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  }
+  LSQ_TRY(linscan_device(dcodes.p, n, m, dq.p, nq, d, dcb.p, dnorm.p, lut_kind, subdim, nn, dd.p, di.p, st));
+  LSQ_CUDA(cudaMemcpyAsync(dists, dd.p, (size_t)nq * nn * 4, cudaMemcpyDeviceToHost, st));
+  LSQ_CUDA(cudaMemcpyAsync(ids, di.p, (size_t)nq * nn * 4, cudaMemcpyDeviceToHost, st));
+  LSQ_CUDA(cudaStreamSynchronize(st));
+  return LSQ_OK;
+}
+
+}  // namespace lsq
+
+using namespace lsq;
+
+extern "C" {
+
+int lsq_linscan_lsq(float* dists, int* idx, const unsigned char* codes, const float* queries,
+                    const float* codebooks, const float* dbnorms, int nqueries, int ncodes, int m, int h, int d,
+                    int nn) {
+  LSQ_CHECK_ARG(h == LSQ_H, "linscan: h must be 256");
+  return linscan_host(dists, idx, codes, queries, codebooks, (size_t)m * h * d, dbnorms, nqueries, ncodes, m, d,
+                      LUT_LSQ, 0, nn);
+}
+
+int lsq_linscan_pq(float* dists, unsigned int* res, const unsigned char* codes, const float* centers,
+                   const float* queries, int N, unsigned int NQ, int B, int K, int dim1codes, int dim1queries,
+                   int subdim) {
+  const int m = B / 8;
+  LSQ_CHECK_ARG(B % 8 == 0 && m == dim1codes, "linscan_pq: expected B = 8*dim1codes (one byte per codebook)");
+  return linscan_host(dists, reinterpret_cast<int32_t*>(res), codes, queries, centers, (size_t)m * LSQ_H * subdim,
+                      nullptr, (int)NQ, N, m, dim1queries, LUT_PQ, subdim, K);
+}
+
+static void die(const char* fn) {
+  fprintf(stderr, "liblsq_b200: %s failed: %s\n", fn, lsq_last_error());
+  abort();
+}
+
+// The reference symbols return void and have no error channel (Linscan.jl:19-23, 63-69): fail loudly.
+void linscan_aqd_query_extra_byte(float* dists, int* idx, unsigned char* codes, float* queries, float* codebooks,
+                                  float* dbnorms, int nqueries, int ncodes, int m, int h, int d, int nn) {
+  if (lsq_linscan_lsq(dists, idx, codes, queries, codebooks, dbnorms, nqueries, ncodes, m, h, d, nn) != LSQ_OK)
+    die("linscan_aqd_query_extra_byte");
+}
+
+void linscan_aqd_query(float* dists, unsigned int* res, unsigned char* codes, float* centers, float* queries, int N,
+                       unsigned int NQ, int B, int K, int dim1codes, int dim1queries, int subdim) {
+  if (lsq_linscan_pq(dists, res, codes, centers, queries, N, NQ, B, K, dim1codes, dim1queries, subdim) != LSQ_OK)
+    die("linscan_aqd_query");
+}
+
+int lsq_dev_linscan(const uint8_t* dcodes, int64_t n, int m, const float* dqueries, int nq, int d,
+                    const float* dcodebooks, const float* dbnorms, int lut_kind, int subdim, int nn, float* ddists,
+                    int32_t* dids, void* stream) {
+  return linscan_device(dcodes, n, m, dqueries, nq, d, dcodebooks, dbnorms, lut_kind, subdim, nn, ddists, dids,
+                        (cudaStream_t)stream);
+}
+
+}  // extern "C"

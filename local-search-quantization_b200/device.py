@@ -1,0 +1,97 @@
+"""Device-resident sessions over the lsq_dev_* entry points (torch = device memory + streams only)."""
+import ctypes as ct
+
+import numpy as np
+import torch
+
+from . import api
+
+
+def _ptr(t):
+    return ct.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(stream=None):
+    s = torch.cuda.current_stream() if stream is None else stream
+    return ct.c_void_p(s.cuda_stream)
+
+
+class EncodeSession:
+    """X, codebooks, unary/pair tables, codes and costs resident in HBM across ILS iterations
+    (the reference re-uploads X and codes every call: encode_icm_cuda.jl:79,134,146-153)."""
+
+    def __init__(self, X, C, codes, g0=0):
+        assert X.is_cuda and X.dtype == torch.float32 and X.is_contiguous()
+        assert C.is_cuda and C.dtype == torch.float32 and C.is_contiguous() and C.shape[1] == 256
+        assert codes.is_cuda and codes.dtype == torch.uint8 and codes.is_contiguous()
+        self.X, self.C, self.codes = X, C, codes
+        self.n, self.d = X.shape
+        self.m = C.shape[0]
+        self.g0 = int(g0)
+        L = api.lib()
+        dev = X.device
+        self.T = torch.empty(L.lsq_dev_tables_bytes(self.m) // 4, dtype=torch.float32, device=dev)
+        self.U = torch.empty((self.m, self.n, 256), dtype=torch.float32, device=dev)
+        self.cost = torch.empty(self.n, dtype=torch.float32, device=dev)
+        self.set_codebooks(C)
+
+    def set_codebooks(self, C):
+        """(Re)build pair tables, unaries and the cost of the current codes for new codebooks."""
+        L = api.lib()
+        self.C = C
+        api._check(L.lsq_dev_build_tables(_ptr(C), self.d, self.m, _ptr(self.T), _stream()))
+        api._check(L.lsq_dev_build_unaries(_ptr(self.X), self.d, ct.c_int64(self.n), _ptr(C), self.m,
+                                           _ptr(self.U), _stream()))
+        self.refresh_cost()
+
+    def refresh_cost(self):
+        api._check(api.lib().lsq_dev_veccost(_ptr(self.X), self.d, ct.c_int64(self.n), _ptr(self.codes),
+                                             _ptr(self.C), self.m, _ptr(self.cost), _stream()))
+
+    def ils(self, niters, icmiter, npert, randord, seed=0, ils_iter0=0, slots=None, vals=None, orders=None):
+        """`niters` ILS iterations in one launch; codes/cost updated in place."""
+        if orders is None:
+            orders = np.stack([api.make_to_look(seed, ils_iter0 + i, self.m, randord) for i in range(niters)])
+        orders = np.ascontiguousarray(orders, np.int8)
+        api._check(api.lib().lsq_dev_icm_ils(
+            _ptr(self.X), self.d, ct.c_int64(self.n), _ptr(self.C), self.m, _ptr(self.U), _ptr(self.T),
+            _ptr(self.codes), _ptr(self.cost), int(icmiter), int(npert), orders.ctypes.data_as(ct.c_void_p),
+            _ptr(slots), _ptr(vals), ct.c_uint64(seed), ct.c_uint32(ils_iter0), int(niters),
+            ct.c_uint64(self.g0), None, None, None, _stream()))
+
+    def qerror(self):
+        return float(self.cost.double().mean().item())
+
+
+def cb_stats(X, codes, m, gram=None, rhs=None):
+    """Accumulate the codebook-update statistics of one shard into float64 device tensors."""
+    n, d = X.shape
+    mh = m * 256
+    if gram is None:
+        gram = torch.zeros((mh, mh), dtype=torch.float64, device=X.device)
+    if rhs is None:
+        rhs = torch.zeros((mh, d), dtype=torch.float64, device=X.device)
+    api._check(api.lib().lsq_dev_cb_stats(_ptr(X), d, ct.c_int64(n), _ptr(codes), m, _ptr(gram), _ptr(rhs),
+                                          _stream()))
+    return gram, rhs
+
+
+def cb_solve(gram, rhs, m, max_iter=0, tol=0.0):
+    d = rhs.shape[1]
+    C = torch.empty((m, 256, d), dtype=torch.float32, device=gram.device)
+    iters = ct.c_int(0)
+    api._check(api.lib().lsq_dev_cb_solve(_ptr(gram), _ptr(rhs), m, d, _ptr(C), int(max_iter), ct.c_double(tol),
+                                          ct.byref(iters), _stream()))
+    return C, iters.value
+
+
+def linscan(codes, queries, codebooks, dbnorms, nn, lut_kind=0, subdim=0):
+    """Device ADC scan; lut_kind 0 = LSQ (ids 1-based), 1 = PQ (ids 0-based)."""
+    n, m = codes.shape
+    nq, d = queries.shape
+    dists = torch.empty((nq, nn), dtype=torch.float32, device=codes.device)
+    ids = torch.empty((nq, nn), dtype=torch.int32, device=codes.device)
+    api._check(api.lib().lsq_dev_linscan(_ptr(codes), ct.c_int64(n), m, _ptr(queries), nq, d, _ptr(codebooks),
+                                         _ptr(dbnorms), int(lut_kind), int(subdim), int(nn), _ptr(dists), _ptr(ids),
+                                         _stream()))
+    return dists, ids

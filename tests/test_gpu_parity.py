@@ -1,0 +1,283 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the C ABI, against the oracle (bit-exact
+for codes / ids / table bits; stated tolerances for floating-point aggregates), the committed golden
+vectors and the reference's own linscan .so.  Nothing here reads /root/reference."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from util import make_problem, make_scan_problem
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+
+
+@pytest.fixture(scope="module")
+def gpu(lsq):
+    assert lsq.device_count() > 0, "no CUDA device: these tests must run on the GPU box"
+    lsq.init(0)
+    return lsq
+
+
+# ---------------------------------------------------------------- tables (a3, a4) and costs (a5)
+@pytest.mark.parametrize("n,d,m", [(300, 128, 8), (77, 32, 7), (130, 20, 3), (1, 128, 16), (513, 6, 2)])
+def test_unaries_bit_exact(gpu, oracle, n, d, m):
+    X, C, _ = make_problem(100 + n, n, d, m)
+    assert np.array_equal(gpu.get_unaries(X, C), oracle.get_unaries(X, C))
+
+
+@pytest.mark.parametrize("d,m", [(128, 8), (32, 4), (10, 3), (64, 16)])
+def test_binaries_bit_exact(gpu, oracle, d, m):
+    _, C, _ = make_problem(200 + d, 4, d, m, kind="gauss")
+    G, cbi = gpu.get_binaries(C)
+    Go, cbo = oracle.get_binaries(C)
+    assert np.array_equal(G, Go)
+    assert np.array_equal(cbi, cbo + 1)  # reference cbi is 1-based (utils.jl:138)
+
+
+@pytest.mark.parametrize("n,d,m,kind", [(1000, 128, 8, "sift"), (257, 100, 7, "gauss"), (64, 7, 16, "gauss")])
+def test_veccost_qerror_reconstruct(gpu, oracle, n, d, m, kind):
+    X, C, B = make_problem(300 + n, n, d, m, kind=kind)
+    B0 = (B - 1).astype(np.int16)
+    assert np.array_equal(gpu.veccost(X, B, C), oracle.veccost(X, B0, C))
+    assert np.array_equal(gpu.reconstruct(B, C), oracle.reconstruct(B0, C))
+    q, qo = gpu.qerror(X, B, C), oracle.qerror(X, B0, C)
+    assert abs(q - qo) <= 1e-6 * abs(qo)  # float64 sum of identical float32 costs, rounded once
+
+
+def test_quantize_norms(gpu, oracle):
+    X, C, B = make_problem(17, 500, 32, 7)
+    rng = np.random.default_rng(0)
+    rec = oracle.reconstruct((B - 1).astype(np.int16), C)
+    cb = np.sort(rng.choice((rec ** 2).sum(1), 256)).astype(np.float32)
+    assert np.array_equal(gpu.quantize_norms(B, C, cb), oracle.quantize_norms((B - 1).astype(np.int16), C, cb) + 1)
+
+
+# ---------------------------------------------------------------- encoding_icm (a1, a2)
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "icm_*.npz"))))
+def test_encoding_icm_golden(gpu, path):
+    g = np.load(path)
+    X, C, B = make_problem(int(g["seed"]), int(g["n"]), int(g["d"]), int(g["m"]))
+    for it in range(int(g["iters"])):
+        B = gpu.encoding_icm(X, B, C, int(g["niter"]), bool(g["randord"]), int(g["npert"]),
+                             seed=int(g["seed"]), ils_iter=it)
+        assert np.array_equal(B, g["codes"][it])
+        assert np.array_equal(gpu.veccost(X, B, C), g["cost"][it])
+
+
+@pytest.mark.parametrize("n,d,m,niter,npert,randord,kind", [
+    (2000, 128, 8, 4, 4, True, "sift"),      # demo hyper-parameters (demo_lsq.jl:34-37), m = 8
+    (1500, 128, 7, 4, 4, True, "sift"),      # the demos' m = 7 (+1 norm byte)
+    (600, 128, 16, 4, 4, True, "sift"),      # 128-bit codes
+    (700, 64, 15, 2, 6, False, "gauss"),
+    (333, 96, 5, 3, 0, True, "gauss"),       # npert = 0: plain ICM
+    (100, 40, 1, 2, 1, True, "gauss"),       # a single codebook: no pair terms at all
+    (1, 128, 8, 4, 4, True, "sift"),         # a single vector
+])
+def test_encoding_icm_bit_exact(gpu, oracle, n, d, m, niter, npert, randord, kind):
+    X, C, B = make_problem(400 + n + m, n, d, m, kind=kind)
+    Bo, _ = oracle.encoding_icm(X, (B - 1).astype(np.int16), C, niter, randord, npert, seed=42, ils_iter=3, g0=7)
+    Bg = gpu.encoding_icm(X, B, C, niter, randord, npert, seed=42, ils_iter=3, g0=7)
+    assert np.array_equal(Bg, Bo + 1)
+
+
+def test_encoding_icm_explicit_schedule(gpu, oracle):
+    """The schedule is an input: any permutation / perturbation the caller draws must give the
+    oracle's codes (this is how a Julia RNG stream would be replayed)."""
+    n, d, m = 800, 128, 8
+    X, C, B = make_problem(500, n, d, m)
+    rng = np.random.default_rng(5)
+    to_look = rng.permutation(m).astype(np.int32)
+    slots = np.sort(np.stack([rng.permutation(m)[:3] for _ in range(n)]), axis=1).astype(np.uint8)
+    vals = rng.integers(0, 256, size=(n, 3)).astype(np.int16)
+    Bo, _ = oracle.encoding_icm_sched(X, (B - 1).astype(np.int16), C, 3, to_look, slots, vals)
+    Bg = gpu.encoding_icm_sched(X, B, C, 3, to_look, slots, vals)
+    assert np.array_equal(Bg, Bo + 1)
+
+
+def test_encoding_icm_empty_and_errors(gpu):
+    X, C, B = make_problem(1, 0, 16, 4)
+    assert gpu.encoding_icm(X, B, C, 2, True, 2).shape == (0, 4)
+    X, C, B = make_problem(1, 10, 16, 4)
+    bad = B.copy()
+    bad[3, 1] = 257
+    with pytest.raises(gpu.LsqError, match="1-based"):
+        gpu.encoding_icm(X, bad, C, 2, True, 2)
+    bad[3, 1] = 0
+    with pytest.raises(gpu.LsqError, match="1-based"):
+        gpu.encoding_icm(X, bad, C, 2, True, 2)
+
+
+def test_encoding_icm_properties_config1(gpu, oracle):
+    """BASELINE config 1 shape (10 K SIFT-like vectors, m = 8): size-independent properties, plus the
+    bit-exact check against the oracle on the same inputs."""
+    n, d, m = 10000, 128, 8
+    X, C, B = make_problem(600, n, d, m)
+    prev = gpu.veccost(X, B, C)
+    cur = B
+    for it in range(3):
+        nxt = gpu.encoding_icm(X, cur, C, 4, True, 4, seed=1, ils_iter=it)
+        cost = gpu.veccost(X, nxt, C)
+        assert nxt.min() >= 1 and nxt.max() <= 256
+        assert np.all(cost <= prev)
+        changed = np.any(nxt != cur, axis=1)
+        assert np.all(cost[changed] < prev[changed])
+        cur, prev = nxt, cost
+    Bo = (B - 1).astype(np.int16)
+    for it in range(3):
+        Bo, _ = oracle.encoding_icm(X, Bo, C, 4, True, 4, seed=1, ils_iter=it, nworkers=oracle.num_threads())
+    assert np.array_equal(cur, Bo + 1)
+    # ICM fixed point: with npert = 0 a converged code does not move, and never gets worse
+    fix = cur
+    for it in range(6):
+        fix = gpu.encoding_icm(X, fix, C, 4, False, 0, seed=1, ils_iter=10 + it)
+    again = gpu.encoding_icm(X, fix, C, 4, False, 0, seed=1, ils_iter=99)
+    assert np.array_equal(again, fix)
+    # sharding invariance: any split gives the same codes (perturbations keyed by global index)
+    parts = gpu.splitarray(n, 3)
+    sharded = np.concatenate([gpu.encoding_icm(X[lo:hi], B[lo:hi], C, 4, True, 4, seed=1, ils_iter=0, g0=lo)
+                              for lo, hi in parts])
+    whole = gpu.encoding_icm(X, B, C, 4, True, 4, seed=1, ils_iter=0)
+    assert np.array_equal(sharded, whole)
+
+
+# ---------------------------------------------------------------- encode_icm_cuda (a6)
+def test_encode_icm_cuda_matches_looped_encoding_icm(gpu, oracle):
+    n, d, m = 3000, 128, 8
+    X, C, B = make_problem(700, n, d, m)
+    Bs, objs = gpu.encode_icm_cuda(X, B, C, [2, 5], 4, 4, True, 3, seed=11)
+    Bo, objo = oracle.encode_icm_ils(X, (B - 1).astype(np.int16), C, [2, 5], 4, 4, True, seed=11,
+                                     nworkers=oracle.num_threads())
+    assert np.array_equal(Bs[0], Bo[0] + 1) and np.array_equal(Bs[1], Bo[1] + 1)
+    assert np.allclose(objs, objo, rtol=1e-6, atol=0)
+    assert objs[1] <= objs[0]
+    # nsplits only bounds memory: 1 split and 4 splits give the same codes
+    Bs1, _ = gpu.encode_icm_cuda(X, B, C, [5], 4, 4, True, 1, seed=11)
+    Bs4, _ = gpu.encode_icm_cuda(X, B, C, [5], 4, 4, True, 4, seed=11)
+    assert np.array_equal(Bs1[0], Bs[1]) and np.array_equal(Bs4[0], Bs[1])
+    # and equals looping the single-iteration call, as train_lsq does (LSQ.jl:45-48)
+    cur = B
+    for i in range(5):
+        cur = gpu.encoding_icm(X, cur, C, 4, True, 4, seed=11, ils_iter=i)
+    assert np.array_equal(cur, Bs[1])
+
+
+# ---------------------------------------------------------------- linscan (a8, a9)
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "linscan_*.npz"))))
+def test_linscan_golden_reference_vectors(gpu, path):
+    g = np.load(path)
+    n, nq, d, m, nn = (int(g[k]) for k in ("n", "nq", "d", "m", "nn"))
+    codes, queries, codebooks, norms = make_scan_problem(int(g["seed"]), n, nq, d, m)
+    if "pq" in os.path.basename(path):
+        centers = codebooks[:, : d // m].reshape(m, 256, d // m).copy()
+        dists, ids = gpu.linscan_pq(codes, queries, centers, 8 * m, nn)
+        ids = ids.astype(np.int64) - 1   # the wrapper adds 1 like Linscan.jl:25
+    else:
+        dists, ids = gpu.linscan_lsq(codes, queries, codebooks.reshape(m, 256, d), norms, np.eye(d, dtype=np.float32), nn)
+    assert np.array_equal(ids.astype(np.int64), g["ids"])
+    assert np.array_equal(dists, g["dists"])
+
+
+def _ref_or_oracle_lsq(oracle, *a):
+    return oracle.ref_linscan_lsq(*a) if oracle.ref_available() else oracle.linscan_lsq(*a)
+
+
+def _ref_or_oracle_pq(oracle, *a):
+    return oracle.ref_linscan_pq(*a) if oracle.ref_available() else oracle.linscan_pq(*a)
+
+
+@pytest.mark.parametrize("n,nq,d,m,nn", [
+    (200000, 64, 128, 8, 1000),    # sampled-threshold path, config-5 shape scaled down
+    (120000, 40, 128, 16, 1000),
+    (100000, 33, 128, 7, 100),
+    (50000, 9, 64, 8, 10000),      # large k -> exhaustive path + radix select
+    (5000, 70, 32, 4, 1),
+    (300, 5, 16, 2, 300),          # nn == n
+])
+def test_linscan_lsq_exact(gpu, oracle, n, nq, d, m, nn):
+    codes, queries, codebooks, norms = make_scan_problem(800 + m + nn, n, nq, d, m)
+    dr, ir = _ref_or_oracle_lsq(oracle, codes, queries, codebooks, norms, nn)
+    dg, ig = gpu.linscan_lsq(codes, queries, codebooks.reshape(m, 256, d), norms, np.eye(d, dtype=np.float32), nn)
+    assert np.array_equal(ig, ir)
+    assert np.array_equal(dg, dr)
+
+
+@pytest.mark.parametrize("n,nq,d,m,nn", [(150000, 50, 128, 8, 1000), (40000, 20, 64, 16, 200), (2000, 3, 32, 8, 50)])
+def test_linscan_pq_exact(gpu, oracle, n, nq, d, m, nn):
+    codes, queries, codebooks, _ = make_scan_problem(900 + m, n, nq, d, m)
+    centers = codebooks[:, : d // m].reshape(m, 256, d // m).copy()
+    dr, ir = _ref_or_oracle_pq(oracle, codes, queries, centers, nn)
+    dg, ig = gpu.linscan_pq(codes, queries, centers, 8 * m, nn)
+    assert np.array_equal(ig.astype(np.int64) - 1, ir.astype(np.int64))
+    assert np.array_equal(dg, dr)
+
+
+def test_linscan_ties_and_adversarial_order(gpu, oracle):
+    """Duplicates (ties -> lower id first) and a base set sorted so that every near neighbour sits at
+    the END (a strided sample under-represents them: exercises the checked-threshold fallback)."""
+    n, nq, d, m, nn = 60000, 12, 32, 8, 500
+    codes, queries, codebooks, norms = make_scan_problem(1000, n, nq, d, m)
+    codes[n // 2:] = codes[: n // 2]
+    norms[n // 2:] = norms[: n // 2]
+    dr, ir = _ref_or_oracle_lsq(oracle, codes, queries, codebooks, norms, nn)
+    dg, ig = gpu.linscan_lsq(codes, queries, codebooks.reshape(m, 256, d), norms, np.eye(d, dtype=np.float32), nn)
+    assert np.array_equal(ig, ir) and np.array_equal(dg, dr)
+    norms2 = norms.copy()
+    norms2[-600:] -= 1e6   # the last 600 vectors are by far the closest for every query
+    dr, ir = _ref_or_oracle_lsq(oracle, codes, queries, codebooks, norms2, nn)
+    dg, ig = gpu.linscan_lsq(codes, queries, codebooks.reshape(m, 256, d), norms2, np.eye(d, dtype=np.float32), nn)
+    assert np.array_equal(ig, ir) and np.array_equal(dg, dr)
+
+
+def test_linscan_reference_symbols_drop_in(gpu, oracle):
+    """Call the two reference-named void symbols exactly as Linscan.jl's ccall does."""
+    import ctypes as ct
+    L = gpu.lib()
+    codes, queries, codebooks, norms = make_scan_problem(1100, 30000, 8, 64, 8)
+    nn = 100
+    dists = np.zeros((8, nn), np.float32)
+    idx = np.zeros((8, nn), np.int32)
+    P = lambda a: a.ctypes.data_as(ct.c_void_p)
+    L.linscan_aqd_query_extra_byte(P(dists), P(idx), P(codes), P(queries), P(codebooks), P(norms), 8, 30000, 8, 256, 64, nn)
+    dr, ir = _ref_or_oracle_lsq(oracle, codes, queries, codebooks, norms, nn)
+    assert np.array_equal(idx, ir) and np.array_equal(dists, dr)
+    centers = codebooks[:, :8].reshape(8, 256, 8).copy()
+    res = np.zeros((8, nn), np.uint32)
+    L.linscan_aqd_query(P(dists), P(res), P(codes), P(centers), P(queries), 30000, ct.c_uint32(8), 64, nn, 8, 64, 8)
+    dr, ir = _ref_or_oracle_pq(oracle, codes, queries, centers, nn)
+    assert np.array_equal(res, ir) and np.array_equal(dists, dr)
+
+
+# ---------------------------------------------------------------- update_codebooks (a7)
+@pytest.mark.parametrize("n,d,m", [(20000, 32, 4), (6000, 128, 8)])
+def test_update_codebooks(gpu, oracle, n, d, m):
+    """Parity unpinned at this boundary (IterativeSolvers.jl is unvendored/unversioned): criterion is
+    qerror(X, B, C_gpu) <= qerror(X, B, C_exact) * (1 + 1e-5), C_exact = float64 pseudo-inverse."""
+    from oracle import codebook_update as cu
+    X, C, B = make_problem(1200 + m, n, d, m)
+    B[:, 0] = np.where(B[:, 0] == 17, 18, B[:, 0])  # make code 17 of codebook 0 unused
+    B0 = (B - 1).astype(np.int16)
+    Cg = gpu.update_codebooks(X, B, 256)
+    Ce = cu.update_codebooks_exact(X, B0, 256)
+    qg, qe = oracle.qerror(X, B0, Cg), oracle.qerror(X, B0, Ce)
+    assert qg <= qe * (1 + 1e-5)
+    assert qg <= oracle.qerror(X, B0, C)            # never worse than the codebooks we started from
+    assert np.all(Cg[0, 16] == 0)                   # unused code -> zero codeword (min-norm solution)
+    assert np.allclose(Cg, Ce, rtol=0, atol=2e-3 * np.abs(Ce).max())  # same min-norm gauge
+
+
+def test_train_lsq_alternation_monotone(gpu):
+    """The caller's loop (LSQ.jl:57-66): update_codebooks <-> encoding_icm never increases qerror."""
+    X, C, B = make_problem(1300, 5000, 64, 4)
+    C = gpu.update_codebooks(X, B, 256)
+    objs = []
+    for it in range(3):
+        objs.append(gpu.qerror(X, B, C))
+        C = gpu.update_codebooks(X, B, 256)
+        assert gpu.qerror(X, B, C) <= objs[-1] * (1 + 1e-6)
+        for i in range(2):
+            B = gpu.encoding_icm(X, B, C, 4, True, 2, seed=3, ils_iter=2 * it + i)
+    objs.append(gpu.qerror(X, B, C))
+    assert all(b <= a * (1 + 1e-6) for a, b in zip(objs, objs[1:]))
