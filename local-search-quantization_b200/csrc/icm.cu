@@ -21,6 +21,12 @@ __device__ __forceinline__ uint32_t get_code(uint64_t lo, uint64_t hi, int k) {
 }
 
 template <int M>
+__device__ __forceinline__ uint32_t get_code_dyn(uint64_t lo, uint64_t hi, int j) {
+  const int sh = 8 * (j & 7);
+  return (uint32_t)(((M <= 8 || j < 8) ? lo : hi) >> sh) & 0xFFu;
+}
+
+template <int M>
 __device__ __forceinline__ void set_code(uint64_t& lo, uint64_t& hi, int j, uint32_t val) {
   const int sh = 8 * (j & 7);
   if (M <= 8 || j < 8) lo = (lo & ~(0xFFull << sh)) | ((uint64_t)val << sh);
@@ -63,21 +69,34 @@ __global__ void __launch_bounds__(256) icm_ils_warp_kernel(const __grid_constant
     float prev = p.cost[v];
     const float* xv = p.X + (size_t)v * p.d;
 
+    // `clean` bit j: code_j is already the argmin of node j given the other current codes, so a visit
+    // would recompute exactly the same code (the node update is a deterministic function of the other
+    // codes).  Such visits are skipped — results are bit-identical, the work drops ~2x because ICM
+    // reaches a fixed point after about two sweeps.  Any code change clears every other node's bit.
+    constexpr uint32_t ALL_CLEAN = (M == 32) ? 0xFFFFFFFFu : ((1u << M) - 1u);
+    uint32_t clean = 0;
     for (int it = 0; it < p.niters; it++) {
       uint64_t wlo = lo, whi = hi;
+      uint32_t wclean = clean;
       // ---- perturbation (encode_icm.jl:56-70) ----
       if (p.slots != nullptr) {
         const size_t base = ((size_t)it * p.n + v) * p.npert;
-        for (int i = 0; i < p.npert; i++) set_code<M>(wlo, whi, p.slots[base + i], p.vals[base + i]);
+        for (int i = 0; i < p.npert; i++) {
+          const int s = p.slots[base + i];
+          const uint32_t x = p.vals[base + i];
+          if (get_code_dyn<M>(wlo, whi, s) != x) { set_code<M>(wlo, whi, s, x); wclean = 0; }
+        }
       } else if (p.npert > 0) {
         uint8_t s[LSQ_MAXM], x[LSQ_MAXM];
         make_perturb_one(p.seed, p.ils_iter0 + it, p.g0 + (uint64_t)v, M, LSQ_H, p.npert, s, x);
-        for (int i = 0; i < p.npert; i++) set_code<M>(wlo, whi, s[i], x[i]);
+        for (int i = 0; i < p.npert; i++)
+          if (get_code_dyn<M>(wlo, whi, s[i]) != x[i]) { set_code<M>(wlo, whi, s[i], x[i]); wclean = 0; }
       }
       // ---- block-ICM sweeps (encode_icm.jl:72-125) ----
-      for (int sweep = 0; sweep < p.icmiter; sweep++) {
+      for (int sweep = 0; sweep < p.icmiter && wclean != ALL_CLEAN; sweep++) {
         for (int jj = 0; jj < M; jj++) {
           const int j = p.orders[it][jj];
+          if ((wclean >> j) & 1u) continue;
           const float4* up = reinterpret_cast<const float4*>(p.U + ((size_t)j * p.n + v) * LSQ_H);
           float4 a0 = __ldg(up + lane);
           float4 a1 = __ldg(up + 32 + lane);
@@ -108,12 +127,16 @@ __global__ void __launch_bounds__(256) icm_ils_warp_kernel(const __grid_constant
             const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, off);
             if (ov < best || (ov == best && oi < bi)) { best = ov; bi = oi; }
           }
-          set_code<M>(wlo, whi, j, (uint32_t)bi);
+          if ((uint32_t)bi != get_code_dyn<M>(wlo, whi, j)) {
+            set_code<M>(wlo, whi, j, (uint32_t)bi);
+            wclean = 0;
+          }
+          wclean |= 1u << j;
         }
       }
       // ---- accept iff strictly better (encode_icm.jl:178-186) ----
       const float newc = warp_veccost<M>(xv, p.C, p.d, wlo, whi, lane);
-      if (newc < prev) { prev = newc; lo = wlo; hi = whi; }
+      if (newc < prev) { prev = newc; lo = wlo; hi = whi; clean = wclean; }
       const int sn = p.snap_of_iter[it];
       if (sn >= 0) {
         if (lane < M) p.snap[((size_t)sn * p.n + v) * M + lane] = (uint8_t)get_code<M>(lo, hi, lane);
