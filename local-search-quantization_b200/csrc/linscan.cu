@@ -116,7 +116,7 @@ struct ScanParams {
   int nq, mode, id_base;
 };
 
-template <int M>
+template <int M, bool NORM>
 __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_constant__ ScanParams p) {
   constexpr int QT = tile_queries(M);
   constexpr uint32_t LUT_BYTES = (uint32_t)M * LSQ_H * QT * 4;
@@ -137,8 +137,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
 
   const int q = tile * QT + lane;
   const bool qvalid = (lane < QT) && (q < p.nq);
-  float tau = INFINITY;
+  float tau = -INFINITY;  // invalid lanes never pass `dist <= tau`
   if (p.mode == MODE_MAIN && qvalid) tau = p.tau[tile * 32 + lane];
+  const char* lane_base = reinterpret_cast<const char*>(lut) + lane * 4;
 
   // slice of the step range handled by this CTA (multiple of 32 steps)
   int64_t per = (p.count + gridDim.y - 1) / gridDim.y;
@@ -172,34 +173,42 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
             else hi |= c << (8 * (k - 8));
           }
         }
-        if (p.norms != nullptr) nrm = p.norms[i];
+        if (NORM) nrm = p.norms[i];
       }
     }
+    // Inner loop, issue-bound: per codebook one PRMT (byte extract), one IMAD (row offset + lane base),
+    // one LDS with the codebook offset folded into the immediate, one FADD.
+    const bool full = (c0 + 32 <= t_end);
+    const int nvalid = full ? 32 : (int)(t_end - c0);
 #pragma unroll 4
     for (int b = 0; b < 32; b++) {
-      const uint64_t clo = __shfl_sync(0xFFFFFFFFu, lo, b);
-      const uint64_t chi = (M > 8) ? __shfl_sync(0xFFFFFFFFu, hi, b) : 0ull;
-      const float nb = __shfl_sync(0xFFFFFFFFu, nrm, b);
+      const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, (uint32_t)lo, b);
+      const uint32_t w1 = (M > 4) ? __shfl_sync(0xFFFFFFFFu, (uint32_t)(lo >> 32), b) : 0u;
+      const uint32_t w2 = (M > 8) ? __shfl_sync(0xFFFFFFFFu, (uint32_t)hi, b) : 0u;
+      const uint32_t w3 = (M > 12) ? __shfl_sync(0xFFFFFFFFu, (uint32_t)(hi >> 32), b) : 0u;
       float dist = 0.0f;
 #pragma unroll
       for (int k = 0; k < M; k++) {
-        const uint32_t c = (k < 8) ? ((uint32_t)(clo >> (8 * k)) & 0xFFu) : ((uint32_t)(chi >> (8 * (k - 8))) & 0xFFu);
-        dist = __fadd_rn(dist, lut[(k * LSQ_H + c) * QT + lane]);
+        const uint32_t w = (k < 4) ? w0 : (k < 8) ? w1 : (k < 12) ? w2 : w3;
+        const uint32_t c = __byte_perm(w, 0u, 0x4440u | (uint32_t)(k & 3));
+        const float v = *reinterpret_cast<const float*>(lane_base + c * (uint32_t)(QT * 4) + (uint32_t)(k * LSQ_H * QT * 4));
+        dist = __fadd_rn(dist, v);
       }
-      if (p.norms != nullptr) dist = __fadd_rn(dist, nb);
+      if (NORM) dist = __fadd_rn(dist, __shfl_sync(0xFFFFFFFFu, nrm, b));
       const int64_t t = c0 + b;
-      if (qvalid && t < t_end) {
+      if (p.mode == MODE_MAIN) {
+        if (dist <= tau && (full || b < nvalid)) {   // tau = -inf for invalid lanes: never taken
+          const uint32_t id = (uint32_t)(t + p.id_base);
+          const unsigned long long key = ((unsigned long long)float_to_ordered(dist) << 32) | id;
+          const int pos = atomicAdd(&p.cnt[q], 1);
+          if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = key;
+        }
+      } else if (qvalid && (full || b < nvalid)) {
         if (p.mode == MODE_SAMPLE) {
           p.sbuf[((size_t)tile * p.count + t) * 32 + lane] = float_to_ordered(dist);
         } else {
           const uint32_t id = (uint32_t)(t * p.stride + p.id_base);
-          const unsigned long long key = ((unsigned long long)float_to_ordered(dist) << 32) | id;
-          if (p.mode == MODE_ALL) {
-            p.cand[(size_t)q * p.cap + t] = key;
-          } else if (dist <= tau) {
-            const int pos = atomicAdd(&p.cnt[q], 1);
-            if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = key;
-          }
+          p.cand[(size_t)q * p.cap + t] = ((unsigned long long)float_to_ordered(dist) << 32) | id;
         }
       }
     }
@@ -348,13 +357,14 @@ template <int M>
 static int launch_scan_m(const ScanParams& p, int ntiles, int nsplit, cudaStream_t st) {
   constexpr int QT = tile_queries(M);
   constexpr size_t smem = (size_t)M * LSQ_H * QT * 4 + 16;
-  static bool configured = false;
-  if (!configured) {
-    LSQ_CUDA(cudaFuncSetAttribute(scan_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
   dim3 grid(ntiles, nsplit, 1);
-  scan_kernel<M><<<grid, SCAN_THREADS, smem, st>>>(p);
+  if (p.norms != nullptr) {
+    LSQ_CUDA(cudaFuncSetAttribute(scan_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    scan_kernel<M, true><<<grid, SCAN_THREADS, smem, st>>>(p);
+  } else {
+    LSQ_CUDA(cudaFuncSetAttribute(scan_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    scan_kernel<M, false><<<grid, SCAN_THREADS, smem, st>>>(p);
+  }
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
 }
@@ -386,11 +396,7 @@ static int launch_lut(int lut_kind, const float* dq, int nq, int qstride, const 
 }
 
 static int configure_topk() {
-  static bool configured = false;
-  if (!configured) {
-    LSQ_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_CAP * 8));
-    configured = true;
-  }
+  LSQ_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_CAP * 8));
   return LSQ_OK;
 }
 
