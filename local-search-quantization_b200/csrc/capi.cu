@@ -20,6 +20,20 @@ static cudaStream_t g_stream = nullptr;
 
 void set_error(const std::string& msg) { g_err = msg; }
 
+// DevBuf allocations are ordered on the stream the current API call works on
+static thread_local cudaStream_t g_alloc_stream = nullptr;
+cudaStream_t alloc_stream() { return g_alloc_stream; }
+void set_alloc_stream(cudaStream_t st) { g_alloc_stream = st; }
+
+static void keep_pool_memory(int dev) {
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t never = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never);
+  }
+  cudaGetLastError();
+}
+
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   char buf[512];
   snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
@@ -46,6 +60,7 @@ static int ensure_init() {
   cudaGetDevice(&dev);
   LSQ_CUDA(cudaSetDevice(dev));
   LSQ_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  keep_pool_memory(dev);
   g_device = dev;
   return LSQ_OK;
 }
@@ -53,6 +68,7 @@ static int ensure_init() {
 int host_ctx(cudaStream_t* st) {
   LSQ_TRY(ensure_init());
   *st = g_stream;
+  set_alloc_stream(g_stream);
   return LSQ_OK;
 }
 
@@ -118,8 +134,8 @@ struct EncodeJob {
 };
 
 static int run_encode_job(const EncodeJob& J) {
-  LSQ_TRY(ensure_init());
-  cudaStream_t st = g_stream;
+  cudaStream_t st;
+  LSQ_TRY(host_ctx(&st));
   const int d = J.d, m = J.m;
   const int64_t n = J.n;
 
@@ -249,6 +265,7 @@ int lsq_init(int device) {
   LSQ_CUDA(cudaSetDevice(device));
   if (g_stream && g_device != device) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
   if (!g_stream) LSQ_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  keep_pool_memory(device);
   g_device = device;
   return LSQ_OK;
 }
@@ -256,6 +273,11 @@ int lsq_init(int device) {
 int lsq_finalize(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_stream) { cudaStreamSynchronize(g_stream); cudaStreamDestroy(g_stream); g_stream = nullptr; }
+  if (g_device >= 0) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, g_device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    cudaGetLastError();
+  }
   g_device = -1;
   return LSQ_OK;
 }
@@ -299,8 +321,8 @@ int lsq_make_perturb(uint64_t seed, uint32_t ils_iter, uint64_t g0, int64_t n, i
 
 int lsq_get_unaries(const float* X, int d, int64_t n, const float* C, int m, int h, float* U) {
   LSQ_TRY(check_encode_args(d, n, m, h, 0, 0));
-  LSQ_TRY(ensure_init());
-  cudaStream_t st = g_stream;
+  cudaStream_t st;
+  LSQ_TRY(host_ctx(&st));
   DevBuf<float> dX, dC, dn, dU;
   LSQ_CUDA(dX.alloc((size_t)n * d));
   LSQ_CUDA(dC.alloc((size_t)m * h * d));
@@ -317,8 +339,8 @@ int lsq_get_unaries(const float* X, int d, int64_t n, const float* C, int m, int
 
 int lsq_get_binaries(const float* C, int d, int m, int h, float* G, int32_t* cbi) {
   LSQ_TRY(check_encode_args(d, 0, m, h, 0, 0));
-  LSQ_TRY(ensure_init());
-  cudaStream_t st = g_stream;
+  cudaStream_t st;
+  LSQ_TRY(host_ctx(&st));
   DevBuf<float> dC, dT;
   LSQ_CUDA(dC.alloc((size_t)m * h * d));
   LSQ_CUDA(dT.alloc((size_t)m * m * h * h));
@@ -339,8 +361,8 @@ int lsq_get_binaries(const float* C, int d, int m, int h, float* G, int32_t* cbi
 static int cost_common(const float* X, int d, int64_t n, const int16_t* B, const float* C, int m, int h,
                        float* cost, float* mean_out) {
   LSQ_TRY(check_encode_args(d, n, m, h, 0, 0));
-  LSQ_TRY(ensure_init());
-  cudaStream_t st = g_stream;
+  cudaStream_t st;
+  LSQ_TRY(host_ctx(&st));
   DevBuf<float> dX, dC, dcost;
   DevBuf<uint8_t> dcodes;
   DevBuf<double> dsum;
@@ -375,8 +397,8 @@ int lsq_qerror(const float* X, int d, int64_t n, const int16_t* B, const float* 
 
 int lsq_reconstruct(const int16_t* B, int64_t n, const float* C, int d, int m, int h, float* CB) {
   LSQ_TRY(check_encode_args(d, n, m, h, 0, 0));
-  LSQ_TRY(ensure_init());
-  cudaStream_t st = g_stream;
+  cudaStream_t st;
+  LSQ_TRY(host_ctx(&st));
   DevBuf<float> dC, dCB;
   DevBuf<uint8_t> dcodes;
   LSQ_CUDA(dC.alloc((size_t)m * h * d));
@@ -394,8 +416,8 @@ int lsq_quantize_norms(const int16_t* B, int64_t n, const float* C, int d, int m
                        int hn, int16_t* out) {
   LSQ_TRY(check_encode_args(d, n, m, h, 0, 0));
   LSQ_CHECK_ARG(hn >= 1, "norm codebook must be non-empty");
-  LSQ_TRY(ensure_init());
-  cudaStream_t st = g_stream;
+  cudaStream_t st;
+  LSQ_TRY(host_ctx(&st));
   DevBuf<float> dC, dcb;
   DevBuf<uint8_t> dcodes;
   DevBuf<int16_t> dout;

@@ -242,6 +242,7 @@ int lsq_dev_cb_stats(const float* dX, int d, int64_t n, const uint8_t* dcodes, i
 int lsq_dev_cb_solve(const double* dGram, const double* dRhs, int m, int d, float* dCout, int max_iter, double tol,
                      int* iters_out, void* stream) {
   LSQ_CHECK_ARG(m >= 1 && m <= LSQ_MAXM && d >= 1, "cb_solve: bad sizes");
+  set_alloc_stream((cudaStream_t)stream);
   return cb_solve(dGram, dRhs, m, d, dCout, max_iter, tol, iters_out, (cudaStream_t)stream);
 }
 

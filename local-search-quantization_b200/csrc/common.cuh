@@ -37,19 +37,24 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     if (rc__ != LSQ_OK) return rc__; \
   } while (0)
 
-// RAII device buffer for the host-pointer wrappers
+// RAII device buffer.  Stream-ordered allocation from the device's default memory pool, whose release
+// threshold lsq_init raises to "never", so repeated calls reuse the same memory instead of paying
+// cudaMalloc/cudaFree (milliseconds per GiB) every time.  Freed in stream order on destruction.
+cudaStream_t alloc_stream();
+void set_alloc_stream(cudaStream_t st);
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
   size_t count = 0;
-  DevBuf() {}
+  cudaStream_t st = nullptr;
+  DevBuf() : st(alloc_stream()) {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
-  ~DevBuf() { if (p) cudaFree(p); }
+  ~DevBuf() { if (p) cudaFreeAsync(p, st); }
   cudaError_t alloc(size_t n) {
-    if (p) { cudaFree(p); p = nullptr; }
+    if (p) { cudaFreeAsync(p, st); p = nullptr; }
     count = n;
-    return cudaMalloc((void**)&p, (n ? n : 1) * sizeof(T));
+    return cudaMallocAsync((void**)&p, (n ? n : 1) * sizeof(T), st);
   }
 };
 

@@ -614,6 +614,7 @@ void linscan_aqd_query(float* dists, unsigned int* res, unsigned char* codes, fl
 int lsq_dev_linscan(const uint8_t* dcodes, int64_t n, int m, const float* dqueries, int nq, int d,
                     const float* dcodebooks, const float* dbnorms, int lut_kind, int subdim, int nn, float* ddists,
                     int32_t* dids, void* stream) {
+  set_alloc_stream((cudaStream_t)stream);
   return linscan_device(dcodes, n, m, dqueries, nq, d, dcodebooks, dbnorms, lut_kind, subdim, nn, ddists, dids,
                         (cudaStream_t)stream);
 }
