@@ -177,38 +177,58 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
       }
     }
     // Inner loop, issue-bound: per codebook one PRMT (byte extract), one IMAD (row offset + lane base),
-    // one LDS with the codebook offset folded into the immediate, one FADD.
+    // one LDS with the codebook offset folded into the immediate, one FADD.  Four base vectors per
+    // group: all shuffles first, then one warp-uniform vote decides whether anything has to be stored,
+    // so the common path has no divergent branch (and no per-shuffle convergence check).
     const bool full = (c0 + 32 <= t_end);
     const int nvalid = full ? 32 : (int)(t_end - c0);
-#pragma unroll 4
-    for (int b = 0; b < 32; b++) {
-      const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, (uint32_t)lo, b);
-      const uint32_t w1 = (M > 4) ? __shfl_sync(0xFFFFFFFFu, (uint32_t)(lo >> 32), b) : 0u;
-      const uint32_t w2 = (M > 8) ? __shfl_sync(0xFFFFFFFFu, (uint32_t)hi, b) : 0u;
-      const uint32_t w3 = (M > 12) ? __shfl_sync(0xFFFFFFFFu, (uint32_t)(hi >> 32), b) : 0u;
-      float dist = 0.0f;
+#pragma unroll 2
+    for (int b0 = 0; b0 < 32; b0 += 4) {
+      float dist[4];
 #pragma unroll
-      for (int k = 0; k < M; k++) {
-        const uint32_t w = (k < 4) ? w0 : (k < 8) ? w1 : (k < 12) ? w2 : w3;
-        const uint32_t c = __byte_perm(w, 0u, 0x4440u | (uint32_t)(k & 3));
-        const float v = *reinterpret_cast<const float*>(lane_base + c * (uint32_t)(QT * 4) + (uint32_t)(k * LSQ_H * QT * 4));
-        dist = __fadd_rn(dist, v);
-      }
-      if (NORM) dist = __fadd_rn(dist, __shfl_sync(0xFFFFFFFFu, nrm, b));
-      const int64_t t = c0 + b;
-      if (p.mode == MODE_MAIN) {
-        if (dist <= tau && (full || b < nvalid)) {   // tau = -inf for invalid lanes: never taken
-          const uint32_t id = (uint32_t)(t + p.id_base);
-          const unsigned long long key = ((unsigned long long)float_to_ordered(dist) << 32) | id;
-          const int pos = atomicAdd(&p.cnt[q], 1);
-          if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = key;
+      for (int u = 0; u < 4; u++) {
+        const int b = b0 + u;
+        const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, (uint32_t)lo, b);
+        const uint32_t w1 = (M > 4) ? __shfl_sync(0xFFFFFFFFu, (uint32_t)(lo >> 32), b) : 0u;
+        const uint32_t w2 = (M > 8) ? __shfl_sync(0xFFFFFFFFu, (uint32_t)hi, b) : 0u;
+        const uint32_t w3 = (M > 12) ? __shfl_sync(0xFFFFFFFFu, (uint32_t)(hi >> 32), b) : 0u;
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < M; k++) {
+          const uint32_t w = (k < 4) ? w0 : (k < 8) ? w1 : (k < 12) ? w2 : w3;
+          const uint32_t c = __byte_perm(w, 0u, 0x4440u | (uint32_t)(k & 3));
+          const float v = *reinterpret_cast<const float*>(lane_base + c * (uint32_t)(QT * 4) + (uint32_t)(k * LSQ_H * QT * 4));
+          acc = __fadd_rn(acc, v);
         }
-      } else if (qvalid && (full || b < nvalid)) {
-        if (p.mode == MODE_SAMPLE) {
-          p.sbuf[((size_t)tile * p.count + t) * 32 + lane] = float_to_ordered(dist);
-        } else {
-          const uint32_t id = (uint32_t)(t * p.stride + p.id_base);
-          p.cand[(size_t)q * p.cap + t] = ((unsigned long long)float_to_ordered(dist) << 32) | id;
+        if (NORM) acc = __fadd_rn(acc, __shfl_sync(0xFFFFFFFFu, nrm, b));
+        dist[u] = acc;
+      }
+      if (p.mode == MODE_MAIN) {
+        // tau = -inf on invalid lanes, so they never vote
+        const bool hit = (dist[0] <= tau) | (dist[1] <= tau) | (dist[2] <= tau) | (dist[3] <= tau);
+        if (__any_sync(0xFFFFFFFFu, hit)) {
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if (dist[u] <= tau && (full || b0 + u < nvalid)) {
+              const uint32_t id = (uint32_t)(c0 + b0 + u + p.id_base);
+              const unsigned long long key = ((unsigned long long)float_to_ordered(dist[u]) << 32) | id;
+              const int pos = atomicAdd(&p.cnt[q], 1);
+              if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = key;
+            }
+          }
+        }
+      } else if (qvalid) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int64_t t = c0 + b0 + u;
+          if (full || b0 + u < nvalid) {
+            if (p.mode == MODE_SAMPLE) {
+              p.sbuf[((size_t)tile * p.count + t) * 32 + lane] = float_to_ordered(dist[u]);
+            } else {
+              const uint32_t id = (uint32_t)(t * p.stride + p.id_base);
+              p.cand[(size_t)q * p.cap + t] = ((unsigned long long)float_to_ordered(dist[u]) << 32) | id;
+            }
+          }
         }
       }
     }
