@@ -87,6 +87,21 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(kernel, n, ils):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture, if it was taken on this
+    launch shape (profiles/r*/traffic.json); else None."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", "traffic.json"))):
+        try:
+            t = json.load(open(path)).get(kernel)
+        except (OSError, ValueError):
+            continue
+        if t and t.get("launch", "").startswith(f"n={n}, {ils} ILS"):
+            best = t["dram_bytes_read"] + t["dram_bytes_write"]
+    return best
+
+
 def cpu_port_rate(n_sample, ils_total, seed=1):
     """Oracle port on all host threads: one ILS iteration over n_sample vectors -> vectors/s for a
     full `ils_total`-iteration encode (per-vector work is independent and identical per iteration)."""
@@ -247,8 +262,9 @@ def main():
             "vector_ils_iters_per_sec": value * ils,
             "qerror": qerr, "e2e_codes_equal_resident_codes": same,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "icm_ils_warp_kernel<8>", "kernel_ms": k_ms.item(),
-                         "peak_source": peak_src, "bytes_per_vector_iter": algorithmic_bytes_per_vec_iter()},
+                         "traffic": ncu_traffic("icm_ils_warp_kernel<8>", n, ils), "kernel": "icm_ils_warp_kernel<8>", "kernel_ms": k_ms.item(),
+                         "peak_source": peak_src, "bytes_per_vector_iter": algorithmic_bytes_per_vec_iter(),
+                         "algorithmic_bytes_per_launch": abytes},
             "e2e": {"value": world * n / (e2e_ms.item() * 1e-3), "unit": "vectors/s",
                     "h2d_bytes_per_step": int(X_h.nbytes + B_h.nbytes + C_h.nbytes), "d2h_bytes_per_step": int(B_h.nbytes),
                     "ms_per_step": e2e_ms.item(), "api": "lsq_encode_icm_cuda (host pointers)"},
