@@ -115,11 +115,17 @@ int lsq_quantize_norms(const int16_t* B, int64_t n, const float* C, int d, int m
 /* bytes of table storage for m codebooks: T[m][m][256][256] floats (both orientations materialised,
  * cf. binaries + binaries_t, encode_icm.jl:25-28) */
 int64_t lsq_dev_tables_bytes(int m);
-/* T[j][k][b][a] = 2<C_j[:,a], C_k[:,b]> for j != k */
-int lsq_dev_build_tables(const float* dC, int d, int m, float* dT, void* stream);
-/* U[m][n][256] */
+/* bytes of the sliced copy Ts[m][8][m-1][256][32] the shared-memory-slice ICM kernel stages by TMA */
+int64_t lsq_dev_sliced_tables_bytes(int m);
+/* which ICM kernel / unary layout serves (m, n): 0 = warp-per-vector kernel, tables gathered from L2,
+ * U[m][n][256]; 1 = slice kernel (m <= 8, large n), tables in shared memory, U[m][8][n][32].
+ * Environment override for testing: LSQ_B200_ICM_KERNEL=warp|slice. */
+int lsq_dev_icm_layout(int m, int64_t n);
+/* T[j][k][b][a] = 2<C_j[:,a], C_k[:,b]> for j != k; dTs (may be NULL) receives the sliced copy */
+int lsq_dev_build_tables(const float* dC, int d, int m, float* dT, float* dTs, void* stream);
+/* sliced = 0: U[m][n][256];  sliced = 1: U[m][8][n][32] */
 int lsq_dev_build_unaries(const float* dX, int d, int64_t n, const float* dC, int m, float* dU,
-                          void* stream);
+                          int sliced, void* stream);
 int lsq_dev_veccost(const float* dX, int d, int64_t n, const uint8_t* dcodes, const float* dC, int m,
                     float* dcost, void* stream);
 /* `niters` ILS iterations, numbered ils_iter0 .. ils_iter0+niters-1, in ONE launch.
@@ -130,7 +136,7 @@ int lsq_dev_veccost(const float* dX, int d, int64_t n, const uint8_t* dcodes, co
  *              snap_of_iter (HOST int32[niters], -1 = none) says which snapshot slot receives the
  *              accepted codes (and their costs) after each iteration. */
 int lsq_dev_icm_ils(const float* dX, int d, int64_t n, const float* dC, int m, const float* dU,
-                    const float* dT, uint8_t* dcodes, float* dcost, int icmiter, int npert,
+                    const float* dT, const float* dTs, int sliced, uint8_t* dcodes, float* dcost, int icmiter, int npert,
                     const int8_t* orders, const uint8_t* dslots, const uint8_t* dvals, uint64_t seed,
                     uint32_t ils_iter0, int niters, uint64_t g0, uint8_t* dsnap, float* dsnapcost,
                     const int32_t* snap_of_iter, void* stream);

@@ -22,7 +22,8 @@ EXPORTED_SYMBOLS = [
     "lsq_make_to_look", "lsq_make_perturb", "lsq_get_unaries", "lsq_get_binaries", "lsq_veccost",
     "lsq_qerror", "lsq_reconstruct", "lsq_encoding_icm", "lsq_encoding_icm_sched", "lsq_encode_icm_cuda",
     "lsq_update_codebooks", "linscan_aqd_query_extra_byte", "linscan_aqd_query", "lsq_linscan_lsq",
-    "lsq_linscan_pq", "lsq_quantize_norms", "lsq_dev_tables_bytes", "lsq_dev_build_tables",
+    "lsq_linscan_pq", "lsq_quantize_norms", "lsq_dev_tables_bytes", "lsq_dev_sliced_tables_bytes",
+    "lsq_dev_icm_layout", "lsq_dev_build_tables",
     "lsq_dev_build_unaries", "lsq_dev_veccost", "lsq_dev_icm_ils", "lsq_dev_cb_stats", "lsq_dev_cb_solve",
     "lsq_dev_linscan",
 ]
@@ -55,6 +56,7 @@ def lib():
         L.lsq_last_error.restype = ct.c_char_p
         L.lsq_version.restype = ct.c_char_p
         L.lsq_dev_tables_bytes.restype = ct.c_int64
+        L.lsq_dev_sliced_tables_bytes.restype = ct.c_int64
         L.linscan_aqd_query_extra_byte.restype = None
         L.linscan_aqd_query.restype = None
         _lib = L

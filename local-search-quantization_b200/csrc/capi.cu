@@ -139,13 +139,14 @@ static int run_encode_job(const EncodeJob& J) {
   const int d = J.d, m = J.m;
   const int64_t n = J.n;
 
-  DevBuf<float> dC, dnorms, dT;
+  DevBuf<float> dC, dnorms, dT, dTs;
   LSQ_CUDA(dC.alloc((size_t)m * LSQ_H * d));
   LSQ_CUDA(dnorms.alloc((size_t)m * LSQ_H));
   LSQ_CUDA(dT.alloc((size_t)m * m * LSQ_H * LSQ_H));
   LSQ_CUDA(cudaMemcpyAsync(dC.p, J.C, (size_t)m * LSQ_H * d * sizeof(float), cudaMemcpyHostToDevice, st));
   LSQ_TRY(build_norms(dC.p, d, m, dnorms.p, st));
   LSQ_TRY(build_tables(dC.p, d, m, dT.p, st));
+  bool have_ts = false;
 
   // snapshot map: ILS iteration i (1-based) -> first r with ilsiters[r] == i (encode_icm_cuda.jl:211-213)
   std::vector<int> snap_of(J.total_iters, -1);
@@ -182,7 +183,13 @@ static int run_encode_job(const EncodeJob& J) {
     if (nc <= 0) continue;
     LSQ_CUDA(cudaMemcpyAsync(dX.p, J.X + (size_t)lo * d, (size_t)nc * d * sizeof(float), cudaMemcpyHostToDevice, st));
     LSQ_TRY(upload_codes(J.B_in + (size_t)lo * m, nc * m, dcodes.p, st));
-    LSQ_TRY(build_unaries(dX.p, d, nc, dC.p, m, dnorms.p, dU.p, st));
+    const int sliced = icm_use_slices(m, nc);
+    if (sliced && !have_ts) {
+      LSQ_CUDA(dTs.alloc((size_t)m * (m - 1) * LSQ_H * LSQ_H));
+      LSQ_TRY(build_sliced_tables(dT.p, m, dTs.p, st));
+      have_ts = true;
+    }
+    LSQ_TRY(build_unaries(dX.p, d, nc, dC.p, m, dnorms.p, dU.p, sliced, st));
     LSQ_TRY(launch_veccost(dX.p, d, nc, dcodes.p, dC.p, m, dcost.p, st));
     if (J.nr > 0) LSQ_CUDA(cudaMemsetAsync(dsnap.p, 0, (size_t)J.nr * nc * m, st));
 
@@ -206,7 +213,7 @@ static int run_encode_job(const EncodeJob& J) {
       const int nit = std::min(ICM_MAX_ITERS_PER_LAUNCH, J.total_iters - it0);
       IcmParams p;
       memset(&p, 0, sizeof(p));
-      p.X = dX.p; p.C = dC.p; p.U = dU.p; p.T = dT.p;
+      p.X = dX.p; p.C = dC.p; p.U = dU.p; p.T = dT.p; p.Ts = dTs.p;
       p.codes = dcodes.p; p.cost = dcost.p;
       p.slots = (J.slots && J.npert > 0) ? dslots.p : nullptr;
       p.vals = (J.slots && J.npert > 0) ? dvals.p : nullptr;
@@ -222,7 +229,7 @@ static int run_encode_job(const EncodeJob& J) {
         else make_to_look_host(J.seed, J.ils_iter0 + (uint32_t)(it0 + i), m, J.randord, order);
         for (int k = 0; k < m; k++) p.orders[i][k] = (int8_t)order[k];
       }
-      LSQ_TRY(launch_icm_warp(p, st));
+      LSQ_TRY(sliced ? launch_icm_slice(p, st) : launch_icm_warp(p, st));
     }
 
     if (J.B_out) LSQ_TRY(download_codes(dcodes.p, nc * m, J.B_out + (size_t)lo * m, st));
@@ -331,7 +338,7 @@ int lsq_get_unaries(const float* X, int d, int64_t n, const float* C, int m, int
   LSQ_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)n * d * 4, cudaMemcpyHostToDevice, st));
   LSQ_CUDA(cudaMemcpyAsync(dC.p, C, (size_t)m * h * d * 4, cudaMemcpyHostToDevice, st));
   LSQ_TRY(build_norms(dC.p, d, m, dn.p, st));
-  LSQ_TRY(build_unaries(dX.p, d, n, dC.p, m, dn.p, dU.p, st));
+  LSQ_TRY(build_unaries(dX.p, d, n, dC.p, m, dn.p, dU.p, 0, st));
   LSQ_CUDA(cudaMemcpyAsync(U, dU.p, (size_t)m * n * h * 4, cudaMemcpyDeviceToHost, st));
   LSQ_CUDA(cudaStreamSynchronize(st));
   return LSQ_OK;
@@ -492,18 +499,27 @@ int lsq_encode_icm_cuda(const float* RX, int d, int64_t n, const int16_t* B, con
 // ---- device-pointer API ----------------------------------------------------------------------
 int64_t lsq_dev_tables_bytes(int m) { return (int64_t)m * m * LSQ_H * LSQ_H * (int64_t)sizeof(float); }
 
-int lsq_dev_build_tables(const float* dC, int d, int m, float* dT, void* stream) {
-  LSQ_TRY(check_encode_args(d, 0, m, LSQ_H, 0, 0));
-  return build_tables(dC, d, m, dT, (cudaStream_t)stream);
+int64_t lsq_dev_sliced_tables_bytes(int m) {
+  return (int64_t)m * (m > 1 ? m - 1 : 1) * LSQ_H * LSQ_H * (int64_t)sizeof(float);
 }
 
-int lsq_dev_build_unaries(const float* dX, int d, int64_t n, const float* dC, int m, float* dU, void* stream) {
+int lsq_dev_icm_layout(int m, int64_t n) { return icm_use_slices(m, n); }
+
+int lsq_dev_build_tables(const float* dC, int d, int m, float* dT, float* dTs, void* stream) {
+  LSQ_TRY(check_encode_args(d, 0, m, LSQ_H, 0, 0));
+  LSQ_TRY(build_tables(dC, d, m, dT, (cudaStream_t)stream));
+  if (dTs != nullptr) LSQ_TRY(build_sliced_tables(dT, m, dTs, (cudaStream_t)stream));
+  return LSQ_OK;
+}
+
+int lsq_dev_build_unaries(const float* dX, int d, int64_t n, const float* dC, int m, float* dU, int sliced,
+                          void* stream) {
   LSQ_TRY(check_encode_args(d, n, m, LSQ_H, 0, 0));
   cudaStream_t st = (cudaStream_t)stream;
   float* dn = nullptr;
   LSQ_CUDA(cudaMallocAsync((void**)&dn, (size_t)m * LSQ_H * sizeof(float), st));
   int rc = build_norms(dC, d, m, dn, st);
-  if (rc == LSQ_OK) rc = build_unaries(dX, d, n, dC, m, dn, dU, st);
+  if (rc == LSQ_OK) rc = build_unaries(dX, d, n, dC, m, dn, dU, sliced, st);
   cudaFreeAsync(dn, st);
   return rc;
 }
@@ -515,16 +531,17 @@ int lsq_dev_veccost(const float* dX, int d, int64_t n, const uint8_t* dcodes, co
 }
 
 int lsq_dev_icm_ils(const float* dX, int d, int64_t n, const float* dC, int m, const float* dU, const float* dT,
-                    uint8_t* dcodes, float* dcost, int icmiter, int npert, const int8_t* orders,
+                    const float* dTs, int sliced, uint8_t* dcodes, float* dcost, int icmiter, int npert, const int8_t* orders,
                     const uint8_t* dslots, const uint8_t* dvals, uint64_t seed, uint32_t ils_iter0, int niters,
                     uint64_t g0, uint8_t* dsnap, float* dsnapcost, const int32_t* snap_of_iter, void* stream) {
   LSQ_TRY(check_encode_args(d, n, m, LSQ_H, icmiter, npert));
   LSQ_CHECK_ARG(niters >= 0 && orders != nullptr, "orders (host int8 [niters][m]) is required");
+  LSQ_CHECK_ARG(!sliced || (dTs != nullptr && m >= 2 && m <= ICM_SLICE_MAX_M), "sliced layout needs dTs and 2 <= m <= 8");
   for (int it0 = 0; it0 < niters; it0 += ICM_MAX_ITERS_PER_LAUNCH) {
     const int nit = std::min(ICM_MAX_ITERS_PER_LAUNCH, niters - it0);
     IcmParams p;
     memset(&p, 0, sizeof(p));
-    p.X = dX; p.C = dC; p.U = dU; p.T = dT; p.codes = dcodes; p.cost = dcost;
+    p.X = dX; p.C = dC; p.U = dU; p.T = dT; p.Ts = dTs; p.codes = dcodes; p.cost = dcost;
     p.slots = dslots ? dslots + (size_t)it0 * n * npert : nullptr;
     p.vals = dvals ? dvals + (size_t)it0 * n * npert : nullptr;
     p.snap = dsnap; p.snapcost = dsnapcost;
@@ -538,7 +555,7 @@ int lsq_dev_icm_ils(const float* dX, int d, int64_t n, const float* dC, int m, c
         p.orders[i][k] = o;
       }
     }
-    LSQ_TRY(launch_icm_warp(p, (cudaStream_t)stream));
+    LSQ_TRY(sliced ? launch_icm_slice(p, (cudaStream_t)stream) : launch_icm_warp(p, (cudaStream_t)stream));
   }
   return LSQ_OK;
 }

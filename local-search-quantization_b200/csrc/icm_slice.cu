@@ -1,0 +1,312 @@
+// icm_slice.cu — ICM / ILS encoding with shared-memory resident pair-table slices (m <= 8, large n).
+//
+// Same algorithm, same bits as icm_ils_warp_kernel (encode_icm.jl:4-189); different data movement.
+// The warp-per-vector kernel gathers the (m-1) x 1 KB conditioning columns of every node visit from L2
+// and saturates it (lts throughput 83 %).  Here the columns come from SHARED MEMORY:
+//
+//   * persistent grid, one CTA per SM; a CTA owns a contiguous range of vectors for the whole launch;
+//   * for node j the CTA walks the 8 candidate slices of 32: slice (j, s) of all m-1 tables is
+//     (m-1)*256 rows x 128 B = 224 KB at m = 8, contiguous in the pre-sliced layout Ts, and is staged
+//     by TMA bulk copies (cp.async.bulk + mbarrier) — one staging serves every active vector of the CTA;
+//   * a quarter-warp (8 lanes x float4) handles one vector: each LDS.128 quarter-wavefront reads one
+//     128-byte table row -> conflict-free, 32 candidates per wavefront, 4 vectors per warp instruction;
+//   * the vector's 32 unary values of the slice are one 128-byte line of the sliced unary layout
+//     U[j][s][v][32]: with the tables on chip, the unary stream is what HBM carries;
+//   * the running (value, index) minimum across slices lives in an L2-resident scratch word per
+//     vector; the last slice writes the new code and updates the clean mask.
+// Node visits whose conditioning codes did not change are skipped exactly as in the warp kernel
+// (per-vector clean masks); a CTA-wide ordered compaction builds the active list of every visit.
+#include "icm.cuh"
+
+#include <stdlib.h>
+
+namespace lsq {
+
+constexpr int SLICE_THREADS = 512;
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// unary line: streamed once, keep it out of L1
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+template <int M>
+__device__ __forceinline__ float warp_veccost_packed(const float* __restrict__ x, const float* __restrict__ C,
+                                                     int d, unsigned long long codes, int lane) {
+  float p = 0.0f;
+  for (int t = lane; t < d; t += 32) {
+    float r = 0.0f;
+#pragma unroll
+    for (int k = 0; k < M; k++)
+      r = __fadd_rn(r, __ldg(C + ((size_t)k * LSQ_H + ((uint32_t)(codes >> (8 * k)) & 0xFFu)) * d + t));
+    const float df = __fsub_rn(r, __ldg(x + t));
+    p = __fadd_rn(p, __fmul_rn(df, df));
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) p = __fadd_rn(p, __shfl_xor_sync(0xFFFFFFFFu, p, off));
+  return p;
+}
+
+template <int M>
+__global__ void __launch_bounds__(SLICE_THREADS, 1) icm_ils_slice_kernel(const __grid_constant__ IcmParams p) {
+  constexpr int NT = SLICE_THREADS, NW = NT / 32;
+  constexpr uint32_t TAB_BYTES = (uint32_t)(M - 1) * LSQ_H * ICM_SLICE_W * 4;
+  constexpr uint32_t ALL_CLEAN = (1u << M) - 1u;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t bar;
+  __shared__ int warp_cnt[NW];
+  __shared__ int s_total;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = lane >> 3, c4 = lane & 7;  // quarter (vector within the group of 4), float4 within the slice
+  const uint32_t tab_base = smem_u32(smem_raw);
+
+  // this CTA's vector range (splitarray rule)
+  int64_t v0, v1;
+  {
+    const int64_t per = p.n / gridDim.x, xtra = p.n % gridDim.x;
+    const int64_t b = blockIdx.x;
+    v0 = (b < xtra) ? b * (per + 1) : xtra * (per + 1) + (b - xtra) * per;
+    v1 = v0 + per + ((b < xtra) ? 1 : 0);
+  }
+  const int nv = (int)(v1 - v0);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < nv; i += NT) p.clean[v0 + i] = 0;
+  uint32_t phase = 0;
+  __syncthreads();
+
+  for (int it = 0; it < p.niters; it++) {
+    // ---- (A) perturbation of every vector of the range (encode_icm.jl:56-70) ----
+    for (int i = tid; i < nv; i += NT) {
+      const int64_t v = v0 + i;
+      unsigned long long c = 0;
+      if (M == 8) {
+        c = *reinterpret_cast<const unsigned long long*>(p.codes + v * M);
+      } else {
+#pragma unroll
+        for (int k = 0; k < M; k++) c |= (unsigned long long)p.codes[v * M + k] << (8 * k);
+      }
+      uint32_t wc = p.clean[v];
+      if (p.slots != nullptr) {
+        const size_t base = ((size_t)it * p.n + v) * p.npert;
+        for (int e = 0; e < p.npert; e++) {
+          const int s = p.slots[base + e];
+          const unsigned long long x = p.vals[base + e];
+          if (((c >> (8 * s)) & 0xFFull) != x) { c = (c & ~(0xFFull << (8 * s))) | (x << (8 * s)); wc = 0; }
+        }
+      } else if (p.npert > 0) {
+        uint8_t s[LSQ_MAXM], x[LSQ_MAXM];
+        make_perturb_one(p.seed, p.ils_iter0 + it, p.g0 + (uint64_t)v, M, LSQ_H, p.npert, s, x);
+        for (int e = 0; e < p.npert; e++)
+          if (((c >> (8 * s[e])) & 0xFFull) != x[e]) {
+            c = (c & ~(0xFFull << (8 * s[e]))) | ((unsigned long long)x[e] << (8 * s[e]));
+            wc = 0;
+          }
+      }
+      p.wcodes[v] = c;
+      p.wclean[v] = (uint16_t)wc;
+    }
+    __syncthreads();
+
+    // ---- (B) block-ICM sweeps (encode_icm.jl:72-125) ----
+    for (int sweep = 0; sweep < p.icmiter; sweep++) {
+      int visited = 0;
+      for (int jj = 0; jj < M; jj++) {
+        const int j = p.orders[it][jj];
+        // B1. ordered compaction of the vectors whose node j is dirty -> act[v0 ..]
+        int n_act = 0;
+        for (int base = 0; base < nv; base += NT) {
+          const int i = base + tid;
+          const bool a = (i < nv) && !((p.wclean[v0 + i] >> j) & 1u);
+          const uint32_t bal = __ballot_sync(0xFFFFFFFFu, a);
+          if (lane == 0) warp_cnt[warp] = __popc(bal);
+          __syncthreads();
+          if (warp == 0) {
+            int cnt = (lane < NW) ? warp_cnt[lane] : 0, incl = cnt;
+#pragma unroll
+            for (int off = 1; off < NW; off <<= 1) {
+              const int t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+              if (lane >= off) incl += t;
+            }
+            if (lane < NW) warp_cnt[lane] = incl - cnt;  // exclusive offsets
+            if (lane == NW - 1) s_total = incl;
+          }
+          __syncthreads();
+          if (a) p.act[v0 + n_act + warp_cnt[warp] + __popc(bal & ((1u << lane) - 1u))] = i;
+          n_act += s_total;
+          __syncthreads();
+        }
+        if (n_act == 0) continue;
+        visited = 1;
+        const int ngroups = (n_act + 3) >> 2;
+
+        for (int s = 0; s < ICM_SLICES; s++) {
+          // B2. stage slice (j, s) of the m-1 tables; everyone has left the previous slice
+          __syncthreads();
+          if (tid == 0)
+            bulk_load_issue(smem_raw, p.Ts + ((size_t)(j * ICM_SLICES + s) * (M - 1)) * LSQ_H * ICM_SLICE_W, TAB_BYTES,
+                            &bar);
+          const float4* uslice = reinterpret_cast<const float4*>(p.U + ((size_t)(j * ICM_SLICES + s) * p.n + v0) * ICM_SLICE_W);
+
+          // software pipeline: the loads of group g+NW are issued before group g is reduced
+          int g = warp;
+          int idx = g * 4 + q;
+          int i_cur = (g < ngroups) ? p.act[v0 + (idx < n_act ? idx : n_act - 1)] : 0;
+          unsigned long long c_cur = (g < ngroups) ? p.wcodes[v0 + i_cur] : 0ull;
+          float4 a_cur = (g < ngroups) ? ldg_stream(uslice + (size_t)i_cur * 8 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          unsigned long long rb_cur = (s > 0 && g < ngroups) ? p.rbest[v0 + i_cur] : 0ull;
+          mbar_wait(&bar, phase);
+          phase ^= 1u;
+
+          for (; g < ngroups; g += NW) {
+            const int gn = g + NW;
+            const int idxn = gn * 4 + q;
+            int i_nxt = 0;
+            unsigned long long c_nxt = 0ull, rb_nxt = 0ull;
+            float4 a_nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gn < ngroups) {
+              i_nxt = p.act[v0 + (idxn < n_act ? idxn : n_act - 1)];
+              c_nxt = p.wcodes[v0 + i_nxt];
+              a_nxt = ldg_stream(uslice + (size_t)i_nxt * 8 + c4);
+              if (s > 0) rb_nxt = p.rbest[v0 + i_nxt];
+            }
+            // conditioning codes with byte j squeezed out: byte kk = code of the kk-th codebook != j
+            const unsigned long long lowmask = (1ull << (8 * j)) - 1ull;
+            const unsigned long long pk = (c_cur & lowmask) | ((c_cur >> 8) & ~lowmask);
+            const uint32_t pk0 = (uint32_t)pk, pk1 = (uint32_t)(pk >> 32);
+            float4 a = a_cur;
+#pragma unroll
+            for (int kk = 0; kk < M - 1; kk++) {
+              const uint32_t c = __byte_perm(kk < 4 ? pk0 : pk1, 0u, 0x4440u | (uint32_t)(kk & 3));
+              const float4 t4 = lds128(tab_base + (uint32_t)(kk * LSQ_H * ICM_SLICE_W * 4) + c * (ICM_SLICE_W * 4) + c4 * 16);
+              a.x = __fadd_rn(a.x, t4.x); a.y = __fadd_rn(a.y, t4.y); a.z = __fadd_rn(a.z, t4.z); a.w = __fadd_rn(a.w, t4.w);
+            }
+            // first strict minimum of this lane's 4 candidates, then of the quarter's 32
+            float best = a.x;
+            int bi = s * ICM_SLICE_W + c4 * 4;
+            if (a.y < best) { best = a.y; bi = s * ICM_SLICE_W + c4 * 4 + 1; }
+            if (a.z < best) { best = a.z; bi = s * ICM_SLICE_W + c4 * 4 + 2; }
+            if (a.w < best) { best = a.w; bi = s * ICM_SLICE_W + c4 * 4 + 3; }
+#pragma unroll
+            for (int off = 4; off >= 1; off >>= 1) {
+              const float ov = __shfl_xor_sync(0xFFFFFFFFu, best, off);
+              const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, off);
+              if (ov < best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+            }
+            if (c4 == 0 && (g * 4 + q) < n_act) {
+              if (s > 0) {  // earlier slices hold lower candidate indices: they win ties
+                const float pv = __uint_as_float((uint32_t)(rb_cur >> 32));
+                if (!(best < pv)) { best = pv; bi = (int)(uint32_t)rb_cur; }
+              }
+              const int64_t v = v0 + i_cur;
+              if (s < ICM_SLICES - 1) {
+                p.rbest[v] = ((unsigned long long)__float_as_uint(best) << 32) | (uint32_t)bi;
+              } else {
+                const uint32_t old = (uint32_t)(c_cur >> (8 * j)) & 0xFFu;
+                if ((uint32_t)bi != old) {
+                  p.wcodes[v] = (c_cur & ~(0xFFull << (8 * j))) | ((unsigned long long)bi << (8 * j));
+                  p.wclean[v] = (uint16_t)(1u << j);
+                } else {
+                  p.wclean[v] = (uint16_t)(p.wclean[v] | (1u << j));
+                }
+              }
+            }
+            i_cur = i_nxt; c_cur = c_nxt; a_cur = a_nxt; rb_cur = rb_nxt;
+          }
+        }
+        __syncthreads();  // codes / clean masks of this visit visible before the next compaction
+      }
+      if (!visited) break;  // every vector of the range is at its ICM fixed point
+    }
+    __syncthreads();
+
+    // ---- (C) accept iff strictly better (encode_icm.jl:178-186); one warp per vector ----
+    const int sn = p.snap_of_iter[it];
+    for (int i = warp; i < nv; i += NW) {
+      const int64_t v = v0 + i;
+      const unsigned long long wc = p.wcodes[v];
+      unsigned long long c;
+      if (M == 8) {
+        c = *reinterpret_cast<const unsigned long long*>(p.codes + v * M);
+      } else {
+        c = 0;
+#pragma unroll
+        for (int k = 0; k < M; k++) c |= (unsigned long long)p.codes[v * M + k] << (8 * k);
+      }
+      float prev = p.cost[v];
+      if (wc != c) {  // identical codes cannot be strictly better
+        const float newc = warp_veccost_packed<M>(p.X + (size_t)v * p.d, p.C, p.d, wc, lane);
+        if (newc < prev) {
+          prev = newc;
+          c = wc;
+          if (lane < M) p.codes[v * M + lane] = (uint8_t)(wc >> (8 * lane));
+          if (lane == 0) { p.cost[v] = newc; p.clean[v] = p.wclean[v]; }
+        }
+      } else if (lane == 0) {
+        p.clean[v] = (uint16_t)(p.clean[v] | p.wclean[v]);  // same codes: keep what the sweeps learned
+      }
+      if (sn >= 0) {
+        if (lane < M) p.snap[((size_t)sn * p.n + v) * M + lane] = (uint8_t)(c >> (8 * lane));
+        if (lane == 0 && p.snapcost != nullptr) p.snapcost[(size_t)sn * p.n + v] = prev;
+      }
+    }
+    __syncthreads();
+  }
+  (void)ALL_CLEAN;
+}
+
+int icm_use_slices(int m, int64_t n) {
+  if (m < 2 || m > ICM_SLICE_MAX_M) return 0;
+  const char* e = getenv("LSQ_B200_ICM_KERNEL");  // testing override
+  if (e != nullptr && strcmp(e, "warp") == 0) return 0;
+  if (e != nullptr && strcmp(e, "slice") == 0) return 1;
+  // one table staging (224 KB) must be amortised over the CTA's share of the vectors
+  return (m >= 2 && m <= ICM_SLICE_MAX_M && n >= (int64_t)LSQ_NUM_SMS_HINT * 1024) ? 1 : 0;
+}
+
+template <int M>
+static int launch_icm_slice_m(const IcmParams& p, cudaStream_t st) {
+  int dev = 0, sms = LSQ_NUM_SMS_HINT;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const size_t smem = (size_t)(M - 1) * LSQ_H * ICM_SLICE_W * 4;
+  LSQ_CUDA(cudaFuncSetAttribute(icm_ils_slice_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  icm_ils_slice_kernel<M><<<sms, SLICE_THREADS, smem, st>>>(p);
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
+}
+
+int launch_icm_slice(IcmParams p, cudaStream_t st) {
+  if (p.n == 0 || p.niters == 0) return LSQ_OK;
+  set_alloc_stream(st);
+  DevBuf<unsigned long long> wcodes, rbest;
+  DevBuf<uint16_t> clean, wclean;
+  DevBuf<int> act;
+  LSQ_CUDA(wcodes.alloc(p.n));
+  LSQ_CUDA(rbest.alloc(p.n));
+  LSQ_CUDA(clean.alloc(p.n));
+  LSQ_CUDA(wclean.alloc(p.n));
+  LSQ_CUDA(act.alloc(p.n));
+  p.wcodes = wcodes.p; p.rbest = rbest.p; p.clean = clean.p; p.wclean = wclean.p; p.act = act.p;
+  switch (p.m) {
+#define LSQ_CASE(MM) case MM: return launch_icm_slice_m<MM>(p, st);
+    LSQ_CASE(2) LSQ_CASE(3) LSQ_CASE(4) LSQ_CASE(5) LSQ_CASE(6) LSQ_CASE(7) LSQ_CASE(8)
+#undef LSQ_CASE
+  }
+  set_error("slice kernel: m must be in 2..8");
+  return LSQ_ERR_ARG;
+}
+
+}  // namespace lsq

@@ -5,7 +5,7 @@
 // exactly that order per output element as long as the K chunks are visited in ascending order, so
 // the kernel below is bit-identical to the oracle.  (A tcgen05 tensor-core version cannot reproduce a
 // sequential fp32 chain; it belongs to the tolerance-checked "fast" mode, not to parity mode.)
-#include "common.cuh"
+#include "icm.cuh"
 
 namespace lsq {
 
@@ -22,7 +22,7 @@ template <int EPI>
 __global__ void __launch_bounds__(256) gemm_tables_kernel(const float* __restrict__ Abase,
                                                           const float* __restrict__ Bbase,
                                                           const float* __restrict__ norms, float* __restrict__ out,
-                                                          int64_t R, int d, int m) {
+                                                          int64_t R, int d, int m, int sliced, int64_t Rs) {
   __shared__ __align__(16) float As[TK][TM + TPAD];
   __shared__ __align__(16) float Bs[TK][TN + TPAD];
 
@@ -125,9 +125,16 @@ __global__ void __launch_bounds__(256) gemm_tables_kernel(const float* __restric
       lo = make_float4(2.0f * acc[i][0], 2.0f * acc[i][1], 2.0f * acc[i][2], 2.0f * acc[i][3]);
       hi = make_float4(2.0f * acc[i][4], 2.0f * acc[i][5], 2.0f * acc[i][6], 2.0f * acc[i][7]);
     }
-    float* orow = O + (size_t)r * LSQ_H + a0;
-    *reinterpret_cast<float4*>(orow + tx * 4) = lo;
-    *reinterpret_cast<float4*>(orow + 64 + tx * 4) = hi;
+    if (!sliced) {
+      float* orow = O + (size_t)r * LSQ_H + a0;
+      *reinterpret_cast<float4*>(orow + tx * 4) = lo;
+      *reinterpret_cast<float4*>(orow + 64 + tx * 4) = hi;
+    } else {
+      // U[slice][r][32]: candidate a lives in slice a/32 at offset a%32
+      const int alo = a0 + tx * 4, ahi = a0 + 64 + tx * 4;
+      *reinterpret_cast<float4*>(O + ((size_t)(alo >> 5) * Rs + r) * ICM_SLICE_W + (alo & 31)) = lo;
+      *reinterpret_cast<float4*>(O + ((size_t)(ahi >> 5) * Rs + r) * ICM_SLICE_W + (ahi & 31)) = hi;
+    }
   }
 }
 
@@ -149,22 +156,22 @@ int build_norms(const float* dC, int d, int m, float* dnorms, cudaStream_t st) {
 }
 
 int build_unaries(const float* dX, int d, int64_t n, const float* dC, int m, const float* dnorms, float* dU,
-                  cudaStream_t st) {
+                  int sliced, cudaStream_t st) {
   if (n == 0) return LSQ_OK;
   // gridDim.y is limited to 65535 tiles of 128 rows (8.3 M vectors) per launch
   const int64_t max_rows = (int64_t)65535 * TN;
   for (int64_t r0 = 0; r0 < n; r0 += max_rows) {
     const int64_t rows = (n - r0 < max_rows) ? (n - r0) : max_rows;
-    // one launch per codebook when the launch is chunked, since U's z-stride is n*256
     if (r0 == 0 && rows == n) {
       dim3 grid(LSQ_H / TM, (unsigned)ceil_div(rows, TN), m);
-      gemm_tables_kernel<EPI_UNARY><<<grid, 256, 0, st>>>(dC, dX, dnorms, dU, n, d, m);
+      gemm_tables_kernel<EPI_UNARY><<<grid, 256, 0, st>>>(dC, dX, dnorms, dU, n, d, m, sliced, n);
     } else {
+      // one launch per codebook when the launch is chunked, since U's z-stride is n*256
       for (int j = 0; j < m; j++) {
         dim3 grid(LSQ_H / TM, (unsigned)ceil_div(rows, TN), 1);
+        float* o = dU + (size_t)j * n * LSQ_H + (sliced ? (size_t)r0 * ICM_SLICE_W : (size_t)r0 * LSQ_H);
         gemm_tables_kernel<EPI_UNARY><<<grid, 256, 0, st>>>(dC + (size_t)j * LSQ_H * d, dX + (size_t)r0 * d,
-                                                            dnorms + j * LSQ_H,
-                                                            dU + ((size_t)j * n + r0) * LSQ_H, rows, d, m);
+                                                            dnorms + j * LSQ_H, o, rows, d, m, sliced, n);
       }
     }
     LSQ_CUDA(cudaGetLastError());
@@ -174,7 +181,30 @@ int build_unaries(const float* dX, int d, int64_t n, const float* dC, int m, con
 
 int build_tables(const float* dC, int d, int m, float* dT, cudaStream_t st) {
   dim3 grid(LSQ_H / TM, LSQ_H / TN, m * m);
-  gemm_tables_kernel<EPI_BINARY><<<grid, 256, 0, st>>>(dC, dC, nullptr, dT, LSQ_H, d, m);
+  gemm_tables_kernel<EPI_BINARY><<<grid, 256, 0, st>>>(dC, dC, nullptr, dT, LSQ_H, d, m, 0, LSQ_H);
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
+}
+
+// Ts[j][s][kk][b][w] = T[j][k(kk)][b][32 s + w], k(kk) = kk-th codebook != j in ascending order: the
+// (m-1)*256 rows of 128 bytes that node j / candidate slice s needs, contiguous for one TMA bulk load.
+__global__ void slice_tables_kernel(const float* __restrict__ T, int m, float* __restrict__ Ts) {
+  const int64_t total = (int64_t)m * ICM_SLICES * (m - 1) * LSQ_H * ICM_SLICE_W;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(e % ICM_SLICE_W);
+    int64_t r = e / ICM_SLICE_W;
+    const int b = (int)(r % LSQ_H); r /= LSQ_H;
+    const int kk = (int)(r % (m - 1)); r /= (m - 1);
+    const int s = (int)(r % ICM_SLICES);
+    const int j = (int)(r / ICM_SLICES);
+    const int k = kk + (kk >= j ? 1 : 0);
+    Ts[e] = T[(((size_t)j * m + k) * LSQ_H + b) * LSQ_H + s * ICM_SLICE_W + w];
+  }
+}
+
+int build_sliced_tables(const float* dT, int m, float* dTs, cudaStream_t st) {
+  if (m < 2) return LSQ_OK;
+  slice_tables_kernel<<<LSQ_NUM_SMS_HINT * 8, 256, 0, st>>>(dT, m, dTs);
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
 }

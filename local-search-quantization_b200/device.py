@@ -20,7 +20,7 @@ class EncodeSession:
     """X, codebooks, unary/pair tables, codes and costs resident in HBM across ILS iterations
     (the reference re-uploads X and codes every call: encode_icm_cuda.jl:79,134,146-153)."""
 
-    def __init__(self, X, C, codes, g0=0):
+    def __init__(self, X, C, codes, g0=0, sliced=None):
         assert X.is_cuda and X.dtype == torch.float32 and X.is_contiguous()
         assert C.is_cuda and C.dtype == torch.float32 and C.is_contiguous() and C.shape[1] == 256
         assert codes.is_cuda and codes.dtype == torch.uint8 and codes.is_contiguous()
@@ -30,8 +30,11 @@ class EncodeSession:
         self.g0 = int(g0)
         L = api.lib()
         dev = X.device
+        self.sliced = int(L.lsq_dev_icm_layout(self.m, ct.c_int64(self.n))) if sliced is None else int(sliced)
         self.T = torch.empty(L.lsq_dev_tables_bytes(self.m) // 4, dtype=torch.float32, device=dev)
-        self.U = torch.empty((self.m, self.n, 256), dtype=torch.float32, device=dev)
+        self.Ts = (torch.empty(L.lsq_dev_sliced_tables_bytes(self.m) // 4, dtype=torch.float32, device=dev)
+                   if self.sliced else None)
+        self.U = torch.empty((self.m, self.n, 256), dtype=torch.float32, device=dev)  # or [m][8][n][32]
         self.cost = torch.empty(self.n, dtype=torch.float32, device=dev)
         self.set_codebooks(C)
 
@@ -39,9 +42,9 @@ class EncodeSession:
         """(Re)build pair tables, unaries and the cost of the current codes for new codebooks."""
         L = api.lib()
         self.C = C
-        api._check(L.lsq_dev_build_tables(_ptr(C), self.d, self.m, _ptr(self.T), _stream()))
+        api._check(L.lsq_dev_build_tables(_ptr(C), self.d, self.m, _ptr(self.T), _ptr(self.Ts), _stream()))
         api._check(L.lsq_dev_build_unaries(_ptr(self.X), self.d, ct.c_int64(self.n), _ptr(C), self.m,
-                                           _ptr(self.U), _stream()))
+                                           _ptr(self.U), self.sliced, _stream()))
         self.refresh_cost()
 
     def refresh_cost(self):
@@ -55,7 +58,7 @@ class EncodeSession:
         orders = np.ascontiguousarray(orders, np.int8)
         api._check(api.lib().lsq_dev_icm_ils(
             _ptr(self.X), self.d, ct.c_int64(self.n), _ptr(self.C), self.m, _ptr(self.U), _ptr(self.T),
-            _ptr(self.codes), _ptr(self.cost), int(icmiter), int(npert), orders.ctypes.data_as(ct.c_void_p),
+            _ptr(self.Ts), self.sliced, _ptr(self.codes), _ptr(self.cost), int(icmiter), int(npert), orders.ctypes.data_as(ct.c_void_p),
             _ptr(slots), _ptr(vals), ct.c_uint64(seed), ct.c_uint32(ils_iter0), int(niters),
             ct.c_uint64(self.g0), None, None, None, _stream()))
 

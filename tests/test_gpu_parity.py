@@ -281,3 +281,55 @@ def test_train_lsq_alternation_monotone(gpu):
             B = gpu.encoding_icm(X, B, C, 4, True, 2, seed=3, ils_iter=2 * it + i)
     objs.append(gpu.qerror(X, B, C))
     assert all(b <= a * (1 + 1e-6) for a, b in zip(objs, objs[1:]))
+
+
+# ---------------------------------------------------------------- both ICM kernels, forced
+@pytest.fixture(params=["warp", "slice"])
+def icm_kernel(request, monkeypatch):
+    """LSQ_B200_ICM_KERNEL forces the warp-per-vector kernel or the shared-memory-slice kernel."""
+    monkeypatch.setenv("LSQ_B200_ICM_KERNEL", request.param)
+    return request.param
+
+
+@pytest.mark.parametrize("n,d,m,niter,npert,randord", [
+    (3000, 128, 8, 4, 4, True), (2500, 128, 7, 4, 4, True), (1111, 64, 4, 3, 2, False), (700, 32, 2, 2, 1, True),
+    (5, 128, 8, 4, 4, True), (149, 16, 8, 1, 8, True),
+])
+def test_both_kernels_bit_exact_single_iteration(gpu, oracle, icm_kernel, n, d, m, niter, npert, randord):
+    X, C, B = make_problem(1500 + n + m, n, d, m)
+    Bo, _ = oracle.encoding_icm(X, (B - 1).astype(np.int16), C, niter, randord, npert, seed=21, ils_iter=2, g0=11)
+    Bg = gpu.encoding_icm(X, B, C, niter, randord, npert, seed=21, ils_iter=2, g0=11)
+    assert np.array_equal(Bg, Bo + 1)
+
+
+def test_both_kernels_bit_exact_ils_with_snapshots(gpu, oracle, icm_kernel):
+    n, d, m = 4000, 128, 8
+    X, C, B = make_problem(1600, n, d, m)
+    Bs, objs = gpu.encode_icm_cuda(X, B, C, [1, 3, 6], 4, 4, True, 2, seed=5, g0=3)
+    Bo, objo = oracle.encode_icm_ils(X, (B - 1).astype(np.int16), C, [1, 3, 6], 4, 4, True, seed=5, g0=3,
+                                     nworkers=oracle.num_threads())
+    for r in range(3):
+        assert np.array_equal(Bs[r], Bo[r] + 1)
+    assert np.allclose(objs, objo, rtol=1e-6, atol=0)
+
+
+def test_both_kernels_explicit_schedule(gpu, oracle, icm_kernel):
+    n, d, m = 1500, 64, 8
+    X, C, B = make_problem(1700, n, d, m)
+    rng = np.random.default_rng(6)
+    to_look = rng.permutation(m).astype(np.int32)
+    slots = np.sort(np.stack([rng.permutation(m)[:4] for _ in range(n)]), axis=1).astype(np.uint8)
+    vals = rng.integers(0, 256, size=(n, 4)).astype(np.int16)
+    Bo, _ = oracle.encoding_icm_sched(X, (B - 1).astype(np.int16), C, 4, to_look, slots, vals)
+    assert np.array_equal(gpu.encoding_icm_sched(X, B, C, 4, to_look, slots, vals), Bo + 1)
+
+
+def test_slice_kernel_large_n_matches_warp_kernel(gpu, monkeypatch):
+    """At a size where the slice kernel is the default (n >= 148 K), both kernels give identical codes."""
+    n, d, m = 200000, 128, 8
+    X, C, B = make_problem(1800, n, d, m)
+    monkeypatch.setenv("LSQ_B200_ICM_KERNEL", "warp")
+    Bw, ow = gpu.encode_icm_cuda(X, B, C, [4], 4, 4, True, 1, seed=2)
+    monkeypatch.delenv("LSQ_B200_ICM_KERNEL")
+    Bs, os_ = gpu.encode_icm_cuda(X, B, C, [4], 4, 4, True, 1, seed=2)
+    assert np.array_equal(Bw[0], Bs[0]) and ow[0] == os_[0]
