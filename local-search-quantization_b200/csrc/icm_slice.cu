@@ -23,6 +23,7 @@
 namespace lsq {
 
 constexpr int SLICE_THREADS = 512;
+constexpr int DEPTH = 4;  // prefetched vector groups per warp
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
@@ -54,6 +55,36 @@ __device__ __forceinline__ float warp_veccost_packed(const float* __restrict__ x
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) p = __fadd_rn(p, __shfl_xor_sync(0xFFFFFFFFu, p, off));
   return p;
+}
+
+// veccost of one vector by a QUARTER-warp (8 lanes), bit-identical to warp_veccost_packed: lane c8 owns
+// the lane-strided partial sums l = 4*c8 .. 4*c8+3 (elements t = l, l+32, ...), so the xor-butterfly
+// offsets 16, 8, 4 are quarter shuffles (4, 2, 1) and offsets 2, 1 stay inside the lane.  Needs d % 4 == 0.
+template <int M>
+__device__ __forceinline__ float quarter_veccost_packed(const float* __restrict__ x, const float* __restrict__ C,
+                                                        int d, unsigned long long codes, int c8) {
+  float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+  for (int t0 = 4 * c8; t0 < d; t0 += 32) {
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < M; k++) {
+      const float4 cv = __ldg(reinterpret_cast<const float4*>(
+          C + ((size_t)k * LSQ_H + ((uint32_t)(codes >> (8 * k)) & 0xFFu)) * d + t0));
+      r.x = __fadd_rn(r.x, cv.x); r.y = __fadd_rn(r.y, cv.y); r.z = __fadd_rn(r.z, cv.z); r.w = __fadd_rn(r.w, cv.w);
+    }
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + t0));
+    const float d0 = __fsub_rn(r.x, xv.x), d1 = __fsub_rn(r.y, xv.y), d2 = __fsub_rn(r.z, xv.z), d3 = __fsub_rn(r.w, xv.w);
+    p0 = __fadd_rn(p0, __fmul_rn(d0, d0)); p1 = __fadd_rn(p1, __fmul_rn(d1, d1));
+    p2 = __fadd_rn(p2, __fmul_rn(d2, d2)); p3 = __fadd_rn(p3, __fmul_rn(d3, d3));
+  }
+#pragma unroll
+  for (int off = 4; off >= 1; off >>= 1) {
+    p0 = __fadd_rn(p0, __shfl_xor_sync(0xFFFFFFFFu, p0, off));
+    p1 = __fadd_rn(p1, __shfl_xor_sync(0xFFFFFFFFu, p1, off));
+    p2 = __fadd_rn(p2, __shfl_xor_sync(0xFFFFFFFFu, p2, off));
+    p3 = __fadd_rn(p3, __shfl_xor_sync(0xFFFFFFFFu, p3, off));
+  }
+  return __fadd_rn(__fadd_rn(p0, p2), __fadd_rn(p1, p3));
 }
 
 template <int M>
@@ -125,32 +156,47 @@ __global__ void __launch_bounds__(SLICE_THREADS, 1) icm_ils_slice_kernel(const _
       int visited = 0;
       for (int jj = 0; jj < M; jj++) {
         const int j = p.orders[it][jj];
-        // B1. ordered compaction of the vectors whose node j is dirty -> act[v0 ..]
+        // B1. ordered compaction of the vectors whose node j is dirty -> act[v0 ..]; 4 vectors per thread
         int n_act = 0;
-        for (int base = 0; base < nv; base += NT) {
-          const int i = base + tid;
-          const bool a = (i < nv) && !((p.wclean[v0 + i] >> j) & 1u);
-          const uint32_t bal = __ballot_sync(0xFFFFFFFFu, a);
-          if (lane == 0) warp_cnt[warp] = __popc(bal);
+        for (int base = 0; base < nv; base += NT * 4) {
+          const int i0 = base + tid * 4;
+          uint32_t am = 0;
+#pragma unroll
+          for (int e = 0; e < 4; e++)
+            if (i0 + e < nv && !((p.wclean[v0 + i0 + e] >> j) & 1u)) am |= 1u << e;
+          const int cnt = __popc(am);
+          int incl = cnt;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+            if (lane >= off) incl += t;
+          }
+          if (lane == 31) warp_cnt[warp] = incl;
           __syncthreads();
           if (warp == 0) {
-            int cnt = (lane < NW) ? warp_cnt[lane] : 0, incl = cnt;
+            const int wc = (lane < NW) ? warp_cnt[lane] : 0;
+            int wincl = wc;
 #pragma unroll
             for (int off = 1; off < NW; off <<= 1) {
-              const int t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-              if (lane >= off) incl += t;
+              const int t = __shfl_up_sync(0xFFFFFFFFu, wincl, off);
+              if (lane >= off) wincl += t;
             }
-            if (lane < NW) warp_cnt[lane] = incl - cnt;  // exclusive offsets
-            if (lane == NW - 1) s_total = incl;
+            if (lane < NW) warp_cnt[lane] = wincl - wc;  // exclusive offsets
+            if (lane == NW - 1) s_total = wincl;
           }
           __syncthreads();
-          if (a) p.act[v0 + n_act + warp_cnt[warp] + __popc(bal & ((1u << lane) - 1u))] = i;
+          int pos = n_act + warp_cnt[warp] + incl - cnt;
+#pragma unroll
+          for (int e = 0; e < 4; e++)
+            if (am & (1u << e)) p.act[v0 + pos++] = i0 + e;
           n_act += s_total;
           __syncthreads();
         }
         if (n_act == 0) continue;
         visited = 1;
         const int ngroups = (n_act + 3) >> 2;
+        // conditioning codes with byte j squeezed out: byte kk = code of the kk-th codebook != j
+        const unsigned long long lowmask = (1ull << (8 * j)) - 1ull;
 
         for (int s = 0; s < ICM_SLICES; s++) {
           // B2. stage slice (j, s) of the m-1 tables; everyone has left the previous slice
@@ -160,70 +206,75 @@ __global__ void __launch_bounds__(SLICE_THREADS, 1) icm_ils_slice_kernel(const _
                             &bar);
           const float4* uslice = reinterpret_cast<const float4*>(p.U + ((size_t)(j * ICM_SLICES + s) * p.n + v0) * ICM_SLICE_W);
 
-          // software pipeline: the loads of group g+NW are issued before group g is reduced
-          int g = warp;
-          int idx = g * 4 + q;
-          int i_cur = (g < ngroups) ? p.act[v0 + (idx < n_act ? idx : n_act - 1)] : 0;
-          unsigned long long c_cur = (g < ngroups) ? p.wcodes[v0 + i_cur] : 0ull;
-          float4 a_cur = (g < ngroups) ? ldg_stream(uslice + (size_t)i_cur * 8 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          unsigned long long rb_cur = (s > 0 && g < ngroups) ? p.rbest[v0 + i_cur] : 0ull;
+          // register ring of DEPTH prefetched groups per warp: index -> (codes, unary line, running best).
+          // DEPTH x NW x 4 vectors are in flight per SM, enough to cover HBM latency at the shared-memory rate.
+          int r_i[DEPTH];
+          unsigned long long r_c[DEPTH], r_b[DEPTH];
+          float4 r_a[DEPTH];
+          auto fetch = [&](int gg, int u) {
+            r_i[u] = 0; r_c[u] = 0ull; r_b[u] = 0ull; r_a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gg < ngroups) {
+              const int idx = gg * 4 + q;
+              const int i = p.act[v0 + (idx < n_act ? idx : n_act - 1)];
+              r_i[u] = i;
+              r_c[u] = p.wcodes[v0 + i];
+              r_a[u] = ldg_stream(uslice + (size_t)i * 8 + c4);
+              if (s > 0) r_b[u] = p.rbest[v0 + i];
+            }
+          };
+#pragma unroll
+          for (int u = 0; u < DEPTH; u++) fetch(warp + u * NW, u);
           mbar_wait(&bar, phase);
           phase ^= 1u;
 
-          for (; g < ngroups; g += NW) {
-            const int gn = g + NW;
-            const int idxn = gn * 4 + q;
-            int i_nxt = 0;
-            unsigned long long c_nxt = 0ull, rb_nxt = 0ull;
-            float4 a_nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gn < ngroups) {
-              i_nxt = p.act[v0 + (idxn < n_act ? idxn : n_act - 1)];
-              c_nxt = p.wcodes[v0 + i_nxt];
-              a_nxt = ldg_stream(uslice + (size_t)i_nxt * 8 + c4);
-              if (s > 0) rb_nxt = p.rbest[v0 + i_nxt];
-            }
-            // conditioning codes with byte j squeezed out: byte kk = code of the kk-th codebook != j
-            const unsigned long long lowmask = (1ull << (8 * j)) - 1ull;
-            const unsigned long long pk = (c_cur & lowmask) | ((c_cur >> 8) & ~lowmask);
-            const uint32_t pk0 = (uint32_t)pk, pk1 = (uint32_t)(pk >> 32);
-            float4 a = a_cur;
+          for (int g = warp; g < ngroups; g += DEPTH * NW) {
 #pragma unroll
-            for (int kk = 0; kk < M - 1; kk++) {
-              const uint32_t c = __byte_perm(kk < 4 ? pk0 : pk1, 0u, 0x4440u | (uint32_t)(kk & 3));
-              const float4 t4 = lds128(tab_base + (uint32_t)(kk * LSQ_H * ICM_SLICE_W * 4) + c * (ICM_SLICE_W * 4) + c4 * 16);
-              a.x = __fadd_rn(a.x, t4.x); a.y = __fadd_rn(a.y, t4.y); a.z = __fadd_rn(a.z, t4.z); a.w = __fadd_rn(a.w, t4.w);
-            }
-            // first strict minimum of this lane's 4 candidates, then of the quarter's 32
-            float best = a.x;
-            int bi = s * ICM_SLICE_W + c4 * 4;
-            if (a.y < best) { best = a.y; bi = s * ICM_SLICE_W + c4 * 4 + 1; }
-            if (a.z < best) { best = a.z; bi = s * ICM_SLICE_W + c4 * 4 + 2; }
-            if (a.w < best) { best = a.w; bi = s * ICM_SLICE_W + c4 * 4 + 3; }
+            for (int u = 0; u < DEPTH; u++) {
+              const int gg = g + u * NW;
+              const int i_cur = r_i[u];
+              const unsigned long long c_cur = r_c[u], rb_cur = r_b[u];
+              float4 a = r_a[u];
+              fetch(gg + DEPTH * NW, u);
+              if (gg >= ngroups) continue;  // warp-uniform
+              const unsigned long long pk = (c_cur & lowmask) | ((c_cur >> 8) & ~lowmask);
+              const uint32_t pk0 = (uint32_t)pk, pk1 = (uint32_t)(pk >> 32);
 #pragma unroll
-            for (int off = 4; off >= 1; off >>= 1) {
-              const float ov = __shfl_xor_sync(0xFFFFFFFFu, best, off);
-              const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, off);
-              if (ov < best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-            }
-            if (c4 == 0 && (g * 4 + q) < n_act) {
-              if (s > 0) {  // earlier slices hold lower candidate indices: they win ties
-                const float pv = __uint_as_float((uint32_t)(rb_cur >> 32));
-                if (!(best < pv)) { best = pv; bi = (int)(uint32_t)rb_cur; }
+              for (int kk = 0; kk < M - 1; kk++) {
+                const uint32_t c = __byte_perm(kk < 4 ? pk0 : pk1, 0u, 0x4440u | (uint32_t)(kk & 3));
+                const float4 t4 = lds128(tab_base + (uint32_t)(kk * LSQ_H * ICM_SLICE_W * 4) + c * (ICM_SLICE_W * 4) + c4 * 16);
+                a.x = __fadd_rn(a.x, t4.x); a.y = __fadd_rn(a.y, t4.y); a.z = __fadd_rn(a.z, t4.z); a.w = __fadd_rn(a.w, t4.w);
               }
-              const int64_t v = v0 + i_cur;
-              if (s < ICM_SLICES - 1) {
-                p.rbest[v] = ((unsigned long long)__float_as_uint(best) << 32) | (uint32_t)bi;
-              } else {
-                const uint32_t old = (uint32_t)(c_cur >> (8 * j)) & 0xFFu;
-                if ((uint32_t)bi != old) {
-                  p.wcodes[v] = (c_cur & ~(0xFFull << (8 * j))) | ((unsigned long long)bi << (8 * j));
-                  p.wclean[v] = (uint16_t)(1u << j);
+              // first strict minimum of this lane's 4 candidates, then of the quarter's 32
+              float best = a.x;
+              int bi = s * ICM_SLICE_W + c4 * 4;
+              if (a.y < best) { best = a.y; bi = s * ICM_SLICE_W + c4 * 4 + 1; }
+              if (a.z < best) { best = a.z; bi = s * ICM_SLICE_W + c4 * 4 + 2; }
+              if (a.w < best) { best = a.w; bi = s * ICM_SLICE_W + c4 * 4 + 3; }
+#pragma unroll
+              for (int off = 4; off >= 1; off >>= 1) {
+                const float ov = __shfl_xor_sync(0xFFFFFFFFu, best, off);
+                const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, off);
+                if (ov < best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+              }
+              if (c4 == 0 && (gg * 4 + q) < n_act) {
+                if (s > 0) {  // earlier slices hold lower candidate indices: they win ties
+                  const float pv = __uint_as_float((uint32_t)(rb_cur >> 32));
+                  if (!(best < pv)) { best = pv; bi = (int)(uint32_t)rb_cur; }
+                }
+                const int64_t v = v0 + i_cur;
+                if (s < ICM_SLICES - 1) {
+                  p.rbest[v] = ((unsigned long long)__float_as_uint(best) << 32) | (uint32_t)bi;
                 } else {
-                  p.wclean[v] = (uint16_t)(p.wclean[v] | (1u << j));
+                  const uint32_t old = (uint32_t)(c_cur >> (8 * j)) & 0xFFu;
+                  if ((uint32_t)bi != old) {
+                    p.wcodes[v] = (c_cur & ~(0xFFull << (8 * j))) | ((unsigned long long)bi << (8 * j));
+                    p.wclean[v] = (uint16_t)(1u << j);
+                  } else {
+                    p.wclean[v] = (uint16_t)(p.wclean[v] | (1u << j));
+                  }
                 }
               }
             }
-            i_cur = i_nxt; c_cur = c_nxt; a_cur = a_nxt; rb_cur = rb_nxt;
           }
         }
         __syncthreads();  // codes / clean masks of this visit visible before the next compaction
@@ -232,10 +283,13 @@ __global__ void __launch_bounds__(SLICE_THREADS, 1) icm_ils_slice_kernel(const _
     }
     __syncthreads();
 
-    // ---- (C) accept iff strictly better (encode_icm.jl:178-186); one warp per vector ----
+    // ---- (C) accept iff strictly better (encode_icm.jl:178-186); a quarter-warp per vector ----
     const int sn = p.snap_of_iter[it];
-    for (int i = warp; i < nv; i += NW) {
-      const int64_t v = v0 + i;
+    const bool quarter_ok = (p.d % 4 == 0);
+    for (int i0 = warp * 4; i0 < nv; i0 += NW * 4) {
+      const int i = i0 + q;
+      const bool valid = i < nv;
+      const int64_t v = v0 + (valid ? i : nv - 1);
       const unsigned long long wc = p.wcodes[v];
       unsigned long long c;
       if (M == 8) {
@@ -246,20 +300,30 @@ __global__ void __launch_bounds__(SLICE_THREADS, 1) icm_ils_slice_kernel(const _
         for (int k = 0; k < M; k++) c |= (unsigned long long)p.codes[v * M + k] << (8 * k);
       }
       float prev = p.cost[v];
-      if (wc != c) {  // identical codes cannot be strictly better
-        const float newc = warp_veccost_packed<M>(p.X + (size_t)v * p.d, p.C, p.d, wc, lane);
-        if (newc < prev) {
-          prev = newc;
-          c = wc;
-          if (lane < M) p.codes[v * M + lane] = (uint8_t)(wc >> (8 * lane));
-          if (lane == 0) { p.cost[v] = newc; p.clean[v] = p.wclean[v]; }
+      const bool differs = valid && (wc != c);  // identical codes cannot be strictly better
+      float newc = prev;
+      if (quarter_ok) {
+        if (__any_sync(0xFFFFFFFFu, differs)) newc = quarter_veccost_packed<M>(p.X + (size_t)v * p.d, p.C, p.d, wc, c4);
+      } else {
+        // generic d: one warp per vector, quarter by quarter
+        for (int qq = 0; qq < 4; qq++) {
+          const unsigned long long wq = __shfl_sync(0xFFFFFFFFu, wc, qq * 8);
+          const int64_t vq = __shfl_sync(0xFFFFFFFFu, v, qq * 8);
+          const float t = warp_veccost_packed<M>(p.X + (size_t)vq * p.d, p.C, p.d, wq, lane);
+          if (q == qq) newc = t;
         }
-      } else if (lane == 0) {
+      }
+      if (differs && newc < prev) {
+        prev = newc;
+        c = wc;
+        if (c4 < M) p.codes[v * M + c4] = (uint8_t)(wc >> (8 * c4));
+        if (c4 == 0) { p.cost[v] = newc; p.clean[v] = p.wclean[v]; }
+      } else if (valid && !differs && c4 == 0) {
         p.clean[v] = (uint16_t)(p.clean[v] | p.wclean[v]);  // same codes: keep what the sweeps learned
       }
-      if (sn >= 0) {
-        if (lane < M) p.snap[((size_t)sn * p.n + v) * M + lane] = (uint8_t)(c >> (8 * lane));
-        if (lane == 0 && p.snapcost != nullptr) p.snapcost[(size_t)sn * p.n + v] = prev;
+      if (sn >= 0 && valid) {
+        if (c4 < M) p.snap[((size_t)sn * p.n + v) * M + c4] = (uint8_t)(c >> (8 * c4));
+        if (c4 == 0 && p.snapcost != nullptr) p.snapcost[(size_t)sn * p.n + v] = prev;
       }
     }
     __syncthreads();
