@@ -110,6 +110,11 @@ __global__ void __launch_bounds__(SLICE_THREADS, 1) icm_ils_slice_kernel(const _
     v1 = v0 + per + ((b < xtra) ? 1 : 0);
   }
   const int nv = (int)(v1 - v0);
+  int* const actp = p.act + v0;
+  unsigned long long* const wcp = p.wcodes + v0;
+  unsigned long long* const rbp = p.rbest + v0;
+  uint16_t* const wclp = p.wclean + v0;
+  const uint32_t tab_lane = tab_base + (uint32_t)c4 * 16u;
   if (tid == 0) {
     mbar_init(&bar, 1);
     fence_mbar_init();
@@ -206,24 +211,31 @@ __global__ void __launch_bounds__(SLICE_THREADS, 1) icm_ils_slice_kernel(const _
                             &bar);
           const float4* uslice = reinterpret_cast<const float4*>(p.U + ((size_t)(j * ICM_SLICES + s) * p.n + v0) * ICM_SLICE_W);
 
-          // register ring of DEPTH prefetched groups per warp: index -> (codes, unary line, running best).
-          // DEPTH x NW x 4 vectors are in flight per SM, enough to cover HBM latency at the shared-memory rate.
-          int r_i[DEPTH];
+          // Two-stage register pipeline per warp.  Stage 1 loads the active-list entry of the group
+          // 2*DEPTH rounds ahead; stage 2 turns the entry loaded DEPTH rounds ago into the data loads
+          // (codes, unary line, running best) of the group DEPTH rounds ahead.  No load result is used
+          // in the round it was issued, and DEPTH x NW x 4 vectors are in flight per SM.
+          const float4* ulane = uslice + c4;
+          int n_i[DEPTH], r_i[DEPTH];
           unsigned long long r_c[DEPTH], r_b[DEPTH];
           float4 r_a[DEPTH];
-          auto fetch = [&](int gg, int u) {
-            r_i[u] = 0; r_c[u] = 0ull; r_b[u] = 0ull; r_a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          auto load_idx = [&](int gg) -> int {
+            const int idx = gg * 4 + q;
+            return (gg < ngroups) ? actp[idx < n_act ? idx : n_act - 1] : 0;
+          };
+          auto load_data = [&](int gg, int u) {
+            const int i = n_i[u];
+            r_i[u] = i;
             if (gg < ngroups) {
-              const int idx = gg * 4 + q;
-              const int i = p.act[v0 + (idx < n_act ? idx : n_act - 1)];
-              r_i[u] = i;
-              r_c[u] = p.wcodes[v0 + i];
-              r_a[u] = ldg_stream(uslice + (size_t)i * 8 + c4);
-              if (s > 0) r_b[u] = p.rbest[v0 + i];
+              r_c[u] = wcp[i];
+              r_a[u] = ldg_stream(ulane + (size_t)(uint32_t)i * 8);
+              if (s > 0) r_b[u] = rbp[i];
             }
           };
 #pragma unroll
-          for (int u = 0; u < DEPTH; u++) fetch(warp + u * NW, u);
+          for (int u = 0; u < DEPTH; u++) { n_i[u] = load_idx(warp + u * NW); r_c[u] = 0ull; r_b[u] = 0ull; r_a[u] = make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+          for (int u = 0; u < DEPTH; u++) { load_data(warp + u * NW, u); n_i[u] = load_idx(warp + (u + DEPTH) * NW); }
           mbar_wait(&bar, phase);
           phase ^= 1u;
 
@@ -234,43 +246,47 @@ __global__ void __launch_bounds__(SLICE_THREADS, 1) icm_ils_slice_kernel(const _
               const int i_cur = r_i[u];
               const unsigned long long c_cur = r_c[u], rb_cur = r_b[u];
               float4 a = r_a[u];
-              fetch(gg + DEPTH * NW, u);
+              load_data(gg + DEPTH * NW, u);
+              n_i[u] = load_idx(gg + 2 * DEPTH * NW);
               if (gg >= ngroups) continue;  // warp-uniform
               const unsigned long long pk = (c_cur & lowmask) | ((c_cur >> 8) & ~lowmask);
               const uint32_t pk0 = (uint32_t)pk, pk1 = (uint32_t)(pk >> 32);
 #pragma unroll
               for (int kk = 0; kk < M - 1; kk++) {
                 const uint32_t c = __byte_perm(kk < 4 ? pk0 : pk1, 0u, 0x4440u | (uint32_t)(kk & 3));
-                const float4 t4 = lds128(tab_base + (uint32_t)(kk * LSQ_H * ICM_SLICE_W * 4) + c * (ICM_SLICE_W * 4) + c4 * 16);
+                const float4 t4 = lds128(tab_lane + (uint32_t)(kk * LSQ_H * ICM_SLICE_W * 4) + c * (ICM_SLICE_W * 4));
                 a.x = __fadd_rn(a.x, t4.x); a.y = __fadd_rn(a.y, t4.y); a.z = __fadd_rn(a.z, t4.z); a.w = __fadd_rn(a.w, t4.w);
               }
-              // first strict minimum of this lane's 4 candidates, then of the quarter's 32
+              // first strict minimum of this lane's 4 candidates ...
               float best = a.x;
               int bi = s * ICM_SLICE_W + c4 * 4;
               if (a.y < best) { best = a.y; bi = s * ICM_SLICE_W + c4 * 4 + 1; }
               if (a.z < best) { best = a.z; bi = s * ICM_SLICE_W + c4 * 4 + 2; }
               if (a.w < best) { best = a.w; bi = s * ICM_SLICE_W + c4 * 4 + 3; }
-#pragma unroll
-              for (int off = 4; off >= 1; off >>= 1) {
-                const float ov = __shfl_xor_sync(0xFFFFFFFFu, best, off);
-                const int oi = __shfl_xor_sync(0xFFFFFFFFu, bi, off);
-                if (ov < best || (ov == best && oi < bi)) { best = ov; bi = oi; }
-              }
+              // ... then of the quarter's 32: value-only min butterfly, lowest lane holding the minimum wins
+              // (lanes hold ascending candidate ranges, so this is the first strict minimum)
+              float mn = best;
+              mn = fminf(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, 4));
+              mn = fminf(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, 2));
+              mn = fminf(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, 1));
+              const uint32_t eq = __ballot_sync(0xFFFFFFFFu, best == mn);
+              const int src = (q << 3) + __ffs((eq >> (q << 3)) & 0xFFu) - 1;
+              bi = __shfl_sync(0xFFFFFFFFu, bi, src);
+              best = mn;
               if (c4 == 0 && (gg * 4 + q) < n_act) {
                 if (s > 0) {  // earlier slices hold lower candidate indices: they win ties
                   const float pv = __uint_as_float((uint32_t)(rb_cur >> 32));
                   if (!(best < pv)) { best = pv; bi = (int)(uint32_t)rb_cur; }
                 }
-                const int64_t v = v0 + i_cur;
                 if (s < ICM_SLICES - 1) {
-                  p.rbest[v] = ((unsigned long long)__float_as_uint(best) << 32) | (uint32_t)bi;
+                  rbp[i_cur] = ((unsigned long long)__float_as_uint(best) << 32) | (uint32_t)bi;
                 } else {
                   const uint32_t old = (uint32_t)(c_cur >> (8 * j)) & 0xFFu;
                   if ((uint32_t)bi != old) {
-                    p.wcodes[v] = (c_cur & ~(0xFFull << (8 * j))) | ((unsigned long long)bi << (8 * j));
-                    p.wclean[v] = (uint16_t)(1u << j);
+                    wcp[i_cur] = (c_cur & ~(0xFFull << (8 * j))) | ((unsigned long long)bi << (8 * j));
+                    wclp[i_cur] = (uint16_t)(1u << j);
                   } else {
-                    p.wclean[v] = (uint16_t)(p.wclean[v] | (1u << j));
+                    wclp[i_cur] = (uint16_t)(wclp[i_cur] | (1u << j));
                   }
                 }
               }
