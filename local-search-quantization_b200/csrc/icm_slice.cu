@@ -240,53 +240,69 @@ __global__ void __launch_bounds__(SLICE_THREADS, 1) icm_ils_slice_kernel(const _
           phase ^= 1u;
 
           for (int g = warp; g < ngroups; g += DEPTH * NW) {
+            // DEPTH independent groups per round, phase by phase and branch-free until the stores, so the
+            // scheduler can overlap their LDS -> FADD -> shuffle chains (only 4 warps per scheduler).
+            int ci[DEPTH], bi[DEPTH];
+            unsigned long long cc[DEPTH], cb[DEPTH];
+            float4 a[DEPTH];
+            float best[DEPTH];
+#pragma unroll
+            for (int u = 0; u < DEPTH; u++) { ci[u] = r_i[u]; cc[u] = r_c[u]; cb[u] = r_b[u]; a[u] = r_a[u]; }
 #pragma unroll
             for (int u = 0; u < DEPTH; u++) {
-              const int gg = g + u * NW;
-              const int i_cur = r_i[u];
-              const unsigned long long c_cur = r_c[u], rb_cur = r_b[u];
-              float4 a = r_a[u];
-              load_data(gg + DEPTH * NW, u);
-              n_i[u] = load_idx(gg + 2 * DEPTH * NW);
-              if (gg >= ngroups) continue;  // warp-uniform
-              const unsigned long long pk = (c_cur & lowmask) | ((c_cur >> 8) & ~lowmask);
+              load_data(g + (u + DEPTH) * NW, u);
+              n_i[u] = load_idx(g + (u + 2 * DEPTH) * NW);
+            }
+#pragma unroll
+            for (int u = 0; u < DEPTH; u++) {
+              const unsigned long long pk = (cc[u] & lowmask) | ((cc[u] >> 8) & ~lowmask);
               const uint32_t pk0 = (uint32_t)pk, pk1 = (uint32_t)(pk >> 32);
 #pragma unroll
               for (int kk = 0; kk < M - 1; kk++) {
                 const uint32_t c = __byte_perm(kk < 4 ? pk0 : pk1, 0u, 0x4440u | (uint32_t)(kk & 3));
                 const float4 t4 = lds128(tab_lane + (uint32_t)(kk * LSQ_H * ICM_SLICE_W * 4) + c * (ICM_SLICE_W * 4));
-                a.x = __fadd_rn(a.x, t4.x); a.y = __fadd_rn(a.y, t4.y); a.z = __fadd_rn(a.z, t4.z); a.w = __fadd_rn(a.w, t4.w);
+                a[u].x = __fadd_rn(a[u].x, t4.x); a[u].y = __fadd_rn(a[u].y, t4.y);
+                a[u].z = __fadd_rn(a[u].z, t4.z); a[u].w = __fadd_rn(a[u].w, t4.w);
               }
+            }
+#pragma unroll
+            for (int u = 0; u < DEPTH; u++) {
               // first strict minimum of this lane's 4 candidates ...
-              float best = a.x;
-              int bi = s * ICM_SLICE_W + c4 * 4;
-              if (a.y < best) { best = a.y; bi = s * ICM_SLICE_W + c4 * 4 + 1; }
-              if (a.z < best) { best = a.z; bi = s * ICM_SLICE_W + c4 * 4 + 2; }
-              if (a.w < best) { best = a.w; bi = s * ICM_SLICE_W + c4 * 4 + 3; }
+              float bv = a[u].x;
+              int bx = s * ICM_SLICE_W + c4 * 4;
+              if (a[u].y < bv) { bv = a[u].y; bx = s * ICM_SLICE_W + c4 * 4 + 1; }
+              if (a[u].z < bv) { bv = a[u].z; bx = s * ICM_SLICE_W + c4 * 4 + 2; }
+              if (a[u].w < bv) { bv = a[u].w; bx = s * ICM_SLICE_W + c4 * 4 + 3; }
               // ... then of the quarter's 32: value-only min butterfly, lowest lane holding the minimum wins
               // (lanes hold ascending candidate ranges, so this is the first strict minimum)
-              float mn = best;
+              float mn = bv;
               mn = fminf(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, 4));
               mn = fminf(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, 2));
               mn = fminf(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, 1));
-              const uint32_t eq = __ballot_sync(0xFFFFFFFFu, best == mn);
+              const uint32_t eq = __ballot_sync(0xFFFFFFFFu, bv == mn);
               const int src = (q << 3) + __ffs((eq >> (q << 3)) & 0xFFu) - 1;
-              bi = __shfl_sync(0xFFFFFFFFu, bi, src);
-              best = mn;
-              if (c4 == 0 && (gg * 4 + q) < n_act) {
+              bi[u] = __shfl_sync(0xFFFFFFFFu, bx, src & 31);
+              best[u] = mn;
+            }
+#pragma unroll
+            for (int u = 0; u < DEPTH; u++) {
+              const int gg = g + u * NW;
+              if (c4 == 0 && gg < ngroups && (gg * 4 + q) < n_act) {
+                float bv = best[u];
+                int bx = bi[u];
                 if (s > 0) {  // earlier slices hold lower candidate indices: they win ties
-                  const float pv = __uint_as_float((uint32_t)(rb_cur >> 32));
-                  if (!(best < pv)) { best = pv; bi = (int)(uint32_t)rb_cur; }
+                  const float pv = __uint_as_float((uint32_t)(cb[u] >> 32));
+                  if (!(bv < pv)) { bv = pv; bx = (int)(uint32_t)cb[u]; }
                 }
                 if (s < ICM_SLICES - 1) {
-                  rbp[i_cur] = ((unsigned long long)__float_as_uint(best) << 32) | (uint32_t)bi;
+                  rbp[ci[u]] = ((unsigned long long)__float_as_uint(bv) << 32) | (uint32_t)bx;
                 } else {
-                  const uint32_t old = (uint32_t)(c_cur >> (8 * j)) & 0xFFu;
-                  if ((uint32_t)bi != old) {
-                    wcp[i_cur] = (c_cur & ~(0xFFull << (8 * j))) | ((unsigned long long)bi << (8 * j));
-                    wclp[i_cur] = (uint16_t)(1u << j);
+                  const uint32_t old = (uint32_t)(cc[u] >> (8 * j)) & 0xFFu;
+                  if ((uint32_t)bx != old) {
+                    wcp[ci[u]] = (cc[u] & ~(0xFFull << (8 * j))) | ((unsigned long long)bx << (8 * j));
+                    wclp[ci[u]] = (uint16_t)(1u << j);
                   } else {
-                    wclp[i_cur] = (uint16_t)(wclp[i_cur] | (1u << j));
+                    wclp[ci[u]] = (uint16_t)(wclp[ci[u]] | (1u << j));
                   }
                 }
               }
