@@ -325,11 +325,11 @@ def test_both_kernels_explicit_schedule(gpu, oracle, icm_kernel):
 
 
 def test_slice_kernel_large_n_matches_warp_kernel(gpu, monkeypatch):
-    """At a size where the slice kernel is the default (n >= 148 K), both kernels give identical codes."""
+    """At a large size (every CTA of the slice kernel owns > 1000 vectors) both kernels give identical codes."""
     n, d, m = 200000, 128, 8
     X, C, B = make_problem(1800, n, d, m)
     monkeypatch.setenv("LSQ_B200_ICM_KERNEL", "warp")
     Bw, ow = gpu.encode_icm_cuda(X, B, C, [4], 4, 4, True, 1, seed=2)
-    monkeypatch.delenv("LSQ_B200_ICM_KERNEL")
+    monkeypatch.setenv("LSQ_B200_ICM_KERNEL", "slice")
     Bs, os_ = gpu.encode_icm_cuda(X, B, C, [4], 4, 4, True, 1, seed=2)
     assert np.array_equal(Bw[0], Bs[0]) and ow[0] == os_[0]
