@@ -16,10 +16,11 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def clustered(rng, n, d, centers):
-    """SIFT-like non-negative data with cluster structure (so that quantisation has something to learn)."""
-    idx = rng.integers(0, len(centers), n)
-    x = centers[idx] + rng.standard_normal((n, d)).astype(np.float32) * 12.0
+def clustered(rng, n, d, W):
+    """SIFT-like non-negative data of low intrinsic dimension (rank-24 latent + small noise), so that a
+    64-bit code has something to learn and recall@1 lands in the range real descriptors give."""
+    z = rng.standard_normal((n, W.shape[0])).astype(np.float32)
+    x = z @ W + rng.standard_normal((n, d)).astype(np.float32) * 2.0
     return np.clip(np.floor(np.abs(x)), 0, 255).astype(np.float32)
 
 
@@ -39,7 +40,7 @@ def main():
     L.init(0)
     rng = np.random.default_rng(0)
     d, m, h = args.d, args.m, 256
-    centers = (np.abs(rng.standard_normal((2000, d))) * 40).astype(np.float32)
+    centers = (rng.standard_normal((24, d)) * 12).astype(np.float32)  # latent -> descriptor map
     x_train = clustered(rng, args.ntrain, d, centers)
     x_base = clustered(rng, args.nbase, d, centers)
     x_query = clustered(rng, args.nquery, d, centers)

@@ -135,11 +135,17 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
   __syncthreads();
   if (tid == 0) bulk_load_issue(lut, p.lut + (size_t)tile * (LUT_BYTES / 4), LUT_BYTES, bar);
 
-  const int q = tile * QT + lane;
-  const bool qvalid = (lane < QT) && (q < p.nq);
+  // QT <= 16 (m >= 14): a half-warp covers the tile's queries, so each warp instruction serves TWO base
+  // vectors (lanes 0-15 / 16-31).  The kernel is issue-bound; the extra shared-memory wavefront when the
+  // two rows share banks costs less than the instruction slots it saves.
+  constexpr int VPS = (QT <= 16) ? 2 : 1;                // base vectors per step
+  const int sub = (VPS == 2) ? (lane >> 4) : 0;          // which of the step's vectors this lane serves
+  const int ql = (VPS == 2) ? (lane & 15) : lane;        // query slot within the tile
+  const int q = tile * QT + ql;
+  const bool qvalid = (ql < QT) && (q < p.nq);
   float tau = -INFINITY;  // invalid lanes never pass `dist <= tau`
-  if (p.mode == MODE_MAIN && qvalid) tau = p.tau[tile * 32 + lane];
-  const char* lane_base = reinterpret_cast<const char*>(lut) + lane * 4;
+  if (p.mode == MODE_MAIN && qvalid) tau = p.tau[tile * 32 + ql];
+  const char* lane_base = reinterpret_cast<const char*>(lut) + ql * 4;
 
   // slice of the step range handled by this CTA (multiple of 32 steps)
   int64_t per = (p.count + gridDim.y - 1) / gridDim.y;
@@ -183,11 +189,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
     const bool full = (c0 + 32 <= t_end);
     const int nvalid = full ? 32 : (int)(t_end - c0);
 #pragma unroll 2
-    for (int b0 = 0; b0 < 32; b0 += 4) {
+    for (int b0 = 0; b0 < 32; b0 += 4 * VPS) {
       float dist[4];
+      int bsrc[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) {
-        const int b = b0 + u;
+        const int b = b0 + u * VPS + sub;  // chunk-relative index of the base vector this lane scores
+        bsrc[u] = b;
         const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, (uint32_t)lo, b);
         const uint32_t w1 = (M > 4) ? __shfl_sync(0xFFFFFFFFu, (uint32_t)(lo >> 32), b) : 0u;
         const uint32_t w2 = (M > 8) ? __shfl_sync(0xFFFFFFFFu, (uint32_t)hi, b) : 0u;
@@ -209,8 +217,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
         if (__any_sync(0xFFFFFFFFu, hit)) {
 #pragma unroll
           for (int u = 0; u < 4; u++) {
-            if (dist[u] <= tau && (full || b0 + u < nvalid)) {
-              const uint32_t id = (uint32_t)(c0 + b0 + u + p.id_base);
+            if (dist[u] <= tau && (full || bsrc[u] < nvalid)) {
+              const uint32_t id = (uint32_t)(c0 + bsrc[u] + p.id_base);
               const unsigned long long key = ((unsigned long long)float_to_ordered(dist[u]) << 32) | id;
               const int pos = atomicAdd(&p.cnt[q], 1);
               if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = key;
@@ -220,10 +228,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
       } else if (qvalid) {
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-          const int64_t t = c0 + b0 + u;
-          if (full || b0 + u < nvalid) {
+          const int64_t t = c0 + bsrc[u];
+          if (full || bsrc[u] < nvalid) {
             if (p.mode == MODE_SAMPLE) {
-              p.sbuf[((size_t)tile * p.count + t) * 32 + lane] = float_to_ordered(dist[u]);
+              p.sbuf[((size_t)tile * p.count + t) * 32 + ql] = float_to_ordered(dist[u]);
             } else {
               const uint32_t id = (uint32_t)(t * p.stride + p.id_base);
               p.cand[(size_t)q * p.cap + t] = ((unsigned long long)float_to_ordered(dist[u]) << 32) | id;
