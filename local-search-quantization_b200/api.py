@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "lsq_update_codebooks", "linscan_aqd_query_extra_byte", "linscan_aqd_query", "lsq_linscan_lsq",
     "lsq_linscan_pq", "lsq_quantize_norms", "lsq_dev_tables_bytes", "lsq_dev_sliced_tables_bytes",
     "lsq_dev_icm_layout", "lsq_dev_build_tables",
-    "lsq_dev_build_unaries", "lsq_dev_veccost", "lsq_dev_icm_ils", "lsq_dev_cb_stats", "lsq_dev_cb_solve",
+    "lsq_dev_build_unaries", "lsq_dev_build_unaries_tc", "lsq_dev_veccost", "lsq_dev_icm_ils", "lsq_dev_cb_stats", "lsq_dev_cb_solve",
     "lsq_dev_linscan",
 ]
 

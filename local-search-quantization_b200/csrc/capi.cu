@@ -1,6 +1,7 @@
 // capi.cu — the extern "C" boundary (include/lsq_b200.h): argument checks, host<->device staging, and
 // the orchestration of the kernels.  No compute happens on the host; without a GPU every compute call
 // fails with LSQ_ERR_CUDA.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -189,7 +190,12 @@ static int run_encode_job(const EncodeJob& J) {
       LSQ_TRY(build_sliced_tables(dT.p, m, dTs.p, st));
       have_ts = true;
     }
-    LSQ_TRY(build_unaries(dX.p, d, nc, dC.p, m, dnorms.p, dU.p, sliced, st));
+    // LSQ_B200_UNARY=tc: tensor-core unaries (fast mode: tolerance-checked, not bit-exact with the oracle)
+    const char* um = getenv("LSQ_B200_UNARY");
+    if (um != nullptr && strcmp(um, "tc") == 0 && !sliced && d % 8 == 0 && d <= 128)
+      LSQ_TRY(build_unaries_tc(dX.p, d, nc, dC.p, m, dnorms.p, dU.p, st));
+    else
+      LSQ_TRY(build_unaries(dX.p, d, nc, dC.p, m, dnorms.p, dU.p, sliced, st));
     LSQ_TRY(launch_veccost(dX.p, d, nc, dcodes.p, dC.p, m, dcost.p, st));
     if (J.nr > 0) LSQ_CUDA(cudaMemsetAsync(dsnap.p, 0, (size_t)J.nr * nc * m, st));
 
@@ -520,6 +526,17 @@ int lsq_dev_build_unaries(const float* dX, int d, int64_t n, const float* dC, in
   LSQ_CUDA(cudaMallocAsync((void**)&dn, (size_t)m * LSQ_H * sizeof(float), st));
   int rc = build_norms(dC, d, m, dn, st);
   if (rc == LSQ_OK) rc = build_unaries(dX, d, n, dC, m, dn, dU, sliced, st);
+  cudaFreeAsync(dn, st);
+  return rc;
+}
+
+int lsq_dev_build_unaries_tc(const float* dX, int d, int64_t n, const float* dC, int m, float* dU, void* stream) {
+  LSQ_TRY(check_encode_args(d, n, m, LSQ_H, 0, 0));
+  cudaStream_t st = (cudaStream_t)stream;
+  float* dn = nullptr;
+  LSQ_CUDA(cudaMallocAsync((void**)&dn, (size_t)m * LSQ_H * sizeof(float), st));
+  int rc = build_norms(dC, d, m, dn, st);
+  if (rc == LSQ_OK) rc = build_unaries_tc(dX, d, n, dC, m, dn, dU, st);
   cudaFreeAsync(dn, st);
   return rc;
 }

@@ -58,6 +58,9 @@ int build_norms(const float* dC, int d, int m, float* dnorms, cudaStream_t st);
 // sliced = 0: U[m][n][256]; sliced = 1: U[m][8][n][32]
 int build_unaries(const float* dX, int d, int64_t n, const float* dC, int m, const float* dnorms, float* dU,
                   int sliced, cudaStream_t st);
+// tensor-core (tcgen05, 3xTF32) build of U[m][n][256]: fast mode, tolerance-checked, d % 8 == 0, d <= 128
+int build_unaries_tc(const float* dX, int d, int64_t n, const float* dC, int m, const float* dnorms, float* dU,
+                     cudaStream_t st);
 int build_tables(const float* dC, int d, int m, float* dT, cudaStream_t st);
 // Ts[j][s][kk][b][32] from T, kk enumerating k != j in ascending order
 int build_sliced_tables(const float* dT, int m, float* dTs, cudaStream_t st);

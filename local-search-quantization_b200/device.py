@@ -20,7 +20,7 @@ class EncodeSession:
     """X, codebooks, unary/pair tables, codes and costs resident in HBM across ILS iterations
     (the reference re-uploads X and codes every call: encode_icm_cuda.jl:79,134,146-153)."""
 
-    def __init__(self, X, C, codes, g0=0, sliced=None):
+    def __init__(self, X, C, codes, g0=0, sliced=None, unary="exact"):
         assert X.is_cuda and X.dtype == torch.float32 and X.is_contiguous()
         assert C.is_cuda and C.dtype == torch.float32 and C.is_contiguous() and C.shape[1] == 256
         assert codes.is_cuda and codes.dtype == torch.uint8 and codes.is_contiguous()
@@ -28,6 +28,7 @@ class EncodeSession:
         self.n, self.d = X.shape
         self.m = C.shape[0]
         self.g0 = int(g0)
+        self.unary = unary  # "exact" (parity) or "tc" (tensor cores, fast mode)
         L = api.lib()
         dev = X.device
         self.sliced = int(L.lsq_dev_icm_layout(self.m, ct.c_int64(self.n))) if sliced is None else int(sliced)
@@ -43,8 +44,12 @@ class EncodeSession:
         L = api.lib()
         self.C = C
         api._check(L.lsq_dev_build_tables(_ptr(C), self.d, self.m, _ptr(self.T), _ptr(self.Ts), _stream()))
-        api._check(L.lsq_dev_build_unaries(_ptr(self.X), self.d, ct.c_int64(self.n), _ptr(C), self.m,
-                                           _ptr(self.U), self.sliced, _stream()))
+        if self.unary == "tc" and not self.sliced:
+            api._check(L.lsq_dev_build_unaries_tc(_ptr(self.X), self.d, ct.c_int64(self.n), _ptr(C), self.m,
+                                                  _ptr(self.U), _stream()))
+        else:
+            api._check(L.lsq_dev_build_unaries(_ptr(self.X), self.d, ct.c_int64(self.n), _ptr(C), self.m,
+                                               _ptr(self.U), self.sliced, _stream()))
         self.refresh_cost()
 
     def refresh_cost(self):

@@ -333,3 +333,36 @@ def test_slice_kernel_large_n_matches_warp_kernel(gpu, monkeypatch):
     monkeypatch.setenv("LSQ_B200_ICM_KERNEL", "slice")
     Bs, os_ = gpu.encode_icm_cuda(X, B, C, [4], 4, 4, True, 1, seed=2)
     assert np.array_equal(Bw[0], Bs[0]) and ow[0] == os_[0]
+
+
+# ---------------------------------------------------------------- tensor-core unaries (fast mode)
+@pytest.mark.parametrize("n,d,m", [(3000, 128, 8), (1000, 64, 7), (129, 128, 16), (5, 8, 2)])
+def test_unaries_tensor_core_tolerance(gpu, oracle, n, d, m):
+    """tcgen05 3xTF32 build of the unary tables: NOT bit-exact by construction; |dU| <= 4e-6 * max|U|."""
+    import ctypes as ct
+    import torch
+    X, C, _ = make_problem(1900 + n, n, d, m, kind="gauss")
+    X *= 37.0
+    Xd, Cd = torch.from_numpy(X).cuda(), torch.from_numpy(C).cuda()
+    U = torch.full((m, n, 256), float("nan"), dtype=torch.float32, device="cuda")
+    L = gpu.lib()
+    P = lambda t: ct.c_void_p(t.data_ptr())
+    rc = L.lsq_dev_build_unaries_tc(P(Xd), d, ct.c_int64(n), P(Cd), m, P(U), ct.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, L.lsq_last_error()
+    torch.cuda.synchronize()
+    Uo = oracle.get_unaries(X, C)
+    err = np.abs(U.cpu().numpy() - Uo).max() / np.abs(Uo).max()
+    assert err <= 4e-6, err
+
+
+def test_tensor_core_unaries_keep_quantisation_error(gpu, oracle, monkeypatch):
+    """Fast mode criterion (BASELINE north_star): quantisation error within 1e-5 relative of the parity path."""
+    n, d, m = 20000, 128, 8
+    X, C, B = make_problem(2000, n, d, m, kind="gauss")
+    X *= 25.0
+    C *= 25.0
+    Bs0, o0 = gpu.encode_icm_cuda(X, B, C, [4], 4, 4, True, 1, seed=3)
+    monkeypatch.setenv("LSQ_B200_UNARY", "tc")
+    Bs1, o1 = gpu.encode_icm_cuda(X, B, C, [4], 4, 4, True, 1, seed=3)
+    assert abs(o1[0] - o0[0]) <= 1e-5 * o0[0]
+    assert np.mean(np.any(Bs0[0] != Bs1[0], axis=1)) < 1e-3
