@@ -14,12 +14,12 @@
 //   * a CTA owns one 128-candidate tile (codebook j, half ah) for its whole life; the tile's hi and lo
 //     operands, pre-split and pre-arranged in the UMMA no-swizzle K-major core-matrix layout by
 //     split_codebooks_kernel, arrive with TMA bulk copies (cp.async.bulk + mbarrier);
-//   * per 128-vector tile of X: all threads stage hi/lo of X into shared memory in the same layout
+//   * per 64-vector tile of X: all threads stage hi/lo of X into shared memory in the same layout
 //     (row-coalesced global reads; the K-direction core-matrix stride is padded by 16 B so the 16-byte
 //     shared stores of a warp spread over all banks), fence.proxy.async, __syncthreads;
-//   * one thread issues 3 x K/8 tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8) and a
+//   * one thread issues 3 x K/8 tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=64, K=8) and a
 //     tcgen05.commit onto an mbarrier;
-//   * 8 warps drain the 128 x 128 fp32 accumulator from TMEM (tcgen05.ld 32x32b.x32), apply
+//   * 8 warps drain the 128 x 64 fp32 accumulator from TMEM (tcgen05.ld 32x32b.x32), apply
 //     -2*acc + ||c||^2 and store 128-byte rows of U[j][v][a0 .. a0+127].
 // CTAs that share a vector tile (the 2m candidate tiles) walk the vector tiles in the same order, so X
 // is read from HBM once and from L2 otherwise.
@@ -28,7 +28,7 @@
 namespace lsq {
 
 constexpr int TC_M = 128;      // candidates per tile (UMMA M)
-constexpr int TC_N = 128;      // vectors per tile (UMMA N)
+constexpr int TC_N = 64;       // vectors per tile (UMMA N): hi+lo of both operands must fit 227 KB
 constexpr int TC_KMAX = 128;   // max d
 constexpr int TC_THREADS = 256;
 
@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unary_tc_kernel(const float* __
     mbar_init(&bar_mma, 1);
     fence_mbar_init();
   }
-  if (warp == 0) {  // TMEM: 128 fp32 accumulator columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(128u) : "memory");
+  if (warp == 0) {  // TMEM: TC_N fp32 accumulator columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)TC_N) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -173,12 +173,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unary_tc_kernel(const float* __
     phase ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- epilogue: warp w drains lanes 32*(w%4).., columns 64*(w/4) .. +63 ----
-    const int quad = warp & 3, half = warp >> 2;
+    // ---- epilogue: warp w drains lanes 32*(w%4) .. +31, columns 32*(w/4) .. +31 ----
+    const int quad = warp & 3, col0 = (warp >> 2) * 32;
     float* ubase = U + ((size_t)j * n + v0) * LSQ_H + a0 + quad * 32 + lane;
-#pragma unroll 1
-    for (int cb = 0; cb < 2; cb++) {
-      const int col0 = half * 64 + cb * 32;
+    {
       uint32_t r[32];
       tc_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)col0, r);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -192,7 +190,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unary_tc_kernel(const float* __
     __syncthreads();  // accumulator drained and sB consumed: next tile may overwrite both
   }
 
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(128u) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)TC_N) : "memory");
 }
 
 // U[m][n][256] (plain layout) with the tensor-core kernel.  d must be a multiple of 8 and <= 128.
