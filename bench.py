@@ -155,6 +155,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=400000)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--unary", default="exact", choices=["exact", "tc"],
+                    help="exact = parity path (sequential fp32 chain); tc = tcgen05 3xTF32 fast mode (tolerance-checked)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -186,7 +188,9 @@ def main():
     C = torch.from_numpy(C_h).to(dev)
     codes0 = torch.from_numpy((B_h - 1).astype(np.uint8)).to(dev)
     codes = codes0.clone()
-    sess = lsqdev.EncodeSession(X, C, codes, g0=g0)
+    sess = lsqdev.EncodeSession(X, C, codes, g0=g0, unary=args.unary)
+    if args.unary == "tc":
+        os.environ["LSQ_B200_UNARY"] = "tc"  # the host-API (e2e) leg follows the same mode
     orders = np.stack([lsq_b200.make_to_look(1, i, M, True) for i in range(ils)])
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -258,7 +262,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"LSQ ICM encode m={M} h={H} d={D}, {ils} ILS iters x icmiter={ICMITER}, npert={NPERT} (BASELINE configs[1] base-set encode)",
                        "n_per_gpu": n, "parallelism": f"shard{world}", "l2": "inputs larger than L2 (8 GB unaries per GPU)",
-                       "step": "pair tables + unaries + cost + all ILS iterations"},
+                       "step": "pair tables + unaries + cost + all ILS iterations",
+                       "unary_mode": "exact fp32 chain (parity)" if args.unary == "exact" else "tcgen05 3xTF32 (fast mode, not bit-exact)"},
             "vector_ils_iters_per_sec": value * ils,
             "qerror": qerr, "e2e_codes_equal_resident_codes": same,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
