@@ -11,4 +11,5 @@ globals().update({k: getattr(_pkg, k) for k in _pkg.__all__})
 device = importlib.import_module("local-search-quantization_b200.device")
 build = importlib.import_module("local-search-quantization_b200.build")
 parallel = importlib.import_module("local-search-quantization_b200.parallel")
-__all__ = list(_pkg.__all__) + ["device", "build", "parallel"]
+io = importlib.import_module("local-search-quantization_b200.io")
+__all__ = list(_pkg.__all__) + ["device", "build", "parallel", "io"]

@@ -216,3 +216,18 @@ def test_eval_recall(lsq):
     pred = np.array([[3, 1, 2], [1, 9, 2], [7, 8, 6]])
     r = lsq.eval_recall(gt, pred, 3)
     assert np.allclose(r, [1 / 3, 2 / 3, 2 / 3])
+
+
+def test_vecs_wire_formats(lsq, tmp_path):
+    """.fvecs/.ivecs/.bvecs round trips and ranges (src/read/*.jl: int32 dim header per vector)."""
+    rng = np.random.default_rng(0)
+    for name, dt, w, r in [("f", np.float32, lsq.io.fvecs_write, lsq.io.fvecs_read),
+                           ("i", np.int32, lsq.io.ivecs_write, lsq.io.ivecs_read),
+                           ("b", np.uint8, lsq.io.bvecs_write, lsq.io.bvecs_read)]:
+        a = (rng.random((37, 12)) * 200).astype(dt)
+        path = str(tmp_path / f"x.{name}vecs")
+        w(path, a)
+        assert os.path.getsize(path) == 37 * (4 + 12 * np.dtype(dt).itemsize)
+        assert np.array_equal(r(path), a)
+        assert np.array_equal(r(path, 5), a[:5])
+        assert np.array_equal(r(path, (3, 9)), a[2:9])
