@@ -18,6 +18,7 @@ static thread_local std::string g_err;
 static std::mutex g_mu;
 static int g_device = -1;
 static cudaStream_t g_stream = nullptr;
+static cudaStream_t g_stream2 = nullptr;  // second slot of the encode pipeline
 
 void set_error(const std::string& msg) { g_err = msg; }
 
@@ -61,6 +62,7 @@ static int ensure_init() {
   cudaGetDevice(&dev);
   LSQ_CUDA(cudaSetDevice(dev));
   LSQ_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  LSQ_CUDA(cudaStreamCreateWithFlags(&g_stream2, cudaStreamNonBlocking));
   keep_pool_memory(dev);
   g_device = dev;
   return LSQ_OK;
@@ -109,15 +111,6 @@ static int upload_codes(const int16_t* hB, int64_t count, uint8_t* d8, cudaStrea
   return LSQ_OK;
 }
 
-static int download_codes(const uint8_t* d8, int64_t count, int16_t* hB, cudaStream_t st) {
-  DevBuf<int16_t> d16;
-  LSQ_CUDA(d16.alloc(count));
-  LSQ_TRY(launch_codes_u8_to_i16(d8, d16.p, count, st));
-  LSQ_CUDA(cudaMemcpyAsync(hB, d16.p, count * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
-  LSQ_CUDA(cudaStreamSynchronize(st));
-  return LSQ_OK;
-}
-
 // The shared driver of lsq_encoding_icm[_sched] and lsq_encode_icm_cuda: uploads, builds tables,
 // walks the base set in memory-bounded chunks, runs `total_iters` ILS iterations per chunk.
 struct EncodeJob {
@@ -134,9 +127,44 @@ struct EncodeJob {
   int nsplits; int verbose;
 };
 
+// Per-chunk device state of the encode pipeline.  Two slots alternate: while the GPU runs the ILS
+// kernel of one chunk, the host stages the next chunk's X and codes into the other slot, so the
+// host->device copies (which the reference pays up front, encode_icm_cuda.jl:79) hide behind compute.
+struct EncodeSlot {
+  cudaStream_t st = nullptr;
+  DevBuf<float> dX, dU, dcost, dsnapcost;
+  DevBuf<uint8_t> dcodes, dsnap, dslots, dvals;
+  DevBuf<int16_t> d16;
+  DevBuf<double> dsum;
+  DevBuf<int> derr;
+  int64_t lo = 0, nc = 0;
+  bool busy = false;
+};
+
+static int slot_alloc(EncodeSlot& S, cudaStream_t st, int64_t maxchunk, int d, int m, int nr) {
+  S.st = st;
+  set_alloc_stream(st);
+  // (DevBuf captures the allocation stream at construction: rebind each member to this slot's stream)
+  S.dX.st = S.dU.st = S.dcost.st = S.dsnapcost.st = st;
+  S.dcodes.st = S.dsnap.st = S.dslots.st = S.dvals.st = st;
+  S.d16.st = st; S.dsum.st = st; S.derr.st = st;
+  LSQ_CUDA(S.dX.alloc((size_t)maxchunk * d));
+  LSQ_CUDA(S.dU.alloc((size_t)maxchunk * m * LSQ_H));
+  LSQ_CUDA(S.dcost.alloc(maxchunk));
+  LSQ_CUDA(S.dcodes.alloc((size_t)maxchunk * m));
+  LSQ_CUDA(S.d16.alloc((size_t)maxchunk * m));
+  LSQ_CUDA(S.dsum.alloc((size_t)(nr > 0 ? nr : 1) * 1025));
+  LSQ_CUDA(S.derr.alloc(1));
+  if (nr > 0) {
+    LSQ_CUDA(S.dsnap.alloc((size_t)nr * maxchunk * m));
+    LSQ_CUDA(S.dsnapcost.alloc((size_t)nr * maxchunk));
+  }
+  return LSQ_OK;
+}
+
 static int run_encode_job(const EncodeJob& J) {
-  cudaStream_t st;
-  LSQ_TRY(host_ctx(&st));
+  cudaStream_t st0;
+  LSQ_TRY(host_ctx(&st0));
   const int d = J.d, m = J.m;
   const int64_t n = J.n;
 
@@ -144,60 +172,95 @@ static int run_encode_job(const EncodeJob& J) {
   LSQ_CUDA(dC.alloc((size_t)m * LSQ_H * d));
   LSQ_CUDA(dnorms.alloc((size_t)m * LSQ_H));
   LSQ_CUDA(dT.alloc((size_t)m * m * LSQ_H * LSQ_H));
-  LSQ_CUDA(cudaMemcpyAsync(dC.p, J.C, (size_t)m * LSQ_H * d * sizeof(float), cudaMemcpyHostToDevice, st));
-  LSQ_TRY(build_norms(dC.p, d, m, dnorms.p, st));
-  LSQ_TRY(build_tables(dC.p, d, m, dT.p, st));
-  bool have_ts = false;
+  LSQ_CUDA(cudaMemcpyAsync(dC.p, J.C, (size_t)m * LSQ_H * d * sizeof(float), cudaMemcpyHostToDevice, st0));
+  LSQ_TRY(build_norms(dC.p, d, m, dnorms.p, st0));
+  LSQ_TRY(build_tables(dC.p, d, m, dT.p, st0));
 
   // snapshot map: ILS iteration i (1-based) -> first r with ilsiters[r] == i (encode_icm_cuda.jl:211-213)
   std::vector<int> snap_of(J.total_iters, -1);
   for (int i = 1; i <= J.total_iters; i++)
     for (int r = 0; r < J.nr; r++)
       if (J.ilsiters[r] == i) { snap_of[i - 1] = r; break; }
+  std::vector<char> snap_used(J.nr > 0 ? J.nr : 1, 0);
+  for (int i = 0; i < J.total_iters; i++)
+    if (snap_of[i] >= 0) snap_used[snap_of[i]] = 1;
   std::vector<double> obj_sum(J.nr > 0 ? J.nr : 1, 0.0);
-  std::vector<char> obj_set(J.nr > 0 ? J.nr : 1, 0);
 
-  // chunking: at least nsplits splitarray parts (encode_icm_cuda.jl:272), more if memory demands
-  int64_t cap = unary_chunk_capacity(m, d);
+  // chunking: at least nsplits splitarray parts (encode_icm_cuda.jl:272), more if memory demands, and
+  // a few parts for large inputs so that the copies of part i+1 overlap the kernels of part i
+  const int64_t cap = unary_chunk_capacity(m, d) / 2;  // two slots
   int nparts = J.nsplits > 1 ? J.nsplits : 1;
+  int pipe_parts = 4;
+  if (const char* e = getenv("LSQ_B200_PIPELINE_PARTS")) pipe_parts = std::max(1, atoi(e));
+  if (n >= 262144 && nparts < pipe_parts) nparts = pipe_parts;
   while (ceil_div(n, nparts) > cap) nparts++;
   if (n == 0) nparts = 1;
   const int64_t maxchunk = ceil_div(n, nparts) + 1;
+  const int nslots = nparts > 1 ? 2 : 1;
 
-  DevBuf<float> dX, dU, dcost, dsnapcost;
-  DevBuf<uint8_t> dcodes, dsnap, dslots, dvals;
-  DevBuf<double> dsum;
-  LSQ_CUDA(dX.alloc((size_t)maxchunk * d));
-  LSQ_CUDA(dU.alloc((size_t)maxchunk * m * LSQ_H));
-  LSQ_CUDA(dcost.alloc(maxchunk));
-  LSQ_CUDA(dcodes.alloc((size_t)maxchunk * m));
-  LSQ_CUDA(dsum.alloc(1025));
-  if (J.nr > 0) {
-    LSQ_CUDA(dsnap.alloc((size_t)J.nr * maxchunk * m));
-    LSQ_CUDA(dsnapcost.alloc((size_t)J.nr * maxchunk));
+  // the sliced layout is decided once for the job (all chunks have the same size up to one vector)
+  const int sliced = icm_use_slices(m, maxchunk - 1);
+  if (sliced) {
+    LSQ_CUDA(dTs.alloc((size_t)m * (m - 1) * LSQ_H * LSQ_H));
+    LSQ_TRY(build_sliced_tables(dT.p, m, dTs.p, st0));
   }
+  const char* um = getenv("LSQ_B200_UNARY");  // "tc": tensor-core unaries (fast mode, tolerance-checked)
+  const bool unary_tc = (um != nullptr && strcmp(um, "tc") == 0 && !sliced && d % 8 == 0 && d <= 128);
+
+  cudaEvent_t ev_tables;
+  LSQ_CUDA(cudaEventCreateWithFlags(&ev_tables, cudaEventDisableTiming));
+  LSQ_CUDA(cudaEventRecord(ev_tables, st0));
+  EncodeSlot slots[2];
+  LSQ_TRY(slot_alloc(slots[0], st0, maxchunk, d, m, J.nr));
+  if (nslots == 2) {
+    LSQ_TRY(slot_alloc(slots[1], g_stream2, maxchunk, d, m, J.nr));
+    LSQ_CUDA(cudaStreamWaitEvent(g_stream2, ev_tables, 0));
+  }
+  set_alloc_stream(st0);
+
+  // copy results of a finished chunk back (D2H into pageable memory blocks the host: call it only
+  // after the next chunk's work has been queued on the other stream)
+  auto finish = [&](EncodeSlot& S) -> int {
+    const int64_t lo = S.lo, nc = S.nc;
+    int herr = 0;
+    LSQ_CUDA(cudaMemcpyAsync(&herr, S.derr.p, sizeof(int), cudaMemcpyDeviceToHost, S.st));
+    if (J.B_out) {
+      LSQ_TRY(launch_codes_u8_to_i16(S.dcodes.p, S.d16.p, nc * m, S.st));
+      LSQ_CUDA(cudaMemcpyAsync(J.B_out + (size_t)lo * m, S.d16.p, (size_t)nc * m * sizeof(int16_t), cudaMemcpyDeviceToHost, S.st));
+    }
+    std::vector<double> sums(J.nr > 0 ? J.nr : 1, 0.0);
+    for (int r = 0; r < J.nr; r++) {
+      if (!snap_used[r]) continue;
+      LSQ_TRY(launch_codes_u8_to_i16(S.dsnap.p + (size_t)r * nc * m, S.d16.p, nc * m, S.st));
+      LSQ_CUDA(cudaMemcpyAsync(J.Bs + ((size_t)r * n + lo) * m, S.d16.p, (size_t)nc * m * sizeof(int16_t), cudaMemcpyDeviceToHost, S.st));
+      LSQ_TRY(launch_sum_f32_to_f64(S.dsnapcost.p + (size_t)r * nc, nc, S.dsum.p + (size_t)r * 1025, S.st));
+      LSQ_CUDA(cudaMemcpyAsync(&sums[r], S.dsum.p + (size_t)r * 1025, sizeof(double), cudaMemcpyDeviceToHost, S.st));
+    }
+    LSQ_CUDA(cudaStreamSynchronize(S.st));
+    S.busy = false;
+    LSQ_CHECK_ARG(herr == 0, "codes must be 1-based in 1..256");
+    for (int r = 0; r < J.nr; r++) obj_sum[r] += sums[r];
+    return LSQ_OK;
+  };
 
   for (int part = 0; part < nparts; part++) {
     int64_t lo, hi;
     lsq_splitarray(n, nparts, part, &lo, &hi);
     const int64_t nc = hi - lo;
     if (nc <= 0) continue;
-    LSQ_CUDA(cudaMemcpyAsync(dX.p, J.X + (size_t)lo * d, (size_t)nc * d * sizeof(float), cudaMemcpyHostToDevice, st));
-    LSQ_TRY(upload_codes(J.B_in + (size_t)lo * m, nc * m, dcodes.p, st));
-    const int sliced = icm_use_slices(m, nc);
-    if (sliced && !have_ts) {
-      LSQ_CUDA(dTs.alloc((size_t)m * (m - 1) * LSQ_H * LSQ_H));
-      LSQ_TRY(build_sliced_tables(dT.p, m, dTs.p, st));
-      have_ts = true;
-    }
-    // LSQ_B200_UNARY=tc: tensor-core unaries (fast mode: tolerance-checked, not bit-exact with the oracle)
-    const char* um = getenv("LSQ_B200_UNARY");
-    if (um != nullptr && strcmp(um, "tc") == 0 && !sliced && d % 8 == 0 && d <= 128)
-      LSQ_TRY(build_unaries_tc(dX.p, d, nc, dC.p, m, dnorms.p, dU.p, st));
-    else
-      LSQ_TRY(build_unaries(dX.p, d, nc, dC.p, m, dnorms.p, dU.p, sliced, st));
-    LSQ_TRY(launch_veccost(dX.p, d, nc, dcodes.p, dC.p, m, dcost.p, st));
-    if (J.nr > 0) LSQ_CUDA(cudaMemsetAsync(dsnap.p, 0, (size_t)J.nr * nc * m, st));
+    EncodeSlot& S = slots[part % nslots];
+    if (S.busy) LSQ_TRY(finish(S));
+    cudaStream_t st = S.st;
+    S.lo = lo; S.nc = nc;
+    LSQ_CUDA(cudaMemsetAsync(S.derr.p, 0, sizeof(int), st));
+    LSQ_CUDA(cudaMemcpyAsync(S.dX.p, J.X + (size_t)lo * d, (size_t)nc * d * sizeof(float), cudaMemcpyHostToDevice, st));
+    LSQ_CUDA(cudaMemcpyAsync(S.d16.p, J.B_in + (size_t)lo * m, (size_t)nc * m * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    LSQ_TRY(launch_codes_i16_to_u8(S.d16.p, S.dcodes.p, nc * m, S.derr.p, st));
+    if (unary_tc) LSQ_TRY(build_unaries_tc(S.dX.p, d, nc, dC.p, m, dnorms.p, S.dU.p, st));
+    else LSQ_TRY(build_unaries(S.dX.p, d, nc, dC.p, m, dnorms.p, S.dU.p, sliced, st));
+    set_alloc_stream(st0);
+    LSQ_TRY(launch_veccost(S.dX.p, d, nc, S.dcodes.p, dC.p, m, S.dcost.p, st));
+    if (J.nr > 0) LSQ_CUDA(cudaMemsetAsync(S.dsnap.p, 0, (size_t)J.nr * nc * m, st));
 
     if (J.slots != nullptr && J.npert > 0) {
       // explicit perturbations: [n][npert] uint8 slots, int16 0-based values -> uint8
@@ -208,23 +271,24 @@ static int run_encode_job(const EncodeJob& J) {
         LSQ_CHECK_ARG(J.slots[(size_t)lo * J.npert + i] < m, "perturbation slots must be < m");
         v8[i] = (uint8_t)x;
       }
-      LSQ_CUDA(dslots.alloc(v8.size()));
-      LSQ_CUDA(dvals.alloc(v8.size()));
-      LSQ_CUDA(cudaMemcpyAsync(dslots.p, J.slots + (size_t)lo * J.npert, v8.size(), cudaMemcpyHostToDevice, st));
-      LSQ_CUDA(cudaMemcpyAsync(dvals.p, v8.data(), v8.size(), cudaMemcpyHostToDevice, st));
-      LSQ_CUDA(cudaStreamSynchronize(st));
+      S.dslots.st = S.dvals.st = st;
+      LSQ_CUDA(S.dslots.alloc(v8.size()));
+      LSQ_CUDA(S.dvals.alloc(v8.size()));
+      LSQ_CUDA(cudaMemcpyAsync(S.dslots.p, J.slots + (size_t)lo * J.npert, v8.size(), cudaMemcpyHostToDevice, st));
+      LSQ_CUDA(cudaMemcpyAsync(S.dvals.p, v8.data(), v8.size(), cudaMemcpyHostToDevice, st));
+      LSQ_CUDA(cudaStreamSynchronize(st));  // v8 dies at the end of this scope
     }
 
     for (int it0 = 0; it0 < J.total_iters; it0 += ICM_MAX_ITERS_PER_LAUNCH) {
       const int nit = std::min(ICM_MAX_ITERS_PER_LAUNCH, J.total_iters - it0);
       IcmParams p;
       memset(&p, 0, sizeof(p));
-      p.X = dX.p; p.C = dC.p; p.U = dU.p; p.T = dT.p; p.Ts = dTs.p;
-      p.codes = dcodes.p; p.cost = dcost.p;
-      p.slots = (J.slots && J.npert > 0) ? dslots.p : nullptr;
-      p.vals = (J.slots && J.npert > 0) ? dvals.p : nullptr;
-      p.snap = J.nr > 0 ? dsnap.p : nullptr;
-      p.snapcost = J.nr > 0 ? dsnapcost.p : nullptr;
+      p.X = S.dX.p; p.C = dC.p; p.U = S.dU.p; p.T = dT.p; p.Ts = dTs.p;
+      p.codes = S.dcodes.p; p.cost = S.dcost.p;
+      p.slots = (J.slots && J.npert > 0) ? S.dslots.p : nullptr;
+      p.vals = (J.slots && J.npert > 0) ? S.dvals.p : nullptr;
+      p.snap = J.nr > 0 ? S.dsnap.p : nullptr;
+      p.snapcost = J.nr > 0 ? S.dsnapcost.p : nullptr;
       p.n = nc; p.seed = J.seed; p.g0 = J.g0 + (uint64_t)lo;
       p.ils_iter0 = J.ils_iter0 + (uint32_t)it0;
       p.d = d; p.m = m; p.icmiter = J.icmiter; p.npert = J.npert; p.niters = nit;
@@ -236,26 +300,20 @@ static int run_encode_job(const EncodeJob& J) {
         for (int k = 0; k < m; k++) p.orders[i][k] = (int8_t)order[k];
       }
       LSQ_TRY(sliced ? launch_icm_slice(p, st) : launch_icm_warp(p, st));
+      set_alloc_stream(st0);
     }
-
-    if (J.B_out) LSQ_TRY(download_codes(dcodes.p, nc * m, J.B_out + (size_t)lo * m, st));
-    for (int r = 0; r < J.nr; r++) {
-      bool used = false;
-      for (int i = 0; i < J.total_iters; i++) used |= (snap_of[i] == r);
-      if (!used) continue;
-      LSQ_TRY(download_codes(dsnap.p + (size_t)r * nc * m, nc * m, J.Bs + ((size_t)r * n + lo) * m, st));
-      LSQ_TRY(launch_sum_f32_to_f64(dsnapcost.p + (size_t)r * nc, nc, dsum.p, st));
-      double s = 0.0;
-      LSQ_CUDA(cudaMemcpyAsync(&s, dsum.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-      LSQ_CUDA(cudaStreamSynchronize(st));
-      obj_sum[r] += s;
-      obj_set[r] = 1;
-    }
-    if (J.verbose) fprintf(stderr, "[lsq_b200] encoded part %d/%d (%lld vectors)\n", part + 1, nparts, (long long)nc);
+    S.busy = true;
+    // now that this chunk is queued, collect the previous one from the other slot
+    if (nslots == 2 && slots[(part + 1) % 2].busy) LSQ_TRY(finish(slots[(part + 1) % 2]));
+    if (J.verbose) fprintf(stderr, "[lsq_b200] queued part %d/%d (%lld vectors)\n", part + 1, nparts, (long long)nc);
   }
-  LSQ_CUDA(cudaStreamSynchronize(st));
+  for (int s = 0; s < nslots; s++)
+    if (slots[s].busy) LSQ_TRY(finish(slots[s]));
+  LSQ_CUDA(cudaStreamSynchronize(st0));
+  if (nslots == 2) LSQ_CUDA(cudaStreamSynchronize(g_stream2));
+  cudaEventDestroy(ev_tables);
   for (int r = 0; r < J.nr; r++)
-    if (J.objs) J.objs[r] = obj_set[r] ? (float)(obj_sum[r] / (double)(n ? n : 1)) : 0.0f;
+    if (J.objs) J.objs[r] = snap_used[r] ? (float)(obj_sum[r] / (double)(n ? n : 1)) : 0.0f;
   return LSQ_OK;
 }
 
@@ -276,8 +334,12 @@ int lsq_init(int device) {
   }
   LSQ_CHECK_ARG(device >= 0 && device < cnt, "device index out of range");
   LSQ_CUDA(cudaSetDevice(device));
-  if (g_stream && g_device != device) { cudaStreamDestroy(g_stream); g_stream = nullptr; }
+  if (g_stream && g_device != device) {
+    cudaStreamDestroy(g_stream); g_stream = nullptr;
+    if (g_stream2) { cudaStreamDestroy(g_stream2); g_stream2 = nullptr; }
+  }
   if (!g_stream) LSQ_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  if (!g_stream2) LSQ_CUDA(cudaStreamCreateWithFlags(&g_stream2, cudaStreamNonBlocking));
   keep_pool_memory(device);
   g_device = device;
   return LSQ_OK;
@@ -286,6 +348,7 @@ int lsq_init(int device) {
 int lsq_finalize(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_stream) { cudaStreamSynchronize(g_stream); cudaStreamDestroy(g_stream); g_stream = nullptr; }
+  if (g_stream2) { cudaStreamSynchronize(g_stream2); cudaStreamDestroy(g_stream2); g_stream2 = nullptr; }
   if (g_device >= 0) {
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, g_device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
