@@ -35,8 +35,8 @@ D, M, H = 128, 8, 256
 ICMITER, NPERT = 4, 4
 
 
-def algorithmic_bytes_per_vec_iter(m=M, d=D, icmiter=ICMITER):
-    return icmiter * m * H * 4 + 2 * m + 4 * d + 8
+def algorithmic_bytes_per_vec_iter():
+    return ICMITER * M * H * 4 + 2 * M + 4 * D + 8
 
 
 def measured_peak():
@@ -155,9 +155,12 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=400000)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--m", type=int, default=8, help="codebooks (BASELINE configs[2] uses 16)")
     ap.add_argument("--unary", default="exact", choices=["exact", "tc"],
                     help="exact = parity path (sequential fp32 chain); tc = tcgen05 3xTF32 fast mode (tolerance-checked)")
     args = ap.parse_args()
+    global M
+    M = args.m
     if args.impl == "reference":
         return run_reference(args)
 
@@ -261,13 +264,13 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"LSQ ICM encode m={M} h={H} d={D}, {ils} ILS iters x icmiter={ICMITER}, npert={NPERT} (BASELINE configs[1] base-set encode)",
-                       "n_per_gpu": n, "parallelism": f"shard{world}", "l2": "inputs larger than L2 (8 GB unaries per GPU)",
+                       "n_per_gpu": n, "parallelism": f"shard{world}", "l2": f"inputs larger than L2 ({M * n * 1024 / 1e9:.0f} GB unaries per GPU)",
                        "step": "pair tables + unaries + cost + all ILS iterations",
                        "unary_mode": "exact fp32 chain (parity)" if args.unary == "exact" else "tcgen05 3xTF32 (fast mode, not bit-exact)"},
             "vector_ils_iters_per_sec": value * ils,
             "qerror": qerr, "e2e_codes_equal_resident_codes": same,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic("icm_ils_warp_kernel<8>", n, ils), "kernel": "icm_ils_warp_kernel<8>", "kernel_ms": k_ms.item(),
+                         "traffic": ncu_traffic(f"icm_ils_warp_kernel<{M}>", n, ils), "kernel": f"icm_ils_warp_kernel<{M}>", "kernel_ms": k_ms.item(),
                          "peak_source": peak_src, "bytes_per_vector_iter": algorithmic_bytes_per_vec_iter(),
                          "algorithmic_bytes_per_launch": abytes},
             "e2e": {"value": world * n / (e2e_ms.item() * 1e-3), "unit": "vectors/s",

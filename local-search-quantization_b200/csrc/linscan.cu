@@ -39,8 +39,13 @@ constexpr int SORT_CAP = LINSCAN_MAX_NN;  // keys the shared-memory bitonic sort
 enum { MODE_SAMPLE = 0, MODE_MAIN = 1, MODE_ALL = 2 };
 enum { ST_OK = 0, ST_REDO = 1 };
 
+// Queries per tile: as many LUTs as fit 224 KB of shared memory (32 for m <= 7, 28 for m = 8).  From
+// m = 9 on fewer than 28 fit; the tile is then capped at 16 so that a HALF-warp covers it and every warp
+// instruction serves two base vectors (the scan is issue-bound, idle lanes are what costs).
 __host__ __device__ constexpr int tile_queries(int m) {
-  return (LUT_SMEM_BUDGET / (m * LSQ_H * 4)) < 32 ? (LUT_SMEM_BUDGET / (m * LSQ_H * 4)) : 32;
+  return (LUT_SMEM_BUDGET / (m * LSQ_H * 4)) >= 32 ? 32
+       : (LUT_SMEM_BUDGET / (m * LSQ_H * 4)) >= 28 ? (LUT_SMEM_BUDGET / (m * LSQ_H * 4))
+       : (LUT_SMEM_BUDGET / (m * LSQ_H * 4)) < 16 ? (LUT_SMEM_BUDGET / (m * LSQ_H * 4)) : 16;
 }
 
 // ------------------------------------------------------------------------------------------------
