@@ -153,7 +153,7 @@ def main():
     ap.add_argument("--n", type=int, default=1_000_000, help="base vectors per GPU")
     ap.add_argument("--ils", type=int, default=16, help="ILS iterations per encode (LSQ-16)")
     ap.add_argument("--cpu-sample", type=int, default=400000)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--m", type=int, default=8, help="codebooks (BASELINE configs[2] uses 16)")
     ap.add_argument("--unary", default="exact", choices=["exact", "tc"],
@@ -250,7 +250,7 @@ def main():
         e2e_out, _ = lsq_b200.encode_icm_cuda(Xp.numpy(), Bp.numpy(), C_h, its, ICMITER, NPERT, True, 1, seed=1, g0=g0)
         if i > 0:
             e2e_t.append(time.perf_counter() - w0)
-    e2e_ms = torch.tensor([1e3 * statistics.mean(e2e_t) if e2e_t else float("nan")], device=dev)
+    e2e_ms = torch.tensor([1e3 * statistics.median(e2e_t) if e2e_t else float("nan")], device=dev)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     same = bool(np.array_equal(e2e_out[0], codes.cpu().numpy().astype(np.int16) + 1)) if e2e_out else None
