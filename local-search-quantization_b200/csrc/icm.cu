@@ -13,6 +13,10 @@
 // lexicographic (value, index) reduction.  Lane l owns candidates 4l..4l+3 and 128+4l..128+4l+3.
 #include "icm.cuh"
 
+#include <stdlib.h>
+
+#include <algorithm>
+
 namespace lsq {
 
 template <int M>
@@ -58,9 +62,28 @@ __device__ __forceinline__ void add4(float4& a, const float4 g) {
   a.x = __fadd_rn(a.x, g.x); a.y = __fadd_rn(a.y, g.y); a.z = __fadd_rn(a.z, g.z); a.w = __fadd_rn(a.w, g.w);
 }
 
-template <int M>
+__device__ __forceinline__ float4 lds128_u(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// USMEM: the warp's m unary rows (m KB) are staged ONCE per vector into shared memory by TMA bulk copies
+// (cp.async.bulk + one mbarrier per warp) and re-read from there on every node visit of every ILS
+// iteration, which takes the unary share (1/m-th... 1 KB of every 8 KB visit at m = 8) off the saturated
+// SM<->L2 path.  Used for m <= 8 (m KB per warp must leave room for >= 24 warps per SM).
+template <int M, bool USMEM>
 __global__ void __launch_bounds__(256) icm_ils_warp_kernel(const __grid_constant__ IcmParams p) {
+  extern __shared__ __align__(128) unsigned char icm_smem[];
   const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;                                  // warp in block
+  uint64_t* ubar = reinterpret_cast<uint64_t*>(icm_smem) + wib;      // 8 barriers, then 8 x M KB of rows
+  const uint32_t urow = smem_u32(icm_smem + 128 + (size_t)wib * M * 1024) + (uint32_t)lane * 16u;
+  uint32_t uphase = 0;
+  if (USMEM) {
+    if (lane == 0) { mbar_init(ubar, 1); fence_mbar_init(); }
+    __syncwarp();
+  }
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); v < p.n; v += nwarps) {
     uint64_t lo = 0, hi = 0;
@@ -71,6 +94,17 @@ __global__ void __launch_bounds__(256) icm_ils_warp_kernel(const __grid_constant
     }
     float prev = p.cost[v];
     const float* xv = p.X + (size_t)v * p.d;
+    if (USMEM) {
+      __syncwarp();  // every lane is done with the previous vector's rows
+      if (lane == 0) {
+        mbar_expect_tx(ubar, (uint32_t)M * 1024u);
+#pragma unroll
+        for (int j = 0; j < M; j++)
+          bulk_g2s(icm_smem + 128 + ((size_t)wib * M + j) * 1024, p.U + ((size_t)j * p.n + v) * LSQ_H, 1024u, ubar);
+      }
+      mbar_wait(ubar, uphase);
+      uphase ^= 1u;
+    }
 
     // `clean` bit j: code_j is already the argmin of node j given the other current codes, so a visit
     // would recompute exactly the same code (the node update is a deterministic function of the other
@@ -100,9 +134,15 @@ __global__ void __launch_bounds__(256) icm_ils_warp_kernel(const __grid_constant
         for (int jj = 0; jj < M; jj++) {
           const int j = p.orders[it][jj];
           if ((wclean >> j) & 1u) continue;
-          const float4* up = reinterpret_cast<const float4*>(p.U + ((size_t)j * p.n + v) * LSQ_H);
-          float4 a0 = __ldg(up + lane);
-          float4 a1 = __ldg(up + 32 + lane);
+          float4 a0, a1;
+          if (USMEM) {
+            a0 = lds128_u(urow + (uint32_t)j * 1024u);
+            a1 = lds128_u(urow + (uint32_t)j * 1024u + 512u);
+          } else {
+            const float4* up = reinterpret_cast<const float4*>(p.U + ((size_t)j * p.n + v) * LSQ_H);
+            a0 = __ldg(up + lane);
+            a1 = __ldg(up + 32 + lane);
+          }
           const float* tj = p.T + (size_t)j * M * LSQ_H * LSQ_H;
 #pragma unroll
           for (int k = 0; k < M; k++) {
@@ -157,9 +197,16 @@ static int launch_icm_warp_m(const IcmParams& p, cudaStream_t st) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t blocks_needed = ceil_div(p.n, 8);
-  const int64_t cap = (int64_t)sms * 8;
+  constexpr bool kUsmem = (M <= 8);
+  const size_t smem = kUsmem ? 128 + (size_t)8 * M * 1024 : 0;
+  int per_sm = kUsmem ? (int)std::min<size_t>(8, (size_t)(224 * 1024) / (smem + 1024)) : 8;
+  if (const char* e = getenv("LSQ_B200_ICM_BLOCKS_PER_SM")) per_sm = std::max(1, atoi(e));  // tuning override
+  const int64_t cap = (int64_t)sms * per_sm;
   const unsigned grid = (unsigned)(blocks_needed < cap ? blocks_needed : cap);
-  icm_ils_warp_kernel<M><<<grid, 256, 0, st>>>(p);
+  if (kUsmem) {
+    LSQ_CUDA(cudaFuncSetAttribute(icm_ils_warp_kernel<M, kUsmem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  icm_ils_warp_kernel<M, kUsmem><<<grid, 256, smem, st>>>(p);
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
 }
