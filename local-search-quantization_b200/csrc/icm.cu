@@ -73,7 +73,7 @@ __device__ __forceinline__ float4 lds128_u(uint32_t addr) {
 // iteration, which takes the unary share (1/m-th... 1 KB of every 8 KB visit at m = 8) off the saturated
 // SM<->L2 path.  Used for m <= 8 (m KB per warp must leave room for >= 24 warps per SM).
 template <int M, bool USMEM>
-__global__ void __launch_bounds__(256) icm_ils_warp_kernel(const __grid_constant__ IcmParams p) {
+__global__ void __launch_bounds__(256, (M > 8) ? 3 : 1) icm_ils_warp_kernel(const __grid_constant__ IcmParams p) {
   extern __shared__ __align__(128) unsigned char icm_smem[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;                                  // warp in block
@@ -208,11 +208,38 @@ static int launch_icm_warp_m(const IcmParams& p, cudaStream_t st) {
   if (const char* e = getenv("LSQ_B200_ICM_BLOCKS_PER_SM")) per_sm = std::max(1, atoi(e));  // tuning override
   const int64_t cap = (int64_t)sms * per_sm;
   const unsigned grid = (unsigned)(blocks_needed < cap ? blocks_needed : cap);
+  // m > 8: the pair tables (m*m*256 KB = 67 MB at m = 16) compete with the streaming unary rows for L2
+  // (hit rate 77 % measured); pin them with a persisting access-policy window for this launch.
+  const size_t tbytes = (size_t)M * M * LSQ_H * LSQ_H * sizeof(float);
+  bool window = false;
+  if (M > 8) {
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    if (max_persist > 0 && max_window > 0) {
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+      cudaStreamAttrValue attr;
+      memset(&attr, 0, sizeof(attr));
+      attr.accessPolicyWindow.base_ptr = const_cast<float*>(p.T);
+      attr.accessPolicyWindow.num_bytes = std::min(tbytes, (size_t)max_window);
+      attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)tbytes);
+      attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      window = (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess);
+      cudaGetLastError();
+    }
+  }
   if (usmem) {
     LSQ_CUDA(cudaFuncSetAttribute(icm_ils_warp_kernel<M, kCanUsmem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     icm_ils_warp_kernel<M, kCanUsmem><<<grid, 256, smem, st>>>(p);
   } else {
     icm_ils_warp_kernel<M, false><<<grid, 256, 0, st>>>(p);
+  }
+  if (window) {
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.num_bytes = 0;  // disable for whatever runs next on this stream
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
   }
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
