@@ -172,14 +172,20 @@ __global__ void __launch_bounds__(256, (M > 8) ? 4 : 1) icm_ils_warp_kernel(cons
           }
           if ((uint32_t)bi != get_code_dyn<M>(wlo, whi, j)) {
             set_code<M>(wlo, whi, j, (uint32_t)bi);
-            wclean = 0;
+            // back at the accepted codes (the usual end of a rejected perturbation): everything already
+            // known about that state applies again — typically "every node clean", which ends the sweeps
+            wclean = (wlo == lo && whi == hi) ? clean : 0u;
           }
           wclean |= 1u << j;
         }
       }
       // ---- accept iff strictly better (encode_icm.jl:178-186) ----
-      const float newc = warp_veccost<M>(xv, p.C, p.d, wlo, whi, lane);
-      if (newc < prev) { prev = newc; lo = wlo; hi = whi; clean = wclean; }
+      if (wlo == lo && whi == hi) {
+        clean |= wclean;  // same codes: cannot be strictly better; keep what the sweeps learned
+      } else {
+        const float newc = warp_veccost<M>(xv, p.C, p.d, wlo, whi, lane);
+        if (newc < prev) { prev = newc; lo = wlo; hi = whi; clean = wclean; }
+      }
       const int sn = p.snap_of_iter[it];
       if (sn >= 0) {
         if (lane < M) p.snap[((size_t)sn * p.n + v) * M + lane] = (uint8_t)get_code<M>(lo, hi, lane);

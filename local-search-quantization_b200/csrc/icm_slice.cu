@@ -299,8 +299,18 @@ __global__ void __launch_bounds__(SLICE_THREADS, 1) icm_ils_slice_kernel(const _
                 } else {
                   const uint32_t old = (uint32_t)(cc[u] >> (8 * j)) & 0xFFu;
                   if ((uint32_t)bx != old) {
-                    wcp[ci[u]] = (cc[u] & ~(0xFFull << (8 * j))) | ((unsigned long long)bx << (8 * j));
-                    wclp[ci[u]] = (uint16_t)(1u << j);
+                    const unsigned long long nc = (cc[u] & ~(0xFFull << (8 * j))) | ((unsigned long long)bx << (8 * j));
+                    wcp[ci[u]] = nc;
+                    // back at the accepted codes: what is known about that state applies again
+                    unsigned long long ac;
+                    if (M == 8) {
+                      ac = *reinterpret_cast<const unsigned long long*>(p.codes + (v0 + ci[u]) * M);
+                    } else {
+                      ac = 0;
+#pragma unroll
+                      for (int k = 0; k < M; k++) ac |= (unsigned long long)p.codes[(v0 + ci[u]) * M + k] << (8 * k);
+                    }
+                    wclp[ci[u]] = (uint16_t)(((nc == ac) ? p.clean[v0 + ci[u]] : 0u) | (1u << j));
                   } else {
                     wclp[ci[u]] = (uint16_t)(wclp[ci[u]] | (1u << j));
                   }
