@@ -102,6 +102,37 @@ def ncu_traffic(kernel, n, ils):
     return best
 
 
+def recall_probe(L, seed=0, ntrain=30000, nbase=200000, nquery=500, m=7, d=D, knn=10):
+    """recall@1 of the full flow (train -> encode base -> quantise norms -> ADC scan) on a small
+    synthetic problem, m = 7 codebooks + 1 norm byte like demos/demo_lsq.jl:14.  Not timed."""
+    rng = np.random.default_rng(seed)
+    W = (rng.standard_normal((24, d)) * 12).astype(np.float32)
+
+    def gen(n):
+        x = rng.standard_normal((n, 24)).astype(np.float32) @ W + rng.standard_normal((n, d)).astype(np.float32) * 2.0
+        return np.clip(np.floor(np.abs(x)), 0, 255).astype(np.float32)
+
+    xt, xb, xq = gen(ntrain), gen(nbase), gen(nquery)
+    B = L.randinit(ntrain, m, H, rng)
+    C = L.update_codebooks(xt, B, H)
+    it = 0
+    for outer in range(4):
+        for _ in range(4):
+            B = L.encoding_icm(xt, B, C, ICMITER, True, NPERT, seed=7, ils_iter=it)
+            it += 1
+        C = L.update_codebooks(xt, B, H)
+    norms = (L.reconstruct(B, C) ** 2).sum(1)
+    cbn = np.quantile(norms, (np.arange(256) + 0.5) / 256).astype(np.float32)
+    Bb = L.encode_icm_cuda(xb, L.randinit(nbase, m, H, rng), C, [8], ICMITER, NPERT, True, 1, seed=8)[0][-1]
+    dbn = cbn[L.quantize_norms(Bb, C, cbn) - 1]
+    _, idx = L.linscan_lsq((Bb - 1).astype(np.uint8), xq, C, dbn, np.eye(d, dtype=np.float32), knn)
+    bn = (xb.astype(np.float64) ** 2).sum(1)
+    gt = np.argmin(bn[None, :] - 2.0 * xq.astype(np.float64) @ xb.T.astype(np.float64), axis=1) + 1
+    rec = L.eval_recall(gt, idx, knn)
+    return {"recall@1": float(rec[0]), f"recall@{knn}": float(rec[-1]),
+            "config": f"synthetic rank-24 descriptors, {ntrain} train / {nbase} base / {nquery} queries, m={m}+norm byte"}
+
+
 def cpu_port_rate(n_sample, ils_total, seed=1):
     """Oracle port on all host threads: one ILS iteration over n_sample vectors -> vectors/s for a
     full `ils_total`-iteration encode (per-vector work is independent and identical per iteration)."""
@@ -155,6 +186,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=400000)
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-recall", action="store_true", help="skip the untimed recall@1 probe of the full flow")
     ap.add_argument("--m", type=int, default=8, help="codebooks (BASELINE configs[2] uses 16)")
     ap.add_argument("--unary", default="exact", choices=["exact", "tc"],
                     help="exact = parity path (sequential fp32 chain); tc = tcgen05 3xTF32 fast mode (tolerance-checked)")
@@ -279,6 +311,8 @@ def main():
             "gpu_launches": 5 * args.steps,
             "clocks": clocks,
         }
+        if not args.no_recall:
+            out["recall"] = recall_probe(lsq_b200)
         if not args.no_cpu:
             r, threads, dt = cpu_port_rate(args.cpu_sample, ils)
             out["cpu_baseline"] = {"value": r, "unit": "vectors/s", "cores": threads, "kind": "port",
