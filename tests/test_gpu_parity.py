@@ -366,3 +366,24 @@ def test_tensor_core_unaries_keep_quantisation_error(gpu, oracle, monkeypatch):
     Bs1, o1 = gpu.encode_icm_cuda(X, B, C, [4], 4, 4, True, 1, seed=3)
     assert abs(o1[0] - o0[0]) <= 1e-5 * o0[0]
     assert np.mean(np.any(Bs0[0] != Bs1[0], axis=1)) < 1e-3
+
+
+# ---------------------------------------------------------------- device-resident training loop
+def test_train_lsq_sharded_single_gpu_matches_host_loop(gpu):
+    """parallel.train_lsq_sharded (world size 1: X / codes / tables resident, no re-uploads) reproduces the
+    caller-side loop of LSQ.jl:57-66 driven through the host API."""
+    import torch
+    n, d, m = 12000, 64, 8
+    X, C, B = make_problem(2100, n, d, m)
+    Xd = torch.from_numpy(X).cuda()
+    cd = torch.from_numpy((B - 1).astype(np.uint8)).cuda()
+    C1, codes, obj = gpu.parallel.train_lsq_sharded(Xd, cd, torch.from_numpy(C).cuda(), 2, 3, 4, True, 4, seed=9)
+    Bc, Cc = B.copy(), C
+    for it in range(2):
+        Cc = gpu.update_codebooks(X, Bc, 256)
+        for i in range(3):
+            Bc = gpu.encoding_icm(X, Bc, Cc, 4, True, 4, seed=9, ils_iter=3 * it + i)
+    assert np.array_equal(codes.cpu().numpy().astype(np.int16) + 1, Bc)
+    q = gpu.qerror(X, Bc, Cc)
+    assert abs(obj[-1] - q) <= 1e-5 * q
+    assert obj[-1] <= obj[0]
