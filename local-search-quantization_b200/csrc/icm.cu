@@ -73,7 +73,7 @@ __device__ __forceinline__ float4 lds128_u(uint32_t addr) {
 // iteration, which takes the unary share (1/m-th... 1 KB of every 8 KB visit at m = 8) off the saturated
 // SM<->L2 path.  Used for m <= 8 (m KB per warp must leave room for >= 24 warps per SM).
 template <int M, bool USMEM>
-__global__ void __launch_bounds__(256, (M > 8) ? 4 : 1) icm_ils_warp_kernel(const __grid_constant__ IcmParams p) {
+__global__ void __launch_bounds__(256, 4) icm_ils_warp_kernel(const __grid_constant__ IcmParams p) {
   extern __shared__ __align__(128) unsigned char icm_smem[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;                                  // warp in block
