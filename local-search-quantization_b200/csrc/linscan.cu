@@ -37,7 +37,8 @@ constexpr int SAMPLE_MAX = 16384;
 constexpr int SORT_CAP = LINSCAN_MAX_NN;  // keys the shared-memory bitonic sorter holds (128 KB)
 
 enum { MODE_SAMPLE = 0, MODE_MAIN = 1, MODE_ALL = 2 };
-enum { ST_OK = 0, ST_REDO = 1 };
+enum { ST_OK = 0, ST_REDO = 1, ST_BIG = 2 };
+constexpr int SORT_SMALL = 4096;  // keys of the small top-k sorter (32 KB of shared memory)
 
 // Queries per tile: as many LUTs as fit 224 KB of shared memory (32 for m <= 7, 28 for m = 8).  From
 // m = 9 on fewer than 28 fit; the tile is then capped at 16 so that a HALF-warp covers it and every warp
@@ -305,11 +306,15 @@ __device__ __forceinline__ void bitonic_sort_smem(unsigned long long* keys, int 
   }
 }
 
-__global__ void __launch_bounds__(1024) topk_kernel(const unsigned long long* __restrict__ cand, int64_t cap,
-                                                    const int* __restrict__ cnt, int64_t fixed_count, int nn,
-                                                    const int* __restrict__ scatter, float* __restrict__ dists,
-                                                    int32_t* __restrict__ ids, int* __restrict__ status) {
-  extern __shared__ __align__(16) unsigned long long keys[];  // SORT_CAP keys
+// CAPK = keys the CTA's shared-memory sorter holds, NT = threads.  phase 0: handle every query;
+// phase 1 (small sorter, several CTAs per SM): handle queries with <= CAPK candidates, flag the rest
+// ST_BIG; phase 2 (big sorter): only the flagged ones.
+template <int CAPK, int NT>
+__global__ void __launch_bounds__(NT) topk_kernel(const unsigned long long* __restrict__ cand, int64_t cap,
+                                                  const int* __restrict__ cnt, int64_t fixed_count, int nn,
+                                                  const int* __restrict__ scatter, float* __restrict__ dists,
+                                                  int32_t* __restrict__ ids, int* __restrict__ status, int phase) {
+  extern __shared__ __align__(16) unsigned long long keys[];  // CAPK keys
   __shared__ int hist[256];
   __shared__ unsigned long long sh_prefix;
   __shared__ int sh_rank, sh_fill;
@@ -317,17 +322,24 @@ __global__ void __launch_bounds__(1024) topk_kernel(const unsigned long long* __
   const int q = blockIdx.x;
   const int64_t c = (fixed_count >= 0) ? fixed_count : (int64_t)cnt[q];
   const int qo = scatter ? scatter[q] : q;
+  const int prior = (phase == 2) ? status[q] : ST_BIG;
+  __syncthreads();  // every thread has read the flag before thread 0 may overwrite it
+  if (prior != ST_BIG) return;
   if (c < nn || c > cap) {
     if (tid == 0) status[q] = ST_REDO;
+    return;
+  }
+  if (phase == 1 && (c > CAPK || nn > CAPK)) {
+    if (tid == 0) status[q] = ST_BIG;
     return;
   }
   if (tid == 0) status[q] = ST_OK;
   const unsigned long long* src = cand + (size_t)q * cap;
   int N;
-  if (c <= SORT_CAP) {
+  if (c <= CAPK) {
     N = 2;
     while (N < c) N <<= 1;
-    for (int i = tid; i < N; i += 1024) keys[i] = (i < c) ? src[i] : ~0ull;
+    for (int i = tid; i < N; i += NT) keys[i] = (i < c) ? src[i] : ~0ull;
     __syncthreads();
   } else {
     // radix-select the nn-th smallest key (keys are unique: the id is part of the key)
@@ -338,7 +350,7 @@ __global__ void __launch_bounds__(1024) topk_kernel(const unsigned long long* __
       if (tid < 256) hist[tid] = 0;
       __syncthreads();
       const unsigned long long pre = sh_prefix;
-      for (int64_t i = tid; i < c; i += 1024) {
+      for (int64_t i = tid; i < c; i += NT) {
         const unsigned long long v = src[i];
         if ((v & pmask) == pre) atomicAdd(&hist[(int)((v >> shift) & 0xFFull)], 1);
       }
@@ -359,16 +371,16 @@ __global__ void __launch_bounds__(1024) topk_kernel(const unsigned long long* __
     if (tid == 0) sh_fill = 0;
     N = 2;
     while (N < nn) N <<= 1;
-    for (int i = tid; i < N; i += 1024) keys[i] = ~0ull;
+    for (int i = tid; i < N; i += NT) keys[i] = ~0ull;
     __syncthreads();
-    for (int64_t i = tid; i < c; i += 1024) {
+    for (int64_t i = tid; i < c; i += NT) {
       const unsigned long long v = src[i];
       if (v <= kth) keys[atomicAdd(&sh_fill, 1)] = v;
     }
     __syncthreads();
   }
-  bitonic_sort_smem(keys, N, tid, 1024);
-  for (int j = tid; j < nn; j += 1024) {
+  bitonic_sort_smem(keys, N, tid, NT);
+  for (int j = tid; j < nn; j += NT) {
     const unsigned long long k = keys[j];
     dists[(size_t)qo * nn + j] = ordered_to_float((uint32_t)(k >> 32));
     ids[(size_t)qo * nn + j] = (int32_t)(uint32_t)(k & 0xFFFFFFFFull);
@@ -429,7 +441,7 @@ static int launch_lut(int lut_kind, const float* dq, int nq, int qstride, const 
 }
 
 static int configure_topk() {
-  LSQ_CUDA(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_CAP * 8));
+  LSQ_CUDA(cudaFuncSetAttribute(topk_kernel<SORT_CAP, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_CAP * 8));
   return LSQ_OK;
 }
 
@@ -467,12 +479,12 @@ static int scan_exhaustive(const ScanCtx& S, const float* dq, int nqc, const int
     LSQ_TRY(launch_scan(S.m, p, ntiles, S.st));
     // outputs of this batch: rows q0.. (or scattered)
     if (dscatter) {
-      topk_kernel<<<nb, 1024, SORT_CAP * 8, S.st>>>(dcand.p, S.n, nullptr, S.n, S.nn, dscatter + q0, S.ddists,
-                                                     S.dids, dstatus.p);
+      topk_kernel<SORT_CAP, 1024><<<nb, 1024, SORT_CAP * 8, S.st>>>(dcand.p, S.n, nullptr, S.n, S.nn, dscatter + q0,
+                                                                     S.ddists, S.dids, dstatus.p, 0);
     } else {
-      topk_kernel<<<nb, 1024, SORT_CAP * 8, S.st>>>(dcand.p, S.n, nullptr, S.n, S.nn, nullptr,
-                                                     S.ddists + (size_t)q0 * S.nn, S.dids + (size_t)q0 * S.nn,
-                                                     dstatus.p);
+      topk_kernel<SORT_CAP, 1024><<<nb, 1024, SORT_CAP * 8, S.st>>>(dcand.p, S.n, nullptr, S.n, S.nn, nullptr,
+                                                                     S.ddists + (size_t)q0 * S.nn,
+                                                                     S.dids + (size_t)q0 * S.nn, dstatus.p, 0);
     }
     LSQ_CUDA(cudaGetLastError());
   }
@@ -549,8 +561,14 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
     LSQ_CUDA(cudaMemsetAsync(dcnt.p, 0, (size_t)nb * sizeof(int), st));
     p.mode = MODE_MAIN; p.stride = 1; p.count = n;
     LSQ_TRY(launch_scan(m, p, ntiles, st));
-    topk_kernel<<<nb, 1024, SORT_CAP * 8, st>>>(dcand.p, cap, dcnt.p, -1, nn, nullptr, ddists + (size_t)q0 * nn,
-                                                 dids + (size_t)q0 * nn, dstatus.p);
+    // most queries end up with a few thousand candidates: a 32 KB sorter lets ~6 CTAs share an SM; the
+    // 128 KB sorter only runs for the queries the first pass flags
+    topk_kernel<SORT_SMALL, 256><<<nb, 256, SORT_SMALL * 8, st>>>(dcand.p, cap, dcnt.p, -1, nn, nullptr,
+                                                                  ddists + (size_t)q0 * nn, dids + (size_t)q0 * nn,
+                                                                  dstatus.p, 1);
+    topk_kernel<SORT_CAP, 1024><<<nb, 1024, SORT_CAP * 8, st>>>(dcand.p, cap, dcnt.p, -1, nn, nullptr,
+                                                                 ddists + (size_t)q0 * nn, dids + (size_t)q0 * nn,
+                                                                 dstatus.p, 2);
     LSQ_CUDA(cudaGetLastError());
     LSQ_CUDA(cudaMemcpyAsync(hstatus.data(), dstatus.p, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, st));
     LSQ_CUDA(cudaStreamSynchronize(st));
