@@ -181,7 +181,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000, help="base vectors per GPU")
+    ap.add_argument("--n", type=int, default=1_000_000, help="base vectors per GPU (weak) or in total (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --n vectors per GPU (the contract's default); strong: --n vectors split over the GPUs")
     ap.add_argument("--ils", type=int, default=16, help="ILS iterations per encode (LSQ-16)")
     ap.add_argument("--cpu-sample", type=int, default=400000)
     ap.add_argument("--e2e-steps", type=int, default=4)
@@ -211,7 +213,12 @@ def main():
     lsq_b200.init(local)
     dev = torch.device("cuda", local)
     n, ils = args.n, args.ils
-    g0 = rank * n  # global index of this shard's first vector
+    if args.scaling == "strong":  # fixed total, contiguous splitarray shards (utils.jl:152-177)
+        lo, hi = lsq_b200.splitarray(args.n, world)[rank]
+        n, g0 = hi - lo, lo
+    else:
+        g0 = rank * n  # global index of this shard's first vector
+    n_total = args.n if args.scaling == "strong" else world * n
 
     # synthetic SIFT-shaped shard; codebooks identical on every rank
     _, C_h, _ = make_problem(0, 16, D, M)
@@ -267,7 +274,7 @@ def main():
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
     ms_per_step = total_ms.item() / args.steps
-    value = world * n / (ms_per_step * 1e-3)
+    value = n_total / (ms_per_step * 1e-3)
     qerr = sess.qerror()
 
     # ---- e2e: the C-ABI host call with pinned host buffers, copies inside the timed region ----
@@ -294,7 +301,7 @@ def main():
         out = {
             "metric": "icm_encode_vectors_per_sec", "value": value, "unit": "vectors/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"LSQ ICM encode m={M} h={H} d={D}, {ils} ILS iters x icmiter={ICMITER}, npert={NPERT} (BASELINE configs[1] base-set encode)",
                        "n_per_gpu": n, "parallelism": f"shard{world}", "l2": f"inputs larger than L2 ({M * n * 1024 / 1e9:.0f} GB unaries per GPU)",
                        "step": "pair tables + unaries + cost + all ILS iterations",
@@ -305,7 +312,7 @@ def main():
                          "traffic": ncu_traffic(f"icm_ils_warp_kernel<{M}>", n, ils), "kernel": f"icm_ils_warp_kernel<{M}>", "kernel_ms": k_ms.item(),
                          "peak_source": peak_src, "bytes_per_vector_iter": algorithmic_bytes_per_vec_iter(),
                          "algorithmic_bytes_per_launch": abytes},
-            "e2e": {"value": world * n / (e2e_ms.item() * 1e-3), "unit": "vectors/s",
+            "e2e": {"value": n_total / (e2e_ms.item() * 1e-3), "unit": "vectors/s",
                     "h2d_bytes_per_step": int(X_h.nbytes + B_h.nbytes + C_h.nbytes), "d2h_bytes_per_step": int(B_h.nbytes),
                     "ms_per_step": e2e_ms.item(), "api": "lsq_encode_icm_cuda (host pointers)"},
             "gpu_launches": 5 * args.steps,
