@@ -11,9 +11,10 @@
 //   1. lut_kernel      LUT tiles, query-fastest: lut[tile][k*256+c][QT]  (QT queries per tile)
 //   2. scan_kernel     one CTA = one query tile x one slice of the base set.  The tile's whole LUT
 //                      (m*256*QT floats, up to 224 KB) is staged in shared memory by TMA bulk copies.
-//                      Lane = query: for a base vector all lanes read the SAME (k, code) row, so every
-//                      shared-memory wavefront is 32 consecutive floats — conflict-free by
-//                      construction, 32 lookups per wavefront.  Code rows are loaded once per 32 base
+//                      A group of 8 lanes scores one base vector for the whole tile: each lane serves 4
+//                      consecutive queries with one LDS.128 of the (k, code) row, so a quarter-warp
+//                      phase reads one contiguous row — conflict-free by construction — and a warp
+//                      instruction scores 4 base vectors.  Code rows are loaded once per 32 base
 //                      vectors (one row per lane) and broadcast by warp shuffles.
 //   3. exact top-k     a strided sample of the base set gives each query a threshold tau that bounds
 //                      its nn-th distance from above (checked, never assumed: a query whose candidate
@@ -38,16 +39,22 @@ constexpr int SORT_CAP = LINSCAN_MAX_NN;  // keys the shared-memory bitonic sort
 
 enum { MODE_SAMPLE = 0, MODE_MAIN = 1, MODE_ALL = 2 };
 enum { ST_OK = 0, ST_REDO = 1, ST_BIG = 2 };
-constexpr int SORT_SMALL = 4096;  // keys of the small top-k sorter (32 KB of shared memory)
+constexpr int SEL_CAP = 4096;    // candidate keys the select kernel holds (32 KB of shared memory)
+constexpr int SEL_SORT = 1024;   // survivors it sorts (8 KB)
 
-// Queries per tile: as many LUTs as fit 224 KB of shared memory (32 for m <= 7, 28 for m = 8).  From
-// m = 9 on fewer than 28 fit; the tile is then capped at 16 so that a HALF-warp covers it and every warp
-// instruction serves two base vectors (the scan is issue-bound, idle lanes are what costs).
-__host__ __device__ constexpr int tile_queries(int m) {
-  return (LUT_SMEM_BUDGET / (m * LSQ_H * 4)) >= 32 ? 32
-       : (LUT_SMEM_BUDGET / (m * LSQ_H * 4)) >= 28 ? (LUT_SMEM_BUDGET / (m * LSQ_H * 4))
-       : (LUT_SMEM_BUDGET / (m * LSQ_H * 4)) < 16 ? (LUT_SMEM_BUDGET / (m * LSQ_H * 4)) : 16;
+// Tile geometry.  A lane serves QPL consecutive queries of the tile with ONE vector shared-memory load
+// per codebook (LDS.128 for QPL = 4, LDS.64 for QPL = 2); GW lanes form a group that scores one base
+// vector, so a warp instruction serves 32/GW base vectors.  The tile holds as many LUTs as fit 224 KB
+// of shared memory:  m <= 7: 32 queries,  m = 8: 28 (7 of 8 lanes of a group active),  m = 9: 24,
+// m = 10..14: 16 (groups of 4 lanes),  m = 15, 16: 14 (two queries per lane).
+struct TileCfg { int qt, qpl, gw; };
+__host__ __device__ constexpr TileCfg tile_cfg(int m) {
+  return (LUT_SMEM_BUDGET / (m * LSQ_H * 4)) >= 32 ? TileCfg{32, 4, 8}
+       : (LUT_SMEM_BUDGET / (m * LSQ_H * 4)) >= 24 ? TileCfg{(LUT_SMEM_BUDGET / (m * LSQ_H * 4)) & ~3, 4, 8}
+       : (LUT_SMEM_BUDGET / (m * LSQ_H * 4)) >= 16 ? TileCfg{16, 4, 4}
+       : TileCfg{(LUT_SMEM_BUDGET / (m * LSQ_H * 4)) & ~1, 2, 8};
 }
+__host__ __device__ constexpr int tile_queries(int m) { return tile_cfg(m).qt; }
 
 // ------------------------------------------------------------------------------------------------
 // 1. LUT construction.  block (32, 8): x = query lane within the tile, y*8.. = 64 table rows.
@@ -76,25 +83,50 @@ __global__ void __launch_bounds__(256) lut_kernel(const float* __restrict__ quer
       const int qq = e / LUT_KC, kk = e % LUT_KC;
       float v = 0.0f;
       if (qq < QT && q0 + qq < nq && kk < kc) v = queries[(size_t)(q0 + qq) * qstride + qoff + k0 + kk];
-      qs[kk][qq] = v;
+      qs[kk][qq] = (KIND == LUT_LSQ) ? __fmul_rn(2.0f, v) : v;  // LSQ: the factor (2*q[k]) of :45-47, exact
     }
     __syncthreads();
+    const float* cbase = cb + (size_t)(jblock + ty * LUT_JPT) * kd + k0;
+    if ((kd & 3) == 0 && (reinterpret_cast<uintptr_t>(cb) & 15) == 0) {
+      // k outer (4 at a time), the thread's 8 rows inner: one LDS per k and one LDG.128 per row and 4 k;
+      // every (query, row) accumulator still sees k in ascending order with separate mul / sub
+      for (int kk = 0; kk < kc; kk += 4) {
+        const float q0v = qs[kk][lane], q1v = qs[kk + 1][lane], q2v = qs[kk + 2][lane], q3v = qs[kk + 3][lane];
 #pragma unroll
-    for (int i = 0; i < LUT_JPT; i++) {
-      const int j = jblock + ty * LUT_JPT + i;
-      const float* c = cb + (size_t)j * kd + k0;
-      float t = acc[i];
-      for (int kk = 0; kk < kc; kk++) {
-        const float cv = __ldg(c + kk);
-        const float qv = qs[kk][lane];
-        if (KIND == LUT_LSQ) {
-          t = __fsub_rn(t, __fmul_rn(__fmul_rn(2.0f, qv), cv));
-        } else {
-          const float df = __fsub_rn(cv, qv);
-          t = __fadd_rn(t, __fmul_rn(df, df));
+        for (int i = 0; i < LUT_JPT; i++) {
+          const float4 cv = __ldg(reinterpret_cast<const float4*>(cbase + (size_t)i * kd + kk));
+          float t = acc[i];
+          if (KIND == LUT_LSQ) {
+            t = __fsub_rn(t, __fmul_rn(q0v, cv.x));
+            t = __fsub_rn(t, __fmul_rn(q1v, cv.y));
+            t = __fsub_rn(t, __fmul_rn(q2v, cv.z));
+            t = __fsub_rn(t, __fmul_rn(q3v, cv.w));
+          } else {
+            float df = __fsub_rn(cv.x, q0v); t = __fadd_rn(t, __fmul_rn(df, df));
+            df = __fsub_rn(cv.y, q1v); t = __fadd_rn(t, __fmul_rn(df, df));
+            df = __fsub_rn(cv.z, q2v); t = __fadd_rn(t, __fmul_rn(df, df));
+            df = __fsub_rn(cv.w, q3v); t = __fadd_rn(t, __fmul_rn(df, df));
+          }
+          acc[i] = t;
         }
       }
-      acc[i] = t;
+    } else {
+#pragma unroll
+      for (int i = 0; i < LUT_JPT; i++) {
+        const float* c = cbase + (size_t)i * kd;
+        float t = acc[i];
+        for (int kk = 0; kk < kc; kk++) {
+          const float cv = __ldg(c + kk);
+          const float qv = qs[kk][lane];
+          if (KIND == LUT_LSQ) {
+            t = __fsub_rn(t, __fmul_rn(qv, cv));
+          } else {
+            const float df = __fsub_rn(cv, qv);
+            t = __fadd_rn(t, __fmul_rn(df, df));
+          }
+        }
+        acc[i] = t;
+      }
     }
   }
   if (lane < QT) {
@@ -122,9 +154,25 @@ struct ScanParams {
   int nq, mode, id_base;
 };
 
+// shared-memory vector loads from a 32-bit shared address (ptxas folds constant offsets into the LDS)
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds_v2(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+
 template <int M, bool NORM>
 __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_constant__ ScanParams p) {
-  constexpr int QT = tile_queries(M);
+  constexpr TileCfg CFG = tile_cfg(M);
+  constexpr int QT = CFG.qt, QPL = CFG.qpl, GW = CFG.gw;
+  constexpr int VPW = 32 / GW;  // base vectors scored per warp instruction
+  constexpr int U = 2;          // steps per vote group
+  static_assert(GW % U == 0 && QT % QPL == 0 && QT <= GW * QPL, "tile geometry");
   constexpr uint32_t LUT_BYTES = (uint32_t)M * LSQ_H * QT * 4;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* lut = reinterpret_cast<float*>(smem_raw);
@@ -141,17 +189,21 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
   __syncthreads();
   if (tid == 0) bulk_load_issue(lut, p.lut + (size_t)tile * (LUT_BYTES / 4), LUT_BYTES, bar);
 
-  // QT <= 16 (m >= 14): a half-warp covers the tile's queries, so each warp instruction serves TWO base
-  // vectors (lanes 0-15 / 16-31).  The kernel is issue-bound; the extra shared-memory wavefront when the
-  // two rows share banks costs less than the instruction slots it saves.
-  constexpr int VPS = (QT <= 16) ? 2 : 1;                // base vectors per step
-  const int sub = (VPS == 2) ? (lane >> 4) : 0;          // which of the step's vectors this lane serves
-  const int ql = (VPS == 2) ? (lane & 15) : lane;        // query slot within the tile
-  const int q = tile * QT + ql;
-  const bool qvalid = (ql < QT) && (q < p.nq);
-  float tau = -INFINITY;  // invalid lanes never pass `dist <= tau`
-  if (p.mode == MODE_MAIN && qvalid) tau = p.tau[tile * 32 + ql];
-  const char* lane_base = reinterpret_cast<const char*>(lut) + ql * 4;
+  // Lane geometry: group `grp` scores base vector (step*VPW + grp) of the chunk for the query slots
+  // qs .. qs+QPL-1.  A group's lanes read one contiguous LUT row (QT floats): with GW = 8 and LDS.128 a
+  // quarter-warp phase is exactly one group, so every shared-memory wavefront is conflict-free by
+  // construction; lanes past the tile (qs >= QT) re-read the row start (a broadcast) and never store.
+  const int grp = lane / GW;
+  const int qs = (lane % GW) * QPL;
+  const bool lane_on = qs < QT;
+  const int q0 = tile * QT + qs;
+  float tau[QPL];
+#pragma unroll
+  for (int i = 0; i < QPL; i++) {
+    tau[i] = -INFINITY;  // slots without a query never pass `dist <= tau`
+    if (p.mode == MODE_MAIN && lane_on && q0 + i < p.nq) tau[i] = p.tau[tile * 32 + qs + i];
+  }
+  const uint32_t lane_base = smem_u32(lut) + (lane_on ? qs * 4 : 0);  // 32-bit shared address: one IMAD per row
 
   // slice of the step range handled by this CTA (multiple of 32 steps)
   int64_t per = (p.count + gridDim.y - 1) / gridDim.y;
@@ -161,86 +213,124 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
 
   mbar_wait(bar, 0);
 
-  for (int64_t c0 = t_begin + (int64_t)warp * 32; c0 < t_end; c0 += (int64_t)W * 32) {
-    // lane l fetches the code row (and norm) of step c0 + l
-    uint64_t lo = 0, hi = 0;
-    float nrm = 0.0f;
-    {
-      const int64_t t = c0 + lane;
-      if (t < t_end) {
-        const int64_t i = t * p.stride;
-        const uint8_t* cp = p.codes + i * M;
-        if (M == 8) {
-          lo = *reinterpret_cast<const uint64_t*>(cp);
-        } else if (M == 16) {
-          const uint2 a = *reinterpret_cast<const uint2*>(cp);
-          const uint2 b = *reinterpret_cast<const uint2*>(cp + 8);
-          lo = ((uint64_t)a.y << 32) | a.x;
-          hi = ((uint64_t)b.y << 32) | b.x;
-        } else {
+  // lane l fetches the code row (and norm) of step c0 + l
+  auto load_rows = [&](int64_t c0, uint64_t& lo, uint64_t& hi, float& nrm) {
+    lo = 0; hi = 0; nrm = 0.0f;
+    const int64_t t = c0 + lane;
+    if (t < t_end) {
+      const int64_t i = t * p.stride;
+      const uint8_t* cp = p.codes + i * M;
+      if (M == 8) {
+        lo = *reinterpret_cast<const uint64_t*>(cp);
+      } else if (M == 16) {
+        const uint2 a = *reinterpret_cast<const uint2*>(cp);
+        const uint2 b = *reinterpret_cast<const uint2*>(cp + 8);
+        lo = ((uint64_t)a.y << 32) | a.x;
+        hi = ((uint64_t)b.y << 32) | b.x;
+      } else {
 #pragma unroll
-          for (int k = 0; k < M; k++) {
-            const uint64_t c = cp[k];
-            if (k < 8) lo |= c << (8 * k);
-            else hi |= c << (8 * (k - 8));
-          }
+        for (int k = 0; k < M; k++) {
+          const uint64_t c = cp[k];
+          if (k < 8) lo |= c << (8 * k);
+          else hi |= c << (8 * (k - 8));
         }
-        if (NORM) nrm = p.norms[i];
       }
+      if (NORM) nrm = p.norms[i];
     }
-    // Inner loop, issue-bound: per codebook one PRMT (byte extract), one IMAD (row offset + lane base),
-    // one LDS with the codebook offset folded into the immediate, one FADD.  Four base vectors per
-    // group: all shuffles first, then one warp-uniform vote decides whether anything has to be stored,
-    // so the common path has no divergent branch (and no per-shuffle convergence check).
+  };
+
+  uint64_t lo, hi, nlo, nhi;
+  float nrm, nnrm;
+  load_rows(t_begin + (int64_t)warp * 32, nlo, nhi, nnrm);
+  for (int64_t c0 = t_begin + (int64_t)warp * 32; c0 < t_end; c0 += (int64_t)W * 32) {
+    // the rows of the NEXT chunk are requested before this chunk is scored (hides the L2 latency)
+    lo = nlo; hi = nhi; nrm = nnrm;
+    load_rows(c0 + (int64_t)W * 32, nlo, nhi, nnrm);
+    // Inner loop: per codebook one PRMT (byte extract), one IMAD (row offset + lane base), ONE vector LDS
+    // with the codebook offset folded into the immediate, and QPL FADDs — (3 + QPL) / QPL issue slots
+    // per lookup instead of 4, which moves the kernel from the issue limit to the shared-memory
+    // wavefront limit (one wavefront per base vector and codebook).  U steps per vote group: all
+    // shuffles first, then one warp-uniform vote decides whether anything has to be stored.
     const bool full = (c0 + 32 <= t_end);
     const int nvalid = full ? 32 : (int)(t_end - c0);
 #pragma unroll 2
-    for (int b0 = 0; b0 < 32; b0 += 4 * VPS) {
-      float dist[4];
-      int bsrc[4];
+    for (int s0 = 0; s0 < GW; s0 += U) {
+      float dist[U][QPL];
+      int bsrc[U];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int b = b0 + u * VPS + sub;  // chunk-relative index of the base vector this lane scores
+      for (int u = 0; u < U; u++) {
+        const int b = (s0 + u) * VPW + grp;  // chunk-relative index of the base vector this lane scores
         bsrc[u] = b;
         const uint32_t w0 = __shfl_sync(0xFFFFFFFFu, (uint32_t)lo, b);
         const uint32_t w1 = (M > 4) ? __shfl_sync(0xFFFFFFFFu, (uint32_t)(lo >> 32), b) : 0u;
         const uint32_t w2 = (M > 8) ? __shfl_sync(0xFFFFFFFFu, (uint32_t)hi, b) : 0u;
         const uint32_t w3 = (M > 12) ? __shfl_sync(0xFFFFFFFFu, (uint32_t)(hi >> 32), b) : 0u;
-        float acc = 0.0f;
+        float acc[QPL];
+#pragma unroll
+        for (int i = 0; i < QPL; i++) acc[i] = 0.0f;
 #pragma unroll
         for (int k = 0; k < M; k++) {
           const uint32_t w = (k < 4) ? w0 : (k < 8) ? w1 : (k < 12) ? w2 : w3;
           const uint32_t c = __byte_perm(w, 0u, 0x4440u | (uint32_t)(k & 3));
-          const float v = *reinterpret_cast<const float*>(lane_base + c * (uint32_t)(QT * 4) + (uint32_t)(k * LSQ_H * QT * 4));
-          acc = __fadd_rn(acc, v);
+          const uint32_t row = lane_base + c * (uint32_t)(QT * 4);
+          if (QPL == 4) {
+            const float4 v = lds_v4(row + (uint32_t)(k * LSQ_H * QT * 4));
+            acc[0] = __fadd_rn(acc[0], v.x);
+            acc[1] = __fadd_rn(acc[1], v.y);
+            acc[QPL - 2] = __fadd_rn(acc[QPL - 2], v.z);
+            acc[QPL - 1] = __fadd_rn(acc[QPL - 1], v.w);
+          } else {
+            const float2 v = lds_v2(row + (uint32_t)(k * LSQ_H * QT * 4));
+            acc[0] = __fadd_rn(acc[0], v.x);
+            acc[1] = __fadd_rn(acc[1], v.y);
+          }
         }
-        if (NORM) acc = __fadd_rn(acc, __shfl_sync(0xFFFFFFFFu, nrm, b));
-        dist[u] = acc;
+        if (NORM) {
+          const float nb = __shfl_sync(0xFFFFFFFFu, nrm, b);
+#pragma unroll
+          for (int i = 0; i < QPL; i++) acc[i] = __fadd_rn(acc[i], nb);
+        }
+#pragma unroll
+        for (int i = 0; i < QPL; i++) dist[u][i] = acc[i];
       }
       if (p.mode == MODE_MAIN) {
-        // tau = -inf on invalid lanes, so they never vote
-        const bool hit = (dist[0] <= tau) | (dist[1] <= tau) | (dist[2] <= tau) | (dist[3] <= tau);
+        bool hit = false;
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+          for (int i = 0; i < QPL; i++) hit |= (dist[u][i] <= tau[i]);
         if (__any_sync(0xFFFFFFFFu, hit)) {
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            if (dist[u] <= tau && (full || bsrc[u] < nvalid)) {
+          for (int u = 0; u < U; u++) {
+            if (full || bsrc[u] < nvalid) {
               const uint32_t id = (uint32_t)(c0 + bsrc[u] + p.id_base);
-              const unsigned long long key = ((unsigned long long)float_to_ordered(dist[u]) << 32) | id;
-              const int pos = atomicAdd(&p.cnt[q], 1);
-              if (pos < p.cap) p.cand[(size_t)q * p.cap + pos] = key;
+#pragma unroll
+              for (int i = 0; i < QPL; i++) {
+                if (dist[u][i] <= tau[i]) {
+                  const unsigned long long key = ((unsigned long long)float_to_ordered(dist[u][i]) << 32) | id;
+                  const int pos = atomicAdd(&p.cnt[q0 + i], 1);
+                  if (pos < p.cap) p.cand[(size_t)(q0 + i) * p.cap + pos] = key;
+                }
+              }
             }
           }
         }
-      } else if (qvalid) {
+      } else if (lane_on) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < U; u++) {
           const int64_t t = c0 + bsrc[u];
           if (full || bsrc[u] < nvalid) {
-            if (p.mode == MODE_SAMPLE) {
-              p.sbuf[((size_t)tile * p.count + t) * 32 + ql] = float_to_ordered(dist[u]);
-            } else {
-              const uint32_t id = (uint32_t)(t * p.stride + p.id_base);
-              p.cand[(size_t)q * p.cap + t] = ((unsigned long long)float_to_ordered(dist[u]) << 32) | id;
+#pragma unroll
+            for (int i = 0; i < QPL; i++) {
+              if (q0 + i < p.nq) {
+                if (p.mode == MODE_SAMPLE) {
+                  p.sbuf[((size_t)tile * p.count + t) * 32 + qs + i] = float_to_ordered(dist[u][i]);
+                } else {
+                  const uint32_t id = (uint32_t)(t * p.stride + p.id_base);
+                  p.cand[(size_t)(q0 + i) * p.cap + t] =
+                      ((unsigned long long)float_to_ordered(dist[u][i]) << 32) | id;
+                }
+              }
             }
           }
         }
@@ -387,6 +477,112 @@ __global__ void __launch_bounds__(NT) topk_kernel(const unsigned long long* __re
   }
 }
 
+// Phase-1 top-k for the common case (a few thousand candidates, nn <= SORTN): the bitonic sort of every
+// candidate was issue-bound (4096 keys x 78 stages per query); here the nn-th smallest key is found by
+// an MSB-first radix select over the keys held in shared memory (early exit as soon as the selected
+// bucket is taken whole), the nn survivors are compacted and only they are sorted.  Keys are unique
+// (the id is part of the key), so exactly nn keys are <= the nn-th.
+template <int CAPK, int SORTN, int NT>
+__global__ void __launch_bounds__(NT) topk_select_kernel(const unsigned long long* __restrict__ cand, int64_t cap,
+                                                         const int* __restrict__ cnt, int nn,
+                                                         float* __restrict__ dists, int32_t* __restrict__ ids,
+                                                         int* __restrict__ status) {
+  extern __shared__ __align__(16) unsigned long long sel_smem[];  // CAPK candidate keys, then SORTN survivors
+  unsigned long long* keys = sel_smem;
+  unsigned long long* out = sel_smem + CAPK;
+  __shared__ int hist[256];
+  __shared__ unsigned long long sh_prefix;
+  __shared__ int sh_rank, sh_fill, sh_done;
+  const int tid = threadIdx.x;
+  const int q = blockIdx.x;
+  const int64_t c64 = (int64_t)cnt[q];
+  if (c64 < nn || c64 > cap) {
+    if (tid == 0) status[q] = ST_REDO;
+    return;
+  }
+  if (c64 > CAPK || nn > SORTN) {
+    if (tid == 0) status[q] = ST_BIG;
+    return;
+  }
+  if (tid == 0) status[q] = ST_OK;
+  const int c = (int)c64;
+  const unsigned long long* src = cand + (size_t)q * cap;
+  for (int i = tid; i < c; i += NT) keys[i] = src[i];
+  if (tid == 0) { sh_prefix = 0ull; sh_rank = nn; sh_done = 0; sh_fill = 0; }
+  int N = 2;
+  while (N < nn) N <<= 1;
+  for (int i = tid; i < N; i += NT) out[i] = ~0ull;
+  unsigned long long below = ~0ull;  // mask of the bits not yet decided
+  for (int pass = 0; pass < 8; pass++) {
+    const int shift = 56 - 8 * pass;
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    if (sh_done) break;
+    const unsigned long long pre = sh_prefix;
+    const unsigned long long pmask = ~below;
+    for (int i = tid; i < c; i += NT) {
+      const unsigned long long v = keys[i];
+      if ((v & pmask) == pre) atomicAdd(&hist[(int)((v >> shift) & 0xFFull)], 1);
+    }
+    __syncthreads();
+    below = (shift == 0) ? 0ull : (~0ull >> (64 - shift));
+    if (tid < 32) {
+      // warp scan over 32 groups of 8 buckets, then the owning lane walks its 8 buckets
+      int part = 0;
+#pragma unroll
+      for (int b = 0; b < 8; b++) part += hist[tid * 8 + b];
+      const int rr = sh_rank;  // read by every lane before the shuffles (convergence points) below
+      int incl = part;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (tid >= off) incl += t;
+      }
+      const int excl = incl - part;
+      if (rr > excl && rr <= incl) {
+        int r2 = rr - excl, dsel = tid * 8 + 7;
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+          const int hcount = hist[tid * 8 + b];
+          if (r2 <= hcount) { dsel = tid * 8 + b; break; }
+          r2 -= hcount;
+        }
+        unsigned long long npre = pre | ((unsigned long long)dsel << shift);
+        // the whole bucket is taken: every key <= (prefix | remaining ones) is a survivor
+        if (r2 == hist[dsel]) { npre |= below; sh_done = 1; }
+        sh_rank = r2;
+        sh_prefix = npre;
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  const unsigned long long kth = sh_prefix;
+  for (int i = tid; i < c; i += NT) {
+    const unsigned long long v = keys[i];
+    if (v <= kth) out[atomicAdd(&sh_fill, 1)] = v;
+  }
+  __syncthreads();
+  // bitonic sort of the N survivors, one compare-exchange per thread and step
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (N >> 1); t += NT) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // index with bit j clear
+        const int ixj = i | j;
+        const unsigned long long a = out[i], b = out[ixj];
+        const bool up = ((i & k) == 0);
+        if ((a > b) == up) { out[i] = b; out[ixj] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = tid; j < nn; j += NT) {
+    const unsigned long long k = out[j];
+    dists[(size_t)q * nn + j] = ordered_to_float((uint32_t)(k >> 32));
+    ids[(size_t)q * nn + j] = (int32_t)(uint32_t)(k & 0xFFFFFFFFull);
+  }
+}
+
 __global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ rows, int nrows, int d,
                                    float* __restrict__ dst) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -442,6 +638,8 @@ static int launch_lut(int lut_kind, const float* dq, int nq, int qstride, const 
 
 static int configure_topk() {
   LSQ_CUDA(cudaFuncSetAttribute(topk_kernel<SORT_CAP, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_CAP * 8));
+  LSQ_CUDA(cudaFuncSetAttribute(topk_select_kernel<SEL_CAP, SEL_SORT, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (SEL_CAP + SEL_SORT) * 8));
   return LSQ_OK;
 }
 
@@ -561,11 +759,10 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
     LSQ_CUDA(cudaMemsetAsync(dcnt.p, 0, (size_t)nb * sizeof(int), st));
     p.mode = MODE_MAIN; p.stride = 1; p.count = n;
     LSQ_TRY(launch_scan(m, p, ntiles, st));
-    // most queries end up with a few thousand candidates: a 32 KB sorter lets ~6 CTAs share an SM; the
-    // 128 KB sorter only runs for the queries the first pass flags
-    topk_kernel<SORT_SMALL, 256><<<nb, 256, SORT_SMALL * 8, st>>>(dcand.p, cap, dcnt.p, -1, nn, nullptr,
-                                                                  ddists + (size_t)q0 * nn, dids + (size_t)q0 * nn,
-                                                                  dstatus.p, 1);
+    // most queries end up with a few thousand candidates and nn <= 1024: select + sort of the survivors
+    // in 40 KB of shared memory (5 CTAs per SM); the 128 KB sorter only runs for the queries it flags
+    topk_select_kernel<SEL_CAP, SEL_SORT, 256><<<nb, 256, (SEL_CAP + SEL_SORT) * 8, st>>>(
+        dcand.p, cap, dcnt.p, nn, ddists + (size_t)q0 * nn, dids + (size_t)q0 * nn, dstatus.p);
     topk_kernel<SORT_CAP, 1024><<<nb, 1024, SORT_CAP * 8, st>>>(dcand.p, cap, dcnt.p, -1, nn, nullptr,
                                                                  ddists + (size_t)q0 * nn, dids + (size_t)q0 * nn,
                                                                  dstatus.p, 2);

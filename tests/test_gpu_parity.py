@@ -192,6 +192,10 @@ def _ref_or_oracle_pq(oracle, *a):
     (200000, 64, 128, 8, 1000),    # sampled-threshold path, config-5 shape scaled down
     (120000, 40, 128, 16, 1000),
     (100000, 33, 128, 7, 100),
+    (90000, 50, 64, 9, 200),       # 24-query tiles (6 of 8 lanes per group)
+    (90000, 37, 64, 12, 200),      # 16-query tiles, groups of 4 lanes
+    (70000, 29, 32, 15, 100),      # 14-query tiles, two queries per lane
+    (60000, 65, 32, 3, 50),        # 32-query tiles
     (50000, 9, 64, 8, 10000),      # large k -> exhaustive path + radix select
     (5000, 70, 32, 4, 1),
     (300, 5, 16, 2, 300),          # nn == n
