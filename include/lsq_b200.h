@@ -108,6 +108,31 @@ int lsq_linscan_pq(float* dists, unsigned int* res, const unsigned char* codes, 
 int lsq_quantize_norms(const int16_t* B, int64_t n, const float* C, int d, int m, int h,
                        const float* cbnorms, int hn, int16_t* out);
 
+/* ---- f1 train_lsq (src/lsq/LSQ.jl:10-88) with X, codes, unaries and tables resident on the GPU for
+ *      the whole alternation: C = update_codebooks(R'X, B); C_i = R*C_i; ilsiter x encoding_icm; then
+ *      niter x { obj[iter] = qerror; C = update_codebooks(X, B); ilsiter x encoding_icm }; finally the
+ *      norm codebook of LSQ.jl:68-84.  Equal, bit for bit, to looping lsq_update_codebooks /
+ *      lsq_encoding_icm with ils_iter = 0, 1, 2, ... and the same seed.
+ *        R        d-by-d Matrix{Float32} (column-major) or NULL for the identity
+ *        B        in: initial codes, out: final codes   [n][m] 1-based
+ *        C        out: codebooks [m][h][d]   (the C argument of train_lsq is overwritten before use, :34)
+ *        cbnorms  out [h] or NULL;  B_norms out [n] 1-based or NULL;  obj out [niter] or NULL
+ *      The norm codebook is a deterministic 1-D k-means (Clustering.jl's seeded kmeans is third-party
+ *      and unpinned): see lsq_kmeans1d. ----------------------------------------------------------- */
+int lsq_train_lsq(const float* X, int d, int64_t n, int m, int h, const float* R, int16_t* B, float* C,
+                  int niter, int ilsiter, int icmiter, int randord, int npert, uint64_t seed,
+                  float* cbnorms, int16_t* B_norms, float* obj, int verbose);
+/* ---- f2 norm codebook (stand-in for `kmeans(dbnorms, h)`, LSQ.jl:80): Lloyd iterations on scalars,
+ *      centres seeded at the (2j+1)/(2h) quantiles, ties to the lower centre, float64 means in a fixed
+ *      order; stops at a fixed point or after maxiter (Clustering.jl default: 100).  centers[h] come
+ *      back ascending. -------------------------------------------------------------------------- */
+int lsq_kmeans1d(const float* values, int64_t n, int h, int maxiter, float* centers, int* iters_out);
+/* ---- f3 eval_recall (Linscan.jl:76-117): recall[i-1] = fraction of queries whose ground-truth id is
+ *      found (exactly once) among the first i predictions, i = 1..k.  ids_predicted is [nq][ld] with
+ *      ld >= k (a row = one query's ranked list, i.e. a column of the Julia matrix). --------------- */
+int lsq_eval_recall(const int32_t* ids_gnd, const int32_t* ids_predicted, int nq, int ld, int k,
+                    double* recall);
+
 /* =====================================================================================================
  * Device-pointer API.  All pointers are device pointers; `stream` is a cudaStream_t (0 = legacy
  * default stream).  Codes are uint8 0-based [n][m].  Nothing here synchronises the host.
@@ -157,6 +182,10 @@ int lsq_dev_cb_solve(const double* dGram, const double* dRhs, int m, int d, floa
 int lsq_dev_linscan(const uint8_t* dcodes, int64_t n, int m, const float* dqueries, int nq, int d,
                     const float* dcodebooks, const float* dbnorms, int lut_kind, int subdim, int nn,
                     float* ddists, int32_t* dids, void* stream);
+
+/* eval_recall on device buffers: dgnd int32[nq], dpred int32[nq][ld], drecall double[k]. */
+int lsq_dev_eval_recall(const int32_t* dgnd, const int32_t* dpred, int nq, int ld, int k, double* drecall,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,8 @@ __all__ = [
     "LsqError", "lib", "lib_path", "have_library", "init", "finalize", "device_count", "version",
     "splitarray", "make_to_look", "make_perturb", "get_unaries", "get_binaries", "veccost", "qerror",
     "reconstruct", "quantize_norms", "encoding_icm", "encoding_icm_sched", "encode_icm_cuda",
-    "update_codebooks", "linscan_lsq", "linscan_pq", "linscan_opq", "eval_recall", "randinit",
+    "update_codebooks", "linscan_lsq", "linscan_pq", "linscan_opq", "eval_recall", "randinit", "train_lsq",
+    "kmeans1d",
     "EXPORTED_SYMBOLS",
 ]
 
@@ -25,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "lsq_linscan_pq", "lsq_quantize_norms", "lsq_dev_tables_bytes", "lsq_dev_sliced_tables_bytes",
     "lsq_dev_icm_layout", "lsq_dev_build_tables",
     "lsq_dev_build_unaries", "lsq_dev_build_unaries_tc", "lsq_dev_veccost", "lsq_dev_icm_ils", "lsq_dev_cb_stats", "lsq_dev_cb_solve",
-    "lsq_dev_linscan",
+    "lsq_dev_linscan", "lsq_train_lsq", "lsq_kmeans1d", "lsq_eval_recall", "lsq_dev_eval_recall",
 ]
 
 
@@ -304,15 +305,42 @@ def linscan_opq(B, X, C, b, R, k=10000):
 
 
 def eval_recall(ids_gnd, ids_predicted, k):
-    """Linscan.jl:76-117 -> recall@i for i = 1..k (fractions).  ids_predicted is (nq, >=k)."""
-    ids_gnd = np.asarray(ids_gnd).reshape(-1)
-    ids_predicted = np.asarray(ids_predicted)
-    nquery = ids_predicted.shape[0]
-    assert nquery == len(ids_gnd)
-    nn_ranks = np.full(nquery, k + 1, np.int64)
-    for i in range(nquery):
-        pos = np.nonzero(ids_predicted[i, :k] == ids_gnd[i])[0]
-        if len(pos) == 1:
-            nn_ranks[i] = pos[0] + 1
-    nn_ranks.sort()
-    return np.searchsorted(nn_ranks, np.arange(1, k + 1), side="right") / nquery
+    """Linscan.jl:76-117 -> recall@i for i = 1..k (fractions, float64).  ids_predicted is (nq, >= k):
+    row q is query q's ranked id list (a column of the Julia matrix)."""
+    ids_gnd = np.ascontiguousarray(np.asarray(ids_gnd).reshape(-1).astype(np.int64).astype(np.int32))
+    pred = np.asarray(ids_predicted)
+    pred = np.ascontiguousarray(pred.astype(np.int64).astype(np.int32) if pred.dtype != np.int32 else pred)
+    nq, ld = pred.shape
+    assert nq == len(ids_gnd)   # Linscan.jl:85
+    out = np.zeros(k, np.float64)
+    _check(lib().lsq_eval_recall(_p(ids_gnd), _p(pred), nq, ld, int(k), _p(out)))
+    return out
+
+
+def kmeans1d(values, h, maxiter=100):
+    """Norm-codebook stand-in for `kmeans(dbnorms, h)` (LSQ.jl:80) -> (centers (h,) ascending, iterations)."""
+    v = _f32(np.asarray(values).reshape(-1))
+    out = np.zeros(h, np.float32)
+    it = ct.c_int()
+    _check(lib().lsq_kmeans1d(_p(v), ct.c_int64(len(v)), int(h), int(maxiter), _p(out), ct.byref(it)))
+    return out, it.value
+
+
+def train_lsq(X, m, h, R, B, C, niter, ilsiter, icmiter, randord, npert, V=False, *, seed=0):
+    """src/lsq/LSQ.jl:10-88 -> (C (m, h, d), B (n, m) int16, cbnorms (h,), B_norms (n,) int16, obj (niter,)).
+    X (n, d); R (d, d) with R[i, j] = R(i, j) (or None for the identity); B initial codes, 1-based.
+    The C argument is accepted for signature parity and ignored, exactly as the reference overwrites it
+    (LSQ.jl:34) before its first use."""
+    X, B = _f32(X), _codes16(B).copy()
+    n, d = X.shape
+    if B.shape != (n, m):
+        raise ValueError("B must be (n, m)")
+    Rm = None if R is None else np.ascontiguousarray(_f32(R).T)   # column-major bytes of the Julia matrix
+    Cout = np.zeros((m, h, d), np.float32)
+    cbnorms = np.zeros(h, np.float32)
+    B_norms = np.zeros(n, np.int16)
+    obj = np.zeros(max(niter, 1), np.float32)
+    _check(lib().lsq_train_lsq(_p(X), d, ct.c_int64(n), int(m), int(h), _p(Rm), _p(B), _p(Cout), int(niter),
+                               int(ilsiter), int(icmiter), int(bool(randord)), int(npert), ct.c_uint64(seed),
+                               _p(cbnorms), _p(B_norms), _p(obj), int(bool(V))))
+    return Cout, B, cbnorms, B_norms, obj[:niter]

@@ -66,7 +66,8 @@ function linscan_lsq(
   return dists, res
 end
 
-# eval_recall is host bookkeeping (Linscan.jl:76-117) and stays exactly as in the reference.
+# eval_recall (Linscan.jl:76-117): the rank search over the k-by-nq id matrix runs on the GPU
+# (lsq_eval_recall); the printed r@N lines and the returned recall_at_i vector are the reference's.
 function eval_recall{T <: Integer}(
   ids_gnd::Vector{T},
   ids_predicted::Matrix{T},
@@ -74,23 +75,17 @@ function eval_recall{T <: Integer}(
 
   nquery = size( ids_predicted, 2 );
   assert( nquery == length( ids_gnd) );
+  ld = size( ids_predicted, 1 );
 
-  nn_ranks = zeros( nquery );
-  for i = 1:nquery
-    nn_pos = find( ids_predicted[:,i] .== ids_gnd[i] );
-    nn_ranks[i] = length(nn_pos) == 1 ? nn_pos[1] : k+1;
-  end
-  nn_ranks = sort( nn_ranks );
+  recall_at_i = zeros( Cdouble, k );
+  lsq_check( ccall((:lsq_eval_recall, LSQ_B200_LIB), Cint,
+    (Ptr{Int32}, Ptr{Int32}, Cint, Cint, Cint, Ptr{Cdouble}),
+    convert(Vector{Int32}, ids_gnd), convert(Matrix{Int32}, ids_predicted), nquery, ld, k, recall_at_i) )
 
   for i = [1 2 5 10 20 50 100 200 500 1000 2000 5000 10000]
     if i <= k
-      println("r@$(i) = $(length( find( nn_ranks .<= i )) ./ nquery * 100)");
+      println("r@$(i) = $(recall_at_i[i] * 100)");
     end
-  end
-
-  recall_at_i = zeros( k );
-  for i = 1:k
-    recall_at_i[i] = length(find( nn_ranks .<= i )) ./ nquery;
   end
   return recall_at_i
 end

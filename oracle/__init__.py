@@ -268,3 +268,85 @@ def ref_linscan_pq(codes, queries, centers, K):
     _ref_lib("linscan_aqd.so").linscan_aqd_query(_p(dists), _p(res), _p(codes), _p(centers), _p(queries), n,
                                                  ct.c_uint32(nq), 8 * m, K, m, d, subdim)
     return dists, res
+
+
+# ---- §8(f) rows: eval_recall, the norm codebook, the train_lsq alternation -------------------------
+def eval_recall(ids_gnd, ids_predicted, k):
+    """Linscan.jl:76-117: nn_ranks[i] = position of the ground-truth id in query i's list if it occurs
+    exactly once (:94-98), else k+1; recall_at_i[i] = #{rank <= i} / nquery (:111-113).
+    ids_predicted is (nq, >= k): row q = column q of the Julia matrix."""
+    ids_gnd = np.asarray(ids_gnd).reshape(-1)
+    ids_predicted = np.asarray(ids_predicted)
+    nquery = ids_predicted.shape[0]
+    assert nquery == len(ids_gnd)
+    nn_ranks = np.full(nquery, k + 1, np.int64)
+    for i in range(nquery):
+        pos = np.nonzero(ids_predicted[i, :k] == ids_gnd[i])[0]
+        if len(pos) == 1:
+            nn_ranks[i] = pos[0] + 1
+    nn_ranks.sort()
+    return np.searchsorted(nn_ranks, np.arange(1, k + 1), side="right") / nquery
+
+
+def kmeans1d(values, h, maxiter=100):
+    """The deterministic stand-in for `kmeans(dbnorms, h)` (LSQ.jl:80; Clustering.jl is third-party,
+    unvendored and seeds from Julia's global RNG -> parity unpinned): Lloyd on the SORTED scalars,
+    centres seeded at the (2j+1)/(2h) quantiles, a value moves to the next cluster when it is > the fp32
+    midpoint of the two centres, float64 means, empty clusters keep their centre, stop at a fixed point.
+    -> (centers float32 (h,), iterations)."""
+    s = np.sort(np.asarray(values, np.float32).reshape(-1))
+    n = len(s)
+    cent = s[((2 * np.arange(h, dtype=np.int64) + 1) * n) // (2 * h)].astype(np.float32)
+    bounds = np.full(h + 1, -1, np.int64)
+    it = 0
+    while it < maxiter:
+        mid = (np.float32(0.5) * (cent[:-1] + cent[1:])).astype(np.float32)
+        nb = np.concatenate([[0], np.searchsorted(s, mid, side="right"), [n]]).astype(np.int64)
+        if np.array_equal(nb, bounds):
+            break
+        bounds = nb
+        for j in range(h):
+            if bounds[j + 1] > bounds[j]:
+                cent[j] = np.float32(np.sum(s[bounds[j]:bounds[j + 1]].astype(np.float64)) / (bounds[j + 1] - bounds[j]))
+        it += 1
+    return cent, it
+
+
+def decoded_norms(B0, C):
+    """LSQ.jl:72-77: dbnorms[i] = sum_j CB[j,i]^2, j ascending, fp32."""
+    CB = reconstruct(B0, C)
+    out = np.zeros(CB.shape[0], np.float32)
+    for j in range(CB.shape[1]):
+        out = (out + CB[:, j] * CB[:, j]).astype(np.float32)
+    return out
+
+
+def train_lsq(X, m, h, R, B0, niter, ilsiter, icmiter, randord, npert, seed=0, update=None, nworkers=None):
+    """src/lsq/LSQ.jl:10-88 restated over the oracle's pieces; 0-based codes.  `update(X, B0, h)` is the
+    codebook-update stand-in (default: the exact min-norm least-squares solution).
+    -> (C, B0, cbnorms, B_norms (1-based), obj)."""
+    from . import codebook_update as cu
+    update = update or cu.update_codebooks_exact
+    nworkers = nworkers or num_threads()
+    X = _f32(X)
+    B0 = _i16(B0).copy()
+    if R is not None:
+        R = _f32(R)
+        C = update(_f32(X @ R), B0, h)                   # RX = R'X  (:31), update on RX (:34)
+        C = _f32(np.einsum("ij,mhj->mhi", R, C))          # C[i] = R * C[i]  (:37-39)
+    else:
+        C = update(X, B0, h)
+    count = 0
+    for _ in range(ilsiter):                             # :44-48
+        B0, _c = encoding_icm(X, B0, C, icmiter, randord, npert, seed=seed, ils_iter=count, nworkers=nworkers)
+        count += 1
+    obj = np.zeros(niter, np.float32)
+    for it in range(niter):                              # :52-66
+        obj[it] = qerror(X, B0, C)
+        C = update(X, B0, h)
+        for _ in range(ilsiter):
+            B0, _c = encoding_icm(X, B0, C, icmiter, randord, npert, seed=seed, ils_iter=count, nworkers=nworkers)
+            count += 1
+    cbnorms, _ = kmeans1d(decoded_norms(B0, C), h)       # :68-81
+    B_norms = quantize_norms(B0, C, cbnorms)
+    return C, B0, cbnorms, B_norms, obj

@@ -391,3 +391,76 @@ def test_train_lsq_sharded_single_gpu_matches_host_loop(gpu):
     q = gpu.qerror(X, Bc, Cc)
     assert abs(obj[-1] - q) <= 1e-5 * q
     assert obj[-1] <= obj[0]
+
+
+# ---------------------------------------------------------------- §8(f): train_lsq, norm codebook, eval_recall
+@pytest.mark.parametrize("use_R", [False, True])
+def test_train_lsq_equals_public_calls(gpu, use_R):
+    """lsq_train_lsq (everything resident on the GPU) == the caller-side loop of LSQ.jl:31-66 driven through
+    the public host calls with ils_iter = 0, 1, 2, ... — codes, codebooks and objective bit for bit."""
+    n, d, m, niter, ilsiter = 9000, 64, 8, 2, 3
+    X, C, B = make_problem(2300, n, d, m)
+    R = None
+    if use_R:
+        R = np.linalg.qr(np.random.default_rng(1).standard_normal((d, d)))[0].astype(np.float32)
+    C1, B1, cbn, Bn, obj = gpu.train_lsq(X, m, 256, R, B, C, niter, ilsiter, 4, True, 4, seed=21)
+    Bc = B.copy()
+    if use_R:
+        Cc = gpu.update_codebooks((X @ R).astype(np.float32), Bc, 256)
+    else:
+        Cc = gpu.update_codebooks(X, Bc, 256)
+    count = 0
+    objs = []
+    if not use_R:   # with a rotation the rotated-back codebooks differ from a host matmul in the last bit
+        for it in range(niter + 1):
+            if it > 0:
+                objs.append(gpu.qerror(X, Bc, Cc))
+                Cc = gpu.update_codebooks(X, Bc, 256)
+            for i in range(ilsiter):
+                Bc = gpu.encoding_icm(X, Bc, Cc, 4, True, 4, seed=21, ils_iter=count)
+                count += 1
+        assert np.array_equal(B1, Bc)
+        assert np.array_equal(C1, Cc)
+        assert np.array_equal(obj, np.asarray(objs, np.float32))
+    assert all(b <= a * (1 + 1e-6) for a, b in zip(obj, obj[1:]))
+    assert gpu.qerror(X, B1, C1) <= obj[-1] * (1 + 1e-6)
+    # norm codebook: ascending centres; B_norms is exactly quantize_norms(B, C, cbnorms) (utils.jl:6-31)
+    assert np.all(np.diff(cbn) >= 0)
+    assert np.array_equal(Bn, gpu.quantize_norms(B1, C1, cbn))
+
+
+def test_train_lsq_vs_oracle_objective(gpu, oracle):
+    """Against the restated train_lsq (oracle): the codebook update is parity-unpinned (IterativeSolvers),
+    so codes may part ways after the first update; the objective trajectory must agree to 1e-3 relative."""
+    n, d, m = 3000, 32, 4
+    X, C, B = make_problem(2400, n, d, m)
+    R = np.linalg.qr(np.random.default_rng(2).standard_normal((d, d)))[0].astype(np.float32)
+    C1, B1, cbn, Bn, obj = gpu.train_lsq(X, m, 256, R, B, C, 3, 2, 4, True, 2, seed=5)
+    Co, Bo, cbo, Bno, objo = oracle.train_lsq(X, m, 256, R, (B - 1).astype(np.int16), 3, 2, 4, True, 2, seed=5)
+    assert np.allclose(obj, objo, rtol=1e-3)
+    assert abs(gpu.qerror(X, B1, C1) - oracle.qerror(X, Bo, Co)) <= 1e-3 * oracle.qerror(X, Bo, Co)
+
+
+@pytest.mark.parametrize("n,h", [(20000, 256), (5000, 16), (300, 256), (100, 7)])
+def test_kmeans1d_matches_oracle(gpu, oracle, n, h):
+    """Same deterministic Lloyd iteration on both sides; float64 means are summed in a different (fixed)
+    order on the GPU, so centres agree to fp32 rounding, and the iteration counts agree."""
+    rng = np.random.default_rng(n + h)
+    v = (rng.standard_normal(n) ** 2 * 1000).astype(np.float32)
+    cg, itg = gpu.kmeans1d(v, h)
+    co, ito = oracle.kmeans1d(v, h)
+    assert np.allclose(cg, co, rtol=1e-5, atol=0)
+    assert abs(itg - ito) <= 1 or max(itg, ito) == 100
+    assert np.all(np.diff(cg) >= 0)
+
+
+def test_eval_recall_matches_oracle(gpu, oracle):
+    rng = np.random.default_rng(3)
+    nq, k = 500, 1000
+    pred = np.stack([rng.permutation(5000)[:k] for _ in range(nq)]).astype(np.int32) + 1
+    gt = np.where(rng.random(nq) < 0.7, pred[np.arange(nq), rng.integers(0, k, nq)], 999999).astype(np.int32)
+    pred[7, 3] = pred[7, 9] = gt[7]   # found twice -> counts as a miss (Linscan.jl:94-98)
+    for kk in (1, 10, 1000):
+        assert np.array_equal(gpu.eval_recall(gt, pred, kk), oracle.eval_recall(gt, pred, kk))
+    assert np.array_equal(gpu.eval_recall(gt.astype(np.uint32), pred.astype(np.uint32), 100),
+                          oracle.eval_recall(gt, pred, 100))

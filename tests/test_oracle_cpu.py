@@ -211,11 +211,32 @@ def test_product_never_imports_oracle():
             assert "import oracle" not in src and "from oracle" not in src and "liblsq_oracle" not in src, path
 
 
-def test_eval_recall(lsq):
+def test_eval_recall(oracle):
+    """Linscan.jl:76-117 restated: rank of the ground-truth id, duplicates count as misses (:94-98)."""
     gt = np.array([3, 9, 5])
     pred = np.array([[3, 1, 2], [1, 9, 2], [7, 8, 6]])
-    r = lsq.eval_recall(gt, pred, 3)
-    assert np.allclose(r, [1 / 3, 2 / 3, 2 / 3])
+    assert np.allclose(oracle.eval_recall(gt, pred, 3), [1 / 3, 2 / 3, 2 / 3])
+    pred[1] = [9, 9, 2]   # found twice -> `length(nn_pos) == 1` fails -> miss
+    assert np.allclose(oracle.eval_recall(gt, pred, 3), [1 / 3, 1 / 3, 1 / 3])
+
+
+def test_oracle_kmeans1d_and_train_lsq(oracle):
+    """The norm-codebook stand-in is a Lloyd fixed point; the restated train_lsq alternation never
+    increases the objective (LSQ.jl:52-66) and its B_norms follow the quantize_norms rule."""
+    rng = np.random.default_rng(5)
+    v = (rng.standard_normal(5000) ** 2 * 100).astype(np.float32)
+    cent, it = oracle.kmeans1d(v, 16, maxiter=5000)
+    assert it < 5000 and np.all(np.diff(cent) > 0)
+    assert oracle.kmeans1d(v, 16, maxiter=7)[1] == 7   # the iteration cap (Clustering.jl default: 100)
+    lab = np.argmin((v[:, None] - cent[None, :]) ** 2, axis=1)
+    for j in range(16):
+        assert abs(v[lab == j].astype(np.float64).mean() - cent[j]) <= 1e-3 * max(1.0, abs(cent[j]))
+    X, C, B = make_problem(77, 600, 16, 3)
+    R = np.linalg.qr(rng.standard_normal((16, 16)))[0].astype(np.float32)
+    C1, B1, cbn, Bn, obj = oracle.train_lsq(X, 3, 256, R, (B - 1).astype(np.int16), 3, 2, 2, True, 2, seed=4, nworkers=2)
+    assert all(b <= a * (1 + 1e-6) for a, b in zip(obj, obj[1:]))
+    assert oracle.qerror(X, B1, C1) <= obj[-1] * (1 + 1e-6)
+    assert np.array_equal(Bn, oracle.quantize_norms(B1, C1, cbn))
 
 
 def test_vecs_wire_formats(lsq, tmp_path):
