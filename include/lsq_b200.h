@@ -133,6 +133,12 @@ int lsq_kmeans1d(const float* values, int64_t n, int h, int maxiter, float* cent
 int lsq_eval_recall(const int32_t* ids_gnd, const int32_t* ids_predicted, int nq, int ld, int k,
                     double* recall);
 
+/* ---- f4 encoding_viterbi (src/encodings/encode_chain.jl:95-127): exact MAP codes on the chain
+ *      1-2-...-m by min-sum dynamic programming (the ChainQ encoder), same unary / pair tables as the
+ *      ICM path.  B out [n][m] 1-based.  Needs 2 <= m <= 16, h == 256.  No randomness. ------------- */
+int lsq_encoding_viterbi(const float* X, int d, int64_t n, const float* C, int m, int h, int16_t* B,
+                         int verbose);
+
 /* =====================================================================================================
  * Device-pointer API.  All pointers are device pointers; `stream` is a cudaStream_t (0 = legacy
  * default stream).  Codes are uint8 0-based [n][m].  Nothing here synchronises the host.
@@ -183,6 +189,9 @@ int lsq_dev_linscan(const uint8_t* dcodes, int64_t n, int m, const float* dqueri
                     const float* dcodebooks, const float* dbnorms, int lut_kind, int subdim, int nn,
                     float* ddists, int32_t* dids, void* stream);
 
+/* chain encoder on device buffers: dU = U[m][n][256] (lsq_dev_build_unaries, plain layout), dT from
+ * lsq_dev_build_tables; dcodes uint8 [n][m] out. */
+int lsq_dev_viterbi(const float* dU, int64_t n, int m, const float* dT, uint8_t* dcodes, void* stream);
 /* eval_recall on device buffers: dgnd int32[nq], dpred int32[nq][ld], drecall double[k]. */
 int lsq_dev_eval_recall(const int32_t* dgnd, const int32_t* dpred, int nq, int ld, int k, double* drecall,
                         void* stream);

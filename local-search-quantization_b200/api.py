@@ -9,7 +9,7 @@ __all__ = [
     "splitarray", "make_to_look", "make_perturb", "get_unaries", "get_binaries", "veccost", "qerror",
     "reconstruct", "quantize_norms", "encoding_icm", "encoding_icm_sched", "encode_icm_cuda",
     "update_codebooks", "linscan_lsq", "linscan_pq", "linscan_opq", "eval_recall", "randinit", "train_lsq",
-    "kmeans1d",
+    "kmeans1d", "encoding_viterbi",
     "EXPORTED_SYMBOLS",
 ]
 
@@ -27,6 +27,7 @@ EXPORTED_SYMBOLS = [
     "lsq_dev_icm_layout", "lsq_dev_build_tables",
     "lsq_dev_build_unaries", "lsq_dev_build_unaries_tc", "lsq_dev_veccost", "lsq_dev_icm_ils", "lsq_dev_cb_stats", "lsq_dev_cb_solve",
     "lsq_dev_linscan", "lsq_train_lsq", "lsq_kmeans1d", "lsq_eval_recall", "lsq_dev_eval_recall",
+    "lsq_encoding_viterbi", "lsq_dev_viterbi",
 ]
 
 
@@ -219,6 +220,16 @@ def encoding_icm(X, oldB, C, niter, randord, npert, V=False, *, seed=0, ils_iter
                                   int(bool(randord)), int(npert), ct.c_uint64(seed), ct.c_uint32(ils_iter),
                                   ct.c_uint64(g0), int(bool(V))))
     return newB
+
+
+def encoding_viterbi(X, C, V=False):
+    """encode_chain.jl:95-127: exact chain (ChainQ) encoding -> (n, m) int16 1-based codes."""
+    X, C = _f32(X), _codebooks(C)
+    n, d = X.shape
+    m, h, _ = C.shape
+    B = np.zeros((n, m), np.int16)
+    _check(lib().lsq_encoding_viterbi(_p(X), d, ct.c_int64(n), _p(C), m, h, _p(B), int(bool(V))))
+    return B
 
 
 def encoding_icm_sched(X, oldB, C, niter, to_look, slots, vals, V=False):

@@ -1,0 +1,193 @@
+// chain.cu — exact chain encoder (ChainQ): encoding_viterbi / encode_viterbi! (src/encodings/
+// encode_chain.jl:1-127), SURVEY.md §8 row f4.  Same unary and pair tables as the ICM path, a chain
+// 1-2-...-m instead of the full graph, min-sum dynamic programming instead of local search.
+//
+// Reference arithmetic, kept bit for bit (oracle: orc_encoding_viterbi):
+//   forward  V_1 = U_1;  mincost_i[j] = min_k ( V_i[k] + bb_i[k,j] ), first strict minimum over k
+//            (encode_chain.jl:50-68, one fp32 add per (k, j));  V_{i+1} = U_{i+1} + mincost_i (:45-47,:72-74)
+//   last     first minimum of V_m (:76);  backward trace through minidx (:78-85)
+//   bb_i[k,j] = 2<C_i[:,k], C_{i+1}[:,j]> (:104-106) = T[i+1][i][k][j] of the table set the ICM path
+//   already builds (both orientations materialised), so row k of that table is contiguous in j.
+//
+// Kernel: one warp scores VPW vectors.  Lane l owns the 8 to-states j = 4l..4l+3, 128+4l..128+4l+3 of
+// every vector; the loop runs over the from-states k in ascending order, so "first strict minimum" is
+// simply `if (c < best)`.  Per k: one 1 KB table row (2 x LDG.128 per lane, shared by the warp's VPW
+// vectors and, through L1, by the CTA's 8 warps), one shared-memory broadcast of V[k] per vector, and
+// 8 x (FADD, FSETP, 2 SEL) per vector.  No shuffles in the inner loop; the kernel is ALU-issue bound
+// (4 instructions per (k, j) pair, (m-1) * 65536 pairs per vector).
+#include "icm.cuh"
+
+#include <algorithm>
+
+namespace lsq {
+
+constexpr int VIT_WARPS = 8;
+
+template <int VPW>
+__global__ void __launch_bounds__(VIT_WARPS * 32) viterbi_kernel(const float* __restrict__ U, const float* __restrict__ T,
+                                                                 int64_t n, int m, uint8_t* __restrict__ codes) {
+  extern __shared__ __align__(16) unsigned char vit_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const size_t per_vec = 1024 + (size_t)(m - 1) * LSQ_H;          // V[256] floats + minidx[m-1][256] bytes
+  unsigned char* wbase = vit_smem + (size_t)wib * VPW * per_vec;
+  const int64_t ngroups = (n + VPW - 1) / VPW;
+  const int64_t nwarps = (int64_t)gridDim.x * VIT_WARPS;
+
+  for (int64_t grp = (int64_t)blockIdx.x * VIT_WARPS + wib; grp < ngroups; grp += nwarps) {
+    int64_t v[VPW];
+#pragma unroll
+    for (int e = 0; e < VPW; e++) v[e] = (grp * VPW + e < n) ? grp * VPW + e : n - 1;  // tail: recompute the last vector
+    // V_1 = U_1
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < VPW; e++) {
+      float4* Vs = reinterpret_cast<float4*>(wbase + e * per_vec);
+      const float4* up = reinterpret_cast<const float4*>(U + (size_t)v[e] * LSQ_H);
+      Vs[lane] = __ldg(up + lane);
+      Vs[32 + lane] = __ldg(up + 32 + lane);
+    }
+    __syncwarp();
+
+    float best[VPW][8];
+    for (int i = 0; i < m - 1; i++) {
+      const float4* trow = reinterpret_cast<const float4*>(T + ((size_t)(i + 1) * m + i) * LSQ_H * LSQ_H);
+      int bi[VPW][8];
+      {
+        const float4 g0 = __ldg(trow + lane), g1 = __ldg(trow + 32 + lane);
+        const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int e = 0; e < VPW; e++) {
+          const float vk = reinterpret_cast<const float*>(wbase + e * per_vec)[0];
+#pragma unroll
+          for (int t = 0; t < 8; t++) { best[e][t] = __fadd_rn(vk, gv[t]); bi[e][t] = 0; }
+        }
+      }
+#pragma unroll 4
+      for (int k = 1; k < LSQ_H; k++) {
+        const float4 g0 = __ldg(trow + k * 64 + lane), g1 = __ldg(trow + k * 64 + 32 + lane);
+        const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int e = 0; e < VPW; e++) {
+          const float vk = reinterpret_cast<const float*>(wbase + e * per_vec)[k];
+#pragma unroll
+          for (int t = 0; t < 8; t++) {
+            const float c = __fadd_rn(vk, gv[t]);
+            if (c < best[e][t]) { best[e][t] = c; bi[e][t] = k; }
+          }
+        }
+      }
+      // minidx_i, then V_{i+1} = U_{i+1} + mincost_i
+      __syncwarp();  // every lane is done reading V_i
+#pragma unroll
+      for (int e = 0; e < VPW; e++) {
+        unsigned char* mi = wbase + e * per_vec + 1024 + (size_t)i * LSQ_H;
+        reinterpret_cast<uint32_t*>(mi)[lane] =
+            (uint32_t)bi[e][0] | ((uint32_t)bi[e][1] << 8) | ((uint32_t)bi[e][2] << 16) | ((uint32_t)bi[e][3] << 24);
+        reinterpret_cast<uint32_t*>(mi)[32 + lane] =
+            (uint32_t)bi[e][4] | ((uint32_t)bi[e][5] << 8) | ((uint32_t)bi[e][6] << 16) | ((uint32_t)bi[e][7] << 24);
+        const float4* up = reinterpret_cast<const float4*>(U + ((size_t)(i + 1) * n + v[e]) * LSQ_H);
+        const float4 u0 = __ldg(up + lane), u1 = __ldg(up + 32 + lane);
+        best[e][0] = __fadd_rn(u0.x, best[e][0]); best[e][1] = __fadd_rn(u0.y, best[e][1]);
+        best[e][2] = __fadd_rn(u0.z, best[e][2]); best[e][3] = __fadd_rn(u0.w, best[e][3]);
+        best[e][4] = __fadd_rn(u1.x, best[e][4]); best[e][5] = __fadd_rn(u1.y, best[e][5]);
+        best[e][6] = __fadd_rn(u1.z, best[e][6]); best[e][7] = __fadd_rn(u1.w, best[e][7]);
+        float4* Vs = reinterpret_cast<float4*>(wbase + e * per_vec);
+        Vs[lane] = make_float4(best[e][0], best[e][1], best[e][2], best[e][3]);
+        Vs[32 + lane] = make_float4(best[e][4], best[e][5], best[e][6], best[e][7]);
+      }
+      __syncwarp();
+    }
+
+    // first minimum of V_m (lane-local ascending, then lexicographic (value, index) butterfly), trace back
+#pragma unroll
+    for (int e = 0; e < VPW; e++) {
+      float bv = best[e][0];
+      int bj = 4 * lane;
+#pragma unroll
+      for (int t = 1; t < 8; t++) {
+        const int j = (t < 4) ? 4 * lane + t : 128 + 4 * lane + (t - 4);
+        if (best[e][t] < bv) { bv = best[e][t]; bj = j; }
+      }
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const float ov = __shfl_xor_sync(0xFFFFFFFFu, bv, off);
+        const int oj = __shfl_xor_sync(0xFFFFFFFFu, bj, off);
+        if (ov < bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+      }
+      int cur = bj, mine = bj;  // lane i keeps the code of node i
+      for (int i = m - 2; i >= 0; i--) {
+        cur = (wbase + e * per_vec + 1024 + (size_t)i * LSQ_H)[cur];
+        if (lane == i) mine = cur;
+      }
+      if (lane == m - 1) mine = bj;
+      if (lane < m && grp * VPW + e < n) codes[v[e] * m + lane] = (uint8_t)mine;
+    }
+  }
+}
+
+int launch_viterbi(const float* dU, int64_t n, int m, const float* dT, uint8_t* dcodes, cudaStream_t st) {
+  if (n == 0) return LSQ_OK;
+  LSQ_CHECK_ARG(m >= 2 && m <= LSQ_MAXM, "viterbi: m must be in 2..16 (a chain needs two nodes)");
+  constexpr int VPW = 2;
+  const size_t smem = (size_t)VIT_WARPS * VPW * (1024 + (size_t)(m - 1) * LSQ_H);
+  int dev = 0, sms = LSQ_NUM_SMS_HINT;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  LSQ_CUDA(cudaFuncSetAttribute(viterbi_kernel<VPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(220 * 1024) / (smem + 1024)));
+  const int64_t need = ceil_div(ceil_div(n, VPW), VIT_WARPS);
+  const unsigned grid = (unsigned)std::min<int64_t>(need, (int64_t)sms * per_sm);
+  viterbi_kernel<VPW><<<grid, VIT_WARPS * 32, smem, st>>>(dU, dT, n, m, dcodes);
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
+}
+
+}  // namespace lsq
+
+using namespace lsq;
+
+extern "C" {
+
+int lsq_dev_viterbi(const float* dU, int64_t n, int m, const float* dT, uint8_t* dcodes, void* stream) {
+  LSQ_CHECK_ARG(n >= 0, "n must be >= 0");
+  return launch_viterbi(dU, n, m, dT, dcodes, (cudaStream_t)stream);
+}
+
+int lsq_encoding_viterbi(const float* X, int d, int64_t n, const float* C, int m, int h, int16_t* B, int verbose) {
+  LSQ_CHECK_ARG(d >= 1 && n >= 0, "bad sizes");
+  LSQ_CHECK_ARG(m >= 2 && m <= LSQ_MAXM, "viterbi: m must be in 2..16 (a chain needs two nodes)");
+  LSQ_CHECK_ARG(h == LSQ_H, "h must be 256");
+  if (n == 0) return LSQ_OK;
+  cudaStream_t st;
+  LSQ_TRY(host_ctx(&st));
+  DevBuf<float> dX, dC, dnorms, dT, dU;
+  DevBuf<uint8_t> dcodes;
+  DevBuf<int16_t> d16;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
+  int64_t chunk = (int64_t)(0.5 * (double)free_b / ((double)m * LSQ_H * 4 + (double)d * 4 + 3.0 * m));
+  chunk = std::max<int64_t>(1024, std::min<int64_t>(chunk, n));
+  LSQ_CUDA(dX.alloc((size_t)chunk * d));
+  LSQ_CUDA(dC.alloc((size_t)m * LSQ_H * d));
+  LSQ_CUDA(dnorms.alloc((size_t)m * LSQ_H));
+  LSQ_CUDA(dT.alloc((size_t)m * m * LSQ_H * LSQ_H));
+  LSQ_CUDA(dU.alloc((size_t)chunk * m * LSQ_H));
+  LSQ_CUDA(dcodes.alloc((size_t)chunk * m));
+  LSQ_CUDA(d16.alloc((size_t)chunk * m));
+  LSQ_CUDA(cudaMemcpyAsync(dC.p, C, (size_t)m * LSQ_H * d * 4, cudaMemcpyHostToDevice, st));
+  LSQ_TRY(build_norms(dC.p, d, m, dnorms.p, st));
+  LSQ_TRY(build_tables(dC.p, d, m, dT.p, st));
+  for (int64_t lo = 0; lo < n; lo += chunk) {
+    const int64_t nc = std::min<int64_t>(chunk, n - lo);
+    LSQ_CUDA(cudaMemcpyAsync(dX.p, X + (size_t)lo * d, (size_t)nc * d * 4, cudaMemcpyHostToDevice, st));
+    LSQ_TRY(build_unaries(dX.p, d, nc, dC.p, m, dnorms.p, dU.p, 0, st));
+    LSQ_TRY(launch_viterbi(dU.p, nc, m, dT.p, dcodes.p, st));
+    LSQ_TRY(launch_codes_u8_to_i16(dcodes.p, d16.p, nc * m, st));
+    LSQ_CUDA(cudaMemcpyAsync(B + (size_t)lo * m, d16.p, (size_t)nc * m * 2, cudaMemcpyDeviceToHost, st));
+    LSQ_CUDA(cudaStreamSynchronize(st));
+    if (verbose) fprintf(stderr, "[lsq_b200] viterbi: %lld / %lld vectors\n", (long long)(lo + nc), (long long)n);
+  }
+  return LSQ_OK;
+}
+
+}  // extern "C"

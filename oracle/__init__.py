@@ -350,3 +350,14 @@ def train_lsq(X, m, h, R, B0, niter, ilsiter, icmiter, randord, npert, seed=0, u
     cbnorms, _ = kmeans1d(decoded_norms(B0, C), h)       # :68-81
     B_norms = quantize_norms(B0, C, cbnorms)
     return C, B0, cbnorms, B_norms, obj
+
+
+def encoding_viterbi(X, C):
+    """encode_chain.jl:95-127 (ChainQ's exact chain encoder) -> (n, m) int16 0-based codes."""
+    X, C = _f32(X), _f32(C)
+    n, d = X.shape
+    m, h, _ = C.shape
+    assert m >= 2
+    B0 = np.zeros((n, m), np.int16)
+    lib().orc_encoding_viterbi(_p(X), _p(C), ct.c_int64(n), m, h, d, _p(B0))
+    return B0

@@ -491,6 +491,70 @@ void orc_quantize_norms(const int16_t* B0, const float* C, const float* cbnorms,
   }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * encoding_viterbi (encode_chain.jl:95-127) + encode_viterbi! (encode_chain.jl:1-92): exact MAP on the
+ * chain 1-2-...-m by dynamic programming (the ChainQ encoder).
+ *   binaries[i] = 2*C[i]'*C[i+1]  (:104-106; canonical dot = sequential-k FMA chain, then *2)
+ *   forward (:41-70): U[:,i] += mincost[:,i-1] (i>1); mincost[j,i] = min_k U[k,i] + bb[k,j], first
+ *   strict minimum over k (:56-65); last node: U[:,m] += mincost[:,m-1], findmin (:72-76);
+ *   backward trace (:78-85).  Codes out 0-based B0[n][m].  Needs m >= 2.
+ * ---------------------------------------------------------------------------------------------- */
+void orc_encoding_viterbi(const float* X, const float* C, int64_t n, int m, int h, int d, int16_t* B0) {
+  float* norms = (float*)malloc(sizeof(float) * m * h);
+  orc_get_norms(C, m, h, d, norms);
+  /* bb[i][j][k] = 2<C_i[:,k], C_{i+1}[:,j]>  (Julia bb[k,j], column-major: k contiguous) */
+  float* bb = (float*)malloc(sizeof(float) * (size_t)(m - 1) * h * h);
+  for (int i = 0; i < m - 1; i++) {
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < h; j++)
+      for (int k = 0; k < h; k++)
+        bb[((size_t)i * h + j) * h + k] =
+            2.0f * dot_fma(C + ((size_t)i * h + k) * d, C + ((size_t)(i + 1) * h + j) * d, d);
+  }
+#pragma omp parallel
+  {
+    float* U = (float*)malloc(sizeof(float) * m * h);
+    float* tmp = (float*)malloc(sizeof(float) * h);
+    float* mincost = (float*)malloc(sizeof(float) * m * h);
+    int* minidx = (int*)malloc(sizeof(int) * m * h);
+#pragma omp for schedule(static)
+    for (int64_t v = 0; v < n; v++) {
+      for (int i = 0; i < m; i++) { /* get_unaries (utils.jl:94-122) for this vector */
+        dots_fma(C + (size_t)i * h * d, X + (size_t)v * d, h, d, tmp);
+        for (int a = 0; a < h; a++) U[i * h + a] = -2.0f * tmp[a] + norms[i * h + a];
+      }
+      for (int i = 0; i < m - 1; i++) {
+        if (i > 0)
+          for (int j = 0; j < h; j++) U[i * h + j] += mincost[(i - 1) * h + j];
+        const float* b = bb + (size_t)i * h * h;
+        for (int j = 0; j < h; j++) {
+          float minv = U[i * h + 0] + b[(size_t)j * h + 0];
+          int mini = 0;
+          for (int k = 1; k < h; k++) {
+            const float c = U[i * h + k] + b[(size_t)j * h + k];
+            if (c < minv) { minv = c; mini = k; }
+          }
+          mincost[i * h + j] = minv;
+          minidx[i * h + j] = mini;
+        }
+      }
+      for (int j = 0; j < h; j++) U[(m - 1) * h + j] += mincost[(m - 2) * h + j];
+      float minv = U[(m - 1) * h];
+      int mini = 0;
+      for (int j = 1; j < h; j++)
+        if (U[(m - 1) * h + j] < minv) { minv = U[(m - 1) * h + j]; mini = j; }
+      B0[v * m + (m - 1)] = (int16_t)mini;
+      for (int i = m - 2; i >= 0; i--) {
+        mini = minidx[i * h + mini];
+        B0[v * m + i] = (int16_t)mini;
+      }
+    }
+    free(U); free(tmp); free(mincost); free(minidx);
+  }
+  free(bb);
+  free(norms);
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -149,3 +149,26 @@ def linscan_lsq(codes, queries, codebooks, dbnorms, nn):
         dists[q] = s[order]
         idx[q] = order + 1
     return dists, idx
+
+
+def encoding_viterbi(X, C):
+    """encode_chain.jl:1-127 -> (n, m) int16 0-based.  Vectorised over the data points; the per-element
+    arithmetic (one fp32 add per (k, j), first minimum over k) is the reference's."""
+    m, h, d = C.shape
+    n = X.shape[0]
+    U = get_unaries(X, C)                       # (m, n, h)
+    minidx = np.zeros((m - 1, n, h), np.int64)
+    V = U[0].copy()
+    for i in range(m - 1):
+        bb = pair_table(C, i + 1, i)            # [k][j] = 2<C_{i+1}[:,j], C_i[:,k]> = bb[k, j]
+        cost = (V[:, :, None] + bb[None, :, :]).astype(np.float32)   # (n, k, j)
+        minidx[i] = np.argmin(cost, axis=1)     # first minimum over k
+        mincost = np.take_along_axis(cost, minidx[i][:, None, :], axis=1)[:, 0, :]
+        V = (U[i + 1] + mincost).astype(np.float32)
+    B = np.zeros((n, m), np.int16)
+    cur = np.argmin(V, axis=1)
+    B[:, m - 1] = cur
+    for i in range(m - 2, -1, -1):
+        cur = minidx[i][np.arange(n), cur]
+        B[:, i] = cur
+    return B

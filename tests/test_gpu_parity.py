@@ -464,3 +464,46 @@ def test_eval_recall_matches_oracle(gpu, oracle):
         assert np.array_equal(gpu.eval_recall(gt, pred, kk), oracle.eval_recall(gt, pred, kk))
     assert np.array_equal(gpu.eval_recall(gt.astype(np.uint32), pred.astype(np.uint32), 100),
                           oracle.eval_recall(gt, pred, 100))
+
+
+# ---------------------------------------------------------------- §8(f4): chain (Viterbi) encoder
+@pytest.mark.parametrize("n,d,m,kind", [(2000, 128, 8, "sift"), (777, 64, 7, "sift"), (501, 32, 2, "gauss"),
+                                        (300, 16, 16, "sift"), (1, 128, 8, "gauss"), (3, 24, 3, "sift")])
+def test_encoding_viterbi_bit_exact(gpu, oracle, n, d, m, kind):
+    """encode_chain.jl:1-127 — deterministic, so the codes must equal the oracle's bit for bit (sift-like
+    quarter-integer codebooks make exact ties plausible: first minimum wins)."""
+    X, C, B = make_problem(3000 + n + m, n, d, m, kind=kind)
+    Bg = gpu.encoding_viterbi(X, C)
+    Bo = oracle.encoding_viterbi(X, C)
+    assert np.array_equal(Bg, Bo + 1)
+
+
+def test_encoding_viterbi_properties(gpu, oracle):
+    """Exact chain MAP: no single-node change (what ICM tries) can lower the CHAIN energy, the result does
+    not depend on how the input is batched, and it beats random codes on the true objective."""
+    n, d, m = 4000, 64, 6
+    X, C, B = make_problem(3100, n, d, m)
+    Bv = gpu.encoding_viterbi(X, C)
+    assert np.array_equal(gpu.encoding_viterbi(X[1000:1700], C), Bv[1000:1700])
+    assert gpu.qerror(X, Bv, C) < gpu.qerror(X, B, C)
+    U = oracle.get_unaries(X[:50], C)
+    G, cbi = oracle.get_binaries(C)
+    pair = {(int(a), int(b)): G[i] for i, (a, b) in enumerate(cbi)}   # G[idx][b][a], (i<j) 0-based
+    def energy(codes):
+        e = sum(float(U[i, v, codes[i]]) for i in range(m))
+        return e + sum(float(pair[(i, i + 1)][codes[i + 1], codes[i]]) for i in range(m - 1))
+    rng = np.random.default_rng(0)
+    for v in range(50):
+        base = (Bv[v] - 1).astype(int)
+        e0 = energy(base)
+        for _ in range(20):
+            alt = base.copy()
+            alt[rng.integers(m)] = rng.integers(256)
+            assert energy(alt) >= e0 - 1e-3 * abs(e0)
+
+
+def test_encoding_viterbi_errors(gpu):
+    X, C, B = make_problem(1, 10, 16, 2)
+    with pytest.raises(gpu.LsqError):
+        gpu.encoding_viterbi(X, C[:1])          # a chain needs two nodes
+    assert gpu.encoding_viterbi(X[:0], C).shape == (0, 2)
