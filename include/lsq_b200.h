@@ -189,9 +189,9 @@ int lsq_dev_linscan(const uint8_t* dcodes, int64_t n, int m, const float* dqueri
                     const float* dcodebooks, const float* dbnorms, int lut_kind, int subdim, int nn,
                     float* ddists, int32_t* dids, void* stream);
 
-/* chain encoder on device buffers: dU = U[m][n][256] (lsq_dev_build_unaries, plain layout), dT from
- * lsq_dev_build_tables; dcodes uint8 [n][m] out. */
-int lsq_dev_viterbi(const float* dU, int64_t n, int m, const float* dT, uint8_t* dcodes, void* stream);
+/* chain encoder on device buffers: dU = U[m][n][256] (lsq_dev_build_unaries, plain layout) is CONSUMED
+ * (the forward messages overwrite it in place); dT from lsq_dev_build_tables; dcodes uint8 [n][m] out. */
+int lsq_dev_viterbi(float* dU, int64_t n, int m, const float* dT, uint8_t* dcodes, void* stream);
 /* eval_recall on device buffers: dgnd int32[nq], dpred int32[nq][ld], drecall double[k]. */
 int lsq_dev_eval_recall(const int32_t* dgnd, const int32_t* dpred, int nq, int ld, int k, double* drecall,
                         void* stream);

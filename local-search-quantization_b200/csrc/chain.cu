@@ -10,11 +10,17 @@
 //   already builds (both orientations materialised), so row k of that table is contiguous in j.
 //
 // Kernel: one warp scores VPW vectors.  Lane l owns the 8 to-states j = 4l..4l+3, 128+4l..128+4l+3 of
-// every vector; the loop runs over the from-states k in ascending order, so "first strict minimum" is
-// simply `if (c < best)`.  Per k: one 1 KB table row (2 x LDG.128 per lane, shared by the warp's VPW
-// vectors and, through L1, by the CTA's 8 warps), one shared-memory broadcast of V[k] per vector, and
-// 8 x (FADD, FSETP, 2 SEL) per vector.  No shuffles in the inner loop; the kernel is ALU-issue bound
-// (4 instructions per (k, j) pair, (m-1) * 65536 pairs per vector).
+// every vector; the forward loop runs over the from-states k.  Only the VALUES mincost_i[j] are tracked
+// there — per (k, j) pair one FADD (FMA pipe) and one FMNMX (ALU pipe), no index bookkeeping — because
+// the backward trace needs minidx_i[j] for a single j per stage, the one on the optimal path: it is
+// recomputed there as the first strict minimum over k of V_i[k] + bb_i[k, j*] from the stored V_i and
+// the 1 KB row T[i][i+1][j*][:] (the other orientation of the same table), i.e. from exactly the values
+// the forward pass minimised, so the codes equal the reference's minidx-based trace bit for bit.  V_i
+// overwrites U_i in place (U is scratch of this call).  Per k the warp reads one 1 KB table row
+// (2 x LDG.128 per lane, shared by its VPW vectors and, through L1, by the CTA's warps) and VPW
+// shared-memory broadcasts of V_i[k].  Bound: the ALU pipe (FMNMX issues every 2nd cycle per SM
+// sub-partition): (m-1) * 65536 pairs per vector at 2 cycles per 32 pairs.
+// Inputs must be finite (fminf drops a NaN where the reference's `<` would keep it).
 #include "icm.cuh"
 
 #include <algorithm>
@@ -23,43 +29,63 @@ namespace lsq {
 
 constexpr int VIT_WARPS = 8;
 
+// first strict minimum of 256 values held 8 per lane (4l..4l+3, 128+4l..128+4l+3): lane-local ascending
+// scan, then a lexicographic (value, index) butterfly — same reduction as the ICM kernel's argmin
+__device__ __forceinline__ int warp_first_argmin(const float (&x)[8], int lane) {
+  float bv = x[0];
+  int bj = 4 * lane;
+#pragma unroll
+  for (int t = 1; t < 8; t++) {
+    const int j = (t < 4) ? 4 * lane + t : 128 + 4 * lane + (t - 4);
+    if (x[t] < bv) { bv = x[t]; bj = j; }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const float ov = __shfl_xor_sync(0xFFFFFFFFu, bv, off);
+    const int oj = __shfl_xor_sync(0xFFFFFFFFu, bj, off);
+    if (ov < bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+  }
+  return bj;
+}
+
 template <int VPW>
-__global__ void __launch_bounds__(VIT_WARPS * 32) viterbi_kernel(const float* __restrict__ U, const float* __restrict__ T,
+__global__ void __launch_bounds__(VIT_WARPS * 32) viterbi_kernel(float* __restrict__ U, const float* __restrict__ T,
                                                                  int64_t n, int m, uint8_t* __restrict__ codes) {
-  extern __shared__ __align__(16) unsigned char vit_smem[];
+  __shared__ __align__(16) float vit_v[VIT_WARPS][VPW][LSQ_H];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const size_t per_vec = 1024 + (size_t)(m - 1) * LSQ_H;          // V[256] floats + minidx[m-1][256] bytes
-  unsigned char* wbase = vit_smem + (size_t)wib * VPW * per_vec;
   const int64_t ngroups = (n + VPW - 1) / VPW;
   const int64_t nwarps = (int64_t)gridDim.x * VIT_WARPS;
 
   for (int64_t grp = (int64_t)blockIdx.x * VIT_WARPS + wib; grp < ngroups; grp += nwarps) {
     int64_t v[VPW];
+    bool valid[VPW];
 #pragma unroll
-    for (int e = 0; e < VPW; e++) v[e] = (grp * VPW + e < n) ? grp * VPW + e : n - 1;  // tail: recompute the last vector
+    for (int e = 0; e < VPW; e++) {
+      valid[e] = grp * VPW + e < n;
+      v[e] = valid[e] ? grp * VPW + e : n - 1;  // tail slots recompute the last vector and never store
+    }
     // V_1 = U_1
     __syncwarp();
 #pragma unroll
     for (int e = 0; e < VPW; e++) {
-      float4* Vs = reinterpret_cast<float4*>(wbase + e * per_vec);
+      float4* Vs = reinterpret_cast<float4*>(vit_v[wib][e]);
       const float4* up = reinterpret_cast<const float4*>(U + (size_t)v[e] * LSQ_H);
-      Vs[lane] = __ldg(up + lane);
-      Vs[32 + lane] = __ldg(up + 32 + lane);
+      Vs[lane] = up[lane];
+      Vs[32 + lane] = up[32 + lane];
     }
     __syncwarp();
 
     float best[VPW][8];
     for (int i = 0; i < m - 1; i++) {
       const float4* trow = reinterpret_cast<const float4*>(T + ((size_t)(i + 1) * m + i) * LSQ_H * LSQ_H);
-      int bi[VPW][8];
       {
         const float4 g0 = __ldg(trow + lane), g1 = __ldg(trow + 32 + lane);
         const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int e = 0; e < VPW; e++) {
-          const float vk = reinterpret_cast<const float*>(wbase + e * per_vec)[0];
+          const float vk = vit_v[wib][e][0];
 #pragma unroll
-          for (int t = 0; t < 8; t++) { best[e][t] = __fadd_rn(vk, gv[t]); bi[e][t] = 0; }
+          for (int t = 0; t < 8; t++) best[e][t] = __fadd_rn(vk, gv[t]);
         }
       }
 #pragma unroll 4
@@ -68,76 +94,64 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) viterbi_kernel(const float* __
         const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int e = 0; e < VPW; e++) {
-          const float vk = reinterpret_cast<const float*>(wbase + e * per_vec)[k];
+          const float vk = vit_v[wib][e][k];
 #pragma unroll
-          for (int t = 0; t < 8; t++) {
-            const float c = __fadd_rn(vk, gv[t]);
-            if (c < best[e][t]) { best[e][t] = c; bi[e][t] = k; }
-          }
+          for (int t = 0; t < 8; t++) best[e][t] = fminf(best[e][t], __fadd_rn(vk, gv[t]));
         }
       }
-      // minidx_i, then V_{i+1} = U_{i+1} + mincost_i
+      // V_{i+1} = U_{i+1} + mincost_i, kept in shared memory for the next stage and in U for the trace
       __syncwarp();  // every lane is done reading V_i
 #pragma unroll
       for (int e = 0; e < VPW; e++) {
-        unsigned char* mi = wbase + e * per_vec + 1024 + (size_t)i * LSQ_H;
-        reinterpret_cast<uint32_t*>(mi)[lane] =
-            (uint32_t)bi[e][0] | ((uint32_t)bi[e][1] << 8) | ((uint32_t)bi[e][2] << 16) | ((uint32_t)bi[e][3] << 24);
-        reinterpret_cast<uint32_t*>(mi)[32 + lane] =
-            (uint32_t)bi[e][4] | ((uint32_t)bi[e][5] << 8) | ((uint32_t)bi[e][6] << 16) | ((uint32_t)bi[e][7] << 24);
-        const float4* up = reinterpret_cast<const float4*>(U + ((size_t)(i + 1) * n + v[e]) * LSQ_H);
-        const float4 u0 = __ldg(up + lane), u1 = __ldg(up + 32 + lane);
+        float4* up = reinterpret_cast<float4*>(U + ((size_t)(i + 1) * n + v[e]) * LSQ_H);
+        const float4 u0 = up[lane], u1 = up[32 + lane];
         best[e][0] = __fadd_rn(u0.x, best[e][0]); best[e][1] = __fadd_rn(u0.y, best[e][1]);
         best[e][2] = __fadd_rn(u0.z, best[e][2]); best[e][3] = __fadd_rn(u0.w, best[e][3]);
         best[e][4] = __fadd_rn(u1.x, best[e][4]); best[e][5] = __fadd_rn(u1.y, best[e][5]);
         best[e][6] = __fadd_rn(u1.z, best[e][6]); best[e][7] = __fadd_rn(u1.w, best[e][7]);
-        float4* Vs = reinterpret_cast<float4*>(wbase + e * per_vec);
-        Vs[lane] = make_float4(best[e][0], best[e][1], best[e][2], best[e][3]);
-        Vs[32 + lane] = make_float4(best[e][4], best[e][5], best[e][6], best[e][7]);
+        const float4 w0 = make_float4(best[e][0], best[e][1], best[e][2], best[e][3]);
+        const float4 w1 = make_float4(best[e][4], best[e][5], best[e][6], best[e][7]);
+        float4* Vs = reinterpret_cast<float4*>(vit_v[wib][e]);
+        Vs[lane] = w0;
+        Vs[32 + lane] = w1;
+        if (valid[e]) { up[lane] = w0; up[32 + lane] = w1; }  // each lane re-reads only its own elements
       }
       __syncwarp();
     }
 
-    // first minimum of V_m (lane-local ascending, then lexicographic (value, index) butterfly), trace back
+    // first minimum of V_m, then the backward trace: code_i = first argmin_k V_i[k] + bb_i[k, code_{i+1}]
 #pragma unroll
     for (int e = 0; e < VPW; e++) {
-      float bv = best[e][0];
-      int bj = 4 * lane;
-#pragma unroll
-      for (int t = 1; t < 8; t++) {
-        const int j = (t < 4) ? 4 * lane + t : 128 + 4 * lane + (t - 4);
-        if (best[e][t] < bv) { bv = best[e][t]; bj = j; }
-      }
-#pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) {
-        const float ov = __shfl_xor_sync(0xFFFFFFFFu, bv, off);
-        const int oj = __shfl_xor_sync(0xFFFFFFFFu, bj, off);
-        if (ov < bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
-      }
-      int cur = bj, mine = bj;  // lane i keeps the code of node i
+      int cur = warp_first_argmin(best[e], lane);
+      int mine = cur;  // lane i keeps the code of node i
       for (int i = m - 2; i >= 0; i--) {
-        cur = (wbase + e * per_vec + 1024 + (size_t)i * LSQ_H)[cur];
+        const float4* vp = reinterpret_cast<const float4*>(U + ((size_t)i * n + v[e]) * LSQ_H);
+        const float4* tp = reinterpret_cast<const float4*>(T + (((size_t)i * m + (i + 1)) * LSQ_H + cur) * LSQ_H);
+        const float4 a0 = vp[lane], a1 = vp[32 + lane];
+        const float4 g0 = __ldg(tp + lane), g1 = __ldg(tp + 32 + lane);
+        const float c[8] = {__fadd_rn(a0.x, g0.x), __fadd_rn(a0.y, g0.y), __fadd_rn(a0.z, g0.z), __fadd_rn(a0.w, g0.w),
+                            __fadd_rn(a1.x, g1.x), __fadd_rn(a1.y, g1.y), __fadd_rn(a1.z, g1.z), __fadd_rn(a1.w, g1.w)};
+        cur = warp_first_argmin(c, lane);
         if (lane == i) mine = cur;
       }
-      if (lane == m - 1) mine = bj;
-      if (lane < m && grp * VPW + e < n) codes[v[e] * m + lane] = (uint8_t)mine;
+      if (lane < m && valid[e]) codes[v[e] * m + lane] = (uint8_t)mine;
     }
   }
 }
 
-int launch_viterbi(const float* dU, int64_t n, int m, const float* dT, uint8_t* dcodes, cudaStream_t st) {
+int launch_viterbi(float* dU, int64_t n, int m, const float* dT, uint8_t* dcodes, cudaStream_t st) {
   if (n == 0) return LSQ_OK;
   LSQ_CHECK_ARG(m >= 2 && m <= LSQ_MAXM, "viterbi: m must be in 2..16 (a chain needs two nodes)");
-  constexpr int VPW = 2;
-  const size_t smem = (size_t)VIT_WARPS * VPW * (1024 + (size_t)(m - 1) * LSQ_H);
+  constexpr int VPW = 4;
   int dev = 0, sms = LSQ_NUM_SMS_HINT;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  LSQ_CUDA(cudaFuncSetAttribute(viterbi_kernel<VPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(220 * 1024) / (smem + 1024)));
+  int per_sm = 1;  // whole waves only: a partial last wave of resident CTAs costs a full pass
+  LSQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, viterbi_kernel<VPW>, VIT_WARPS * 32, 0));
+  if (per_sm < 1) per_sm = 1;
   const int64_t need = ceil_div(ceil_div(n, VPW), VIT_WARPS);
   const unsigned grid = (unsigned)std::min<int64_t>(need, (int64_t)sms * per_sm);
-  viterbi_kernel<VPW><<<grid, VIT_WARPS * 32, smem, st>>>(dU, dT, n, m, dcodes);
+  viterbi_kernel<VPW><<<grid, VIT_WARPS * 32, 0, st>>>(dU, dT, n, m, dcodes);
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
 }
@@ -148,7 +162,7 @@ using namespace lsq;
 
 extern "C" {
 
-int lsq_dev_viterbi(const float* dU, int64_t n, int m, const float* dT, uint8_t* dcodes, void* stream) {
+int lsq_dev_viterbi(float* dU, int64_t n, int m, const float* dT, uint8_t* dcodes, void* stream) {
   LSQ_CHECK_ARG(n >= 0, "n must be >= 0");
   return launch_viterbi(dU, n, m, dT, dcodes, (cudaStream_t)stream);
 }
