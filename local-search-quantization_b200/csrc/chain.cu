@@ -23,6 +23,9 @@
 // Inputs must be finite (fminf drops a NaN where the reference's `<` would keep it).
 #include "icm.cuh"
 
+#include <stdlib.h>
+#include <string.h>
+
 #include <algorithm>
 
 namespace lsq {
@@ -139,6 +142,147 @@ __global__ void __launch_bounds__(VIT_WARPS * 32) viterbi_kernel(float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pipelined variant for large n: one persistent CTA per SM, 16 consumer warps x 4 vectors = 64 vectors
+// per pass, all walking the same (stage, from-state) sequence.  A dedicated producer warp streams the
+// stage tables through a 4-slot ring of 16-row chunks (16 KB each) with TMA bulk copies
+// (cp.async.bulk + mbarrier full/empty pairs), so every table row is fetched once per CTA instead of
+// once per warp and the consumers' inner loop only touches shared memory: 2 x LDS.128 per row and
+// lane + one broadcast of V_i[k] per vector, then 32 x (FADD, FMNMX).  Same arithmetic, same codes.
+// ------------------------------------------------------------------------------------------------
+constexpr int VC_WARPS = 16;    // consumer warps
+constexpr int VC_VPW = 4;       // vectors per warp
+constexpr int VC_ROWS = 16;     // table rows per chunk
+constexpr int VC_SLOTS = 4;     // ring depth
+constexpr int VC_CHUNKS = LSQ_H / VC_ROWS;
+constexpr uint32_t VC_CHUNK_BYTES = VC_ROWS * LSQ_H * 4;
+constexpr size_t VC_SMEM = (size_t)VC_SLOTS * VC_CHUNK_BYTES + (size_t)VC_WARPS * VC_VPW * LSQ_H * 4 + 2 * VC_SLOTS * 8;
+
+__global__ void __launch_bounds__((VC_WARPS + 1) * 32, 1) viterbi_tma_kernel(float* __restrict__ U,
+                                                                             const float* __restrict__ T, int64_t n,
+                                                                             int m, uint8_t* __restrict__ codes) {
+  extern __shared__ __align__(128) unsigned char vc_smem[];
+  float* ring = reinterpret_cast<float*>(vc_smem);
+  float* vall = reinterpret_cast<float*>(vc_smem + (size_t)VC_SLOTS * VC_CHUNK_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(vc_smem + (size_t)VC_SLOTS * VC_CHUNK_BYTES +
+                                               (size_t)VC_WARPS * VC_VPW * LSQ_H * 4);
+  uint64_t* empty = full + VC_SLOTS;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  constexpr int VPC = VC_WARPS * VC_VPW;  // vectors per CTA pass
+  const int64_t npasses_all = (n + VPC - 1) / VPC;
+  const int64_t my_passes = (npasses_all > (int64_t)blockIdx.x)
+                                ? (npasses_all - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t total_chunks = my_passes * (m - 1) * VC_CHUNKS;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < VC_SLOTS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], VC_WARPS); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (wib == VC_WARPS) {
+    // ---- producer warp: one elected lane keeps the ring full ----
+    if (lane == 0) {
+      for (int64_t p = 0; p < total_chunks; p++) {
+        const int slot = (int)(p % VC_SLOTS);
+        if (p >= VC_SLOTS) mbar_wait(&empty[slot], (uint32_t)(((p / VC_SLOTS) - 1) & 1));
+        const int i = (int)((p / VC_CHUNKS) % (m - 1));
+        const int c = (int)(p % VC_CHUNKS);
+        const float* src = T + ((size_t)(i + 1) * m + i) * LSQ_H * LSQ_H + (size_t)c * VC_ROWS * LSQ_H;
+        mbar_expect_tx(&full[slot], VC_CHUNK_BYTES);
+        bulk_g2s(ring + (size_t)slot * VC_ROWS * LSQ_H, src, VC_CHUNK_BYTES, &full[slot]);
+      }
+    }
+    return;
+  }
+
+  // ---- consumer warps ----
+  float* vmine = vall + (size_t)wib * VC_VPW * LSQ_H;
+  const uint32_t ring_u32 = smem_u32(ring) + (uint32_t)lane * 16u;
+  int64_t q = 0;  // chunk counter, identical in every consumer warp
+  for (int64_t pass = blockIdx.x; pass < npasses_all; pass += gridDim.x) {
+    int64_t v[VC_VPW];
+    bool valid[VC_VPW];
+#pragma unroll
+    for (int e = 0; e < VC_VPW; e++) {
+      const int64_t idx = pass * VPC + (int64_t)wib * VC_VPW + e;
+      valid[e] = idx < n;
+      v[e] = valid[e] ? idx : n - 1;  // tail slots recompute the last vector and never store
+    }
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < VC_VPW; e++) {
+      float4* Vs = reinterpret_cast<float4*>(vmine + e * LSQ_H);
+      const float4* up = reinterpret_cast<const float4*>(U + (size_t)v[e] * LSQ_H);
+      Vs[lane] = up[lane];
+      Vs[32 + lane] = up[32 + lane];
+    }
+    __syncwarp();
+
+    float best[VC_VPW][8];
+    for (int i = 0; i < m - 1; i++) {
+#pragma unroll
+      for (int e = 0; e < VC_VPW; e++)
+#pragma unroll
+        for (int t = 0; t < 8; t++) best[e][t] = INFINITY;  // min(+inf, c) = c: same as starting from k = 0
+      for (int c = 0; c < VC_CHUNKS; c++, q++) {
+        const int slot = (int)(q % VC_SLOTS);
+        mbar_wait(&full[slot], (uint32_t)((q / VC_SLOTS) & 1));
+        const uint32_t base = ring_u32 + (uint32_t)slot * VC_CHUNK_BYTES;
+#pragma unroll 4
+        for (int r = 0; r < VC_ROWS; r++) {
+          float4 g0, g1;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g0.x), "=f"(g0.y), "=f"(g0.z), "=f"(g0.w) : "r"(base + (uint32_t)r * 1024u));
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g1.x), "=f"(g1.y), "=f"(g1.z), "=f"(g1.w) : "r"(base + (uint32_t)r * 1024u + 512u));
+          const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+          for (int e = 0; e < VC_VPW; e++) {
+            const float vk = vmine[e * LSQ_H + c * VC_ROWS + r];
+#pragma unroll
+            for (int t = 0; t < 8; t++) best[e][t] = fminf(best[e][t], __fadd_rn(vk, gv[t]));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+      }
+      // V_{i+1} = U_{i+1} + mincost_i (per-warp state: only warp-level synchronisation)
+#pragma unroll
+      for (int e = 0; e < VC_VPW; e++) {
+        float4* up = reinterpret_cast<float4*>(U + ((size_t)(i + 1) * n + v[e]) * LSQ_H);
+        const float4 u0 = up[lane], u1 = up[32 + lane];
+        best[e][0] = __fadd_rn(u0.x, best[e][0]); best[e][1] = __fadd_rn(u0.y, best[e][1]);
+        best[e][2] = __fadd_rn(u0.z, best[e][2]); best[e][3] = __fadd_rn(u0.w, best[e][3]);
+        best[e][4] = __fadd_rn(u1.x, best[e][4]); best[e][5] = __fadd_rn(u1.y, best[e][5]);
+        best[e][6] = __fadd_rn(u1.z, best[e][6]); best[e][7] = __fadd_rn(u1.w, best[e][7]);
+        const float4 w0 = make_float4(best[e][0], best[e][1], best[e][2], best[e][3]);
+        const float4 w1 = make_float4(best[e][4], best[e][5], best[e][6], best[e][7]);
+        float4* Vs = reinterpret_cast<float4*>(vmine + e * LSQ_H);
+        Vs[lane] = w0;
+        Vs[32 + lane] = w1;
+        if (valid[e]) { up[lane] = w0; up[32 + lane] = w1; }
+      }
+      __syncwarp();
+    }
+
+#pragma unroll
+    for (int e = 0; e < VC_VPW; e++) {
+      int cur = warp_first_argmin(best[e], lane);
+      int mine = cur;
+      for (int i = m - 2; i >= 0; i--) {
+        const float4* vp = reinterpret_cast<const float4*>(U + ((size_t)i * n + v[e]) * LSQ_H);
+        const float4* tp = reinterpret_cast<const float4*>(T + (((size_t)i * m + (i + 1)) * LSQ_H + cur) * LSQ_H);
+        const float4 a0 = vp[lane], a1 = vp[32 + lane];
+        const float4 g0 = __ldg(tp + lane), g1 = __ldg(tp + 32 + lane);
+        const float cc[8] = {__fadd_rn(a0.x, g0.x), __fadd_rn(a0.y, g0.y), __fadd_rn(a0.z, g0.z), __fadd_rn(a0.w, g0.w),
+                             __fadd_rn(a1.x, g1.x), __fadd_rn(a1.y, g1.y), __fadd_rn(a1.z, g1.z), __fadd_rn(a1.w, g1.w)};
+        cur = warp_first_argmin(cc, lane);
+        if (lane == i) mine = cur;
+      }
+      if (lane < m && valid[e]) codes[v[e] * m + lane] = (uint8_t)mine;
+    }
+  }
+}
+
 int launch_viterbi(float* dU, int64_t n, int m, const float* dT, uint8_t* dcodes, cudaStream_t st) {
   if (n == 0) return LSQ_OK;
   LSQ_CHECK_ARG(m >= 2 && m <= LSQ_MAXM, "viterbi: m must be in 2..16 (a chain needs two nodes)");
@@ -146,6 +290,17 @@ int launch_viterbi(float* dU, int64_t n, int m, const float* dT, uint8_t* dcodes
   int dev = 0, sms = LSQ_NUM_SMS_HINT;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // large inputs: the TMA-pipelined kernel (64 vectors per CTA pass); LSQ_B200_VITERBI=simple|tma overrides
+  const char* ve = getenv("LSQ_B200_VITERBI");
+  const bool want_tma = ve ? (strcmp(ve, "tma") == 0) : (n >= (int64_t)sms * VC_WARPS * VC_VPW);
+  if (want_tma) {
+    LSQ_CUDA(cudaFuncSetAttribute(viterbi_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VC_SMEM));
+    const int64_t passes = ceil_div(n, VC_WARPS * VC_VPW);
+    const unsigned grid = (unsigned)std::min<int64_t>(passes, sms);
+    viterbi_tma_kernel<<<grid, (VC_WARPS + 1) * 32, VC_SMEM, st>>>(dU, dT, n, m, dcodes);
+    LSQ_CUDA(cudaGetLastError());
+    return LSQ_OK;
+  }
   int per_sm = 1;  // whole waves only: a partial last wave of resident CTAs costs a full pass
   LSQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, viterbi_kernel<VPW>, VIT_WARPS * 32, 0));
   if (per_sm < 1) per_sm = 1;

@@ -478,6 +478,22 @@ def test_encoding_viterbi_bit_exact(gpu, oracle, n, d, m, kind):
     assert np.array_equal(Bg, Bo + 1)
 
 
+@pytest.mark.parametrize("kernel", ["simple", "tma"])
+@pytest.mark.parametrize("n,d,m", [(777, 32, 8), (64, 16, 2), (1, 16, 5), (4099, 24, 16)])
+def test_encoding_viterbi_both_kernels(gpu, oracle, monkeypatch, kernel, n, d, m):
+    """LSQ_B200_VITERBI forces the warp-per-4-vectors kernel or the TMA-pipelined persistent kernel (ragged
+    tails, fewer vectors than one CTA pass): both must give the oracle's codes."""
+    monkeypatch.setenv("LSQ_B200_VITERBI", kernel)
+    X, C, B = make_problem(3200 + n + m, n, d, m)
+    assert np.array_equal(gpu.encoding_viterbi(X, C), oracle.encoding_viterbi(X, C) + 1)
+
+
+def test_encoding_viterbi_large_n_default_dispatch(gpu, oracle):
+    """n >= 148 x 64 takes the TMA-pipelined kernel by default."""
+    X, C, B = make_problem(3300, 12345, 32, 8)
+    assert np.array_equal(gpu.encoding_viterbi(X, C), oracle.encoding_viterbi(X, C) + 1)
+
+
 def test_encoding_viterbi_properties(gpu, oracle):
     """Exact chain MAP: no single-node change (what ICM tries) can lower the CHAIN energy, the result does
     not depend on how the input is batched, and it beats random codes on the true objective."""
