@@ -229,17 +229,25 @@ __global__ void __launch_bounds__((VC_WARPS + 1) * 32, 1) viterbi_tma_kernel(flo
         const int slot = (int)(q % VC_SLOTS);
         mbar_wait(&full[slot], (uint32_t)((q / VC_SLOTS) & 1));
         const uint32_t base = ring_u32 + (uint32_t)slot * VC_CHUNK_BYTES;
-#pragma unroll 4
-        for (int r = 0; r < VC_ROWS; r++) {
-          float4 g0, g1;
-          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g0.x), "=f"(g0.y), "=f"(g0.z), "=f"(g0.w) : "r"(base + (uint32_t)r * 1024u));
-          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g1.x), "=f"(g1.y), "=f"(g1.z), "=f"(g1.w) : "r"(base + (uint32_t)r * 1024u + 512u));
-          const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll 1
+        for (int r4 = 0; r4 < VC_ROWS; r4 += 4) {
+          float4 vk4[VC_VPW];  // V_i[k..k+3] of each vector: one broadcast LDS.128 per vector and 4 rows
 #pragma unroll
-          for (int e = 0; e < VC_VPW; e++) {
-            const float vk = vmine[e * LSQ_H + c * VC_ROWS + r];
+          for (int e = 0; e < VC_VPW; e++)
+            vk4[e] = *reinterpret_cast<const float4*>(vmine + e * LSQ_H + c * VC_ROWS + r4);
 #pragma unroll
-            for (int t = 0; t < 8; t++) best[e][t] = fminf(best[e][t], __fadd_rn(vk, gv[t]));
+          for (int rr = 0; rr < 4; rr++) {
+            const int r = r4 + rr;
+            float4 g0, g1;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g0.x), "=f"(g0.y), "=f"(g0.z), "=f"(g0.w) : "r"(base + (uint32_t)r * 1024u));
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(g1.x), "=f"(g1.y), "=f"(g1.z), "=f"(g1.w) : "r"(base + (uint32_t)r * 1024u + 512u));
+            const float gv[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+            for (int e = 0; e < VC_VPW; e++) {
+              const float vk = (rr == 0) ? vk4[e].x : (rr == 1) ? vk4[e].y : (rr == 2) ? vk4[e].z : vk4[e].w;
+#pragma unroll
+              for (int t = 0; t < 8; t++) best[e][t] = fminf(best[e][t], __fadd_rn(vk, gv[t]));
+            }
           }
         }
         __syncwarp();
