@@ -4,6 +4,7 @@ the linscan vectors, which come from the reference's own C++ compiled unmodified
 The reference ships no tests or fixtures, so:
   * icm_*.npz     — outputs of oracle/lsq_oracle.c, accepted only if oracle/np_twin.py (an independent
                     restatement of the same reference lines) agrees bit for bit;
+  * viterbi_*.npz — chain-encoder codes (encode_chain.jl), same rule: oracle and twin must agree;
   * linscan_*.npz — outputs of the REAL reference linscan_aqd_query[_extra_byte].
 Inputs are regenerated from the stored seeds by tests/util.py, so the files stay tiny.
 """
@@ -24,6 +25,11 @@ ICM_CASES = [  # name, seed, n, d, m, niter, npert, randord, ils_iters
     ("icm_m8_d128", 12, 24, 128, 8, 4, 4, True, 2),
     ("icm_m7_d32_noshuffle", 13, 32, 32, 7, 2, 3, False, 1),
     ("icm_m16_d32", 14, 12, 32, 16, 2, 4, True, 1),
+]
+VITERBI_CASES = [  # name, seed, n, d, m, kind
+    ("viterbi_m8_d128", 31, 40, 128, 8, "sift"),
+    ("viterbi_m16_d32", 32, 30, 32, 16, "sift"),
+    ("viterbi_m3_d16_gauss", 33, 64, 16, 3, "gauss"),
 ]
 SCAN_CASES = [  # name, seed, n, nq, d, m, nn
     ("linscan_lsq_m8", 21, 3000, 6, 32, 8, 25),
@@ -49,6 +55,13 @@ def main():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), seed=seed, n=n, d=d, m=m, niter=niter, npert=npert,
                             randord=randord, iters=iters, codes=np.stack(outs).astype(np.int16),
                             cost=np.stack(costs))
+        print("wrote", name)
+    for name, seed, n, d, m, kind in VITERBI_CASES:
+        X, C, _ = make_problem(seed, n, d, m, kind=kind)
+        a, b = oracle.encoding_viterbi(X, C), np_twin.encoding_viterbi(X, C)
+        assert np.array_equal(a, b), f"{name}: oracle != twin"
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), seed=seed, n=n, d=d, m=m, kind=kind,
+                            codes=(a + 1).astype(np.int16))
         print("wrote", name)
     assert oracle.ref_available(), "oracle/_ref missing: run `make -C oracle` with /root/reference present"
     for name, seed, n, nq, d, m, nn in SCAN_CASES:

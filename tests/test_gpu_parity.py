@@ -478,6 +478,13 @@ def test_encoding_viterbi_bit_exact(gpu, oracle, n, d, m, kind):
     assert np.array_equal(Bg, Bo + 1)
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "viterbi_*.npz"))))
+def test_encoding_viterbi_golden(gpu, path):
+    g = np.load(path)
+    X, C, _ = make_problem(int(g["seed"]), int(g["n"]), int(g["d"]), int(g["m"]), kind=str(g["kind"]))
+    assert np.array_equal(gpu.encoding_viterbi(X, C), g["codes"])
+
+
 @pytest.mark.parametrize("kernel", ["simple", "tma"])
 @pytest.mark.parametrize("n,d,m", [(777, 32, 8), (64, 16, 2), (1, 16, 5), (4099, 24, 16)])
 def test_encoding_viterbi_both_kernels(gpu, oracle, monkeypatch, kernel, n, d, m):

@@ -51,6 +51,29 @@ def test_oracle_matches_golden_linscan(oracle, path):
     assert np.array_equal(dists, g["dists"])
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLD, "viterbi_*.npz"))))
+def test_oracle_matches_golden_viterbi(oracle, path):
+    g = np.load(path)
+    X, C, _ = make_problem(int(g["seed"]), int(g["n"]), int(g["d"]), int(g["m"]), kind=str(g["kind"]))
+    assert np.array_equal(oracle.encoding_viterbi(X, C) + 1, g["codes"])
+
+
+def test_oracle_vs_twin_viterbi(oracle):
+    """encode_chain.jl:1-127: the C restatement and the NumPy twin agree, and the result is the exact chain
+    optimum (brute force over all 256^2 / 4^3 configurations on tiny problems)."""
+    from oracle import np_twin
+    X, C, _ = make_problem(5, 30, 12, 4)
+    assert np.array_equal(oracle.encoding_viterbi(X, C), np_twin.encoding_viterbi(X, C))
+    X, C, _ = make_problem(6, 6, 8, 2, kind="gauss")
+    U = oracle.get_unaries(X, C)
+    G, _ = oracle.get_binaries(C)          # G[0][b][a] = 2<C_0[:,a], C_1[:,b]>
+    Bv = oracle.encoding_viterbi(X, C)
+    for v in range(6):
+        E = U[0, v][:, None] + U[1, v][None, :] + G[0].T   # E[a][b]
+        a, b = np.unravel_index(np.argmin(E), E.shape)
+        assert abs(E[Bv[v, 0], Bv[v, 1]] - E[a, b]) <= 1e-4 * abs(E[a, b])
+
+
 def test_oracle_vs_twin_icm(oracle):
     from oracle import np_twin
     X, C, B1 = make_problem(3, 20, 24, 5)
