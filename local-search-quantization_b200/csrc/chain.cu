@@ -175,7 +175,7 @@ __global__ void __launch_bounds__((VC_WARPS + 1) * 32, 1) viterbi_tma_kernel(flo
   const int64_t total_chunks = my_passes * (m - 1) * VC_CHUNKS;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < VC_SLOTS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], VC_WARPS); }
+    for (int s = 0; s < VC_SLOTS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], VC_WARPS * 32); }
     fence_mbar_init();
   }
   __syncthreads();
@@ -250,10 +250,10 @@ __global__ void __launch_bounds__((VC_WARPS + 1) * 32, 1) viterbi_tma_kernel(flo
             }
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[slot]);
+        mbar_arrive(&empty[slot]);  // every reading thread releases the slot itself
       }
       // V_{i+1} = U_{i+1} + mincost_i (per-warp state: only warp-level synchronisation)
+      __syncwarp();  // every lane is done reading V_i
 #pragma unroll
       for (int e = 0; e < VC_VPW; e++) {
         float4* up = reinterpret_cast<float4*>(U + ((size_t)(i + 1) * n + v[e]) * LSQ_H);

@@ -531,7 +531,8 @@ __global__ void __launch_bounds__(NT) topk_select_kernel(const unsigned long lon
       int part = 0;
 #pragma unroll
       for (int b = 0; b < 8; b++) part += hist[tid * 8 + b];
-      const int rr = sh_rank;  // read by every lane before the shuffles (convergence points) below
+      const int rr = sh_rank;
+      __syncwarp();  // every lane has read the rank before the owning lane overwrites it below
       int incl = part;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
