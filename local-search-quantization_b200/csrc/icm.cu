@@ -85,7 +85,12 @@ __global__ void __launch_bounds__(256, 4) icm_ils_warp_kernel(const __grid_const
     __syncwarp();
   }
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); v < p.n; v += nwarps) {
+  // The time a vector takes depends on how many node visits it needs; with a static grid-stride split the
+  // early finishers idle (ncu: 6 % of the resident warp slots empty on average).  Each warp therefore draws
+  // its next vector from a global counter: the first `nwarps` vectors are assigned statically, the rest
+  // on demand.
+  int64_t v = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (; v < p.n;) {
     uint64_t lo = 0, hi = 0;
     {
       const uint8_t* cp = p.codes + v * M;
@@ -194,6 +199,13 @@ __global__ void __launch_bounds__(256, 4) icm_ils_warp_kernel(const __grid_const
     }
     if (lane < M) p.codes[v * M + lane] = (uint8_t)get_code<M>(lo, hi, lane);
     if (lane == 0) p.cost[v] = prev;
+    if (p.next_vector != nullptr) {
+      unsigned long long t = 0;
+      if (lane == 0) t = atomicAdd(p.next_vector, 1ull);
+      v = nwarps + (int64_t)__shfl_sync(0xFFFFFFFFu, t, 0);
+    } else {
+      v += nwarps;
+    }
   }
 }
 
@@ -235,11 +247,23 @@ static int launch_icm_warp_m(const IcmParams& p, cudaStream_t st) {
       cudaGetLastError();
     }
   }
+  // dynamic work distribution (LSQ_B200_ICM_STATIC=1 restores the static split for A/B runs)
+  IcmParams q = p;
+  DevBuf<unsigned long long> counter;
+  const char* se = getenv("LSQ_B200_ICM_STATIC");
+  if (!(se != nullptr && atoi(se) != 0) && blocks_needed > cap) {
+    counter.st = st;
+    LSQ_CUDA(counter.alloc(1));
+    LSQ_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
+    q.next_vector = counter.p;
+  } else {
+    q.next_vector = nullptr;
+  }
   if (usmem) {
     LSQ_CUDA(cudaFuncSetAttribute(icm_ils_warp_kernel<M, kCanUsmem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    icm_ils_warp_kernel<M, kCanUsmem><<<grid, 256, smem, st>>>(p);
+    icm_ils_warp_kernel<M, kCanUsmem><<<grid, 256, smem, st>>>(q);
   } else {
-    icm_ils_warp_kernel<M, false><<<grid, 256, 0, st>>>(p);
+    icm_ils_warp_kernel<M, false><<<grid, 256, 0, st>>>(q);
   }
   if (window) {
     cudaStreamAttrValue attr;

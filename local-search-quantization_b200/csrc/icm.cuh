@@ -29,6 +29,10 @@ struct IcmParams {
   uint16_t* clean;              // accepted-state clean mask
   uint16_t* wclean;             // working clean mask
   int* act;                     // per-CTA active lists (stored in the CTA's own vector range)
+  // warp kernel: dynamic work distribution — a zero-initialised counter from which every warp draws its
+  // next vector (vectors are independent, so the processing order cannot change any result); nullptr =
+  // static grid-stride assignment
+  unsigned long long* next_vector;
   int64_t n;
   uint64_t seed;
   uint64_t g0;      // global index of vector 0 (sharding invariance)
