@@ -403,25 +403,30 @@ template <int CAPK, int NT>
 __global__ void __launch_bounds__(NT) topk_kernel(const unsigned long long* __restrict__ cand, int64_t cap,
                                                   const int* __restrict__ cnt, int64_t fixed_count, int nn,
                                                   const int* __restrict__ scatter, float* __restrict__ dists,
-                                                  int32_t* __restrict__ ids, int* __restrict__ status, int phase) {
+                                                  int32_t* __restrict__ ids, int* __restrict__ status, int phase,
+                                                  const int* __restrict__ worklist, const int* __restrict__ nwork) {
   extern __shared__ __align__(16) unsigned long long keys[];  // CAPK keys
   __shared__ int hist[256];
   __shared__ unsigned long long sh_prefix;
   __shared__ int sh_rank, sh_fill;
   const int tid = threadIdx.x;
-  const int q = blockIdx.x;
+  // without a worklist: one query per CTA (q = blockIdx.x); with one (phase 2): the flagged queries only,
+  // a few persistent CTAs instead of a launch of one mostly idle 128 KB CTA per query
+  const int nitems = worklist ? *nwork : (int)gridDim.x;
+  for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
+  const int q = worklist ? worklist[w] : w;
   const int64_t c = (fixed_count >= 0) ? fixed_count : (int64_t)cnt[q];
   const int qo = scatter ? scatter[q] : q;
   const int prior = (phase == 2) ? status[q] : ST_BIG;
-  __syncthreads();  // every thread has read the flag before thread 0 may overwrite it
-  if (prior != ST_BIG) return;
+  __syncthreads();  // flag read by every thread before thread 0 may overwrite it; shared memory of the previous item is free
+  if (prior != ST_BIG) continue;
   if (c < nn || c > cap) {
     if (tid == 0) status[q] = ST_REDO;
-    return;
+    continue;
   }
   if (phase == 1 && (c > CAPK || nn > CAPK)) {
     if (tid == 0) status[q] = ST_BIG;
-    return;
+    continue;
   }
   if (tid == 0) status[q] = ST_OK;
   const unsigned long long* src = cand + (size_t)q * cap;
@@ -475,6 +480,7 @@ __global__ void __launch_bounds__(NT) topk_kernel(const unsigned long long* __re
     dists[(size_t)qo * nn + j] = ordered_to_float((uint32_t)(k >> 32));
     ids[(size_t)qo * nn + j] = (int32_t)(uint32_t)(k & 0xFFFFFFFFull);
   }
+  }
 }
 
 // Phase-1 top-k for the common case (a few thousand candidates, nn <= SORTN): the bitonic sort of every
@@ -486,7 +492,8 @@ template <int CAPK, int SORTN, int NT>
 __global__ void __launch_bounds__(NT) topk_select_kernel(const unsigned long long* __restrict__ cand, int64_t cap,
                                                          const int* __restrict__ cnt, int nn,
                                                          float* __restrict__ dists, int32_t* __restrict__ ids,
-                                                         int* __restrict__ status) {
+                                                         int* __restrict__ status, int* __restrict__ biglist,
+                                                         int* __restrict__ nbig) {
   extern __shared__ __align__(16) unsigned long long sel_smem[];  // CAPK candidate keys, then SORTN survivors
   unsigned long long* keys = sel_smem;
   unsigned long long* out = sel_smem + CAPK;
@@ -501,7 +508,7 @@ __global__ void __launch_bounds__(NT) topk_select_kernel(const unsigned long lon
     return;
   }
   if (c64 > CAPK || nn > SORTN) {
-    if (tid == 0) status[q] = ST_BIG;
+    if (tid == 0) { status[q] = ST_BIG; biglist[atomicAdd(nbig, 1)] = q; }
     return;
   }
   if (tid == 0) status[q] = ST_OK;
@@ -687,11 +694,11 @@ static int scan_exhaustive(const ScanCtx& S, const float* dq, int nqc, const int
     // outputs of this batch: rows q0.. (or scattered)
     if (dscatter) {
       topk_kernel<SORT_CAP, 1024><<<nb, 1024, SORT_CAP * 8, S.st>>>(dcand.p, S.n, nullptr, S.n, S.nn, dscatter + q0,
-                                                                     S.ddists, S.dids, dstatus.p, 0);
+                                                                     S.ddists, S.dids, dstatus.p, 0, nullptr, nullptr);
     } else {
       topk_kernel<SORT_CAP, 1024><<<nb, 1024, SORT_CAP * 8, S.st>>>(dcand.p, S.n, nullptr, S.n, S.nn, nullptr,
                                                                      S.ddists + (size_t)q0 * S.nn,
-                                                                     S.dids + (size_t)q0 * S.nn, dstatus.p, 0);
+                                                                     S.dids + (size_t)q0 * S.nn, dstatus.p, 0, nullptr, nullptr);
     }
     LSQ_CUDA(cudaGetLastError());
   }
@@ -741,7 +748,8 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
   DevBuf<float> dlut, dtau;
   DevBuf<uint32_t> dsbuf;
   DevBuf<unsigned long long> dcand;
-  DevBuf<int> dcnt, dstatus;
+  DevBuf<int> dcnt, dstatus, dbig;  // dbig: worklist of the queries the select kernel flags + its length
+  LSQ_CUDA(dbig.alloc(qbatch + 1));
   LSQ_CUDA(dlut.alloc((size_t)max_tiles * m * LSQ_H * QT));
   LSQ_CUDA(dtau.alloc((size_t)max_tiles * 32));
   LSQ_CUDA(dsbuf.alloc((size_t)max_tiles * s * 32));
@@ -766,15 +774,16 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
     LSQ_CUDA(cudaGetLastError());
     // main pass
     LSQ_CUDA(cudaMemsetAsync(dcnt.p, 0, (size_t)nb * sizeof(int), st));
+    LSQ_CUDA(cudaMemsetAsync(dbig.p + qbatch, 0, sizeof(int), st));
     p.mode = MODE_MAIN; p.stride = 1; p.count = n;
     LSQ_TRY(launch_scan(m, p, ntiles, st));
     // most queries end up with a few thousand candidates and nn <= 1024: select + sort of the survivors
     // in 40 KB of shared memory (5 CTAs per SM); the 128 KB sorter only runs for the queries it flags
     topk_select_kernel<SEL_CAP, SEL_SORT, 256><<<nb, 256, (SEL_CAP + SEL_SORT) * 8, st>>>(
-        dcand.p, cap, dcnt.p, nn, ddists + (size_t)q0 * nn, dids + (size_t)q0 * nn, dstatus.p);
-    topk_kernel<SORT_CAP, 1024><<<nb, 1024, SORT_CAP * 8, st>>>(dcand.p, cap, dcnt.p, -1, nn, nullptr,
+        dcand.p, cap, dcnt.p, nn, ddists + (size_t)q0 * nn, dids + (size_t)q0 * nn, dstatus.p, dbig.p, dbig.p + qbatch);
+    topk_kernel<SORT_CAP, 1024><<<std::min(nb, LSQ_NUM_SMS_HINT), 1024, SORT_CAP * 8, st>>>(dcand.p, cap, dcnt.p, -1, nn, nullptr,
                                                                  ddists + (size_t)q0 * nn, dids + (size_t)q0 * nn,
-                                                                 dstatus.p, 2);
+                                                                 dstatus.p, 2, dbig.p, dbig.p + qbatch);
     LSQ_CUDA(cudaGetLastError());
     LSQ_CUDA(cudaMemcpyAsync(hstatus.data(), dstatus.p, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, st));
     LSQ_CUDA(cudaStreamSynchronize(st));
