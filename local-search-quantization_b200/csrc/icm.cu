@@ -57,7 +57,9 @@ __device__ __forceinline__ float warp_veccost(const float* __restrict__ x, const
 
 // Cache policy note (measured, 1 M x 16 iterations): default caching for both the unary rows and the
 // pair-table columns = 136 ms; table columns with L1::no_allocate = 159 ms; unary rows with
-// L1::no_allocate = 147 ms.  Plain __ldg everywhere.
+// L1::no_allocate = 147 ms.  Later (104.8 ms baseline): unary rows with L1::evict_last = no change, table
+// columns additionally L1::evict_first = +23 %; a RUN-TIME switch between such load flavours costs 20 ms
+// by itself (the volatile asm loads stop ptxas from batching the 16 loads of a visit).  Plain __ldg everywhere.
 __device__ __forceinline__ void add4(float4& a, const float4 g) {
   a.x = __fadd_rn(a.x, g.x); a.y = __fadd_rn(a.y, g.y); a.z = __fadd_rn(a.z, g.z); a.w = __fadd_rn(a.w, g.w);
 }
