@@ -185,18 +185,44 @@ static int run_encode_job(const EncodeJob& J) {
   for (int i = 0; i < J.total_iters; i++)
     if (snap_of[i] >= 0) snap_used[snap_of[i]] = 1;
   std::vector<double> obj_sum(J.nr > 0 ? J.nr : 1, 0.0);
+  // a snapshot slot no iteration maps to (duplicate or zero iteration count) stays all-zero, like the
+  // reference's preallocated Bs entries; every other slot is fully overwritten, so it is not touched here
+  // (zeroing 16 MB of fresh host pages costs ~4 ms per million vectors)
+  for (int r = 0; r < J.nr; r++)
+    if (!snap_used[r] && J.Bs) memset(J.Bs + (size_t)r * J.n * J.m, 0, (size_t)J.n * J.m * sizeof(int16_t));
 
   // chunking: at least nsplits splitarray parts (encode_icm_cuda.jl:272), more if memory demands, and
   // a few parts for large inputs so that the copies of part i+1 overlap the kernels of part i
   const int64_t cap = unary_chunk_capacity(m, d) / 2;  // two slots
   int nparts = J.nsplits > 1 ? J.nsplits : 1;
-  // measured on B200, 1 M vectors: 1 part 165.6 ms, 2: 158.0, 4: 151.3, 8: 149.7 (resident-data step: 148.4)
-  int pipe_parts = (int)std::min<int64_t>(8, n / 32768);
-  if (const char* e = getenv("LSQ_B200_PIPELINE_PARTS")) pipe_parts = std::max(1, atoi(e));
-  if (n >= 262144 && nparts < pipe_parts) nparts = pipe_parts;
-  while (ceil_div(n, nparts) > cap) nparts++;
-  if (n == 0) nparts = 1;
-  const int64_t maxchunk = ceil_div(n, nparts) + 1;
+  // Pipeline schedule.  Equal parts (measured on B200, 1 M vectors, static ICM split: 1 part 165.6 ms,
+  // 2: 158.0, 4: 151.3, 8: 149.7, resident-data step 148.4) expose the first part's H2D copy and pay one
+  // kernel tail + launch gap per part; with the dynamic ICM split the resident step dropped to 117 ms while
+  // 8 equal parts stayed at 128 ms.  A GEOMETRIC schedule (each part twice the previous one) exposes only
+  // the copy of a small first part and needs half as many launches: part i+1's copy still hides behind
+  // part i's kernels because copying a vector is ~12x cheaper than encoding it.
+  // LSQ_B200_PIPELINE_PARTS=k forces k equal parts (k = 1: no pipelining).
+  std::vector<int64_t> cuts;  // part p = [cuts[p], cuts[p+1])
+  const char* pe = getenv("LSQ_B200_PIPELINE_PARTS");
+  bool geometric = (pe == nullptr) && n >= 262144 && nparts <= 4 && (n * 8 / 15 + 1) <= cap;
+  if (geometric) {
+    cuts = {0, n / 15, n / 15 + 2 * n / 15, n / 15 + 2 * n / 15 + 4 * n / 15, n};
+    nparts = 4;
+  } else {
+    int pipe_parts = (int)std::min<int64_t>(8, n / 32768);
+    if (pe) pipe_parts = std::max(1, atoi(pe));
+    if (n >= 262144 && nparts < pipe_parts) nparts = pipe_parts;
+    while (ceil_div(n, nparts) > cap) nparts++;
+    if (n == 0) nparts = 1;
+    for (int part = 0; part <= nparts; part++) {
+      int64_t lo = n, hi = n;
+      if (part < nparts) lsq_splitarray(n, nparts, part, &lo, &hi);
+      cuts.push_back(lo);
+    }
+  }
+  int64_t maxchunk = 1;
+  for (int part = 0; part < nparts; part++) maxchunk = std::max(maxchunk, cuts[part + 1] - cuts[part]);
+  maxchunk += 1;
   const int nslots = nparts > 1 ? 2 : 1;
 
   // the sliced layout is decided once for the job (all chunks have the same size up to one vector)
@@ -245,8 +271,7 @@ static int run_encode_job(const EncodeJob& J) {
   };
 
   for (int part = 0; part < nparts; part++) {
-    int64_t lo, hi;
-    lsq_splitarray(n, nparts, part, &lo, &hi);
+    const int64_t lo = cuts[part], hi = cuts[part + 1];
     const int64_t nc = hi - lo;
     if (nc <= 0) continue;
     EncodeSlot& S = slots[part % nslots];
@@ -562,7 +587,7 @@ int lsq_encode_icm_cuda(const float* RX, int d, int64_t n, const int16_t* B, con
   J.seed = seed; J.g0 = g0; J.ils_iter0 = 0; J.total_iters = (int)maxit;
   J.ilsiters = ilsiters; J.nr = nr; J.Bs = Bs; J.objs = objs;
   J.nsplits = nsplits; J.verbose = verbose;
-  if (Bs) memset(Bs, 0, (size_t)nr * n * m * sizeof(int16_t));
+  // (snapshots that no iteration fills are zeroed in run_encode_job; the others are fully overwritten)
   return run_encode_job(J);
 }
 
