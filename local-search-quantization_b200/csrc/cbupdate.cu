@@ -102,16 +102,22 @@ __global__ void __launch_bounds__(256) cg_init_kernel(const double* __restrict__
   if (threadIdx.x == 0) { rs[c] = tot; rs0[c] = tot; done[c] = (tot == 0.0) ? 1 : 0; }
 }
 
-// APt[c][r] = sum_k Pt[c][k] * G[k][r]   (G symmetric).  Tile 32 (c) x 64 (r), K step 16.
+// APt[z][c][r] = sum_{k in slice z} Pt[c][k] * G[k][r]   (G symmetric).  Tile 32 (c) x 64 (r), K step 16.
+// The K range is split over gridDim.z CTAs (the 2048 x 128 output alone gives only 128 tiles, fewer than
+// SMs, each looping over all of K: latency-bound); cg_step_kernel adds the partial products in slice
+// order, so the result does not depend on scheduling.
+constexpr int CG_KSPLIT = 4;
 __global__ void __launch_bounds__(256) cg_gemm_kernel(const double* __restrict__ G, const double* __restrict__ Pt,
-                                                      int mh, int d, double* __restrict__ APt) {
+                                                      int mh, int d, double* __restrict__ APt_all) {
   __shared__ double Ps[16][32 + 1];
   __shared__ double Gs[16][64];
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;  // tx: 4 r's, ty: 2 c's
   const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
   double acc[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-  for (int k0 = 0; k0 < mh; k0 += 16) {
+  const int kslice = mh / (int)gridDim.z;
+  double* APt = APt_all + (size_t)blockIdx.z * mh * d;
+  for (int k0 = (int)blockIdx.z * kslice; k0 < ((int)blockIdx.z + 1) * kslice; k0 += 16) {
     {  // Pt tile: 32 c x 16 k
       const int cc = tid >> 4, kk = tid & 15;
       for (int h = 0; h < 2; h++) {
@@ -148,7 +154,8 @@ __global__ void __launch_bounds__(256) cg_gemm_kernel(const double* __restrict__
 // one CTA per right-hand side: step sizes, updates, convergence flag
 __global__ void __launch_bounds__(256) cg_step_kernel(int mh, double tol2, double* __restrict__ Xt,
                                                       double* __restrict__ Rt, double* __restrict__ Pt,
-                                                      const double* __restrict__ APt, double* __restrict__ rs,
+                                                      double* __restrict__ APt, int ksplit, int d,
+                                                      double* __restrict__ rs,
                                                       const double* __restrict__ rs0, int* __restrict__ done) {
   __shared__ double sm[256];
   const int c = blockIdx.x;
@@ -156,7 +163,13 @@ __global__ void __launch_bounds__(256) cg_step_kernel(int mh, double tol2, doubl
   double* x = Xt + (size_t)c * mh;
   double* r = Rt + (size_t)c * mh;
   double* p = Pt + (size_t)c * mh;
-  const double* ap = APt + (size_t)c * mh;
+  double* ap = APt + (size_t)c * mh;
+  // fold the K slices of the product in slice order (deterministic)
+  for (int i = threadIdx.x; i < mh; i += 256) {
+    double t = ap[i];
+    for (int z = 1; z < ksplit; z++) t += ap[(size_t)z * mh * d + i];
+    ap[i] = t;
+  }
   double acc = 0.0;
   for (int i = threadIdx.x; i < mh; i += 256) acc += p[i] * ap[i];
   const double pAp = block_sum_256(acc, sm);
@@ -199,18 +212,19 @@ int cb_solve(const double* dGram, const double* dRhs, int m, int d, float* dCout
   LSQ_CUDA(Xt.alloc((size_t)mh * d));
   LSQ_CUDA(Rt.alloc((size_t)mh * d));
   LSQ_CUDA(Pt.alloc((size_t)mh * d));
-  LSQ_CUDA(APt.alloc((size_t)mh * d));
+  const int ksplit = (mh % (16 * CG_KSPLIT) == 0) ? CG_KSPLIT : 1;
+  LSQ_CUDA(APt.alloc((size_t)ksplit * mh * d));
   LSQ_CUDA(rs.alloc(d));
   LSQ_CUDA(rs0.alloc(d));
   LSQ_CUDA(done.alloc(d));
   cg_init_kernel<<<d, 256, 0, st>>>(dRhs, mh, d, Xt.p, Rt.p, Pt.p, rs.p, rs0.p, done.p);
   LSQ_CUDA(cudaGetLastError());
   std::vector<int> hdone(d);
-  dim3 ggrid(mh / 64, (unsigned)ceil_div(d, 32), 1);
+  dim3 ggrid(mh / 64, (unsigned)ceil_div(d, 32), ksplit);
   int it = 0;
   for (; it < max_iter; it++) {
     cg_gemm_kernel<<<ggrid, 256, 0, st>>>(dGram, Pt.p, mh, d, APt.p);
-    cg_step_kernel<<<d, 256, 0, st>>>(mh, tol * tol, Xt.p, Rt.p, Pt.p, APt.p, rs.p, rs0.p, done.p);
+    cg_step_kernel<<<d, 256, 0, st>>>(mh, tol * tol, Xt.p, Rt.p, Pt.p, APt.p, ksplit, d, rs.p, rs0.p, done.p);
     if ((it & 15) == 15) {
       LSQ_CUDA(cudaMemcpyAsync(hdone.data(), done.p, (size_t)d * sizeof(int), cudaMemcpyDeviceToHost, st));
       LSQ_CUDA(cudaStreamSynchronize(st));
