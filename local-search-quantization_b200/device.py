@@ -103,3 +103,26 @@ def linscan(codes, queries, codebooks, dbnorms, nn, lut_kind=0, subdim=0):
                                          _ptr(dbnorms), int(lut_kind), int(subdim), int(nn), _ptr(dists), _ptr(ids),
                                          _stream()))
     return dists, ids
+
+
+def viterbi(X, C):
+    """Chain (ChainQ) encoder with device tensors: builds the tables and unaries, runs the DP
+    (encode_chain.jl:95-127); returns uint8 0-based codes (n, m).  The unary buffer is scratch."""
+    n, d = X.shape
+    m = C.shape[0]
+    L = api.lib()
+    T = torch.empty(L.lsq_dev_tables_bytes(m) // 4, dtype=torch.float32, device=X.device)
+    U = torch.empty((m, n, 256), dtype=torch.float32, device=X.device)
+    codes = torch.empty((n, m), dtype=torch.uint8, device=X.device)
+    api._check(L.lsq_dev_build_tables(_ptr(C), d, m, _ptr(T), None, _stream()))
+    api._check(L.lsq_dev_build_unaries(_ptr(X), d, ct.c_int64(n), _ptr(C), m, _ptr(U), 0, _stream()))
+    api._check(L.lsq_dev_viterbi(_ptr(U), ct.c_int64(n), m, _ptr(T), _ptr(codes), _stream()))
+    return codes
+
+
+def eval_recall(ids_gnd, ids_predicted, k):
+    """recall@1..k (float64 device tensor) from int32 device tensors: ground truth (nq,), ranked ids (nq, >= k)."""
+    nq, ld = ids_predicted.shape
+    out = torch.empty(k, dtype=torch.float64, device=ids_predicted.device)
+    api._check(api.lib().lsq_dev_eval_recall(_ptr(ids_gnd), _ptr(ids_predicted), nq, ld, int(k), _ptr(out), _stream()))
+    return out

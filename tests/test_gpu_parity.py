@@ -530,3 +530,16 @@ def test_encoding_viterbi_errors(gpu):
     with pytest.raises(gpu.LsqError):
         gpu.encoding_viterbi(X, C[:1])          # a chain needs two nodes
     assert gpu.encoding_viterbi(X[:0], C).shape == (0, 2)
+
+
+def test_device_api_viterbi_and_recall(gpu, oracle):
+    """lsq_dev_viterbi / lsq_dev_eval_recall on torch-owned device buffers == the host-pointer calls."""
+    import torch
+    X, C, B = make_problem(3400, 5000, 32, 6)
+    codes = gpu.device.viterbi(torch.from_numpy(X).cuda(), torch.from_numpy(C).cuda())
+    assert np.array_equal(codes.cpu().numpy().astype(np.int16) + 1, gpu.encoding_viterbi(X, C))
+    rng = np.random.default_rng(0)
+    pred = np.stack([rng.permutation(2000)[:100] for _ in range(64)]).astype(np.int32)
+    gt = pred[np.arange(64), rng.integers(0, 100, 64)].astype(np.int32)
+    r = gpu.device.eval_recall(torch.from_numpy(gt).cuda(), torch.from_numpy(pred).cuda(), 100)
+    assert np.array_equal(r.cpu().numpy(), oracle.eval_recall(gt, pred, 100))
