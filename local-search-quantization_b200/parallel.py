@@ -53,19 +53,36 @@ def global_mean(local_sum, local_count, device=None):
 
 def gather_codes(codes):
     """All shards' codes, concatenated in rank order, on every rank (shards may differ by one row)."""
+    if codes.dtype == torch.int16 and world()[1] > 1:  # gloo has no int16 collectives
+        return gather_rows(codes.to(torch.int32)).to(torch.int16)
+    return gather_rows(codes)
+
+
+def gather_rows(t):
+    """Concatenate per-rank row blocks (shards may differ by one row) in rank order on every rank."""
     _, size = world()
     if size == 1:
-        return codes
-    if codes.dtype == torch.int16:  # gloo has no int16 collectives
-        return gather_codes(codes.to(torch.int32)).to(torch.int16)
-    counts = [torch.zeros(1, dtype=torch.int64, device=codes.device) for _ in range(size)]
-    dist.all_gather(counts, torch.tensor([codes.shape[0]], dtype=torch.int64, device=codes.device))
+        return t
+    counts = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(size)]
+    dist.all_gather(counts, torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device))
     nmax = int(max(int(c) for c in counts))
-    pad = torch.zeros((nmax,) + tuple(codes.shape[1:]), dtype=codes.dtype, device=codes.device)
-    pad[: codes.shape[0]] = codes
+    pad = torch.zeros((nmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[: t.shape[0]] = t
     parts = [torch.empty_like(pad) for _ in range(size)]
     dist.all_gather(parts, pad)
     return torch.cat([p[: int(c)] for p, c in zip(parts, counts)])
+
+
+def linscan_sharded(queries, scan_fn, gather=True):
+    """ADC scan over several GPUs by QUERY partitioning: codes, norms and codebooks are
+    replicated (12-20 MB per million vectors), every rank scans its contiguous `splitarray` slice of the
+    queries with `scan_fn(queries_slice) -> (dists, ids)`, and the per-query results are disjoint, so no
+    merge is needed — only an optional all-gather of the (nq, nn) outputs."""
+    lo, hi = shard_bounds(queries.shape[0])
+    dists, ids = scan_fn(queries[lo:hi])
+    if not gather:
+        return dists, ids, (lo, hi)
+    return gather_rows(dists), gather_rows(ids), (lo, hi)
 
 
 def update_codebooks_sharded(X, codes, m, stats_fn=None, solve_fn=None):

@@ -54,6 +54,16 @@ def _worker(rank, size, port, out):
         cost = oracle.veccost(X[lo:hi], whole[lo:hi], Cs)
         q = par.global_mean(float(cost.astype(np.float64).sum()), hi - lo)
         assert abs(q - oracle.qerror(X, whole, Cs)) <= 1e-9 * q
+        # --- linscan: queries partitioned, codes replicated, no merge ---
+        from util import make_scan_problem
+        codes, queries, codebooks, norms = make_scan_problem(9, 3000, 11, 16, 4)
+        def scan(qs):
+            dd, ii = oracle.linscan_lsq(codes, qs, codebooks, norms, 20)
+            return torch.from_numpy(dd), torch.from_numpy(ii)
+        dd, ii, (qlo, qhi) = par.linscan_sharded(queries, scan)
+        dw, iw = oracle.linscan_lsq(codes, queries, codebooks, norms, 20)
+        assert (qlo, qhi) == oracle.splitarray(11, size)[rank]
+        assert np.array_equal(ii.numpy(), iw) and np.array_equal(dd.numpy(), dw)
         out[rank] = "ok"
     except Exception as e:  # pragma: no cover
         import traceback

@@ -27,6 +27,11 @@ lo, hi = par.shard_bounds(n)
 Xs = torch.from_numpy(X[lo:hi]).cuda(); cs = torch.from_numpy((B[lo:hi] - 1).astype(np.uint8)).cuda()
 C1, codes, obj = par.train_lsq_sharded(Xs, cs, torch.from_numpy(C).cuda(), 2, 3, 4, True, 4, seed=9, g0=lo)
 allc = par.gather_codes(codes).cpu().numpy()
+# linscan by query partitioning: replicated codes, disjoint outputs, all-gather over NCCL
+from util import make_scan_problem
+sc, sq, scb, sn = make_scan_problem(78, 50000, 37, 64, 8)
+dc, dcb, dn = torch.from_numpy(sc).cuda(), torch.from_numpy(scb).cuda(), torch.from_numpy(sn).cuda()
+sd, si, _ = par.linscan_sharded(torch.from_numpy(sq).cuda(), lambda qs: dev.linscan(dc, qs.contiguous(), dcb, dn, 100))
 if rank == 0:
     # single-process reference run of the same loop through the host API
     Bc, Cc = B.copy(), C
@@ -36,7 +41,9 @@ if rank == 0:
             Bc = lsq_b200.encoding_icm(X, Bc, Cc, 4, True, 4, seed=9, ils_iter=3 * it + i)
     same = np.array_equal(allc.astype(np.int16) + 1, Bc)
     q = lsq_b200.qerror(X, Bc, Cc)
-    print("RESULT", same, abs(obj[-1] - q) / q, obj.tolist())
+    wd, wi = dev.linscan(dc, torch.from_numpy(sq).cuda(), dcb, dn, 100)
+    scan_same = bool(torch.equal(wd, sd) and torch.equal(wi, si))
+    print("RESULT", same, abs(obj[-1] - q) / q, scan_same, obj.tolist())
 dist.destroy_process_group()
 '''
 
@@ -58,3 +65,4 @@ def test_two_gpu_training_matches_single():
     # compared exactly, and would differ only if that last-bit noise flipped an argmin
     assert float(parts[2]) < 1e-5
     assert parts[1] == "True"
+    assert parts[3] == "True"   # sharded scan == single-GPU scan, bit for bit
