@@ -19,7 +19,7 @@ enum { EPI_UNARY = 0, EPI_BINARY = 1 };
 // out[z][r][a] = epi( sum_k A_z[a][k] * B_z[r][k] ),  a < 256, r < R
 //   A_z = Abase + az(z) * 256*d        B_z = Bbase + bz(z) * R*d (binary) / Bbase (unary)
 template <int EPI>
-__global__ void __launch_bounds__(256) gemm_tables_kernel(const float* __restrict__ Abase,
+__global__ void __launch_bounds__(256, 2) gemm_tables_kernel(const float* __restrict__ Abase,
                                                           const float* __restrict__ Bbase,
                                                           const float* __restrict__ norms, float* __restrict__ out,
                                                           int64_t R, int d, int m, int sliced, int64_t Rs) {
@@ -53,6 +53,23 @@ __global__ void __launch_bounds__(256) gemm_tables_kernel(const float* __restric
     for (int j = 0; j < 8; j++) acc[i][j] = 0.0f;
 
   const bool vec_ok = (d % 4 == 0);
+  // register-staged prefetch (vector path): the global loads of K tile t+1 are issued before the FMAs of
+  // tile t, so their latency hides behind 16 x 64 FMAs per thread instead of sitting between two barriers
+  float4 pa[2], pb[2];
+  auto fetch = [&](int kk) {
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const int row = (tid >> 2) + 64 * i;
+      const int k4 = (tid & 3) * 4;
+      pa[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      pb[i] = pa[i];
+      if (kk + k4 < d) {
+        pa[i] = *reinterpret_cast<const float4*>(A + (size_t)(a0 + row) * d + kk + k4);
+        if (r0 + row < R) pb[i] = *reinterpret_cast<const float4*>(B + (size_t)(r0 + row) * d + kk + k4);
+      }
+    }
+  };
+  if (vec_ok) fetch(0);
   for (int kk = 0; kk < d; kk += TK) {
     // stage A[a0..a0+127][kk..kk+15] and B[r0..r0+127][kk..kk+15], transposed to k-major
     if (vec_ok) {
@@ -60,13 +77,8 @@ __global__ void __launch_bounds__(256) gemm_tables_kernel(const float* __restric
       for (int i = 0; i < 2; i++) {
         const int row = (tid >> 2) + 64 * i;
         const int k4 = (tid & 3) * 4;
-        float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-        if (kk + k4 < d) {
-          va = *reinterpret_cast<const float4*>(A + (size_t)(a0 + row) * d + kk + k4);
-          if (r0 + row < R) vb = *reinterpret_cast<const float4*>(B + (size_t)(r0 + row) * d + kk + k4);
-        }
-        As[k4 + 0][row] = va.x; As[k4 + 1][row] = va.y; As[k4 + 2][row] = va.z; As[k4 + 3][row] = va.w;
-        Bs[k4 + 0][row] = vb.x; Bs[k4 + 1][row] = vb.y; Bs[k4 + 2][row] = vb.z; Bs[k4 + 3][row] = vb.w;
+        As[k4 + 0][row] = pa[i].x; As[k4 + 1][row] = pa[i].y; As[k4 + 2][row] = pa[i].z; As[k4 + 3][row] = pa[i].w;
+        Bs[k4 + 0][row] = pb[i].x; Bs[k4 + 1][row] = pb[i].y; Bs[k4 + 2][row] = pb[i].z; Bs[k4 + 3][row] = pb[i].w;
       }
     } else {
       for (int e = tid; e < TM * TK; e += 256) {
@@ -81,6 +93,7 @@ __global__ void __launch_bounds__(256) gemm_tables_kernel(const float* __restric
       }
     }
     __syncthreads();
+    if (vec_ok && kk + TK < d) fetch(kk + TK);
 #pragma unroll
     for (int k = 0; k < TK; k++) {
       const float4 a_lo = *reinterpret_cast<const float4*>(&As[k][tx * 4]);
