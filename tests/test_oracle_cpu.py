@@ -214,6 +214,17 @@ def test_argument_errors_without_gpu(lsq):
         lsq.encoding_icm(X, np.ones((4, 17), np.int16), np.zeros((17, 256, 8), np.float32), 1, True, 1)
     with pytest.raises(TypeError):
         lsq.encoding_icm(X, B.astype(np.int32), C, 1, True, 1)
+    # the entry points added for SURVEY §8(f): train_lsq, chain encoder, norm codebook, eval_recall
+    with pytest.raises(lsq.LsqError, match="npert"):
+        lsq.train_lsq(X, 2, 256, None, B, None, 1, 1, 1, True, 3)
+    with pytest.raises(lsq.LsqError, match="h must be 256"):
+        lsq.train_lsq(X, 2, 128, None, B, None, 1, 1, 1, True, 1)
+    with pytest.raises(lsq.LsqError, match="chain needs two nodes"):
+        lsq.encoding_viterbi(X, C[:1])
+    with pytest.raises(lsq.LsqError, match="kmeans1d"):
+        lsq.kmeans1d(np.zeros(0, np.float32), 4)
+    with pytest.raises(lsq.LsqError, match="eval_recall"):
+        lsq.eval_recall(np.arange(3), np.zeros((3, 5), np.int32), 9)      # k > row length
 
 
 def test_no_cpu_fallback(lsq):
@@ -225,6 +236,12 @@ def test_no_cpu_fallback(lsq):
         lsq.encoding_icm(X, B, C, 1, True, 1)
     with pytest.raises(lsq.LsqError, match="no CUDA device"):
         lsq.update_codebooks(X, B, 256)
+    with pytest.raises(lsq.LsqError, match="no CUDA device"):
+        lsq.train_lsq(X, 2, 256, None, B, None, 1, 1, 1, True, 1)
+    with pytest.raises(lsq.LsqError, match="no CUDA device"):
+        lsq.encoding_viterbi(X, C)
+    with pytest.raises(lsq.LsqError, match="no CUDA device"):
+        lsq.eval_recall(np.arange(3), np.zeros((3, 5), np.int32), 5)
 
 
 def test_product_never_imports_oracle():
