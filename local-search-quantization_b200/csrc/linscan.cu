@@ -624,7 +624,7 @@ static int launch_scan(int m, const ScanParams& p, int ntiles, cudaStream_t st) 
   // 2 slices = 4.84 waves -> 5, 3.2 % idle; 7 slices = 16.93 -> 17, 0.4 %), slices of at least 4096 steps.
   const size_t smem = (size_t)m * LSQ_H * tile_queries(m) * 4 + 16;
   const int64_t slots = (int64_t)LSQ_NUM_SMS_HINT * std::max<int64_t>(1, (int64_t)(227 * 1024) / (int64_t)(smem + 1024));
-  const int64_t max_split = std::max<int64_t>(1, std::min<int64_t>(32, p.count / 4096));
+  const int64_t max_split = std::max<int64_t>(1, std::min<int64_t>(1024, p.count / 4096));  // few tiles (small query batches): up to one slice per SM slot
   int nsplit = 1;
   double best = 1e30;
   const double staging = 6000.0 / ((double)std::max<int64_t>(p.count, 1) * m);  // LUT load vs one CTA scanning everything
