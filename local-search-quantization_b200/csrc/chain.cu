@@ -344,6 +344,7 @@ int lsq_encoding_viterbi(const float* X, int d, int64_t n, const float* C, int m
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
   int64_t chunk = (int64_t)(0.5 * (double)free_b / ((double)m * LSQ_H * 4 + (double)d * 4 + 3.0 * m));
   chunk = std::max<int64_t>(1024, std::min<int64_t>(chunk, n));
+  if (const char* ce = getenv("LSQ_B200_CHUNK_VECTORS")) chunk = std::max<int64_t>(1, std::min<int64_t>(atoll(ce), n));  // tests
   LSQ_CUDA(dX.alloc((size_t)chunk * d));
   LSQ_CUDA(dC.alloc((size_t)m * LSQ_H * d));
   LSQ_CUDA(dnorms.alloc((size_t)m * LSQ_H));

@@ -396,9 +396,9 @@ __device__ __forceinline__ void bitonic_sort_smem(unsigned long long* keys, int 
   }
 }
 
-// CAPK = keys the CTA's shared-memory sorter holds, NT = threads.  phase 0: handle every query;
-// phase 1 (small sorter, several CTAs per SM): handle queries with <= CAPK candidates, flag the rest
-// ST_BIG; phase 2 (big sorter): only the flagged ones.
+// CAPK = keys the CTA's shared-memory sorter holds, NT = threads.  phase 0 (exhaustive path): handle every
+// query; phase 2: only the queries topk_select_kernel flagged ST_BIG (more candidates or a larger nn than it
+// holds), taken from its worklist.
 template <int CAPK, int NT>
 __global__ void __launch_bounds__(NT) topk_kernel(const unsigned long long* __restrict__ cand, int64_t cap,
                                                   const int* __restrict__ cnt, int64_t fixed_count, int nn,
@@ -422,10 +422,6 @@ __global__ void __launch_bounds__(NT) topk_kernel(const unsigned long long* __re
   if (prior != ST_BIG) continue;
   if (c < nn || c > cap) {
     if (tid == 0) status[q] = ST_REDO;
-    continue;
-  }
-  if (phase == 1 && (c > CAPK || nn > CAPK)) {
-    if (tid == 0) status[q] = ST_BIG;
     continue;
   }
   if (tid == 0) status[q] = ST_OK;

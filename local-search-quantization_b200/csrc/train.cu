@@ -307,6 +307,7 @@ int lsq_train_lsq(const float* X, int d, int64_t n, int m, int h, const float* R
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
   int64_t chunk = (int64_t)(0.6 * (double)free_b / ((double)m * LSQ_H * 4));
   chunk = std::max<int64_t>(1024, std::min<int64_t>(chunk, n));
+  if (const char* ce = getenv("LSQ_B200_CHUNK_VECTORS")) chunk = std::max<int64_t>(1, std::min<int64_t>(atoll(ce), n));  // tests
   LSQ_CUDA(dU.alloc((size_t)chunk * mh));
 
   TrainCtx T;

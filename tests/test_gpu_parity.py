@@ -543,3 +543,17 @@ def test_device_api_viterbi_and_recall(gpu, oracle):
     gt = pred[np.arange(64), rng.integers(0, 100, 64)].astype(np.int32)
     r = gpu.device.eval_recall(torch.from_numpy(gt).cuda(), torch.from_numpy(pred).cuda(), 100)
     assert np.array_equal(r.cpu().numpy(), oracle.eval_recall(gt, pred, 100))
+
+
+def test_memory_bounded_chunking_does_not_change_results(gpu, monkeypatch):
+    """train_lsq and encoding_viterbi walk the data in chunks when the unaries would not fit; the chunk size
+    is forced small here (LSQ_B200_CHUNK_VECTORS) and nothing may change: vectors are independent and the
+    perturbation stream is keyed by the global vector index."""
+    X, C, B = make_problem(3500, 7001, 32, 5)
+    ref_train = gpu.train_lsq(X, 5, 256, None, B, None, 2, 2, 3, True, 2, seed=8)
+    ref_vit = gpu.encoding_viterbi(X, C)
+    monkeypatch.setenv("LSQ_B200_CHUNK_VECTORS", "1234")
+    got = gpu.train_lsq(X, 5, 256, None, B, None, 2, 2, 3, True, 2, seed=8)
+    for a, b in zip(ref_train, got):
+        assert np.array_equal(a, b)
+    assert np.array_equal(gpu.encoding_viterbi(X, C), ref_vit)
