@@ -75,6 +75,10 @@ def cb_stats(X, codes, m, gram=None, rhs=None):
     """Accumulate the codebook-update statistics of one shard into float64 device tensors."""
     n, d = X.shape
     mh = m * 256
+    if gram is None and rhs is None:
+        # one buffer, Gram then Rhs: parallel.allreduce_stats reduces it with a single collective
+        flat = torch.zeros(mh * mh + mh * d, dtype=torch.float64, device=X.device)
+        gram, rhs = flat[: mh * mh].view(mh, mh), flat[mh * mh:].view(mh, d)
     if gram is None:
         gram = torch.zeros((mh, mh), dtype=torch.float64, device=X.device)
     if rhs is None:

@@ -34,11 +34,22 @@ def shard_bounds(n, size=None, rank=None):
 
 
 def allreduce_stats(gram, rhs):
-    """The one collective of the path: sum the codebook-update statistics over all ranks, in place."""
+    """The one collective of the path: sum the codebook-update statistics over all ranks, in place.
+    Gram and Rhs travel in ONE all-reduce: `device.cb_stats` allocates them back to back in one buffer,
+    which is then reduced as a whole; separately allocated tensors are packed into one buffer first."""
     _, size = world()
     if size > 1:
-        dist.all_reduce(gram, op=dist.ReduceOp.SUM)
-        dist.all_reduce(rhs, op=dist.ReduceOp.SUM)
+        adjacent = (gram.is_contiguous() and rhs.is_contiguous() and gram.dtype == rhs.dtype
+                    and gram.untyped_storage().data_ptr() == rhs.untyped_storage().data_ptr()
+                    and rhs.storage_offset() == gram.storage_offset() + gram.numel())
+        if adjacent:
+            flat = torch.as_strided(gram, (gram.numel() + rhs.numel(),), (1,), gram.storage_offset())
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        else:
+            flat = torch.cat([gram.reshape(-1), rhs.reshape(-1).to(gram.dtype)])
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            gram.copy_(flat[: gram.numel()].view_as(gram))
+            rhs.copy_(flat[gram.numel():].view_as(rhs).to(rhs.dtype))
     return gram, rhs
 
 
