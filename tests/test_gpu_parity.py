@@ -199,6 +199,8 @@ def _ref_or_oracle_pq(oracle, *a):
     (50000, 9, 64, 8, 10000),      # large k -> exhaustive path + radix select
     (5000, 70, 32, 4, 1),
     (300, 5, 16, 2, 300),          # nn == n
+    (40000, 21, 30, 8, 64),        # d % 4 != 0: scalar LUT build
+    (40000, 3, 128, 1, 10),        # a single codebook
 ])
 def test_linscan_lsq_exact(gpu, oracle, n, nq, d, m, nn):
     codes, queries, codebooks, norms = make_scan_problem(800 + m + nn, n, nq, d, m)
@@ -208,7 +210,8 @@ def test_linscan_lsq_exact(gpu, oracle, n, nq, d, m, nn):
     assert np.array_equal(dg, dr)
 
 
-@pytest.mark.parametrize("n,nq,d,m,nn", [(150000, 50, 128, 8, 1000), (40000, 20, 64, 16, 200), (2000, 3, 32, 8, 50)])
+@pytest.mark.parametrize("n,nq,d,m,nn", [(150000, 50, 128, 8, 1000), (40000, 20, 64, 16, 200), (2000, 3, 32, 8, 50),
+                                         (30000, 9, 32, 16, 100)])   # subdim = 2: scalar LUT build
 def test_linscan_pq_exact(gpu, oracle, n, nq, d, m, nn):
     codes, queries, codebooks, _ = make_scan_problem(900 + m, n, nq, d, m)
     centers = codebooks[:, : d // m].reshape(m, 256, d // m).copy()
