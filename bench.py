@@ -140,7 +140,7 @@ def cpu_port_rate(n_sample, ils_total, seed=1):
     from util import make_problem
     X, C, B = make_problem(seed, n_sample, D, M)
     B0 = (B - 1).astype(np.int16)
-    threads = oracle.num_threads()
+    threads = oracle.use_all_cores()   # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     oracle.encoding_icm(X[:256], B0[:256], C, ICMITER, True, NPERT, seed=seed, ils_iter=0, nworkers=threads)
     t0 = time.perf_counter()
     oracle.encoding_icm(X, B0, C, ICMITER, True, NPERT, seed=seed, ils_iter=0, nworkers=threads)

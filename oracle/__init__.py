@@ -58,6 +58,14 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def use_all_cores():
+    """Make the oracle use every core this process may run on, whatever OMP_NUM_THREADS says (torchrun sets
+    it to 1 in its workers).  -> the thread count."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
+
+
 def philox(ctr, key):
     out = np.zeros(4, np.uint32)
     lib().orc_philox4x32_10(_p(np.asarray(ctr, np.uint32)), _p(np.asarray(key, np.uint32)), _p(out))

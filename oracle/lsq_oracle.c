@@ -555,6 +555,16 @@ void orc_encoding_viterbi(const float* X, const float* C, int64_t n, int m, int 
   free(norms);
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline legs of bench.py ask for all host
+ * cores explicitly so that the reference arm is not handicapped under N > 1 launches. */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n >= 1) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
