@@ -560,3 +560,20 @@ def test_memory_bounded_chunking_does_not_change_results(gpu, monkeypatch):
     for a, b in zip(ref_train, got):
         assert np.array_equal(a, b)
     assert np.array_equal(gpu.encoding_viterbi(X, C), ref_vit)
+
+
+def test_c_level_dropin_against_reference_so(gpu, oracle, tmp_path):
+    """examples/dropin_linscan.c: a plain C program dlopen()s liblsq_b200.so and the reference's own
+    linscan .so, calls the SAME symbol with the SAME arguments in both, and compares the outputs bit for bit
+    — the drop-in boundary exercised without Python or Julia in between."""
+    import shutil
+    import subprocess
+    if not oracle.ref_available() or shutil.which("gcc") is None:
+        pytest.skip("needs oracle/_ref (built from the reference) and gcc")
+    root = os.path.dirname(HERE)
+    exe = str(tmp_path / "dropin_linscan")
+    subprocess.run(["gcc", "-O2", "-o", exe, os.path.join(root, "examples", "dropin_linscan.c"), "-ldl"], check=True)
+    r = subprocess.run([exe, gpu.lib_path(), os.path.join(root, "oracle", "_ref", "linscan_aqd_pairwise_byte.so")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ids identical, distances identical" in r.stdout
