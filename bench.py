@@ -175,8 +175,201 @@ def run_reference(args):
     }))
 
 
-def main():
+
+# ----------------------------------------------------------------------------------------------------
+# Secondary workloads (python bench.py --workload adc|chain|legacy ...): they live in this file because
+# their CPU legs run the oracle / the reference's own binaries, which only bench.py and tests/ may do.
+# benchmarks/bench_adc.py, bench_chain.py and legacy_kernel.py are thin shims onto these.
+# ----------------------------------------------------------------------------------------------------
+# ADC linear scan (BASELINE configs[4]): n base codes x nq queries, top-nn.  Reports queries/s, the effective
+# scan bandwidth nq*n*(m+4)/t against the measured HBM peak (an *effective* figure — the
+# query-tiled kernel re-serves the code array from L2), the LUT lookup rate against the shared-memory bound
+# 148 SMs x 32 banks x f_SM, and the reference's own C++ (oracle/_ref, OpenMP) on a query subsample.
+def run_adc(argv):
     ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--nq", type=int, default=10_000)
+    ap.add_argument("--nn", type=int, default=1000)
+    ap.add_argument("--m", type=int, nargs="+", default=[8, 16])
+    ap.add_argument("--d", type=int, default=128)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--cpu-queries", type=int, default=64)
+    ap.add_argument("--check-queries", type=int, default=16)
+    args = ap.parse_args(argv)
+    import torch
+    import lsq_b200
+    from lsq_b200 import device as dev
+    import oracle
+    from util import make_scan_problem
+    lsq_b200.init(0)
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+    for m in args.m:
+        codes, queries, codebooks, norms = make_scan_problem(50 + m, args.n, args.nq, args.d, m)
+        dc, dq = torch.from_numpy(codes).cuda(), torch.from_numpy(queries).cuda()
+        dcb, dn = torch.from_numpy(codebooks).cuda(), torch.from_numpy(norms).cuda()
+        for _ in range(2):
+            dd, di = dev.linscan(dc, dq, dcb, dn, args.nn)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.reps):
+            dd, di = dev.linscan(dc, dq, dcb, dn, args.nn)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / args.reps
+        # exactness spot check against the reference .so (or the oracle restatement)
+        k = args.check_queries
+        fn = oracle.ref_linscan_lsq if oracle.ref_available() else oracle.linscan_lsq
+        t0 = time.perf_counter()
+        dr, ir = fn(codes, queries[: args.cpu_queries], codebooks, norms, args.nn)
+        cpu_s = time.perf_counter() - t0
+        exact = bool(np.array_equal(ir[:k], di[:k].cpu().numpy()) and np.array_equal(dr[:k], dd[:k].cpu().numpy()))
+        eff = args.nq * args.n * (m + 4) / (ms * 1e-3) / 1e9
+        lookups = args.nq * args.n * m / (ms * 1e-3)
+        print(json.dumps({
+            "metric": "adc_scan_queries_per_sec", "value": args.nq / (ms * 1e-3), "unit": "queries/s", "m": m,
+            "n": args.n, "nq": args.nq, "nn": args.nn, "ms": ms, "exact_vs_reference": exact,
+            "effective_scan_GBps": eff, "effective_frac_of_hbm_peak": eff / peak,
+            "lookups_per_s": lookups, "lookup_frac_of_smem_bound": lookups / (148 * 32 * 1.965e9),
+            "cpu_baseline": {"kind": "reference" if oracle.ref_available() else "port", "cores": oracle.num_threads(),
+                             "queries_per_s": args.cpu_queries / cpu_s,
+                             "sample": f"{args.cpu_queries} queries x {args.n} codes"},
+        }))
+
+
+# Chain (Viterbi / ChainQ) encoder: resident-data timing of the kernel, the whole host call, and the CPU
+# oracle on a subsample.  (m-1)*65536 candidate transitions per vector, one FADD + one FMNMX each: bound by
+# the ALU pipe (one FMNMX per 2 cycles per SM sub-partition).
+def run_chain(argv):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--m", type=int, nargs="+", default=[8])
+    ap.add_argument("--d", type=int, default=128)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--cpu-n", type=int, default=4000)
+    args = ap.parse_args(argv)
+    import ctypes as ct
+    import torch
+    import lsq_b200
+    import oracle
+    from util import make_problem
+    lsq_b200.init(0)
+    L = lsq_b200.lib()
+    for m in args.m:
+        X, C, _ = make_problem(60 + m, args.n, args.d, m)
+        dX, dC = torch.from_numpy(X).cuda(), torch.from_numpy(C).cuda()
+        dU = torch.empty((m, args.n, 256), dtype=torch.float32, device="cuda")
+        dT = torch.empty((m, m, 256, 256), dtype=torch.float32, device="cuda")
+        codes = torch.empty((args.n, m), dtype=torch.uint8, device="cuda")
+        st = ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+        P = lambda t: ct.c_void_p(t.data_ptr())
+        assert L.lsq_dev_build_tables(P(dC), args.d, m, P(dT), None, st) == 0
+        # lsq_dev_viterbi consumes dU (forward messages overwrite it in place): rebuild it before every run
+        # and time only the chain kernel
+        ms = 0.0
+        for rep in range(args.reps + 1):
+            assert L.lsq_dev_build_unaries(P(dX), args.d, ct.c_int64(args.n), P(dC), m, P(dU), 0, st) == 0
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            assert L.lsq_dev_viterbi(P(dU), ct.c_int64(args.n), m, P(dT), P(codes), st) == 0
+            b.record()
+            torch.cuda.synchronize()
+            if rep > 0:
+                ms += a.elapsed_time(b) / args.reps
+        t0 = time.perf_counter()
+        Bh = lsq_b200.encoding_viterbi(X, C)
+        host_s = time.perf_counter() - t0
+        same = bool(np.array_equal(Bh, codes.cpu().numpy().astype(np.int16) + 1))
+        t0 = time.perf_counter()
+        Bo = oracle.encoding_viterbi(X[: args.cpu_n], C)
+        cpu_s = time.perf_counter() - t0
+        exact = bool(np.array_equal(Bo + 1, Bh[: args.cpu_n]))
+        pairs = args.n * (m - 1) * 65536
+        print(json.dumps({
+            "metric": "viterbi_encode_vectors_per_sec", "value": args.n / (ms * 1e-3), "unit": "vectors/s", "m": m,
+            "n": args.n, "kernel_ms": ms, "host_call_s": host_s, "host_equals_device": same, "exact_vs_oracle": exact,
+            "pairs_per_s": pairs / (ms * 1e-3), "alu_pipe_frac_at_2_cycles_per_pair": pairs / 32 * 2 / (ms * 1e-3) / (148 * 4 * 1.965e9),
+            "cpu_baseline": {"kind": "port", "cores": oracle.num_threads(), "vectors_per_s": args.cpu_n / cpu_s,
+                             "sample": f"{args.cpu_n} vectors"},
+        }))
+
+
+# The reference's own GPU kernel on the same B200: src/encodings/cuda/cudautils.cu compiled UNMODIFIED for
+# sm_100a (oracle/Makefile -> oracle/_ref/cudautils_sm100a.cubin) and launched as encode_icm_cuda.jl:158-186
+# launches it, with the pair tables already resident and without its per-visit H2D upload / host sync /
+# perturb / veccost: a generous lower bound on its time.  A timing baseline only, not an oracle.
+def run_legacy(argv, n=1_000_000, m=8, d=128, ils=16, icmiter=4):
+    import torch
+    from cuda.bindings import driver as cu
+    import lsq_b200 as L
+    from lsq_b200 import device as dev
+    from util import make_problem, sift_like
+    cubin = os.path.join(ROOT, "oracle", "_ref", "cudautils_sm100a.cubin")
+    if not os.path.exists(cubin):
+        print(json.dumps({"legacy_kernel": "unavailable", "why": "oracle/_ref/cudautils_sm100a.cubin not built"}))
+        return
+    L.init(0)
+    torch.cuda.init()
+    _, C_h, _ = make_problem(0, 16, d, m)
+    rng = np.random.default_rng(1000)
+    X = torch.from_numpy(sift_like(rng, n, d)).cuda()
+    C = torch.from_numpy(C_h).cuda()
+    codes = torch.from_numpy(rng.integers(0, 256, size=(n, m)).astype(np.uint8)).cuda()
+    sess = dev.EncodeSession(X, C, codes.clone(), sliced=0)
+    torch.cuda.synchronize()
+    # --- ours: the ILS kernel alone ---
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sess.ils(ils, icmiter, 4, True, seed=1)
+    sess.codes.copy_(codes); sess.refresh_cost()
+    a.record(); sess.ils(ils, icmiter, 4, True, seed=1); b.record(); torch.cuda.synchronize()
+    ours_ms = a.elapsed_time(b)
+    # --- legacy: condition_icm3 per node visit ---
+    err, mod = cu.cuModuleLoad(cubin.encode())
+    assert err == cu.CUresult.CUDA_SUCCESS, err
+    err, fn = cu.cuModuleGetFunction(mod, b"condition_icm3")
+    assert err == cu.CUresult.CUDA_SUCCESS, err
+    T = sess.T.view(m, m, 256, 256)
+    bbs = [torch.cat([T[k, l] for l in range(m) if l != k]).contiguous() for k in range(m)]  # cat(2, bbs...)
+    codes_soa = codes.t().contiguous()  # d_codek[i_idx + n*i]
+    U = sess.U  # [m][n][256]
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def visit(k):
+        args = [ct.c_void_p(U[k].data_ptr()), ct.c_void_p(bbs[k].data_ptr()), ct.c_void_p(codes_soa.data_ptr()),
+                ct.c_int(k), ct.c_int(m), ct.c_int(n)]
+        arr = (ct.c_void_p * len(args))(*[ct.cast(ct.pointer(x), ct.c_void_p) for x in args])
+        (e,) = cu.cuLaunchKernel(fn, n, 1, 1, 1, 256, 1, 0, stream, ct.addressof(arr), 0)
+        assert e == cu.CUresult.CUDA_SUCCESS, e
+
+    orders = [L.make_to_look(1, i, m, True) for i in range(ils)]
+    for k in range(m):
+        visit(k)
+    torch.cuda.synchronize()
+    a.record()
+    for i in range(ils):
+        for _ in range(icmiter):
+            for k in orders[i]:
+                visit(int(k))
+    b.record(); torch.cuda.synchronize()
+    legacy_ms = a.elapsed_time(b)
+    print(json.dumps({
+        "workload": f"n={n} m={m} d={d}, {ils} ILS iterations x icmiter={icmiter}",
+        "lsq_b200_icm_kernel_ms": ours_ms,
+        "legacy_condition_icm3_ms": legacy_ms, "legacy_launches": ils * icmiter * m,
+        "legacy_note": "tables pre-resident, no perturb/veccost/H2D/sync (generous to the legacy path)",
+        "speedup_kernel_only": legacy_ms / ours_ms,
+    }))
+
+
+def main():
+    pre = argparse.ArgumentParser(add_help=False)
+    pre.add_argument("--workload", default="icm", choices=["icm", "adc", "chain", "legacy"])
+    ns, rest = pre.parse_known_args()
+    if ns.workload != "icm":
+        return {"adc": run_adc, "chain": run_chain, "legacy": run_legacy}[ns.workload](rest)
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="icm", help="icm (headline, default) | adc | chain | legacy")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
