@@ -300,6 +300,7 @@ def run_chain(argv):
 # launches it, with the pair tables already resident and without its per-visit H2D upload / host sync /
 # perturb / veccost: a generous lower bound on its time.  A timing baseline only, not an oracle.
 def run_legacy(argv, n=1_000_000, m=8, d=128, ils=16, icmiter=4):
+    import ctypes as ct
     import torch
     from cuda.bindings import driver as cu
     import lsq_b200 as L
