@@ -577,3 +577,41 @@ def test_c_level_dropin_against_reference_so(gpu, oracle, tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "ids identical, distances identical" in r.stdout
+
+
+def test_edge_cases_empty_and_degenerate(gpu, oracle):
+    """Empty / degenerate inputs across the boundary: nothing to scan, nothing to return, zero outer
+    iterations, snapshot slots that no iteration fills (they must come back zeroed even if the caller's
+    buffer held garbage, like the reference's preallocated Bs)."""
+    import ctypes as ct
+    codes, queries, codebooks, norms = make_scan_problem(9, 5000, 4, 16, 4)
+    R = np.eye(16, dtype=np.float32)
+    d0, i0 = gpu.linscan_lsq(codes, queries[:0], codebooks.reshape(4, 256, 16), norms, R, 10)
+    assert d0.shape == (0, 10) and i0.shape == (0, 10)
+    d0, i0 = gpu.linscan_lsq(codes, queries, codebooks.reshape(4, 256, 16), norms, R, 0)
+    assert d0.shape == (4, 0)
+    with pytest.raises(gpu.LsqError, match="nn"):
+        gpu.linscan_lsq(codes[:5], queries, codebooks.reshape(4, 256, 16), norms[:5], R, 6)   # nn > ncodes
+    # train_lsq with zero outer iterations: initial codebook update + ilsiter encodes only
+    X, C, B = make_problem(3600, 800, 16, 3)
+    Ct, Bt, cbn, Bn, obj = gpu.train_lsq(X, 3, 256, None, B, None, 0, 2, 2, True, 2, seed=3)
+    assert obj.shape == (0,) and Bt.min() >= 1 and Bt.max() <= 256
+    Cc = gpu.update_codebooks(X, B, 256)
+    Bc = B
+    for i in range(2):
+        Bc = gpu.encoding_icm(X, Bc, Cc, 2, True, 2, seed=3, ils_iter=i)
+    assert np.array_equal(Bt, Bc) and np.array_equal(Ct, Cc)
+    # snapshots: [2, 2, 0] -> the first slot holds iteration 2, the duplicate and the zero stay all-zero
+    n, m = X.shape[0], 3
+    its = np.array([2, 2, 0], np.int64)
+    Bs = np.full((3, n, m), 12345, np.int16)          # garbage the library must not leave behind
+    objs = np.full(3, -1.0, np.float32)
+    P = lambda a: a.ctypes.data_as(ct.c_void_p)
+    rc = gpu.lib().lsq_encode_icm_cuda(P(X), 16, ct.c_int64(n), P(B), P(np.ascontiguousarray(C)), m, 256, P(its), 3, 2, 2, 1, 1,
+                                       ct.c_uint64(3), ct.c_uint64(0), P(Bs), P(objs), 0)
+    assert rc == 0
+    ref, _ = gpu.encode_icm_cuda(X, B, C, [2], 2, 2, True, 1, seed=3)
+    assert np.array_equal(Bs[0], ref[0]) and not Bs[1].any() and not Bs[2].any()
+    assert objs[0] > 0 and objs[1] == 0 and objs[2] == 0
+    # eval_recall at k = 1
+    assert np.array_equal(gpu.eval_recall(np.array([5, 6]), np.array([[5, 1], [2, 6]]), 1), oracle.eval_recall([5, 6], np.array([[5, 1], [2, 6]]), 1))
