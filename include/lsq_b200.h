@@ -35,6 +35,16 @@ extern "C" {
 /* ---- runtime (replaces CudaUtilsModule.init / finit, cudaUtilsModule.jl:37-43, and the
  *      CuDevice(0)/CuContext of encode_icm_cuda.jl:59-64) ------------------------------------------ */
 int lsq_init(int device);
+/* Binds SEVERAL GPUs of one box (devices == NULL or n <= 0: all visible ones).  The reference is hard-wired to
+ * device 0 (encode_icm_cuda.jl:59-64); here the calls that shard naturally — lsq_encoding_icm[_sched],
+ * lsq_encode_icm_cuda, lsq_update_codebooks, lsq_train_lsq, and the linscan symbols (by queries) — split their
+ * input over the bound devices by the splitarray rule (utils.jl:152-177), one internal worker thread per
+ * device, from the single calling thread; results are bit-identical for any number of devices.  The only
+ * collective is the all-reduce of the codebook-update statistics (NCCL, bound with dlopen at first use; a
+ * peer-memory reduction kernel when NCCL is absent or LSQ_B200_ALLREDUCE=p2p).  devices[0] is the primary
+ * device: every other host-pointer call runs there. */
+int lsq_init_devices(const int* devices, int n);
+int lsq_num_bound_devices(void);
 int lsq_finalize(void);
 const char* lsq_last_error(void);
 int lsq_device_count(void);
@@ -172,13 +182,33 @@ int lsq_dev_veccost(const float* dX, int d, int64_t n, const uint8_t* dcodes, co
  *   dsnap    : NULL or uint8 [nsnap][n][m]; dsnapcost: NULL or float [nsnap][n];
  *              snap_of_iter (HOST int32[niters], -1 = none) says which snapshot slot receives the
  *              accepted codes (and their costs) after each iteration. */
+/* Measurement hook: every later ICM launch of the calling thread adds the number of node visits it actually
+ * executed to *dcounter (device memory; NULL switches it off).  The kernel skips visits whose outcome is
+ * already known, so the count is data dependent (nominal: n * niters * icmiter * m). */
+int lsq_dev_icm_visit_counter(unsigned long long* dcounter);
 int lsq_dev_icm_ils(const float* dX, int d, int64_t n, const float* dC, int m, const float* dU,
                     const float* dT, const float* dTs, int sliced, uint8_t* dcodes, float* dcost, int icmiter, int npert,
                     const int8_t* orders, const uint8_t* dslots, const uint8_t* dvals, uint64_t seed,
                     uint32_t ils_iter0, int niters, uint64_t g0, uint8_t* dsnap, float* dsnapcost,
                     const int32_t* snap_of_iter, void* stream);
-/* codebook-update statistics of one shard: Gram[mh][mh] += co-occurrence counts (float64),
- * Rhs[mh][d] += per-code sums of X (float64).  Sum over shards (ncclAllReduce), then solve. */
+/* Codebook-update statistics (codebook_update.jl:8-46 in normal-equation form), EXACT and order-independent:
+ * one int64 buffer S[mh*mh + mh*d] (mh = m*256): co-occurrence counts, then per-code sums of x in fixed
+ * point, x rounded once to rint(x * 2^scale_exp).  Integer sums do not depend on thread order, chunking or
+ * sharding, so summing the S of several shards (ONE all-reduce of int64) gives bit-identical codebooks for
+ * any number of GPUs.  scale_exp = lsq_cb_scale_exp(max|x| over ALL shards, total vector count) keeps every
+ * sum below 2^62; max|x| comes from lsq_dev_absmax (it only changes when X changes, not per iteration).
+ *   lsq_dev_absmax        *dmax = max(*dmax, max|x|) over `count` floats (zero *dmax first)
+ *   lsq_dev_cb_accumulate S += this shard (zero S once per update)
+ *   lsq_dev_cb_finalize   summed S -> Gram[mh][mh], Rhs[mh][d] (float64) for lsq_dev_cb_solve
+ *   lsq_dev_cb_stats      single-shard convenience: absmax + accumulate + finalize; OVERWRITES Gram / Rhs
+ *                         (synchronises the stream once to read max|x|) */
+int64_t lsq_cb_stats_len(int m, int d);
+int lsq_cb_scale_exp(float absmax, int64_t n_total);
+int lsq_dev_absmax(const float* dX, int64_t count, float* dmax, void* stream);
+int lsq_dev_cb_accumulate(const float* dX, int d, int64_t n, const uint8_t* dcodes, int m, int scale_exp,
+                          int64_t* dstats, void* stream);
+int lsq_dev_cb_finalize(const int64_t* dstats, int m, int d, int scale_exp, double* dGram, double* dRhs,
+                        void* stream);
 int lsq_dev_cb_stats(const float* dX, int d, int64_t n, const uint8_t* dcodes, int m, double* dGram,
                      double* dRhs, void* stream);
 /* min-norm solve of Gram * K = Rhs by conjugate gradients from K0 = 0; dCout float [m][256][d]. */

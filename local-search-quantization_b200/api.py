@@ -5,9 +5,9 @@ import os
 import numpy as np
 
 __all__ = [
-    "LsqError", "lib", "lib_path", "have_library", "init", "finalize", "device_count", "version",
+    "LsqError", "lib", "lib_path", "have_library", "init", "init_devices", "num_bound_devices", "finalize", "device_count", "version",
     "splitarray", "make_to_look", "make_perturb", "get_unaries", "get_binaries", "veccost", "qerror",
-    "reconstruct", "quantize_norms", "encoding_icm", "encoding_icm_sched", "encode_icm_cuda",
+    "reconstruct", "quantize_norms", "encoding_icm", "reset_ils_counter", "encoding_icm_sched", "encode_icm_cuda",
     "update_codebooks", "linscan_lsq", "linscan_pq", "linscan_opq", "eval_recall", "randinit", "train_lsq",
     "kmeans1d", "encoding_viterbi",
     "EXPORTED_SYMBOLS",
@@ -19,13 +19,15 @@ _lib = None
 
 # every symbol include/lsq_b200.h declares (tests check the .so exports exactly these)
 EXPORTED_SYMBOLS = [
-    "lsq_init", "lsq_finalize", "lsq_last_error", "lsq_device_count", "lsq_version", "lsq_splitarray",
+    "lsq_init", "lsq_init_devices", "lsq_num_bound_devices", "lsq_finalize", "lsq_last_error", "lsq_device_count", "lsq_version", "lsq_splitarray",
     "lsq_make_to_look", "lsq_make_perturb", "lsq_get_unaries", "lsq_get_binaries", "lsq_veccost",
     "lsq_qerror", "lsq_reconstruct", "lsq_encoding_icm", "lsq_encoding_icm_sched", "lsq_encode_icm_cuda",
     "lsq_update_codebooks", "linscan_aqd_query_extra_byte", "linscan_aqd_query", "lsq_linscan_lsq",
     "lsq_linscan_pq", "lsq_quantize_norms", "lsq_dev_tables_bytes", "lsq_dev_sliced_tables_bytes",
     "lsq_dev_icm_layout", "lsq_dev_build_tables",
-    "lsq_dev_build_unaries", "lsq_dev_build_unaries_tc", "lsq_dev_veccost", "lsq_dev_icm_ils", "lsq_dev_cb_stats", "lsq_dev_cb_solve",
+    "lsq_dev_build_unaries", "lsq_dev_build_unaries_tc", "lsq_dev_veccost", "lsq_dev_icm_ils", "lsq_dev_icm_visit_counter",
+    "lsq_cb_stats_len", "lsq_cb_scale_exp", "lsq_dev_absmax", "lsq_dev_cb_accumulate", "lsq_dev_cb_finalize",
+    "lsq_dev_cb_stats", "lsq_dev_cb_solve",
     "lsq_dev_linscan", "lsq_train_lsq", "lsq_kmeans1d", "lsq_eval_recall", "lsq_dev_eval_recall",
     "lsq_encoding_viterbi", "lsq_dev_viterbi",
 ]
@@ -59,6 +61,7 @@ def lib():
         L.lsq_version.restype = ct.c_char_p
         L.lsq_dev_tables_bytes.restype = ct.c_int64
         L.lsq_dev_sliced_tables_bytes.restype = ct.c_int64
+        L.lsq_cb_stats_len.restype = ct.c_int64
         L.linscan_aqd_query_extra_byte.restype = None
         L.linscan_aqd_query.restype = None
         _lib = L
@@ -98,6 +101,21 @@ def _codes16(B, n=None):
 def init(device=0):
     """CudaUtilsModule.init (cudaUtilsModule.jl:41-43) equivalent."""
     _check(lib().lsq_init(int(device)))
+
+
+def init_devices(devices=None):
+    """Bind several GPUs of the box (None = all visible): encode / update_codebooks / train_lsq / linscan calls
+    then shard over them inside the library (the reference hard-codes device 0, encode_icm_cuda.jl:59-64)."""
+    if devices is None:
+        _check(lib().lsq_init_devices(None, 0))
+    else:
+        devs = np.ascontiguousarray(list(devices), np.int32)
+        _check(lib().lsq_init_devices(_p(devs), len(devs)))
+    return int(lib().lsq_num_bound_devices())
+
+
+def num_bound_devices():
+    return int(lib().lsq_num_bound_devices())
 
 
 def finalize():
@@ -204,12 +222,29 @@ def quantize_norms(B, C, cbnorms):
     return out
 
 
-def encoding_icm(X, oldB, C, niter, randord, npert, V=False, *, seed=0, ils_iter=0, g0=0):
+_ils_counter = 0
+
+
+def reset_ils_counter(value=0):
+    """Restart the implicit ILS-iteration counter of encoding_icm (see there)."""
+    global _ils_counter
+    _ils_counter = int(value)
+
+
+def encoding_icm(X, oldB, C, niter, randord, npert, V=False, *, seed=0, ils_iter=None, g0=0):
     """encode_icm.jl:131-189: one ILS iteration; returns the new (n, m) int16 1-based codes.
 
-    The reference draws its schedule from Julia's global RNG; here it is Philox(seed, ils_iter, global
-    vector index), so callers that loop (`for i = 1:ilsiter`, LSQ.jl:45-48) should pass ils_iter=i.
+    The reference draws its schedule from Julia's global RNG, so every call perturbs differently; here the
+    schedule is Philox(seed, ils_iter, global vector index).  With ils_iter=None (the default) the
+    iteration number comes from a module-level counter that advances on every call — like the Julia
+    overlay's LSQ_B200_COUNTER — so the reference loop `for i = 1:ilsiter; B = encoding_icm(...)`
+    (LSQ.jl:45-48, demo_lsq.jl:48-51) ported verbatim gets fresh perturbations each iteration.  Pass
+    ils_iter explicitly for reproducible / sharded runs.
     """
+    global _ils_counter
+    if ils_iter is None:
+        ils_iter = _ils_counter
+        _ils_counter += 1
     X, C, oldB = _f32(X), _codebooks(C), _codes16(oldB)
     n, d = X.shape
     m, h, _ = C.shape

@@ -11,69 +11,9 @@
 #include "icm.cuh"
 #include "linscan.cuh"
 #include "cbupdate.cuh"
+#include "runtime.cuh"
 
 namespace lsq {
-
-static thread_local std::string g_err;
-static std::mutex g_mu;
-static int g_device = -1;
-static cudaStream_t g_stream = nullptr;
-static cudaStream_t g_stream2 = nullptr;  // second slot of the encode pipeline
-
-void set_error(const std::string& msg) { g_err = msg; }
-
-// DevBuf allocations are ordered on the stream the current API call works on
-static thread_local cudaStream_t g_alloc_stream = nullptr;
-cudaStream_t alloc_stream() { return g_alloc_stream; }
-void set_alloc_stream(cudaStream_t st) { g_alloc_stream = st; }
-
-static void keep_pool_memory(int dev) {
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-    uint64_t never = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never);
-  }
-  cudaGetLastError();
-}
-
-int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
-  char buf[512];
-  snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
-  g_err = buf;
-  cudaGetLastError();  // clear sticky-free errors
-  return LSQ_ERR_CUDA;
-}
-
-// lazily bind a device + private stream for the host-pointer API
-static int ensure_init() {
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (g_device >= 0) {
-    LSQ_CUDA(cudaSetDevice(g_device));
-    return LSQ_OK;
-  }
-  int cnt = 0;
-  cudaError_t e = cudaGetDeviceCount(&cnt);
-  if (e != cudaSuccess || cnt == 0) {
-    cudaGetLastError();
-    set_error("no CUDA device available: liblsq_b200 has no CPU fallback");
-    return LSQ_ERR_CUDA;
-  }
-  int dev = 0;
-  cudaGetDevice(&dev);
-  LSQ_CUDA(cudaSetDevice(dev));
-  LSQ_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
-  LSQ_CUDA(cudaStreamCreateWithFlags(&g_stream2, cudaStreamNonBlocking));
-  keep_pool_memory(dev);
-  g_device = dev;
-  return LSQ_OK;
-}
-
-int host_ctx(cudaStream_t* st) {
-  LSQ_TRY(ensure_init());
-  *st = g_stream;
-  set_alloc_stream(g_stream);
-  return LSQ_OK;
-}
 
 static int check_encode_args(int d, int64_t n, int m, int h, int niter, int npert) {
   LSQ_CHECK_ARG(d >= 1, "d must be >= 1");
@@ -125,6 +65,8 @@ struct EncodeJob {
   int16_t* B_out;                 // final codes (may be null)
   const int64_t* ilsiters; int nr; int16_t* Bs; float* objs;  // snapshots (may be null/0)
   int nsplits; int verbose;
+  // sharding over the bound devices: this job covers vectors [off, off + n) of a set of n_total
+  int64_t n_total, off;
 };
 
 // Per-chunk device state of the encode pipeline.  Two slots alternate: while the GPU runs the ILS
@@ -162,9 +104,11 @@ static int slot_alloc(EncodeSlot& S, cudaStream_t st, int64_t maxchunk, int d, i
   return LSQ_OK;
 }
 
-static int run_encode_job(const EncodeJob& J) {
-  cudaStream_t st0;
-  LSQ_TRY(host_ctx(&st0));
+// One device's share of an encode call.  obj_sum[r] receives the float64 sum of the snapshot-r costs of this
+// shard (the caller adds the shards in order and divides by n_total).
+static int run_encode_job(const EncodeJob& J, int devidx, double* obj_sum) {
+  LSQ_TRY(rt_bind(devidx));
+  const cudaStream_t st0 = rt_ctx(devidx).st, st1 = rt_ctx(devidx).st2;
   const int d = J.d, m = J.m;
   const int64_t n = J.n;
 
@@ -184,12 +128,7 @@ static int run_encode_job(const EncodeJob& J) {
   std::vector<char> snap_used(J.nr > 0 ? J.nr : 1, 0);
   for (int i = 0; i < J.total_iters; i++)
     if (snap_of[i] >= 0) snap_used[snap_of[i]] = 1;
-  std::vector<double> obj_sum(J.nr > 0 ? J.nr : 1, 0.0);
-  // a snapshot slot no iteration maps to (duplicate or zero iteration count) stays all-zero, like the
-  // reference's preallocated Bs entries; every other slot is fully overwritten, so it is not touched here
-  // (zeroing 16 MB of fresh host pages costs ~4 ms per million vectors)
-  for (int r = 0; r < J.nr; r++)
-    if (!snap_used[r] && J.Bs) memset(J.Bs + (size_t)r * J.n * J.m, 0, (size_t)J.n * J.m * sizeof(int16_t));
+  for (int r = 0; r < J.nr; r++) obj_sum[r] = 0.0;
 
   // chunking: at least nsplits splitarray parts (encode_icm_cuda.jl:272), more if memory demands, and
   // a few parts for large inputs so that the copies of part i+1 overlap the kernels of part i
@@ -234,14 +173,22 @@ static int run_encode_job(const EncodeJob& J) {
   const char* um = getenv("LSQ_B200_UNARY");  // "tc": tensor-core unaries (fast mode, tolerance-checked)
   const bool unary_tc = (um != nullptr && strcmp(um, "tc") == 0 && !sliced && d % 8 == 0 && d <= 128);
 
-  cudaEvent_t ev_tables;
-  LSQ_CUDA(cudaEventCreateWithFlags(&ev_tables, cudaEventDisableTiming));
-  LSQ_CUDA(cudaEventRecord(ev_tables, st0));
+  int fin_err = 0;                                       // D2H targets of finish(): they must outlive `drain`
+  std::vector<double> fin_sums(J.nr > 0 ? J.nr : 1, 0.0);
   EncodeSlot slots[2];
+  // Declared after every device buffer of the job, so it is destroyed first: on ANY exit (also the error
+  // returns below) both streams are drained before a buffer is freed or a host output buffer is left behind
+  // with a copy still in flight.
+  struct Drain {
+    cudaStream_t a, b; cudaEvent_t ev = nullptr;
+    ~Drain() { cudaStreamSynchronize(a); cudaStreamSynchronize(b); if (ev) cudaEventDestroy(ev); cudaGetLastError(); }
+  } drain{st0, st1};
+  LSQ_CUDA(cudaEventCreateWithFlags(&drain.ev, cudaEventDisableTiming));
+  LSQ_CUDA(cudaEventRecord(drain.ev, st0));
   LSQ_TRY(slot_alloc(slots[0], st0, maxchunk, d, m, J.nr));
   if (nslots == 2) {
-    LSQ_TRY(slot_alloc(slots[1], g_stream2, maxchunk, d, m, J.nr));
-    LSQ_CUDA(cudaStreamWaitEvent(g_stream2, ev_tables, 0));
+    LSQ_TRY(slot_alloc(slots[1], st1, maxchunk, d, m, J.nr));
+    LSQ_CUDA(cudaStreamWaitEvent(st1, drain.ev, 0));
   }
   set_alloc_stream(st0);
 
@@ -249,17 +196,19 @@ static int run_encode_job(const EncodeJob& J) {
   // after the next chunk's work has been queued on the other stream)
   auto finish = [&](EncodeSlot& S) -> int {
     const int64_t lo = S.lo, nc = S.nc;
-    int herr = 0;
+    int& herr = fin_err;
+    std::vector<double>& sums = fin_sums;
+    herr = 0;
+    std::fill(sums.begin(), sums.end(), 0.0);
     LSQ_CUDA(cudaMemcpyAsync(&herr, S.derr.p, sizeof(int), cudaMemcpyDeviceToHost, S.st));
     if (J.B_out) {
       LSQ_TRY(launch_codes_u8_to_i16(S.dcodes.p, S.d16.p, nc * m, S.st));
       LSQ_CUDA(cudaMemcpyAsync(J.B_out + (size_t)lo * m, S.d16.p, (size_t)nc * m * sizeof(int16_t), cudaMemcpyDeviceToHost, S.st));
     }
-    std::vector<double> sums(J.nr > 0 ? J.nr : 1, 0.0);
     for (int r = 0; r < J.nr; r++) {
       if (!snap_used[r]) continue;
       LSQ_TRY(launch_codes_u8_to_i16(S.dsnap.p + (size_t)r * nc * m, S.d16.p, nc * m, S.st));
-      LSQ_CUDA(cudaMemcpyAsync(J.Bs + ((size_t)r * n + lo) * m, S.d16.p, (size_t)nc * m * sizeof(int16_t), cudaMemcpyDeviceToHost, S.st));
+      LSQ_CUDA(cudaMemcpyAsync(J.Bs + ((size_t)r * J.n_total + J.off + lo) * m, S.d16.p, (size_t)nc * m * sizeof(int16_t), cudaMemcpyDeviceToHost, S.st));
       LSQ_TRY(launch_sum_f32_to_f64(S.dsnapcost.p + (size_t)r * nc, nc, S.dsum.p + (size_t)r * 1025, S.st));
       LSQ_CUDA(cudaMemcpyAsync(&sums[r], S.dsum.p + (size_t)r * 1025, sizeof(double), cudaMemcpyDeviceToHost, S.st));
     }
@@ -279,8 +228,8 @@ static int run_encode_job(const EncodeJob& J) {
     cudaStream_t st = S.st;
     S.lo = lo; S.nc = nc;
     LSQ_CUDA(cudaMemsetAsync(S.derr.p, 0, sizeof(int), st));
-    LSQ_CUDA(cudaMemcpyAsync(S.dX.p, J.X + (size_t)lo * d, (size_t)nc * d * sizeof(float), cudaMemcpyHostToDevice, st));
-    LSQ_CUDA(cudaMemcpyAsync(S.d16.p, J.B_in + (size_t)lo * m, (size_t)nc * m * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    LSQ_TRY(rt_h2d(S.dX.p, J.X + (size_t)lo * d, (size_t)nc * d * sizeof(float), st));
+    LSQ_TRY(rt_h2d(S.d16.p, J.B_in + (size_t)lo * m, (size_t)nc * m * sizeof(int16_t), st));
     LSQ_TRY(launch_codes_i16_to_u8(S.d16.p, S.dcodes.p, nc * m, S.derr.p, st));
     if (unary_tc) LSQ_TRY(build_unaries_tc(S.dX.p, d, nc, dC.p, m, dnorms.p, S.dU.p, st));
     else LSQ_TRY(build_unaries(S.dX.p, d, nc, dC.p, m, dnorms.p, S.dU.p, sliced, st));
@@ -290,13 +239,9 @@ static int run_encode_job(const EncodeJob& J) {
 
     if (J.slots != nullptr && J.npert > 0) {
       // explicit perturbations: [n][npert] uint8 slots, int16 0-based values -> uint8
+      // (range-checked by lsq_encoding_icm_sched before anything was queued)
       std::vector<uint8_t> v8((size_t)nc * J.npert);
-      for (size_t i = 0; i < v8.size(); i++) {
-        const int16_t x = J.vals[(size_t)lo * J.npert + i];
-        LSQ_CHECK_ARG(x >= 0 && x < LSQ_H, "perturbation values must be 0-based in 0..255");
-        LSQ_CHECK_ARG(J.slots[(size_t)lo * J.npert + i] < m, "perturbation slots must be < m");
-        v8[i] = (uint8_t)x;
-      }
+      for (size_t i = 0; i < v8.size(); i++) v8[i] = (uint8_t)J.vals[(size_t)lo * J.npert + i];
       S.dslots.st = S.dvals.st = st;
       LSQ_CUDA(S.dslots.alloc(v8.size()));
       LSQ_CUDA(S.dvals.alloc(v8.size()));
@@ -336,10 +281,44 @@ static int run_encode_job(const EncodeJob& J) {
   for (int s = 0; s < nslots; s++)
     if (slots[s].busy) LSQ_TRY(finish(slots[s]));
   LSQ_CUDA(cudaStreamSynchronize(st0));
-  if (nslots == 2) LSQ_CUDA(cudaStreamSynchronize(g_stream2));
-  cudaEventDestroy(ev_tables);
+  if (nslots == 2) LSQ_CUDA(cudaStreamSynchronize(st1));
+  return LSQ_OK;
+}
+
+// Shards the job over the bound devices by the reference's splitarray rule (utils.jl:152-177), one worker
+// thread per device, no communication: the schedule is keyed by the global vector index, so the codes do
+// not depend on the number of devices.
+static int run_encode(EncodeJob J) {
+  LSQ_TRY(rt_ensure_init());
+  J.n_total = J.n; J.off = 0;
+  const int nr = J.nr > 0 ? J.nr : 1;
+  std::vector<char> snap_used(nr, 0);
+  for (int i = 1; i <= J.total_iters; i++)
+    for (int r = 0; r < J.nr; r++)
+      if (J.ilsiters[r] == i) { snap_used[r] = 1; break; }
+  // a snapshot slot no iteration maps to (duplicate or zero iteration count) stays all-zero, like the
+  // reference's preallocated Bs entries; every other slot is fully overwritten, so it is not touched here
+  // (zeroing 16 MB of fresh host pages costs ~4 ms per million vectors)
   for (int r = 0; r < J.nr; r++)
-    if (J.objs) J.objs[r] = snap_used[r] ? (float)(obj_sum[r] / (double)(n ? n : 1)) : 0.0f;
+    if (!snap_used[r] && J.Bs) memset(J.Bs + (size_t)r * J.n * J.m, 0, (size_t)J.n * J.m * sizeof(int16_t));
+  const int k = rt_devices_for(J.n, 4096);
+  std::vector<double> sums((size_t)k * nr, 0.0);
+  LSQ_TRY(rt_parallel(k, [&](int r) -> int {
+    EncodeJob S = J;
+    int64_t lo = 0, hi = J.n;
+    lsq_splitarray(J.n, k, r, &lo, &hi);
+    S.n = hi - lo; S.off = lo; S.g0 = J.g0 + (uint64_t)lo;
+    S.X = J.X + (size_t)lo * J.d;
+    S.B_in = J.B_in + (size_t)lo * J.m;
+    if (J.B_out) S.B_out = J.B_out + (size_t)lo * J.m;
+    if (J.slots) { S.slots = J.slots + (size_t)lo * J.npert; S.vals = J.vals + (size_t)lo * J.npert; }
+    return run_encode_job(S, r, sums.data() + (size_t)r * nr);
+  }));
+  for (int r = 0; r < J.nr; r++) {
+    double tot = 0.0;
+    for (int i = 0; i < k; i++) tot += sums[(size_t)i * nr + r];  // shard order: deterministic
+    if (J.objs) J.objs[r] = snap_used[r] ? (float)(tot / (double)(J.n ? J.n : 1)) : 0.0f;
+  }
   return LSQ_OK;
 }
 
@@ -348,51 +327,6 @@ static int run_encode_job(const EncodeJob& J) {
 using namespace lsq;
 
 extern "C" {
-
-int lsq_init(int device) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  int cnt = 0;
-  cudaError_t e = cudaGetDeviceCount(&cnt);
-  if (e != cudaSuccess || cnt == 0) {
-    cudaGetLastError();
-    set_error("no CUDA device available: liblsq_b200 has no CPU fallback");
-    return LSQ_ERR_CUDA;
-  }
-  LSQ_CHECK_ARG(device >= 0 && device < cnt, "device index out of range");
-  LSQ_CUDA(cudaSetDevice(device));
-  if (g_stream && g_device != device) {
-    cudaStreamDestroy(g_stream); g_stream = nullptr;
-    if (g_stream2) { cudaStreamDestroy(g_stream2); g_stream2 = nullptr; }
-  }
-  if (!g_stream) LSQ_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
-  if (!g_stream2) LSQ_CUDA(cudaStreamCreateWithFlags(&g_stream2, cudaStreamNonBlocking));
-  keep_pool_memory(device);
-  g_device = device;
-  return LSQ_OK;
-}
-
-int lsq_finalize(void) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (g_stream) { cudaStreamSynchronize(g_stream); cudaStreamDestroy(g_stream); g_stream = nullptr; }
-  if (g_stream2) { cudaStreamSynchronize(g_stream2); cudaStreamDestroy(g_stream2); g_stream2 = nullptr; }
-  if (g_device >= 0) {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, g_device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
-    cudaGetLastError();
-  }
-  g_device = -1;
-  return LSQ_OK;
-}
-
-const char* lsq_last_error(void) { return g_err.c_str(); }
-
-int lsq_device_count(void) {
-  int cnt = 0;
-  if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }
-  return cnt;
-}
-
-const char* lsq_version(void) { return "lsq_b200 0.1 (sm_100a)"; }
 
 int lsq_splitarray(int64_t n, int nparts, int p, int64_t* lo, int64_t* hi) {
   LSQ_CHECK_ARG(nparts >= 1 && p >= 0 && p < nparts && n >= 0, "splitarray: need 0 <= p < nparts, n >= 0");
@@ -546,7 +480,7 @@ int lsq_encoding_icm(const float* X, int d, int64_t n, const int16_t* oldB, int1
   J.icmiter = niter; J.npert = npert; J.randord = randord;
   J.seed = seed; J.g0 = g0; J.ils_iter0 = ils_iter; J.total_iters = 1;
   J.B_out = newB; J.nsplits = 1; J.verbose = verbose;
-  return run_encode_job(J);
+  return run_encode(J);
 }
 
 int lsq_encoding_icm_sched(const float* X, int d, int64_t n, const int16_t* oldB, int16_t* newB,
@@ -561,13 +495,17 @@ int lsq_encoding_icm_sched(const float* X, int d, int64_t n, const int16_t* oldB
     seen |= 1u << to_look[i];
   }
   LSQ_CHECK_ARG(seen == (m == 32 ? 0xFFFFFFFFu : ((1u << m) - 1)), "to_look must be a permutation");
+  for (int64_t i = 0; i < n * npert; i++) {  // before any work is queued (nothing to unwind on failure)
+    LSQ_CHECK_ARG(vals[i] >= 0 && vals[i] < LSQ_H, "perturbation values must be 0-based in 0..255");
+    LSQ_CHECK_ARG(slots[i] < m, "perturbation slots must be < m");
+  }
   EncodeJob J;
   memset(&J, 0, sizeof(J));
   J.X = X; J.d = d; J.n = n; J.B_in = oldB; J.C = C; J.m = m;
   J.icmiter = niter; J.npert = npert; J.randord = 0;
   J.total_iters = 1; J.to_look = to_look; J.slots = slots; J.vals = vals;
   J.B_out = newB; J.nsplits = 1; J.verbose = verbose;
-  return run_encode_job(J);
+  return run_encode(J);
 }
 
 int lsq_encode_icm_cuda(const float* RX, int d, int64_t n, const int16_t* B, const float* C, int m, int h,
@@ -588,7 +526,7 @@ int lsq_encode_icm_cuda(const float* RX, int d, int64_t n, const int16_t* B, con
   J.ilsiters = ilsiters; J.nr = nr; J.Bs = Bs; J.objs = objs;
   J.nsplits = nsplits; J.verbose = verbose;
   // (snapshots that no iteration fills are zeroed in run_encode_job; the others are fully overwritten)
-  return run_encode_job(J);
+  return run_encode(J);
 }
 
 // ---- device-pointer API ----------------------------------------------------------------------
@@ -634,6 +572,11 @@ int lsq_dev_veccost(const float* dX, int d, int64_t n, const uint8_t* dcodes, co
                     float* dcost, void* stream) {
   LSQ_TRY(check_encode_args(d, n, m, LSQ_H, 0, 0));
   return launch_veccost(dX, d, n, dcodes, dC, m, dcost, (cudaStream_t)stream);
+}
+
+int lsq_dev_icm_visit_counter(unsigned long long* dcounter) {
+  set_icm_visit_counter(dcounter);
+  return LSQ_OK;
 }
 
 int lsq_dev_icm_ils(const float* dX, int d, int64_t n, const float* dC, int m, const float* dU, const float* dT,

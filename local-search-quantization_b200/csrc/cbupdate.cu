@@ -4,28 +4,70 @@
 // one-hot matrix A (updatecb!, codebook_update.jl:8-46; sparsify_codes, utils.jl:50-69).  LSQR from
 // x0 = 0 is, analytically, conjugate gradients on the normal equations A'A k = A'x and converges to
 // the minimum-norm least-squares solution.  Here:
-//   cb_stats : ONE pass over the shard: Gram = A'A (integer co-occurrence counts, exact) and
-//              Rhs = A'X' (float64 sums).  HBM-bound: reads 4d + m bytes per vector.  These two
-//              matrices are the only thing a multi-GPU run has to all-reduce (one collective per outer
-//              iteration); everything after is independent of n.
+//   cb_accumulate : ONE pass over the shard: Gram = A'A (integer co-occurrence counts) and Rhs = A'X'
+//              (64-bit fixed-point sums), both EXACT integers in one int64 buffer.  HBM-bound: reads
+//              4d + m bytes per vector.  That buffer is the only thing a multi-GPU run has to all-reduce
+//              (one collective per outer iteration), and because integer sums do not depend on the
+//              order, the codebooks are bit-identical for any number of shards / GPUs.
+//   cb_finalize : the summed integers -> float64 Gram / Rhs.
 //   cb_solve : CG on Gram*K = Rhs from K0 = 0 in float64 for all d right-hand sides in lock-step
 //              (per-column step sizes), i.e. the same Krylov iteration LSQR performs, run to a far
 //              tighter tolerance than LSQR's sqrt(eps(Float32)).  Unused codes stay exactly zero, as
 //              in the reference (Appendix A.13 of SURVEY.md).
 #include "cbupdate.cuh"
 #include "icm.cuh"
+#include "runtime.cuh"
+
+#include <math.h>
 
 #include <algorithm>
-
+#include <atomic>
 #include <vector>
 
 namespace lsq {
 
-__global__ void __launch_bounds__(256) cb_stats_kernel(const float* __restrict__ X, int d, int64_t n,
-                                                       const uint8_t* __restrict__ codes, int m,
-                                                       int* __restrict__ cnt, double* __restrict__ rhs) {
+// ---- statistics: exact integer accumulation -------------------------------------------------------
+// Layout of the statistics buffer S (int64): S[0 .. mh*mh) = co-occurrence counts (the Gram matrix A'A),
+// S[mh*mh .. mh*(mh+d)) = per-code sums of x in FIXED POINT: every x is rounded once to q = rint(x * 2^e)
+// (e = scale exponent, chosen from max|x| and the total number of vectors so that no sum can overflow) and
+// the q are added as 64-bit integers.  Integer addition is associative, so the result is bit-identical for
+// any thread schedule, any chunking, and any number of shards / GPUs — which float64 atomics are not (their
+// last bit depends on the arrival order).  The one rounding per element is 2^-(62 - log2 n) relative to
+// max|x| (2^-42 at n = 1 M), far below the float32 codebooks the solve produces.
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ X, int64_t count, unsigned* __restrict__ out) {
+  unsigned mx = 0;  // |x| as raw bits: for non-negative floats the integer order is the float order (NaN sorts last)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    mx = max(mx, __float_as_uint(X[i]) & 0x7FFFFFFFu);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, off));
+  if ((threadIdx.x & 31) == 0 && mx != 0) atomicMax(out, mx);
+}
+
+int cb_absmax(const float* dX, int64_t count, float* dmax, cudaStream_t st) {
+  if (count == 0) return LSQ_OK;
+  const int64_t blocks = std::min<int64_t>(ceil_div(count, 256 * 8), (int64_t)LSQ_NUM_SMS_HINT * 8);
+  absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(dX, count, reinterpret_cast<unsigned*>(dmax));
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
+}
+
+// e with  n_total * max|x| * 2^e < 2^62
+int cb_scale_exp(float absmax, int64_t n_total) {
+  if (!(absmax > 0.0f) || !(absmax <= 3.4e38f)) return 0;  // all-zero, NaN or Inf data: any scale is as good
+  int ex = 0;
+  frexpf(absmax, &ex);  // absmax < 2^ex
+  int nb = 0;
+  while (((int64_t)1 << nb) < n_total && nb < 62) nb++;
+  return 62 - nb - ex;
+}
+
+__global__ void __launch_bounds__(256) cb_accumulate_kernel(const float* __restrict__ X, int d, int64_t n,
+                                                            const uint8_t* __restrict__ codes, int m, int scale_exp,
+                                                            unsigned long long* __restrict__ S) {
   const int lane = threadIdx.x & 31;
   const int mh = m * LSQ_H;
+  unsigned long long* cnt = S;
+  unsigned long long* acc = S + (size_t)mh * mh;
   const int64_t nwarps = (int64_t)gridDim.x * 8;
   for (int64_t v = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); v < n; v += nwarps) {
     const int mycode = (lane < m) ? (int)codes[v * m + lane] : 0;
@@ -35,36 +77,66 @@ __global__ void __launch_bounds__(256) cb_stats_kernel(const float* __restrict__
       const int i = (p < m * m) ? p / m : 0, j = (p < m * m) ? p % m : 0;
       const int bi = __shfl_sync(0xFFFFFFFFu, mycode, i);
       const int bj = __shfl_sync(0xFFFFFFFFu, mycode, j);
-      if (p < m * m) atomicAdd(&cnt[(size_t)(i * LSQ_H + bi) * mh + (j * LSQ_H + bj)], 1);
+      if (p < m * m) atomicAdd(&cnt[(size_t)(i * LSQ_H + bi) * mh + (j * LSQ_H + bj)], 1ull);
     }
-    // per-code sums of x
+    // per-code fixed-point sums of x
     const float* x = X + (size_t)v * d;
-    for (int i = 0; i < m; i++) {
-      const int row = i * LSQ_H + __shfl_sync(0xFFFFFFFFu, mycode, i);
-      double* dst = rhs + (size_t)row * d;
-      for (int t = lane; t < d; t += 32) atomicAdd(dst + t, (double)__ldg(x + t));
+    for (int t = lane; t < d; t += 32) {
+      const unsigned long long q = (unsigned long long)__double2ll_rn(scalbn((double)__ldg(x + t), scale_exp));
+      for (int i = 0; i < m; i++) {
+        const int row = i * LSQ_H + __shfl_sync(0xFFFFFFFFu, mycode, i);
+        atomicAdd(acc + (size_t)row * d + t, q);  // two's complement: unsigned add == signed add
+      }
     }
   }
 }
 
-__global__ void add_counts_kernel(const int* __restrict__ cnt, double* __restrict__ gram, int64_t count) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < count) gram[i] += (double)cnt[i];
+// Accumulates one shard into S (which the caller zeroes once per update).
+int cb_accumulate(const float* dX, int d, int64_t n, const uint8_t* dcodes, int m, int scale_exp, int64_t* dS,
+                  cudaStream_t st) {
+  if (n == 0) return LSQ_OK;
+  const int64_t blocks = std::min<int64_t>(ceil_div(n, 8), (int64_t)LSQ_NUM_SMS_HINT * 8);
+  cb_accumulate_kernel<<<(unsigned)blocks, 256, 0, st>>>(dX, d, n, dcodes, m, scale_exp,
+                                                         reinterpret_cast<unsigned long long*>(dS));
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
 }
 
+__global__ void cb_finalize_kernel(const int64_t* __restrict__ S, int64_t ngram, int64_t total, int scale_exp,
+                                   double* __restrict__ gram, double* __restrict__ rhs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  if (i < ngram) gram[i] = (double)S[i];
+  else rhs[i - ngram] = scalbn((double)S[i], -scale_exp);
+}
+
+// Gram[mh][mh] / Rhs[mh][d] (float64) from the (summed) statistics buffer.
+int cb_finalize(const int64_t* dS, int m, int d, int scale_exp, double* dGram, double* dRhs, cudaStream_t st) {
+  const int64_t mh = (int64_t)m * LSQ_H;
+  const int64_t total = mh * (mh + d);
+  cb_finalize_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(dS, mh * mh, total, scale_exp, dGram, dRhs);
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
+}
+
+// single-shard convenience: scale from this X alone
 int cb_stats(const float* dX, int d, int64_t n, const uint8_t* dcodes, int m, double* dGram, double* dRhs,
              cudaStream_t st) {
-  if (n == 0) return LSQ_OK;
   const int64_t mh = (int64_t)m * LSQ_H;
-  int* dcnt = nullptr;
-  LSQ_CUDA(cudaMallocAsync((void**)&dcnt, (size_t)mh * mh * sizeof(int), st));
-  LSQ_CUDA(cudaMemsetAsync(dcnt, 0, (size_t)mh * mh * sizeof(int), st));
-  const int64_t blocks = std::min<int64_t>(ceil_div(n, 8), (int64_t)LSQ_NUM_SMS_HINT * 8);
-  cb_stats_kernel<<<(unsigned)blocks, 256, 0, st>>>(dX, d, n, dcodes, m, dcnt, dRhs);
-  add_counts_kernel<<<(unsigned)ceil_div(mh * mh, 256), 256, 0, st>>>(dcnt, dGram, mh * mh);
-  cudaError_t e = cudaGetLastError();
-  cudaFreeAsync(dcnt, st);
-  LSQ_CUDA(e);
+  DevBuf<int64_t> dS;
+  DevBuf<float> dmax;
+  dS.st = dmax.st = st;
+  LSQ_CUDA(dS.alloc((size_t)(mh * (mh + d))));
+  LSQ_CUDA(dmax.alloc(1));
+  LSQ_CUDA(cudaMemsetAsync(dS.p, 0, (size_t)(mh * (mh + d)) * sizeof(int64_t), st));
+  LSQ_CUDA(cudaMemsetAsync(dmax.p, 0, sizeof(float), st));
+  LSQ_TRY(cb_absmax(dX, n * d, dmax.p, st));
+  float hmax = 0.0f;
+  LSQ_CUDA(cudaMemcpyAsync(&hmax, dmax.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+  LSQ_CUDA(cudaStreamSynchronize(st));
+  const int e = cb_scale_exp(hmax, n);
+  LSQ_TRY(cb_accumulate(dX, d, n, dcodes, m, e, dS.p, st));
+  LSQ_TRY(cb_finalize(dS.p, m, d, e, dGram, dRhs, st));
   return LSQ_OK;
 }
 
@@ -241,11 +313,120 @@ int cb_solve(const double* dGram, const double* dRhs, int m, int d, float* dCout
   return LSQ_OK;
 }
 
+// update_codebooks over the bound devices: splitarray shards of (X, B), local statistics, ONE all-reduce of
+// the integer statistics, solve on the primary device.
+static int update_codebooks_host(const float* X, int d, int64_t n, const int16_t* B, int m, int h, float* Cout,
+                                 int verbose) {
+  LSQ_TRY(rt_ensure_init());
+  const int64_t mh = (int64_t)m * h;
+  const size_t slen = (size_t)(mh * (mh + d));
+  const int k = rt_devices_for(n, 4096);
+  AllReduceGroup* grp = nullptr;
+  if (k > 1) {
+    grp = rt_allreduce_group(k);
+    if (grp == nullptr) return LSQ_ERR_CUDA;
+  }
+  PhaseSync sync(k);
+  HostBarrier& bar = sync.bar;
+  std::vector<float> hmax(k, 0.0f);
+  int scale_exp = 0;
+  auto phase_ok = [&](int rc) { return sync.ok(rc); };
+  return rt_parallel(k, [&](int r) -> int {
+    int rc = rt_bind(r);
+    cudaStream_t st = rt_ctx(r).st;
+    int64_t lo = 0, hi = n;
+    lsq_splitarray(n, k, r, &lo, &hi);
+    const int64_t nl = hi - lo;
+    DevBuf<float> dX, dC, dmax;
+    DevBuf<int16_t> d16;
+    DevBuf<uint8_t> dcodes;
+    DevBuf<int64_t> dS, dS2;
+    DevBuf<double> dG, dR;
+    DevBuf<int> derr;
+    int herr = 0;
+    auto stage1 = [&]() -> int {
+      LSQ_TRY(rc);
+      LSQ_CUDA(dX.alloc((size_t)nl * d));
+      LSQ_CUDA(d16.alloc((size_t)nl * m));
+      LSQ_CUDA(dcodes.alloc((size_t)nl * m));
+      LSQ_CUDA(dS.alloc(slen));
+      if (k > 1) LSQ_CUDA(dS2.alloc(slen));
+      LSQ_CUDA(dmax.alloc(1));
+      LSQ_CUDA(derr.alloc(1));
+      LSQ_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), st));
+      LSQ_CUDA(cudaMemsetAsync(dmax.p, 0, sizeof(float), st));
+      LSQ_CUDA(cudaMemsetAsync(dS.p, 0, slen * sizeof(int64_t), st));
+      LSQ_TRY(rt_h2d(dX.p, X + (size_t)lo * d, (size_t)nl * d * 4, st));
+      LSQ_TRY(rt_h2d(d16.p, B + (size_t)lo * m, (size_t)nl * m * 2, st));
+      LSQ_TRY(launch_codes_i16_to_u8(d16.p, dcodes.p, nl * m, derr.p, st));
+      LSQ_TRY(cb_absmax(dX.p, nl * d, dmax.p, st));
+      LSQ_CUDA(cudaMemcpyAsync(&herr, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+      LSQ_CUDA(cudaMemcpyAsync(&hmax[r], dmax.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+      LSQ_CUDA(cudaStreamSynchronize(st));
+      LSQ_CHECK_ARG(herr == 0, "codes must be 1-based in 1..256");
+      return LSQ_OK;
+    };
+    rc = stage1();
+    if (!phase_ok(rc)) return rc != LSQ_OK ? rc : LSQ_ERR_CUDA;
+    if (r == 0) {
+      float mx = 0.0f;
+      for (int i = 0; i < k; i++) mx = (hmax[i] > mx || hmax[i] != hmax[i]) ? hmax[i] : mx;
+      scale_exp = cb_scale_exp(mx, n);
+    }
+    bar.wait();
+    rc = cb_accumulate(dX.p, d, nl, dcodes.p, m, scale_exp, dS.p, st);
+    if (!phase_ok(rc)) return rc != LSQ_OK ? rc : LSQ_ERR_CUDA;
+    if (k > 1) rc = rt_allreduce_sum_i64(grp, r, dS.p, dS2.p, slen, st, &bar);
+    auto stage3 = [&]() -> int {
+      LSQ_TRY(rc);
+      if (r == 0) {
+        LSQ_CUDA(dG.alloc((size_t)mh * mh));
+        LSQ_CUDA(dR.alloc((size_t)mh * d));
+        LSQ_CUDA(dC.alloc((size_t)mh * d));
+        LSQ_TRY(cb_finalize(dS.p, m, d, scale_exp, dG.p, dR.p, st));
+        int iters = 0;
+        LSQ_TRY(cb_solve(dG.p, dR.p, m, d, dC.p, 0, 0.0, &iters, st));
+        if (verbose) fprintf(stderr, "[lsq_b200] codebook update: CG converged in %d iterations (%d device%s)\n", iters, k, k > 1 ? "s" : "");
+        LSQ_CUDA(cudaMemcpyAsync(Cout, dC.p, (size_t)mh * d * 4, cudaMemcpyDeviceToHost, st));
+      }
+      LSQ_CUDA(cudaStreamSynchronize(st));
+      return LSQ_OK;
+    };
+    rc = stage3();
+    phase_ok(rc);  // nobody frees its statistics while a peer may still be reading them
+    return rc;
+  });
+}
+
 }  // namespace lsq
 
 using namespace lsq;
 
 extern "C" {
+
+int64_t lsq_cb_stats_len(int m, int d) {
+  const int64_t mh = (int64_t)m * LSQ_H;
+  return mh * (mh + d);
+}
+
+int lsq_cb_scale_exp(float absmax, int64_t n_total) { return cb_scale_exp(absmax, n_total); }
+
+int lsq_dev_absmax(const float* dX, int64_t count, float* dmax, void* stream) {
+  LSQ_CHECK_ARG(count >= 0 && dmax != nullptr, "absmax: bad arguments");
+  return cb_absmax(dX, count, dmax, (cudaStream_t)stream);
+}
+
+int lsq_dev_cb_accumulate(const float* dX, int d, int64_t n, const uint8_t* dcodes, int m, int scale_exp,
+                          int64_t* dstats, void* stream) {
+  LSQ_CHECK_ARG(m >= 1 && m <= LSQ_MAXM && d >= 1 && n >= 0, "cb_accumulate: bad sizes");
+  return cb_accumulate(dX, d, n, dcodes, m, scale_exp, dstats, (cudaStream_t)stream);
+}
+
+int lsq_dev_cb_finalize(const int64_t* dstats, int m, int d, int scale_exp, double* dGram, double* dRhs,
+                        void* stream) {
+  LSQ_CHECK_ARG(m >= 1 && m <= LSQ_MAXM && d >= 1, "cb_finalize: bad sizes");
+  return cb_finalize(dstats, m, d, scale_exp, dGram, dRhs, (cudaStream_t)stream);
+}
 
 int lsq_dev_cb_stats(const float* dX, int d, int64_t n, const uint8_t* dcodes, int m, double* dGram, double* dRhs,
                      void* stream) {
@@ -268,38 +449,7 @@ int lsq_update_codebooks(const float* X, int d, int64_t n, const int16_t* B, int
   LSQ_CHECK_ARG(m >= 1 && m <= LSQ_MAXM, "m must be in 1..16");
   LSQ_CHECK_ARG(h == LSQ_H, "h must be 256");
   LSQ_CHECK_ARG(d >= 1 && n >= 0, "bad sizes");
-  cudaStream_t st;
-  LSQ_TRY(host_ctx(&st));
-  const int64_t mh = (int64_t)m * h;
-  DevBuf<float> dX, dC;
-  DevBuf<int16_t> d16;
-  DevBuf<uint8_t> dcodes;
-  DevBuf<double> dG, dR;
-  DevBuf<int> derr;
-  LSQ_CUDA(dX.alloc((size_t)n * d));
-  LSQ_CUDA(dC.alloc((size_t)mh * d));
-  LSQ_CUDA(d16.alloc((size_t)n * m));
-  LSQ_CUDA(dcodes.alloc((size_t)n * m));
-  LSQ_CUDA(dG.alloc((size_t)mh * mh));
-  LSQ_CUDA(dR.alloc((size_t)mh * d));
-  LSQ_CUDA(derr.alloc(1));
-  LSQ_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), st));
-  LSQ_CUDA(cudaMemsetAsync(dG.p, 0, (size_t)mh * mh * sizeof(double), st));
-  LSQ_CUDA(cudaMemsetAsync(dR.p, 0, (size_t)mh * d * sizeof(double), st));
-  LSQ_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)n * d * 4, cudaMemcpyHostToDevice, st));
-  LSQ_CUDA(cudaMemcpyAsync(d16.p, B, (size_t)n * m * 2, cudaMemcpyHostToDevice, st));
-  LSQ_TRY(launch_codes_i16_to_u8(d16.p, dcodes.p, n * m, derr.p, st));
-  int herr = 0;
-  LSQ_CUDA(cudaMemcpyAsync(&herr, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  LSQ_CUDA(cudaStreamSynchronize(st));
-  LSQ_CHECK_ARG(herr == 0, "codes must be 1-based in 1..256");
-  LSQ_TRY(cb_stats(dX.p, d, n, dcodes.p, m, dG.p, dR.p, st));
-  int iters = 0;
-  LSQ_TRY(cb_solve(dG.p, dR.p, m, d, dC.p, 0, 0.0, &iters, st));
-  if (verbose) fprintf(stderr, "[lsq_b200] codebook update: CG converged in %d iterations\n", iters);
-  LSQ_CUDA(cudaMemcpyAsync(Cout, dC.p, (size_t)mh * d * 4, cudaMemcpyDeviceToHost, st));
-  LSQ_CUDA(cudaStreamSynchronize(st));
-  return LSQ_OK;
+  return update_codebooks_host(X, d, n, B, m, h, Cout, verbose);
 }
 
 }  // extern "C"

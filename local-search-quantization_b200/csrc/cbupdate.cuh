@@ -4,7 +4,13 @@
 
 namespace lsq {
 
-// Gram[mh][mh] += co-occurrence counts, Rhs[mh][d] += per-code sums of X (both float64, device).
+// statistics buffer S: int64 [mh*mh + mh*d] (counts, then fixed-point sums scaled by 2^scale_exp); see cbupdate.cu
+int cb_absmax(const float* dX, int64_t count, float* dmax, cudaStream_t st);   // *dmax = max(*dmax, max|x|)
+int cb_scale_exp(float absmax, int64_t n_total);                               // host: e with n*max|x|*2^e < 2^62
+int cb_accumulate(const float* dX, int d, int64_t n, const uint8_t* dcodes, int m, int scale_exp, int64_t* dS,
+                  cudaStream_t st);                                            // S += shard
+int cb_finalize(const int64_t* dS, int m, int d, int scale_exp, double* dGram, double* dRhs, cudaStream_t st);
+// single shard: absmax + accumulate + finalize; OVERWRITES Gram[mh][mh] and Rhs[mh][d] (float64, device)
 int cb_stats(const float* dX, int d, int64_t n, const uint8_t* dcodes, int m, double* dGram, double* dRhs,
              cudaStream_t st);
 // conjugate gradients on Gram*K = Rhs from K0 = 0 (-> minimum-norm solution); Cout float [m][256][d].

@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(256, 4) icm_ils_warp_kernel(const __grid_const
     // reaches a fixed point after about two sweeps.  Any code change clears every other node's bit.
     constexpr uint32_t ALL_CLEAN = (M == 32) ? 0xFFFFFFFFu : ((1u << M) - 1u);
     uint32_t clean = 0;
+    uint32_t nvis = 0;  // node visits executed for this vector
     for (int it = 0; it < p.niters; it++) {
       uint64_t wlo = lo, whi = hi;
       uint32_t wclean = clean;
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(256, 4) icm_ils_warp_kernel(const __grid_const
         for (int jj = 0; jj < M; jj++) {
           const int j = p.orders[it][jj];
           if ((wclean >> j) & 1u) continue;
+          nvis++;
           float4 a0, a1;
           if (USMEM) {
             a0 = lds128_u(urow + (uint32_t)j * 1024u);
@@ -201,6 +203,7 @@ __global__ void __launch_bounds__(256, 4) icm_ils_warp_kernel(const __grid_const
     }
     if (lane < M) p.codes[v * M + lane] = (uint8_t)get_code<M>(lo, hi, lane);
     if (lane == 0) p.cost[v] = prev;
+    if (p.visits != nullptr && lane == 0) atomicAdd(p.visits, (unsigned long long)nvis);
     if (p.next_vector != nullptr) {
       unsigned long long t = 0;
       if (lane == 0) t = atomicAdd(p.next_vector, 1ull);
@@ -210,6 +213,9 @@ __global__ void __launch_bounds__(256, 4) icm_ils_warp_kernel(const __grid_const
     }
   }
 }
+
+static thread_local unsigned long long* g_visit_counter = nullptr;
+void set_icm_visit_counter(unsigned long long* dcounter) { g_visit_counter = dcounter; }
 
 template <int M>
 static int launch_icm_warp_m(const IcmParams& p, cudaStream_t st) {
@@ -251,6 +257,7 @@ static int launch_icm_warp_m(const IcmParams& p, cudaStream_t st) {
   }
   // dynamic work distribution (LSQ_B200_ICM_STATIC=1 restores the static split for A/B runs)
   IcmParams q = p;
+  q.visits = g_visit_counter;
   DevBuf<unsigned long long> counter;
   const char* se = getenv("LSQ_B200_ICM_STATIC");
   if (!(se != nullptr && atoi(se) != 0) && blocks_needed > cap) {

@@ -33,6 +33,9 @@ struct IcmParams {
   // next vector (vectors are independent, so the processing order cannot change any result); nullptr =
   // static grid-stride assignment
   unsigned long long* next_vector;
+  // warp kernel: optional device counter that receives the number of node visits actually executed (the
+  // clean-node skip makes it data dependent); nullptr = not counted
+  unsigned long long* visits;
   int64_t n;
   uint64_t seed;
   uint64_t g0;      // global index of vector 0 (sharding invariance)
@@ -47,6 +50,8 @@ struct IcmParams {
 int icm_use_slices(int m, int64_t n);
 
 int launch_icm_warp(const IcmParams& p, cudaStream_t st);
+// executed-visit counter picked up by every later launch_icm_warp of the calling thread (nullptr = off)
+void set_icm_visit_counter(unsigned long long* dcounter);
 int launch_icm_slice(IcmParams p, cudaStream_t st);  // allocates its scratch from the pool
 int launch_veccost(const float* dX, int d, int64_t n, const uint8_t* dcodes, const float* dC, int m,
                    float* dcost, cudaStream_t st);

@@ -23,6 +23,7 @@
 //                      64-bit keys (ordered(dist) << 32 | id) in shared memory (bitonic), or, when the
 //                      candidate list is longer than the sorter, radix-selects the nn-th key first.
 #include "linscan.cuh"
+#include "runtime.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -670,7 +671,8 @@ static int scan_exhaustive(const ScanCtx& S, const float* dq, int nqc, const int
   // batch so that the candidate buffer stays <= 1 GiB
   int64_t batch = ((int64_t)1 << 27) / std::max<int64_t>(S.n, 1);
   batch = std::max<int64_t>(1, std::min<int64_t>(batch, nqc));
-  batch = ceil_div(batch, QT) * QT;  // whole tiles
+  // MODE_ALL writes candidate rows only for q < nq, so only the LUT needs whole query tiles: rounding the
+  // key buffer up to a tile (up to 32 rows of n keys) would exceed the 1 GiB budget 32-fold for large n
   DevBuf<unsigned long long> dcand;
   DevBuf<float> dlut;
   DevBuf<int> dstatus;
@@ -802,34 +804,46 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
   return LSQ_OK;
 }
 
-// host-pointer front end shared by the four exported symbols
+// host-pointer front end shared by the four exported symbols.  With several bound devices the QUERIES are
+// partitioned (splitarray rule), codes / norms / codebooks are replicated (12-20 MB per million vectors): the
+// per-query results are disjoint, so there is no merge and no communication.
 static int linscan_host(float* dists, int32_t* ids, const unsigned char* codes, const float* queries,
                         const float* codebooks, size_t cb_floats, const float* dbnorms, int nq, int64_t n, int m,
                         int d, int lut_kind, int subdim, int nn) {
   LSQ_CHECK_ARG(m >= 1 && m <= LSQ_MAXM, "linscan: m must be in 1..16");
   LSQ_CHECK_ARG(nq >= 0 && n >= 0 && d >= 1 && nn >= 0, "linscan: bad sizes");
-  cudaStream_t st;
-  LSQ_TRY(host_ctx(&st));
-  DevBuf<uint8_t> dcodes;
-  DevBuf<float> dq, dcb, dnorm, dd;
-  DevBuf<int32_t> di;
-  LSQ_CUDA(dcodes.alloc((size_t)n * m));
-  LSQ_CUDA(dq.alloc((size_t)nq * d));
-  LSQ_CUDA(dcb.alloc(cb_floats));
-  LSQ_CUDA(dd.alloc((size_t)nq * nn));
-  LSQ_CUDA(di.alloc((size_t)nq * nn));
-  LSQ_CUDA(cudaMemcpyAsync(dcodes.p, codes, (size_t)n * m, cudaMemcpyHostToDevice, st));
-  LSQ_CUDA(cudaMemcpyAsync(dq.p, queries, (size_t)nq * d * 4, cudaMemcpyHostToDevice, st));
-  LSQ_CUDA(cudaMemcpyAsync(dcb.p, codebooks, cb_floats * 4, cudaMemcpyHostToDevice, st));
-  if (lut_kind == LUT_LSQ) {
-    LSQ_CUDA(dnorm.alloc(n));
-    LSQ_CUDA(cudaMemcpyAsync(dnorm.p, dbnorms, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-  }
-  LSQ_TRY(linscan_device(dcodes.p, n, m, dq.p, nq, d, dcb.p, dnorm.p, lut_kind, subdim, nn, dd.p, di.p, st));
-  LSQ_CUDA(cudaMemcpyAsync(dists, dd.p, (size_t)nq * nn * 4, cudaMemcpyDeviceToHost, st));
-  LSQ_CUDA(cudaMemcpyAsync(ids, di.p, (size_t)nq * nn * 4, cudaMemcpyDeviceToHost, st));
-  LSQ_CUDA(cudaStreamSynchronize(st));
-  return LSQ_OK;
+  LSQ_TRY(rt_ensure_init());
+  const int k = rt_devices_for(nq, 32);
+  return rt_parallel(k, [&](int r) -> int {
+    LSQ_TRY(rt_bind(r));
+    const cudaStream_t st = rt_ctx(r).st;
+    int64_t qlo = 0, qhi = nq;
+    lsq_splitarray(nq, k, r, &qlo, &qhi);
+    const int nql = (int)(qhi - qlo);
+    DevBuf<uint8_t> dcodes;
+    DevBuf<float> dq, dcb, dnorm, dd;
+    DevBuf<int32_t> di;
+    LSQ_CUDA(dcodes.alloc((size_t)n * m));
+    LSQ_CUDA(dq.alloc((size_t)nql * d));
+    LSQ_CUDA(dcb.alloc(cb_floats));
+    LSQ_CUDA(dd.alloc((size_t)nql * nn));
+    LSQ_CUDA(di.alloc((size_t)nql * nn));
+    LSQ_TRY(rt_h2d(dcodes.p, codes, (size_t)n * m, st));
+    LSQ_TRY(rt_h2d(dq.p, queries + (size_t)qlo * d, (size_t)nql * d * 4, st));
+    LSQ_CUDA(cudaMemcpyAsync(dcb.p, codebooks, cb_floats * 4, cudaMemcpyHostToDevice, st));
+    if (lut_kind == LUT_LSQ) {
+      LSQ_CUDA(dnorm.alloc(n));
+      LSQ_TRY(rt_h2d(dnorm.p, dbnorms, (size_t)n * 4, st));
+    }
+    int rc = linscan_device(dcodes.p, n, m, dq.p, nql, d, dcb.p, dnorm.p, lut_kind, subdim, nn, dd.p, di.p, st);
+    if (rc == LSQ_OK && nql > 0 && nn > 0) {
+      cudaError_t e = cudaMemcpyAsync(dists + (size_t)qlo * nn, dd.p, (size_t)nql * nn * 4, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(ids + (size_t)qlo * nn, di.p, (size_t)nql * nn * 4, cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) rc = cuda_fail(e, "linscan result copy", __FILE__, __LINE__);
+    }
+    cudaStreamSynchronize(st);  // also on the error path: the buffers above are about to be freed
+    return rc;
+  });
 }
 
 }  // namespace lsq

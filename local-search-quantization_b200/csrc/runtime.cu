@@ -1,0 +1,508 @@
+// runtime.cu — bound devices, worker threads, staged copies and the statistics all-reduce (runtime.cuh).
+#include "runtime.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: libnccl.so.2 is bound with dlopen at first use
+#include <stdlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <thread>
+#include <vector>
+
+namespace lsq {
+
+// ------------------------------------------------------------------------------------------------
+// error text (thread-local, like errno) and allocation stream
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error_cstr() { return g_err.c_str(); }
+
+static thread_local cudaStream_t g_alloc_stream = nullptr;
+cudaStream_t alloc_stream() { return g_alloc_stream; }
+void set_alloc_stream(cudaStream_t st) { g_alloc_stream = st; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, what);
+  g_err = buf;
+  cudaGetLastError();  // clear sticky-free errors
+  return LSQ_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------------
+// copy pool: a few persistent threads that split one large memcpy
+// ------------------------------------------------------------------------------------------------
+class CopyPool {
+ public:
+  explicit CopyPool(int helpers) {
+    for (int i = 0; i < helpers; i++) th_.emplace_back([this, i] { run(i); });
+  }
+  ~CopyPool() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; gen_++; }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  void copy(void* dst, const void* src, size_t bytes) {
+    const int parts = (int)th_.size() + 1;
+    if (parts == 1 || bytes < ((size_t)1 << 20)) { memcpy(dst, src, bytes); return; }
+    const size_t per = ((bytes / parts) + 4095) & ~(size_t)4095;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes; per_ = per; pending_ = (int)th_.size(); gen_++;
+    }
+    cv_.notify_all();
+    memcpy(dst, src, std::min(per, bytes));
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+  }
+ private:
+  void run(int idx) {
+    unsigned seen = 0;
+    for (;;) {
+      char* d; const char* s; size_t bytes, per;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        d = dst_; s = src_; bytes = bytes_; per = per_;
+      }
+      const size_t off = per * (size_t)(idx + 1);
+      if (off < bytes) memcpy(d + off, s + off, std::min(per, bytes - off));
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        pending_--;
+      }
+      done_cv_.notify_one();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_cv_;
+  char* dst_ = nullptr; const char* src_ = nullptr;
+  size_t bytes_ = 0, per_ = 0;
+  int pending_ = 0;
+  unsigned gen_ = 0;
+  bool stop_ = false;
+};
+
+// ------------------------------------------------------------------------------------------------
+// bound devices
+// ------------------------------------------------------------------------------------------------
+constexpr int STAGE_SLOTS = 4;
+constexpr size_t STAGE_BYTES = (size_t)8 << 20;
+
+struct DevState {
+  DevCtx ctx;
+  // pinned staging ring for pageable sources (allocated at first use)
+  void* stage[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t stage_ev[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+  bool stage_busy[STAGE_SLOTS] = {false, false, false, false};
+  int stage_next = 0;
+  CopyPool* pool = nullptr;
+};
+
+struct AllReduceGroup {
+  int k = 0;
+  bool nccl = false;
+  std::vector<ncclComm_t> comms;
+  // p2p backend
+  std::vector<int64_t*> bufs;
+  std::vector<cudaEvent_t> ready, done;
+};
+
+static std::mutex g_mu;
+static thread_local struct DevState* tl_dev = nullptr;  // the bound device the calling thread works for
+static std::vector<DevState*> g_dev;   // bound devices; [0] is the primary one
+static AllReduceGroup* g_group = nullptr;
+
+struct NcclApi {
+  void* handle = nullptr;
+  bool tried = false;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static bool load_nccl() {
+  if (g_nccl.tried) return g_nccl.handle != nullptr;
+  g_nccl.tried = true;
+  for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+    void* h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+    if (!h) continue;
+    g_nccl.CommInitAll = (decltype(g_nccl.CommInitAll))dlsym(h, "ncclCommInitAll");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (g_nccl.CommInitAll && g_nccl.CommDestroy && g_nccl.AllReduce && g_nccl.GetErrorString) {
+      g_nccl.handle = h;
+      return true;
+    }
+    dlclose(h);
+  }
+  return false;
+}
+
+static void keep_pool_memory(int dev) {
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t never = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &never);
+  }
+  cudaGetLastError();
+}
+
+static void destroy_group_locked() {
+  if (!g_group) return;
+  if (g_group->nccl)
+    for (ncclComm_t c : g_group->comms) g_nccl.CommDestroy(c);
+  for (size_t i = 0; i < g_group->ready.size(); i++) {
+    cudaSetDevice(g_dev[i]->ctx.dev);
+    cudaEventDestroy(g_group->ready[i]);
+    cudaEventDestroy(g_group->done[i]);
+  }
+  delete g_group;
+  g_group = nullptr;
+}
+
+static void release_devices_locked() {
+  destroy_group_locked();
+  tl_dev = nullptr;
+  for (DevState* D : g_dev) {
+    cudaSetDevice(D->ctx.dev);
+    if (D->ctx.st) { cudaStreamSynchronize(D->ctx.st); cudaStreamDestroy(D->ctx.st); }
+    if (D->ctx.st2) { cudaStreamSynchronize(D->ctx.st2); cudaStreamDestroy(D->ctx.st2); }
+    for (int s = 0; s < STAGE_SLOTS; s++) {
+      if (D->stage_ev[s]) cudaEventDestroy(D->stage_ev[s]);
+      if (D->stage[s]) cudaFreeHost(D->stage[s]);
+    }
+    delete D->pool;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, D->ctx.dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    cudaGetLastError();
+    delete D;
+  }
+  g_dev.clear();
+}
+
+static int bind_devices_locked(const int* devs, int n) {
+  int cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess || cnt == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available: liblsq_b200 has no CPU fallback");
+    return LSQ_ERR_CUDA;
+  }
+  std::vector<int> want;
+  if (devs == nullptr || n <= 0) {
+    for (int i = 0; i < cnt; i++) want.push_back(i);  // all visible devices
+  } else {
+    for (int i = 0; i < n; i++) {
+      LSQ_CHECK_ARG(devs[i] >= 0 && devs[i] < cnt, "device index out of range");
+      // (testing hook: LSQ_B200_ALLOW_DUPLICATE_DEVICES=1 lets one GPU appear several times, which exercises the
+      // sharding / worker / reduction logic on a single-GPU box; NCCL refuses such a clique -> p2p reduction)
+      const char* dup = getenv("LSQ_B200_ALLOW_DUPLICATE_DEVICES");
+      LSQ_CHECK_ARG((dup != nullptr && atoi(dup) != 0) || std::find(want.begin(), want.end(), devs[i]) == want.end(),
+                    "duplicate device index");
+      want.push_back(devs[i]);
+    }
+  }
+  bool same = want.size() == g_dev.size();
+  for (size_t i = 0; same && i < want.size(); i++) same = (g_dev[i]->ctx.dev == want[i]);
+  if (same) {
+    LSQ_CUDA(cudaSetDevice(want[0]));
+    return LSQ_OK;
+  }
+  release_devices_locked();
+  const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+  for (size_t i = 0; i < want.size(); i++) {
+    LSQ_CUDA(cudaSetDevice(want[i]));
+    DevState* D = new DevState();
+    D->ctx.dev = want[i];
+    g_dev.push_back(D);
+    LSQ_CUDA(cudaStreamCreateWithFlags(&D->ctx.st, cudaStreamNonBlocking));
+    LSQ_CUDA(cudaStreamCreateWithFlags(&D->ctx.st2, cudaStreamNonBlocking));
+    keep_pool_memory(want[i]);
+    int helpers = hw / (int)want.size() - 1;
+    if (const char* he = getenv("LSQ_B200_COPY_THREADS")) helpers = atoi(he) - 1;
+    D->pool = new CopyPool(std::max(0, std::min(helpers, 5)));
+  }
+  // peer access for the device set (P2P all-reduce backend; also lets NCCL pick its P2P transport)
+  for (size_t i = 0; i < want.size(); i++)
+    for (size_t j = 0; j < want.size(); j++) {
+      if (i == j || want[i] == want[j]) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, want[i], want[j]);
+      if (!can) continue;
+      cudaSetDevice(want[i]);
+      cudaDeviceEnablePeerAccess(want[j], 0);
+      cudaGetLastError();  // "already enabled" is fine
+      // stream-ordered allocations of device j must be mapped for device i explicitly
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, want[j]) == cudaSuccess) {
+        cudaMemAccessDesc desc;
+        memset(&desc, 0, sizeof(desc));
+        desc.location.type = cudaMemLocationTypeDevice;
+        desc.location.id = want[i];
+        desc.flags = cudaMemAccessFlagsProtReadWrite;
+        cudaMemPoolSetAccess(pool, &desc, 1);
+      }
+      cudaGetLastError();
+    }
+  LSQ_CUDA(cudaSetDevice(want[0]));
+  return LSQ_OK;
+}
+
+int rt_init_devices(const int* devs, int n) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return bind_devices_locked(devs, n);
+}
+
+int rt_ensure_init() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_dev.empty()) {
+    LSQ_CUDA(cudaSetDevice(g_dev[0]->ctx.dev));
+    return LSQ_OK;
+  }
+  int cnt = 0;
+  cudaError_t e = cudaGetDeviceCount(&cnt);
+  if (e != cudaSuccess || cnt == 0) {
+    cudaGetLastError();
+    set_error("no CUDA device available: liblsq_b200 has no CPU fallback");
+    return LSQ_ERR_CUDA;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return bind_devices_locked(&dev, 1);
+}
+
+int rt_finalize() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  release_devices_locked();
+  return LSQ_OK;
+}
+
+int rt_num_devices() { return (int)g_dev.size(); }
+const DevCtx& rt_ctx(int i) { return g_dev[i]->ctx; }
+
+int rt_bind(int i) {
+  LSQ_CUDA(cudaSetDevice(g_dev[i]->ctx.dev));
+  set_alloc_stream(g_dev[i]->ctx.st);
+  tl_dev = g_dev[i];
+  return LSQ_OK;
+}
+
+int host_ctx(cudaStream_t* st) {
+  LSQ_TRY(rt_ensure_init());
+  *st = g_dev[0]->ctx.st;
+  set_alloc_stream(*st);
+  tl_dev = g_dev[0];
+  return LSQ_OK;
+}
+
+int rt_devices_for(int64_t n, int64_t min_per_device) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>(rt_num_devices(), n / std::max<int64_t>(1, min_per_device)));
+}
+
+int rt_parallel(int k, const std::function<int(int)>& fn) {
+  if (k <= 1) return fn(0);
+  std::vector<int> rc(k, LSQ_OK);
+  std::vector<std::string> msg(k);
+  std::vector<std::thread> th;
+  for (int i = 1; i < k; i++)
+    th.emplace_back([&, i] {
+      rc[i] = fn(i);
+      if (rc[i] != LSQ_OK) msg[i] = last_error_cstr();
+    });
+  rc[0] = fn(0);
+  if (rc[0] != LSQ_OK) msg[0] = last_error_cstr();
+  for (auto& t : th) t.join();
+  cudaSetDevice(g_dev[0]->ctx.dev);
+  set_alloc_stream(g_dev[0]->ctx.st);
+  tl_dev = g_dev[0];
+  for (int i = 0; i < k; i++)
+    if (rc[i] != LSQ_OK) {
+      set_error(msg[i] + (i > 0 ? " [device " + std::to_string(g_dev[i]->ctx.dev) + "]" : std::string()));
+      return rc[i];
+    }
+  return LSQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host -> device copies for pageable callers
+// ------------------------------------------------------------------------------------------------
+static DevState* current_state() {
+  for (DevState* D : g_dev)
+    if (D == tl_dev) return D;  // (stale after a re-init: then not found)
+  return nullptr;
+}
+
+int rt_h2d(void* ddst, const void* hsrc, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return LSQ_OK;
+  static const int mode = [] {
+    const char* e = getenv("LSQ_B200_H2D");
+    return (e != nullptr && strcmp(e, "direct") == 0) ? 0 : 1;
+  }();
+  DevState* D = (mode == 1 && bytes >= ((size_t)1 << 20)) ? current_state() : nullptr;
+  if (D != nullptr) {
+    cudaPointerAttributes attr;
+    memset(&attr, 0, sizeof(attr));
+    const cudaError_t e = cudaPointerGetAttributes(&attr, hsrc);
+    cudaGetLastError();
+    if (e == cudaSuccess && attr.type != cudaMemoryTypeUnregistered) D = nullptr;  // pinned / registered / managed
+  }
+  if (D == nullptr) {
+    LSQ_CUDA(cudaMemcpyAsync(ddst, hsrc, bytes, cudaMemcpyHostToDevice, st));
+    return LSQ_OK;
+  }
+  for (size_t off = 0; off < bytes; off += STAGE_BYTES) {
+    const size_t sz = std::min(STAGE_BYTES, bytes - off);
+    const int s = D->stage_next;
+    D->stage_next = (s + 1) % STAGE_SLOTS;
+    if (D->stage[s] == nullptr) {
+      LSQ_CUDA(cudaHostAlloc(&D->stage[s], STAGE_BYTES, cudaHostAllocPortable));
+      LSQ_CUDA(cudaEventCreateWithFlags(&D->stage_ev[s], cudaEventDisableTiming));
+    }
+    if (D->stage_busy[s]) LSQ_CUDA(cudaEventSynchronize(D->stage_ev[s]));  // its previous DMA has drained
+    D->pool->copy(D->stage[s], (const char*)hsrc + off, sz);
+    LSQ_CUDA(cudaMemcpyAsync((char*)ddst + off, D->stage[s], sz, cudaMemcpyHostToDevice, st));
+    LSQ_CUDA(cudaEventRecord(D->stage_ev[s], st));
+    D->stage_busy[s] = true;
+  }
+  return LSQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the statistics all-reduce
+// ------------------------------------------------------------------------------------------------
+struct PeerPtrs { const int64_t* p[16]; };
+
+// out[i] = sum_j peers[j][i], j ascending: every device reads its peers' buffers through NVLink peer memory
+__global__ void __launch_bounds__(256) reduce_peers_kernel(PeerPtrs peers, int k, size_t count, int64_t* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i * 2 < count; i += stride) {
+    if (2 * i + 1 < count) {
+      longlong2 acc = make_longlong2(0, 0);
+      for (int j = 0; j < k; j++) {
+        const longlong2 v = *reinterpret_cast<const longlong2*>(peers.p[j] + 2 * i);
+        acc.x += v.x; acc.y += v.y;
+      }
+      *reinterpret_cast<longlong2*>(out + 2 * i) = acc;
+    } else {
+      int64_t acc = 0;
+      for (int j = 0; j < k; j++) acc += peers.p[j][2 * i];
+      out[2 * i] = acc;
+    }
+  }
+}
+
+AllReduceGroup* rt_allreduce_group(int k) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_group && g_group->k == k) return g_group;
+  destroy_group_locked();
+  if (k > 16 || k > (int)g_dev.size()) { set_error("all-reduce group larger than the bound device set"); return nullptr; }
+  AllReduceGroup* g = new AllReduceGroup();
+  g->k = k;
+  const char* be = getenv("LSQ_B200_ALLREDUCE");
+  const bool want_p2p = (be != nullptr && strcmp(be, "p2p") == 0);
+  if (!want_p2p && load_nccl()) {
+    std::vector<int> devs(k);
+    for (int i = 0; i < k; i++) devs[i] = g_dev[i]->ctx.dev;
+    g->comms.resize(k);
+    const ncclResult_t r = g_nccl.CommInitAll(g->comms.data(), k, devs.data());
+    if (r == ncclSuccess) g->nccl = true;
+    else {
+      fprintf(stderr, "[lsq_b200] ncclCommInitAll failed (%s): using the peer-memory reduction\n", g_nccl.GetErrorString(r));
+      g->comms.clear();
+    }
+  }
+  if (!g->nccl) {
+    for (int i = 0; i < k; i++)
+      for (int j = 0; j < k; j++) {
+        int can = (g_dev[i]->ctx.dev == g_dev[j]->ctx.dev);
+        if (!can) cudaDeviceCanAccessPeer(&can, g_dev[i]->ctx.dev, g_dev[j]->ctx.dev);
+        if (!can) {
+          set_error("statistics all-reduce: NCCL unavailable and the devices have no peer access");
+          delete g;
+          return nullptr;
+        }
+      }
+    g->bufs.assign(k, nullptr);
+    g->ready.resize(k);
+    g->done.resize(k);
+    for (int i = 0; i < k; i++) {
+      cudaSetDevice(g_dev[i]->ctx.dev);
+      cudaEventCreateWithFlags(&g->ready[i], cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&g->done[i], cudaEventDisableTiming);
+    }
+  }
+  cudaSetDevice(g_dev[0]->ctx.dev);
+  g_group = g;
+  return g;
+}
+
+const char* rt_allreduce_backend(const AllReduceGroup* g) { return g->nccl ? "nccl" : "p2p"; }
+
+int rt_allreduce_sum_i64(AllReduceGroup* g, int rank, int64_t* dbuf, int64_t* dscratch, size_t count,
+                         cudaStream_t st, HostBarrier* bar) {
+  if (g->k == 1) return LSQ_OK;
+  if (g->nccl) {
+    const ncclResult_t r = g_nccl.AllReduce(dbuf, dbuf, count, ncclInt64, ncclSum, g->comms[rank], st);
+    if (r != ncclSuccess) {
+      set_error(std::string("ncclAllReduce failed: ") + g_nccl.GetErrorString(r));
+      return LSQ_ERR_CUDA;
+    }
+    return LSQ_OK;
+  }
+  // peer-memory reduction: publish the buffer, wait until every peer's statistics are complete, read them
+  // all in rank order, and only overwrite the own buffer once every peer has finished reading it
+  g->bufs[rank] = dbuf;
+  cudaError_t e = cudaEventRecord(g->ready[rank], st);
+  bar->wait();
+  PeerPtrs pp;
+  for (int j = 0; j < g->k; j++) {
+    pp.p[j] = g->bufs[j];
+    if (j != rank && e == cudaSuccess) e = cudaStreamWaitEvent(st, g->ready[j], 0);
+  }
+  if (e == cudaSuccess) {
+    reduce_peers_kernel<<<LSQ_NUM_SMS_HINT * 4, 256, 0, st>>>(pp, g->k, count, dscratch);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaEventRecord(g->done[rank], st);
+  bar->wait();
+  for (int j = 0; j < g->k; j++)
+    if (j != rank && e == cudaSuccess) e = cudaStreamWaitEvent(st, g->done[j], 0);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dbuf, dscratch, count * sizeof(int64_t), cudaMemcpyDeviceToDevice, st);
+  LSQ_CUDA(e);
+  return LSQ_OK;
+}
+
+}  // namespace lsq
+
+using namespace lsq;
+
+extern "C" {
+
+int lsq_init(int device) { return rt_init_devices(&device, 1); }
+
+int lsq_init_devices(const int* devices, int n) { return rt_init_devices(devices, n); }
+
+int lsq_num_bound_devices(void) { return rt_num_devices(); }
+
+int lsq_finalize(void) { return rt_finalize(); }
+
+const char* lsq_last_error(void) { return last_error_cstr(); }
+
+int lsq_device_count(void) {
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return cnt;
+}
+
+const char* lsq_version(void) { return "lsq_b200 0.2 (sm_100a)"; }
+
+}  // extern "C"

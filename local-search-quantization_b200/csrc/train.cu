@@ -24,6 +24,7 @@
 
 #include "cbupdate.cuh"
 #include "icm.cuh"
+#include "runtime.cuh"
 
 namespace lsq {
 
@@ -158,7 +159,8 @@ static int kmeans1d_device(const float* dvals, int64_t n, int h, float* dcent, i
 }
 
 // ---- eval_recall (Linscan.jl:76-117) --------------------------------------------------------------
-// rank[q] = 1-based position of gnd[q] in pred[q][0..k) if it occurs exactly once, else k+1; hist[r]++.
+// rank[q] = 1-based position of gnd[q] in query q's WHOLE list pred[q][0..ld) if it occurs exactly once there
+// (`find` over the full column, Linscan.jl:91-98), else k+1; positions beyond k are misses (:112); hist[r]++.
 __global__ void __launch_bounds__(256) recall_rank_kernel(const int32_t* __restrict__ gnd,
                                                           const int32_t* __restrict__ pred, int nq, int ld, int k,
                                                           int* __restrict__ hist) {
@@ -166,15 +168,15 @@ __global__ void __launch_bounds__(256) recall_rank_kernel(const int32_t* __restr
   const int q = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (q >= nq) return;
   const int32_t g = gnd[q];
-  int count = 0, first = k;
-  for (int i = lane; i < k; i += 32)
+  int count = 0, first = ld;
+  for (int i = lane; i < ld; i += 32)
     if (pred[(size_t)q * ld + i] == g) { count++; first = min(first, i); }
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
     count += __shfl_xor_sync(0xFFFFFFFFu, count, off);
     first = min(first, __shfl_xor_sync(0xFFFFFFFFu, first, off));
   }
-  if (lane == 0) atomicAdd(&hist[(count == 1) ? first : k], 1);  // integer counts: order-independent
+  if (lane == 0) atomicAdd(&hist[(count == 1 && first < k) ? first : k], 1);  // integer counts: order-independent
 }
 
 // recall[i] = #{rank <= i+1} / nq  (float64 division of integer counts, like the reference's `./ nquery`)
@@ -202,6 +204,7 @@ struct TrainCtx {
   int64_t chunk;   // vectors per chunk (U holds m*chunk*256 floats)
   int icmiter, npert, randord;
   uint64_t seed;
+  uint64_t g0;     // global index of this shard's first vector
 };
 
 // `niters` ILS iterations (ils_iter0, ils_iter0+1, ...) over the whole set with the current codebooks
@@ -218,7 +221,7 @@ static int train_encode(const TrainCtx& T, uint32_t ils_iter0, int niters) {
       memset(&p, 0, sizeof(p));
       p.X = T.dX + (size_t)lo * T.d; p.C = T.dC; p.U = T.dU; p.T = T.dT;
       p.codes = T.dcodes + (size_t)lo * T.m; p.cost = T.dcost + lo;
-      p.n = nc; p.seed = T.seed; p.g0 = (uint64_t)lo; p.ils_iter0 = ils_iter0 + (uint32_t)it0;
+      p.n = nc; p.seed = T.seed; p.g0 = T.g0 + (uint64_t)lo; p.ils_iter0 = ils_iter0 + (uint32_t)it0;
       p.d = T.d; p.m = T.m; p.icmiter = T.icmiter; p.npert = T.npert; p.niters = nit;
       for (int i = 0; i < nit; i++) {
         p.snap_of_iter[i] = -1;
@@ -232,24 +235,12 @@ static int train_encode(const TrainCtx& T, uint32_t ils_iter0, int niters) {
   return LSQ_OK;
 }
 
-static int train_qerror(const TrainCtx& T, double* dsum, float* out) {
+// float64 sum of the costs of this shard's current codes
+static int train_cost_sum(const TrainCtx& T, double* dsum, double* out) {
   LSQ_TRY(launch_veccost(T.dX, T.d, T.n, T.dcodes, T.dC, T.m, T.dcost, T.st));
   LSQ_TRY(launch_sum_f32_to_f64(T.dcost, T.n, dsum, T.st));
-  double s = 0;
-  LSQ_CUDA(cudaMemcpyAsync(&s, dsum, sizeof(double), cudaMemcpyDeviceToHost, T.st));
+  LSQ_CUDA(cudaMemcpyAsync(out, dsum, sizeof(double), cudaMemcpyDeviceToHost, T.st));
   LSQ_CUDA(cudaStreamSynchronize(T.st));
-  *out = (float)(T.n ? s / (double)T.n : 0.0);
-  return LSQ_OK;
-}
-
-static int train_update(const TrainCtx& T, const float* dXsrc, double* dG, double* dR, int verbose) {
-  const int64_t mh = (int64_t)T.m * LSQ_H;
-  LSQ_CUDA(cudaMemsetAsync(dG, 0, (size_t)mh * mh * sizeof(double), T.st));
-  LSQ_CUDA(cudaMemsetAsync(dR, 0, (size_t)mh * T.d * sizeof(double), T.st));
-  LSQ_TRY(cb_stats(dXsrc, T.d, T.n, T.dcodes, T.m, dG, dR, T.st));
-  int iters = 0;
-  LSQ_TRY(cb_solve(dG, dR, T.m, T.d, T.dC, 0, 0.0, &iters, T.st));
-  if (verbose) fprintf(stderr, "[lsq_b200] codebook update: CG converged in %d iterations\n", iters);
   return LSQ_OK;
 }
 
@@ -259,6 +250,12 @@ using namespace lsq;
 
 extern "C" {
 
+// The training set is sharded over the bound devices (splitarray, contiguous): every device keeps its shard of
+// X, the codes, the unaries and a replica of the tables resident for the whole alternation.  Per outer
+// iteration the devices exchange exactly one buffer — the integer codebook-update statistics (one all-reduce)
+// — and one float64 per device for the objective; the solve is replicated (deterministic kernels on identical
+// inputs give identical codebooks, no broadcast).  The statistics are exact integers and the schedule is
+// keyed by the global vector index, so the result is bit-identical for any number of devices.
 int lsq_train_lsq(const float* X, int d, int64_t n, int m, int h, const float* R, int16_t* B, float* C, int niter,
                   int ilsiter, int icmiter, int randord, int npert, uint64_t seed, float* cbnorms,
                   int16_t* B_norms, float* obj, int verbose) {
@@ -268,106 +265,198 @@ int lsq_train_lsq(const float* X, int d, int64_t n, int m, int h, const float* R
   LSQ_CHECK_ARG(niter >= 0 && ilsiter >= 0 && icmiter >= 0, "iteration counts must be >= 0");
   LSQ_CHECK_ARG(npert >= 0 && npert <= m, "npert must be in 0..m (sample without replacement, encode_icm.jl:58)");
   LSQ_CHECK_ARG(X != nullptr && B != nullptr && C != nullptr, "X, B and C are required");
-  cudaStream_t st;
-  LSQ_TRY(host_ctx(&st));
+  LSQ_TRY(rt_ensure_init());
   const int64_t mh = (int64_t)m * h;
+  const size_t slen = (size_t)(mh * (mh + d));
   if (verbose) {
     // LSQ.jl:25-29 prints this banner unconditionally; here it follows V
     fprintf(stderr, "Doing local search with %d codebooks, %d perturbations, %d icm iterations and random order = %s\n",
             m, npert, icmiter, randord ? "true" : "false");
   }
-
-  DevBuf<float> dX, dRX, dRm, dC, dC2, dnorms, dT, dU, dcost, dvn, dcent;
-  DevBuf<int16_t> d16;
-  DevBuf<uint8_t> dcodes;
-  DevBuf<double> dG, dRhs, dsum;
-  DevBuf<int> derr;
-  LSQ_CUDA(dX.alloc((size_t)n * d));
-  LSQ_CUDA(dC.alloc((size_t)mh * d));
-  LSQ_CUDA(dnorms.alloc(mh));
-  LSQ_CUDA(dT.alloc((size_t)m * m * LSQ_H * LSQ_H));
-  LSQ_CUDA(dcost.alloc(n));
-  LSQ_CUDA(d16.alloc((size_t)n * m));
-  LSQ_CUDA(dcodes.alloc((size_t)n * m));
-  LSQ_CUDA(dG.alloc((size_t)mh * mh));
-  LSQ_CUDA(dRhs.alloc((size_t)mh * d));
-  LSQ_CUDA(dsum.alloc(1025));
-  LSQ_CUDA(derr.alloc(1));
-  LSQ_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), st));
-  LSQ_CUDA(cudaMemcpyAsync(dX.p, X, (size_t)n * d * 4, cudaMemcpyHostToDevice, st));
-  LSQ_CUDA(cudaMemcpyAsync(d16.p, B, (size_t)n * m * 2, cudaMemcpyHostToDevice, st));
-  LSQ_TRY(launch_codes_i16_to_u8(d16.p, dcodes.p, n * m, derr.p, st));
-  int herr = 0;
-  LSQ_CUDA(cudaMemcpyAsync(&herr, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  LSQ_CUDA(cudaStreamSynchronize(st));
-  LSQ_CHECK_ARG(herr == 0, "codes must be 1-based in 1..256");
-
-  // unaries: as many vectors per chunk as fit comfortably (all of them for the usual training sets)
-  size_t free_b = 0, total_b = 0;
-  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
-  int64_t chunk = (int64_t)(0.6 * (double)free_b / ((double)m * LSQ_H * 4));
-  chunk = std::max<int64_t>(1024, std::min<int64_t>(chunk, n));
-  if (const char* ce = getenv("LSQ_B200_CHUNK_VECTORS")) chunk = std::max<int64_t>(1, std::min<int64_t>(atoll(ce), n));  // tests
-  LSQ_CUDA(dU.alloc((size_t)chunk * mh));
-
-  TrainCtx T;
-  T.d = d; T.m = m; T.n = n; T.st = st; T.dX = dX.p; T.dcodes = dcodes.p; T.dcost = dcost.p; T.dC = dC.p;
-  T.dnorms = dnorms.p; T.dT = dT.p; T.dU = dU.p; T.chunk = chunk;
-  T.icmiter = icmiter; T.npert = npert; T.randord = randord; T.seed = seed;
-
-  // C = update_codebooks(R'X, B); C_i = R*C_i  (LSQ.jl:31-41)
-  if (R != nullptr) {
-    LSQ_CUDA(dRX.alloc((size_t)n * d));
-    LSQ_CUDA(dRm.alloc((size_t)d * d));
-    LSQ_CUDA(dC2.alloc((size_t)mh * d));
-    LSQ_CUDA(cudaMemcpyAsync(dRm.p, R, (size_t)d * d * 4, cudaMemcpyHostToDevice, st));
-    LSQ_TRY(launch_rows_times_matrix(dX.p, n, d, dRm.p, d, 1, dRX.p, st));
-    LSQ_TRY(train_update(T, dRX.p, dG.p, dRhs.p, verbose));
-    LSQ_TRY(launch_rows_times_matrix(dC.p, mh, d, dRm.p, 1, d, dC2.p, st));
-    LSQ_CUDA(cudaMemcpyAsync(dC.p, dC2.p, (size_t)mh * d * 4, cudaMemcpyDeviceToDevice, st));
-  } else {
-    LSQ_TRY(train_update(T, dX.p, dG.p, dRhs.p, verbose));
+  const int k = rt_devices_for(n, 4096);
+  AllReduceGroup* grp = nullptr;
+  if (k > 1) {
+    grp = rt_allreduce_group(k);
+    if (grp == nullptr) return LSQ_ERR_CUDA;
+    if (verbose) fprintf(stderr, "[lsq_b200] train_lsq on %d devices, statistics all-reduce: %s\n", k, rt_allreduce_backend(grp));
   }
-  float q = 0.0f;
-  if (verbose) { LSQ_TRY(train_qerror(T, dsum.p, &q)); fprintf(stderr, "%3d %e \n", -2, q); }
+  PhaseSync sync(k);
+  std::vector<float> hmax(k, 0.0f);
+  std::vector<double> hsum(k, 0.0);
+  std::vector<float> hnorms, hcent(h, 0.0f);
+  if (cbnorms != nullptr || B_norms != nullptr) hnorms.resize(n);
+  const bool want_norms = !hnorms.empty();
 
-  // Initialize B (LSQ.jl:44-49)
-  uint32_t ils_count = 0;
-  LSQ_TRY(train_encode(T, ils_count, ilsiter));
-  ils_count += (uint32_t)ilsiter;
-  if (verbose) { LSQ_TRY(train_qerror(T, dsum.p, &q)); fprintf(stderr, "%3d %e \n", -1, q); }
+  return rt_parallel(k, [&](int r) -> int {
+    int rc = rt_bind(r);
+    const cudaStream_t st = rt_ctx(r).st;
+    int64_t lo = 0, hi = n;
+    lsq_splitarray(n, k, r, &lo, &hi);
+    const int64_t nl = hi - lo;
+#define STEP(expr) do { if (rc == LSQ_OK) rc = (expr); } while (0)
+#define STEP_CUDA(expr) do { if (rc == LSQ_OK) { cudaError_t e__ = (expr); if (e__ != cudaSuccess) rc = cuda_fail(e__, #expr, __FILE__, __LINE__); } } while (0)
+#define SYNC() do { if (!sync.ok(rc)) return rc != LSQ_OK ? rc : LSQ_ERR_CUDA; } while (0)
 
-  for (int iter = 0; iter < niter; iter++) {
-    LSQ_TRY(train_qerror(T, dsum.p, &q));  // LSQ.jl:55
-    if (obj) obj[iter] = q;
-    if (verbose) fprintf(stderr, "%3d %e \n", iter + 1, q);
-    LSQ_TRY(train_update(T, dX.p, dG.p, dRhs.p, verbose));
-    LSQ_TRY(train_encode(T, ils_count, ilsiter));
-    ils_count += (uint32_t)ilsiter;
-  }
+    DevBuf<float> dX, dRX, dRm, dC, dC2, dnorms, dT, dU, dcost, dvn, dcent, dmax;
+    DevBuf<int16_t> d16;
+    DevBuf<uint8_t> dcodes;
+    DevBuf<int64_t> dS, dS2;
+    DevBuf<double> dG, dRhs, dsum;
+    DevBuf<int> derr;
+    int herr = 0;
+    STEP_CUDA(dX.alloc((size_t)nl * d));
+    STEP_CUDA(dC.alloc((size_t)mh * d));
+    STEP_CUDA(dnorms.alloc(mh));
+    STEP_CUDA(dT.alloc((size_t)m * m * LSQ_H * LSQ_H));
+    STEP_CUDA(dcost.alloc(nl));
+    STEP_CUDA(d16.alloc((size_t)nl * m));
+    STEP_CUDA(dcodes.alloc((size_t)nl * m));
+    STEP_CUDA(dS.alloc(slen));
+    if (k > 1) STEP_CUDA(dS2.alloc(slen));
+    STEP_CUDA(dG.alloc((size_t)mh * mh));
+    STEP_CUDA(dRhs.alloc((size_t)mh * d));
+    STEP_CUDA(dsum.alloc(1025));
+    STEP_CUDA(derr.alloc(1));
+    STEP_CUDA(dmax.alloc(1));
+    STEP_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), st));
+    STEP(rt_h2d(dX.p, X + (size_t)lo * d, (size_t)nl * d * 4, st));
+    STEP(rt_h2d(d16.p, B + (size_t)lo * m, (size_t)nl * m * 2, st));
+    STEP(launch_codes_i16_to_u8(d16.p, dcodes.p, nl * m, derr.p, st));
+    STEP_CUDA(cudaMemcpyAsync(&herr, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    STEP_CUDA(cudaStreamSynchronize(st));
+    if (rc == LSQ_OK && herr != 0) { set_error("invalid argument: codes must be 1-based in 1..256"); rc = LSQ_ERR_ARG; }
 
-  // norm codebook (LSQ.jl:68-84)
-  if (cbnorms != nullptr || B_norms != nullptr) {
-    LSQ_CUDA(dvn.alloc(n));
-    LSQ_CUDA(dcent.alloc(h));
-    decoded_norms_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(dcodes.p, n, dC.p, d, m, dvn.p);
-    LSQ_CUDA(cudaGetLastError());
-    int kit = 0;
-    LSQ_TRY(kmeans1d_device(dvn.p, n, h, dcent.p, 100, &kit, st));
-    if (verbose) fprintf(stderr, "[lsq_b200] norm codebook: 1-D k-means stopped after %d iterations\n", kit);
-    if (cbnorms) LSQ_CUDA(cudaMemcpyAsync(cbnorms, dcent.p, (size_t)h * 4, cudaMemcpyDeviceToHost, st));
-    if (B_norms) {
-      LSQ_TRY(launch_quantize_norms(dcodes.p, n, dC.p, d, m, dcent.p, h, d16.p, st));
-      LSQ_CUDA(cudaMemcpyAsync(B_norms, d16.p, (size_t)n * 2, cudaMemcpyDeviceToHost, st));
-      LSQ_CUDA(cudaStreamSynchronize(st));
+    // unaries: as many vectors per chunk as fit comfortably (all of them for the usual training sets)
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
+    int64_t chunk = (int64_t)(0.6 * (double)free_b / ((double)m * LSQ_H * 4));
+    chunk = std::max<int64_t>(1024, std::min<int64_t>(chunk, nl));
+    if (const char* ce = getenv("LSQ_B200_CHUNK_VECTORS")) chunk = std::max<int64_t>(1, std::min<int64_t>(atoll(ce), nl));  // tests
+    STEP_CUDA(dU.alloc((size_t)chunk * mh));
+
+    TrainCtx T;
+    T.d = d; T.m = m; T.n = nl; T.g0 = (uint64_t)lo; T.st = st; T.dX = dX.p; T.dcodes = dcodes.p; T.dcost = dcost.p;
+    T.dC = dC.p; T.dnorms = dnorms.p; T.dT = dT.p; T.dU = dU.p; T.chunk = chunk;
+    T.icmiter = icmiter; T.npert = npert; T.randord = randord; T.seed = seed;
+
+    // scale exponent of the fixed-point statistics for data source `src` (global max|x| over the shards)
+    int scale_exp = 0;
+    auto exchange_scale = [&](const float* src) -> int {
+      STEP_CUDA(cudaMemsetAsync(dmax.p, 0, sizeof(float), st));
+      STEP(cb_absmax(src, nl * d, dmax.p, st));
+      STEP_CUDA(cudaMemcpyAsync(&hmax[r], dmax.p, sizeof(float), cudaMemcpyDeviceToHost, st));
+      STEP_CUDA(cudaStreamSynchronize(st));
+      SYNC();
+      float mx = 0.0f;
+      for (int i = 0; i < k; i++) mx = (hmax[i] > mx || hmax[i] != hmax[i]) ? hmax[i] : mx;
+      scale_exp = cb_scale_exp(mx, n);
+      return LSQ_OK;
+    };
+    // update_codebooks(src, codes): local statistics -> ONE all-reduce -> replicated solve into dC
+    auto update = [&](const float* src) -> int {
+      STEP_CUDA(cudaMemsetAsync(dS.p, 0, slen * sizeof(int64_t), st));
+      STEP(cb_accumulate(src, d, nl, dcodes.p, m, scale_exp, dS.p, st));
+      SYNC();
+      if (k > 1) rc = rt_allreduce_sum_i64(grp, r, dS.p, dS2.p, slen, st, &sync.bar);
+      STEP(cb_finalize(dS.p, m, d, scale_exp, dG.p, dRhs.p, st));
+      int iters = 0;
+      STEP(cb_solve(dG.p, dRhs.p, m, d, dC.p, 0, 0.0, &iters, st));
+      if (verbose && r == 0 && rc == LSQ_OK) fprintf(stderr, "[lsq_b200] codebook update: CG converged in %d iterations\n", iters);
+      SYNC();
+      return LSQ_OK;
+    };
+    // objective over all shards: one float64 per device, added in shard order
+    float q = 0.0f;
+    auto qerror_all = [&]() -> int {
+      STEP(train_cost_sum(T, dsum.p, &hsum[r]));
+      SYNC();
+      double tot = 0.0;
+      for (int i = 0; i < k; i++) tot += hsum[i];
+      q = (float)(tot / (double)n);
+      return LSQ_OK;
+    };
+#define RUN(call) do { const int rr__ = (call); if (rr__ != LSQ_OK) return rr__; } while (0)
+
+    // C = update_codebooks(R'X, B); C_i = R*C_i  (LSQ.jl:31-41)
+    if (R != nullptr) {
+      STEP_CUDA(dRX.alloc((size_t)nl * d));
+      STEP_CUDA(dRm.alloc((size_t)d * d));
+      STEP_CUDA(dC2.alloc((size_t)mh * d));
+      STEP_CUDA(cudaMemcpyAsync(dRm.p, R, (size_t)d * d * 4, cudaMemcpyHostToDevice, st));
+      STEP(launch_rows_times_matrix(dX.p, nl, d, dRm.p, d, 1, dRX.p, st));
+      RUN(exchange_scale(dRX.p));
+      RUN(update(dRX.p));
+      STEP(launch_rows_times_matrix(dC.p, mh, d, dRm.p, 1, d, dC2.p, st));
+      STEP_CUDA(cudaMemcpyAsync(dC.p, dC2.p, (size_t)mh * d * 4, cudaMemcpyDeviceToDevice, st));
+      RUN(exchange_scale(dX.p));
+    } else {
+      RUN(exchange_scale(dX.p));
+      RUN(update(dX.p));
     }
-  }
+    if (verbose) { RUN(qerror_all()); if (r == 0) fprintf(stderr, "%3d %e \n", -2, q); }
 
-  LSQ_TRY(launch_codes_u8_to_i16(dcodes.p, d16.p, n * m, st));
-  LSQ_CUDA(cudaMemcpyAsync(B, d16.p, (size_t)n * m * 2, cudaMemcpyDeviceToHost, st));
-  LSQ_CUDA(cudaMemcpyAsync(C, dC.p, (size_t)mh * d * 4, cudaMemcpyDeviceToHost, st));
-  LSQ_CUDA(cudaStreamSynchronize(st));
-  return LSQ_OK;
+    // Initialize B (LSQ.jl:44-49)
+    uint32_t ils_count = 0;
+    STEP(train_encode(T, ils_count, ilsiter));
+    ils_count += (uint32_t)ilsiter;
+    if (verbose) { RUN(qerror_all()); if (r == 0) fprintf(stderr, "%3d %e \n", -1, q); }
+
+    for (int iter = 0; iter < niter; iter++) {
+      RUN(qerror_all());  // LSQ.jl:55
+      if (r == 0 && obj) obj[iter] = q;
+      if (verbose && r == 0) fprintf(stderr, "%3d %e \n", iter + 1, q);
+      RUN(update(dX.p));
+      STEP(train_encode(T, ils_count, ilsiter));
+      ils_count += (uint32_t)ilsiter;
+    }
+
+    // norm codebook (LSQ.jl:68-84): norms of all shards -> one 1-D k-means on the primary device -> every
+    // shard quantises its own norms with the shared centres
+    if (want_norms) {
+      STEP_CUDA(dvn.alloc(nl));
+      STEP_CUDA(dcent.alloc(h));
+      if (rc == LSQ_OK) {
+        decoded_norms_kernel<<<(unsigned)ceil_div(nl, 128), 128, 0, st>>>(dcodes.p, nl, dC.p, d, m, dvn.p);
+        STEP_CUDA(cudaGetLastError());
+      }
+      STEP_CUDA(cudaMemcpyAsync(hnorms.data() + lo, dvn.p, (size_t)nl * 4, cudaMemcpyDeviceToHost, st));
+      STEP_CUDA(cudaStreamSynchronize(st));
+      SYNC();
+      if (r == 0) {
+        DevBuf<float> dall;
+        const float* src = dvn.p;
+        if (k > 1) {
+          STEP_CUDA(dall.alloc(n));
+          STEP_CUDA(cudaMemcpyAsync(dall.p, hnorms.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+          src = dall.p;
+        }
+        int kit = 0;
+        STEP(kmeans1d_device(src, n, h, dcent.p, 100, &kit, st));
+        if (verbose && rc == LSQ_OK) fprintf(stderr, "[lsq_b200] norm codebook: 1-D k-means stopped after %d iterations\n", kit);
+        STEP_CUDA(cudaMemcpyAsync(hcent.data(), dcent.p, (size_t)h * 4, cudaMemcpyDeviceToHost, st));
+        STEP_CUDA(cudaStreamSynchronize(st));
+        if (cbnorms && rc == LSQ_OK) memcpy(cbnorms, hcent.data(), (size_t)h * 4);
+      }
+      SYNC();
+      if (B_norms) {
+        if (r != 0) STEP_CUDA(cudaMemcpyAsync(dcent.p, hcent.data(), (size_t)h * 4, cudaMemcpyHostToDevice, st));
+        STEP(launch_quantize_norms(dcodes.p, nl, dC.p, d, m, dcent.p, h, d16.p, st));
+        STEP_CUDA(cudaMemcpyAsync(B_norms + lo, d16.p, (size_t)nl * 2, cudaMemcpyDeviceToHost, st));
+        STEP_CUDA(cudaStreamSynchronize(st));
+      }
+    }
+
+    STEP(launch_codes_u8_to_i16(dcodes.p, d16.p, nl * m, st));
+    STEP_CUDA(cudaMemcpyAsync(B + (size_t)lo * m, d16.p, (size_t)nl * m * 2, cudaMemcpyDeviceToHost, st));
+    if (r == 0) STEP_CUDA(cudaMemcpyAsync(C, dC.p, (size_t)mh * d * 4, cudaMemcpyDeviceToHost, st));
+    STEP_CUDA(cudaStreamSynchronize(st));
+    SYNC();  // no device frees its buffers while a peer might still be inside the last collective
+    return LSQ_OK;
+#undef STEP
+#undef STEP_CUDA
+#undef SYNC
+#undef RUN
+  });
 }
 
 int lsq_kmeans1d(const float* values, int64_t n, int h, int maxiter, float* centers, int* iters_out) {

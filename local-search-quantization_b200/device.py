@@ -71,21 +71,43 @@ class EncodeSession:
         return float(self.cost.double().mean().item())
 
 
-def cb_stats(X, codes, m, gram=None, rhs=None):
-    """Accumulate the codebook-update statistics of one shard into float64 device tensors."""
+def absmax(X):
+    """max|x| of a float32 device tensor (one pass; needed once per data set, not per iteration)."""
+    out = torch.zeros(1, dtype=torch.float32, device=X.device)
+    api._check(api.lib().lsq_dev_absmax(_ptr(X), ct.c_int64(X.numel()), _ptr(out), _stream()))
+    return float(out.item())
+
+
+def cb_scale_exp(absmax_all, n_total):
+    """Scale exponent of the fixed-point statistics from the GLOBAL max|x| and vector count."""
+    return int(api.lib().lsq_cb_scale_exp(ct.c_float(absmax_all), ct.c_int64(n_total)))
+
+
+def cb_accumulate(X, codes, m, scale_exp, stats=None):
+    """Exact integer codebook-update statistics of one shard: int64 device tensor [mh*mh + mh*d] (counts,
+    then fixed-point sums).  Shards add up with ONE all-reduce of this buffer, in any order, bit-exactly."""
     n, d = X.shape
+    if stats is None:
+        stats = torch.zeros(int(api.lib().lsq_cb_stats_len(m, d)), dtype=torch.int64, device=X.device)
+    api._check(api.lib().lsq_dev_cb_accumulate(_ptr(X), d, ct.c_int64(n), _ptr(codes), m, int(scale_exp),
+                                               _ptr(stats), _stream()))
+    return stats
+
+
+def cb_finalize(stats, m, d, scale_exp):
+    """Summed statistics -> (Gram (mh, mh), Rhs (mh, d)) float64 for cb_solve."""
     mh = m * 256
-    if gram is None and rhs is None:
-        # one buffer, Gram then Rhs: parallel.allreduce_stats reduces it with a single collective
-        flat = torch.zeros(mh * mh + mh * d, dtype=torch.float64, device=X.device)
-        gram, rhs = flat[: mh * mh].view(mh, mh), flat[mh * mh:].view(mh, d)
-    if gram is None:
-        gram = torch.zeros((mh, mh), dtype=torch.float64, device=X.device)
-    if rhs is None:
-        rhs = torch.zeros((mh, d), dtype=torch.float64, device=X.device)
-    api._check(api.lib().lsq_dev_cb_stats(_ptr(X), d, ct.c_int64(n), _ptr(codes), m, _ptr(gram), _ptr(rhs),
-                                          _stream()))
+    gram = torch.empty((mh, mh), dtype=torch.float64, device=stats.device)
+    rhs = torch.empty((mh, d), dtype=torch.float64, device=stats.device)
+    api._check(api.lib().lsq_dev_cb_finalize(_ptr(stats), m, d, int(scale_exp), _ptr(gram), _ptr(rhs), _stream()))
     return gram, rhs
+
+
+def cb_stats(X, codes, m):
+    """Single-shard convenience: (Gram, Rhs) float64 of this X alone."""
+    n, d = X.shape
+    e = cb_scale_exp(absmax(X), n)
+    return cb_finalize(cb_accumulate(X, codes, m, e), m, d, e)
 
 
 def cb_solve(gram, rhs, m, max_iter=0, tol=0.0):

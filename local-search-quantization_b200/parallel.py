@@ -5,9 +5,12 @@ The path shards naturally:
     communication; the perturbation RNG is keyed by the GLOBAL vector index (`g0` + local index), so the
     codes are identical for any number of GPUs.
   * codebook update — the single exchange step of the path: every rank accumulates its shard's
-    Gram = A'A and Rhs = A'X' (float64), ONE all-reduce (NCCL over NVLink/NVSwitch on the GPU box, gloo
-    in the CPU tests) sums them, then every rank runs the same deterministic solve and ends up with
-    identical codebooks (no broadcast needed).
+    Gram = A'A (counts) and Rhs = A'X' (fixed-point sums) as exact int64, ONE all-reduce (NCCL over
+    NVLink/NVSwitch on the GPU box, gloo in the CPU tests) sums them, then every rank runs the same
+    deterministic solve and ends up with identical codebooks (no broadcast needed) — the same bits as a
+    single-GPU run, because integer sums do not depend on the order.
+This module is the one-process-per-GPU (torchrun) plumbing; a single process can instead bind several GPUs
+with lsq_b200.init_devices() and the library shards the host-pointer calls internally.
 Nothing here touches the oracle; the statistics/solve functions are injected by the caller so that the
 host logic can be exercised on CPU tensors with gloo.
 """
@@ -33,24 +36,38 @@ def shard_bounds(n, size=None, rank=None):
     return api.splitarray(n, size)[rank]
 
 
-def allreduce_stats(gram, rhs):
+def allreduce_stats(stats):
     """The one collective of the path: sum the codebook-update statistics over all ranks, in place.
-    Gram and Rhs travel in ONE all-reduce: `device.cb_stats` allocates them back to back in one buffer,
-    which is then reduced as a whole; separately allocated tensors are packed into one buffer first."""
+    `stats` is ONE buffer (device.cb_accumulate: int64 counts + fixed-point sums), reduced by ONE all-reduce.
+    Integer sums are exact, so the result — and the codebooks solved from it — do not depend on the number
+    of ranks or on the reduction order.  (A (gram, rhs) pair of float tensors, as the CPU tests inject, is
+    packed into one buffer first.)"""
     _, size = world()
-    if size > 1:
-        adjacent = (gram.is_contiguous() and rhs.is_contiguous() and gram.dtype == rhs.dtype
-                    and gram.untyped_storage().data_ptr() == rhs.untyped_storage().data_ptr()
-                    and rhs.storage_offset() == gram.storage_offset() + gram.numel())
-        if adjacent:
-            flat = torch.as_strided(gram, (gram.numel() + rhs.numel(),), (1,), gram.storage_offset())
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
-        else:
+    if isinstance(stats, (tuple, list)):
+        gram, rhs = stats
+        if size > 1:
             flat = torch.cat([gram.reshape(-1), rhs.reshape(-1).to(gram.dtype)])
             dist.all_reduce(flat, op=dist.ReduceOp.SUM)
             gram.copy_(flat[: gram.numel()].view_as(gram))
             rhs.copy_(flat[gram.numel():].view_as(rhs).to(rhs.dtype))
-    return gram, rhs
+        return gram, rhs
+    if size > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    return stats
+
+
+def global_scale_exp(X, n_total=None):
+    """Scale exponent of the fixed-point statistics: needs max|x| and the vector count over ALL ranks (two
+    scalars, exchanged once per data set — X does not change between outer iterations)."""
+    from . import device as dev
+    t = torch.tensor([dev.absmax(X)], dtype=torch.float32, device=X.device)
+    c = torch.tensor([X.shape[0]], dtype=torch.int64, device=X.device)
+    _, size = world()
+    if size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if n_total is None:
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+    return dev.cb_scale_exp(float(t.item()), int(n_total if n_total is not None else c.item()))
 
 
 def global_mean(local_sum, local_count, device=None):
@@ -96,16 +113,19 @@ def linscan_sharded(queries, scan_fn, gather=True):
     return gather_rows(dists), gather_rows(ids), (lo, hi)
 
 
-def update_codebooks_sharded(X, codes, m, stats_fn=None, solve_fn=None):
-    """update_codebooks (codebook_update.jl:52-86) over sharded data: local statistics -> all-reduce
-    -> replicated solve.  Defaults run the CUDA kernels (lsq_dev_cb_stats / lsq_dev_cb_solve)."""
-    if stats_fn is None or solve_fn is None:
-        from . import device as dev
-        stats_fn = stats_fn or (lambda X_, c_: dev.cb_stats(X_, c_, m))
-        solve_fn = solve_fn or (lambda g_, r_: dev.cb_solve(g_, r_, m)[0])
-    gram, rhs = stats_fn(X, codes)
-    allreduce_stats(gram, rhs)
-    return solve_fn(gram, rhs)
+def update_codebooks_sharded(X, codes, m, stats_fn=None, solve_fn=None, scale_exp=None):
+    """update_codebooks (codebook_update.jl:52-86) over sharded data: local statistics -> ONE all-reduce
+    -> replicated solve.  Defaults run the CUDA kernels (exact integer statistics: bit-identical codebooks for
+    any number of ranks); stats_fn / solve_fn let the CPU tests inject stand-ins."""
+    if stats_fn is not None or solve_fn is not None:
+        gram, rhs = allreduce_stats(tuple(stats_fn(X, codes)))
+        return solve_fn(gram, rhs)
+    from . import device as dev
+    if scale_exp is None:
+        scale_exp = global_scale_exp(X)
+    stats = allreduce_stats(dev.cb_accumulate(X, codes, m, scale_exp))
+    gram, rhs = dev.cb_finalize(stats, m, X.shape[1], scale_exp)
+    return dev.cb_solve(gram, rhs, m)[0]
 
 
 def train_lsq_sharded(X, codes, C, niter, ilsiter, icmiter, randord, npert, seed=0, g0=0, verbose=False):
@@ -116,13 +136,14 @@ def train_lsq_sharded(X, codes, C, niter, ilsiter, icmiter, randord, npert, seed
     from . import device as dev
     m = C.shape[0]
     sess = dev.EncodeSession(X, C, codes, g0=g0)
+    scale_exp = global_scale_exp(X)   # once: X is fixed for the whole alternation
     obj = []
     it_count = 0
     for it in range(niter):
         obj.append(global_mean(float(sess.cost.double().sum().item()), X.shape[0], device=X.device))
         if verbose and world()[0] == 0:
             print(f"{it + 1:3d} {obj[-1]:e}")
-        C = update_codebooks_sharded(X, codes, m)
+        C = update_codebooks_sharded(X, codes, m, scale_exp=scale_exp)
         sess.set_codebooks(C)
         sess.ils(ilsiter, icmiter, npert, randord, seed=seed, ils_iter0=it_count)
         it_count += ilsiter

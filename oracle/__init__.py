@@ -103,6 +103,16 @@ def get_unaries(X, C):
     return U
 
 
+def get_unary_gemm(X, C):
+    """-2*C_i'*X without the norms (the gemm of utils.jl:108 / encode_icm_cuda.jl:92) -> (m, n, h)."""
+    X, C = _f32(X), _f32(C)
+    n, d = X.shape
+    m, h, _ = C.shape
+    G = np.zeros((m, n, h), np.float32)
+    lib().orc_get_unary_gemm(_p(X), _p(C), ct.c_int64(n), m, h, d, _p(G))
+    return G
+
+
 def get_binaries(C):
     C = _f32(C)
     m, h, d = C.shape
@@ -280,8 +290,9 @@ def ref_linscan_pq(codes, queries, centers, K):
 
 # ---- §8(f) rows: eval_recall, the norm codebook, the train_lsq alternation -------------------------
 def eval_recall(ids_gnd, ids_predicted, k):
-    """Linscan.jl:76-117: nn_ranks[i] = position of the ground-truth id in query i's list if it occurs
-    exactly once (:94-98), else k+1; recall_at_i[i] = #{rank <= i} / nquery (:111-113).
+    """Linscan.jl:76-117: nn_ranks[i] = position of the ground-truth id in query i's WHOLE list (`find`
+    over the full column, :91) if it occurs exactly once (:94-98), else k+1;
+    recall_at_i[i] = #{rank <= i and rank <= k} / nquery (:111-113).
     ids_predicted is (nq, >= k): row q = column q of the Julia matrix."""
     ids_gnd = np.asarray(ids_gnd).reshape(-1)
     ids_predicted = np.asarray(ids_predicted)
@@ -289,8 +300,8 @@ def eval_recall(ids_gnd, ids_predicted, k):
     assert nquery == len(ids_gnd)
     nn_ranks = np.full(nquery, k + 1, np.int64)
     for i in range(nquery):
-        pos = np.nonzero(ids_predicted[i, :k] == ids_gnd[i])[0]
-        if len(pos) == 1:
+        pos = np.nonzero(ids_predicted[i] == ids_gnd[i])[0]
+        if len(pos) == 1 and pos[0] < k:
             nn_ranks[i] = pos[0] + 1
     nn_ranks.sort()
     return np.searchsorted(nn_ranks, np.arange(1, k + 1), side="right") / nquery

@@ -141,6 +141,24 @@ void orc_get_norms(const float* C, int m, int h, int d, float* norms /*[m][h]*/)
   for (int i = 0; i < m * h; i++) norms[i] = dot_fma(C + (size_t)i * d, C + (size_t)i * d, d);
 }
 
+/* The sgemm part of get_unaries alone: G_i = -2*C_i'*X (utils.jl:108; on the reference GPU path this is the
+ * cuBLAS gemm of encode_icm_cuda.jl:92, to which the reference's own vec_add kernel then adds the norms). */
+void orc_get_unary_gemm(const float* X, const float* C, int64_t n, int m, int h, int d,
+                        float* G /*[m][n][h]*/) {
+#pragma omp parallel
+  {
+    float* tmp = (float*)malloc(sizeof(float) * h);
+#pragma omp for collapse(2) schedule(static)
+    for (int i = 0; i < m; i++)
+      for (int64_t v = 0; v < n; v++) {
+        dots_fma(C + (size_t)i * h * d, X + (size_t)v * d, h, d, tmp);
+        float* g = G + ((size_t)i * n + v) * h;
+        for (int a = 0; a < h; a++) g[a] = -2.0f * tmp[a];
+      }
+    free(tmp);
+  }
+}
+
 /* get_unaries (utils.jl:94-122): U_i = -2*C_i'*X, then += ||c||^2 per row. */
 void orc_get_unaries(const float* X, const float* C, int64_t n, int m, int h, int d,
                      float* U /*[m][n][h]*/) {

@@ -45,23 +45,20 @@ def _worker(rank, size, port, out):
         Cs = par.update_codebooks_sharded(X[lo:hi], whole[lo:hi], m, stats_fn=stats, solve_fn=solve)
         Cw = cu.update_codebooks_exact(X, whole, 256)
         assert np.allclose(Cs, Cw, rtol=0, atol=1e-4 * np.abs(Cw).max())
-        # Gram and Rhs allocated back to back (as device.cb_stats does) travel in ONE all-reduce of the
-        # whole buffer; the result must equal the packed path above
-        def stats_adjacent(Xs, cs):
-            G, R = cu.gram_stats(Xs, cs, 256)
-            flat = torch.zeros(G.size + R.size, dtype=torch.float64)
-            g, r = flat[: G.size].view(G.shape), flat[G.size:].view(R.shape)
-            g.copy_(torch.from_numpy(G)); r.copy_(torch.from_numpy(R))
-            return g, r
+        # integer statistics (the layout of device.cb_accumulate) travel in ONE all-reduce of ONE int64 buffer,
+        # and the result is exactly the statistics of the whole set (integer sums are order-independent)
+        def int_stats(Xs, cs, e):
+            G, R = cu.gram_stats(Xs, cs, 256)   # R exact here: the test data are small integers
+            return torch.from_numpy(np.concatenate([G.reshape(-1), np.rint(R * 2.0 ** e).reshape(-1)]).astype(np.int64))
         calls = []
         orig = dist.all_reduce
-        dist.all_reduce = lambda t, *a, **k: (calls.append(t.numel()), orig(t, *a, **k))[1]
+        dist.all_reduce = lambda t, *a, **k: (calls.append((t.numel(), t.dtype)), orig(t, *a, **k))[1]
         try:
-            Cs2 = par.update_codebooks_sharded(X[lo:hi], whole[lo:hi], m, stats_fn=stats_adjacent, solve_fn=solve)
+            S = par.allreduce_stats(int_stats(X[lo:hi], whole[lo:hi], 20))
         finally:
             dist.all_reduce = orig
-        assert calls == [(m * 256) ** 2 + m * 256 * d], calls      # exactly one collective, Gram + Rhs
-        assert np.array_equal(Cs2, Cs)
+        assert calls == [((m * 256) ** 2 + m * 256 * d, torch.int64)], calls   # exactly one collective
+        assert torch.equal(S, int_stats(X, whole, 20))
         # every rank holds the same codebooks (replicated solve, no broadcast)
         t = torch.from_numpy(Cs.copy())
         ts = [torch.empty_like(t) for _ in range(size)]

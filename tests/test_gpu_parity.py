@@ -22,9 +22,11 @@ def gpu(lsq):
 
 
 # ---------------------------------------------------------------- tables (a3, a4) and costs (a5)
-@pytest.mark.parametrize("n,d,m", [(300, 128, 8), (77, 32, 7), (130, 20, 3), (1, 128, 16), (513, 6, 2)])
-def test_unaries_bit_exact(gpu, oracle, n, d, m):
-    X, C, _ = make_problem(100 + n, n, d, m)
+@pytest.mark.parametrize("kind", ["sift", "gauss"])
+@pytest.mark.parametrize("n,d,m", [(300, 128, 8), (77, 32, 7), (130, 20, 3), (1, 128, 16), (513, 6, 2), (1000, 100, 5)])
+def test_unaries_bit_exact(gpu, oracle, n, d, m, kind):
+    # "sift" data sums exactly in fp32 (any order passes); "gauss" exercises the sequential-k FMA chain
+    X, C, _ = make_problem(100 + n, n, d, m, kind=kind)
     assert np.array_equal(gpu.get_unaries(X, C), oracle.get_unaries(X, C))
 
 
@@ -467,6 +469,54 @@ def test_eval_recall_matches_oracle(gpu, oracle):
         assert np.array_equal(gpu.eval_recall(gt, pred, kk), oracle.eval_recall(gt, pred, kk))
     assert np.array_equal(gpu.eval_recall(gt.astype(np.uint32), pred.astype(np.uint32), 100),
                           oracle.eval_recall(gt, pred, 100))
+
+
+def test_eval_recall_searches_the_whole_list(gpu, oracle):
+    """Linscan.jl:91 runs find() over the WHOLE column: an id inside the top k that occurs again beyond
+    position k is a miss, and an id found once beyond k is a miss too."""
+    rng = np.random.default_rng(4)
+    nq, ld, k = 64, 200, 50
+    pred = np.stack([rng.permutation(10000)[:ld] for _ in range(nq)]).astype(np.int32) + 1
+    gt = pred[np.arange(nq), rng.integers(0, k, nq)].copy()
+    pred[3, 120] = gt[3]            # second occurrence beyond k -> miss in the reference
+    gt[5] = pred[5, 150]            # only occurrence beyond k -> miss
+    rg, ro = gpu.eval_recall(gt, pred, k), oracle.eval_recall(gt, pred, k)
+    assert np.array_equal(rg, ro)
+    assert rg[-1] == (nq - 2) / nq
+
+
+def test_encoding_icm_default_iteration_counter(gpu, oracle):
+    """The reference loop `for i = 1:ilsiter; B = encoding_icm(X, B, C, ...)` (LSQ.jl:45-48) ported verbatim:
+    with ils_iter left at its default every call must draw a fresh perturbation schedule (iterations
+    0, 1, 2, ... of the Philox stream), not replay the first one."""
+    X, C, B = make_problem(4100, 3000, 32, 8)
+    gpu.reset_ils_counter()
+    Bd = B
+    for _ in range(3):
+        Bd = gpu.encoding_icm(X, Bd, C, 2, True, 4, seed=11)
+    Be = B
+    for i in range(3):
+        Be = gpu.encoding_icm(X, Be, C, 2, True, 4, seed=11, ils_iter=i)
+    assert np.array_equal(Bd, Be)
+    Bo = (B - 1).astype(np.int16)
+    for i in range(3):
+        Bo, _ = oracle.encoding_icm(X, Bo, C, 2, True, 4, seed=11, ils_iter=i)
+    assert np.array_equal(Bd, Bo + 1)
+    Br = B
+    for _ in range(3):   # what the old default (always iteration 0) did: a different, weaker result
+        Br = gpu.encoding_icm(X, Br, C, 2, True, 4, seed=11, ils_iter=0)
+    assert not np.array_equal(Bd, Br)
+
+
+def test_pageable_and_pinned_host_buffers_agree(gpu):
+    """Julia arrays are pageable: the staged host->device copy must deliver the same bytes as a pinned source."""
+    import torch
+    X, C, B = make_problem(4200, 70000, 128, 8)
+    its = [2]
+    Bp, op = gpu.encode_icm_cuda(X, B, C, its, 2, 4, True, 1, seed=3)
+    Xp, Bpin = torch.from_numpy(X).pin_memory(), torch.from_numpy(B).pin_memory()
+    Bq, oq = gpu.encode_icm_cuda(Xp.numpy(), Bpin.numpy(), C, its, 2, 4, True, 1, seed=3)
+    assert np.array_equal(Bp[0], Bq[0]) and np.array_equal(op, oq)
 
 
 # ---------------------------------------------------------------- §8(f4): chain (Viterbi) encoder
