@@ -148,9 +148,21 @@ def cpu_port_rate(n_sample, ils_total, seed=1):
     return n_sample / (dt * ils_total), threads, dt
 
 
+def workload_config(args, world):
+    """`config` of the JSON line — identical for the b200 arm and the reference arm."""
+    n_per_gpu = args.n // world if args.scaling == "strong" else args.n
+    return {"workload": f"LSQ ICM encode m={M} h={H} d={D}, {args.ils} ILS iters x icmiter={ICMITER}, npert={NPERT} "
+                        f"(BASELINE configs[1] base-set encode)",
+            "n_total": args.n if args.scaling == "strong" else args.n * world, "n_per_gpu": n_per_gpu,
+            "parallelism": f"shard{world}", "l2": f"inputs larger than L2 ({M * n_per_gpu * 1024 / 1e9:.1f} GB unaries per GPU)",
+            "step": "pair tables + unaries + cost + all ILS iterations",
+            "unary_mode": "exact fp32 chain (parity)" if args.unary == "exact" else "tcgen05 3xTF32 (fast mode, not bit-exact)"}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm (oracle port; Julia absent) on host cores."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     ns = args.cpu_sample
@@ -166,10 +178,9 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": "icm_encode_vectors_per_sec", "value": value, "unit": "vectors/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * statistics.median(t_steps), "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * statistics.median(t_steps), "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"LSQ ICM encode m={M} h={H} d={D}, {args.ils} ILS iters x icmiter={ICMITER}, npert={NPERT}",
-                   "n_per_gpu": args.n, "cpu_sample": ns},
+        "config": workload_config(args, world),
         "cpu_baseline": {"value": value, "unit": "vectors/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -185,6 +196,56 @@ def run_reference(args):
 # scan bandwidth nq*n*(m+4)/t against the measured HBM peak (an *effective* figure — the
 # query-tiled kernel re-serves the code array from L2), the LUT lookup rate against the shared-memory bound
 # 148 SMs x 32 banks x f_SM, and the reference's own C++ (oracle/_ref, OpenMP) on a query subsample.
+def adc_measure(m, n, nq, nn, d=128, reps=3, cpu_queries=64, check_queries=16, rank=0, world=1, cpu_leg=True):
+    """One ADC configuration on the current device.  With world > 1 the QUERIES are partitioned over the ranks
+    (codes replicated, no merge: SURVEY.md §8e) and the time is the max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import lsq_b200
+    from lsq_b200 import device as dev
+    from util import make_scan_problem
+    peak, _ = measured_peak()
+    codes, queries, codebooks, norms = make_scan_problem(50 + m, n, nq, d, m)
+    qlo, qhi = lsq_b200.splitarray(nq, world)[rank]
+    dc, dq = torch.from_numpy(codes).cuda(), torch.from_numpy(queries[qlo:qhi]).cuda()
+    dcb, dn = torch.from_numpy(codebooks).cuda(), torch.from_numpy(norms).cuda()
+    for _ in range(2):
+        dd, di = dev.linscan(dc, dq, dcb, dn, nn)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    l0 = lsq_b200.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        dd, di = dev.linscan(dc, dq, dcb, dn, nn)
+    b.record()
+    torch.cuda.synchronize()
+    launches = (lsq_b200.launch_count() - l0) // reps
+    t = torch.tensor([a.elapsed_time(b) / reps], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    out = {"m": m, "n": n, "nq": nq, "nn": nn, "ms": ms, "queries_per_s": nq / (ms * 1e-3), "launches_per_call": launches}
+    eff = nq * n * (m + 4) / (ms * 1e-3) / 1e9
+    lookups = nq * n * m / (ms * 1e-3)
+    out.update({"effective_scan_GBps": eff, "effective_frac_of_hbm_peak": eff / peak / world,
+                "lookups_per_s": lookups, "lookup_frac_of_smem_bound": lookups / (world * 148 * 32 * 1.965e9)})
+    if cpu_leg and rank == 0:
+        import oracle
+        # exactness spot check against the reference .so (or the oracle restatement), which is also the CPU baseline
+        fn = oracle.ref_linscan_lsq if oracle.ref_available() else oracle.linscan_lsq
+        t0 = time.perf_counter()
+        dr, ir = fn(codes, queries[:cpu_queries], codebooks, norms, nn)
+        cpu_s = time.perf_counter() - t0
+        k = min(check_queries, qhi - qlo)
+        out["exact_vs_reference"] = bool(np.array_equal(ir[:k], di[:k].cpu().numpy()) and np.array_equal(dr[:k], dd[:k].cpu().numpy()))
+        out["cpu_baseline"] = {"kind": "reference" if oracle.ref_available() else "port", "cores": oracle.num_threads(),
+                               "queries_per_s": cpu_queries / cpu_s, "sample": f"{cpu_queries} queries x {n} codes"}
+    return out
+
+
 def run_adc(argv):
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=1_000_000)
@@ -196,46 +257,12 @@ def run_adc(argv):
     ap.add_argument("--cpu-queries", type=int, default=64)
     ap.add_argument("--check-queries", type=int, default=16)
     args = ap.parse_args(argv)
-    import torch
     import lsq_b200
-    from lsq_b200 import device as dev
-    import oracle
-    from util import make_scan_problem
     lsq_b200.init(0)
-    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(
-        os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     for m in args.m:
-        codes, queries, codebooks, norms = make_scan_problem(50 + m, args.n, args.nq, args.d, m)
-        dc, dq = torch.from_numpy(codes).cuda(), torch.from_numpy(queries).cuda()
-        dcb, dn = torch.from_numpy(codebooks).cuda(), torch.from_numpy(norms).cuda()
-        for _ in range(2):
-            dd, di = dev.linscan(dc, dq, dcb, dn, args.nn)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(args.reps):
-            dd, di = dev.linscan(dc, dq, dcb, dn, args.nn)
-        b.record()
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / args.reps
-        # exactness spot check against the reference .so (or the oracle restatement)
-        k = args.check_queries
-        fn = oracle.ref_linscan_lsq if oracle.ref_available() else oracle.linscan_lsq
-        t0 = time.perf_counter()
-        dr, ir = fn(codes, queries[: args.cpu_queries], codebooks, norms, args.nn)
-        cpu_s = time.perf_counter() - t0
-        exact = bool(np.array_equal(ir[:k], di[:k].cpu().numpy()) and np.array_equal(dr[:k], dd[:k].cpu().numpy()))
-        eff = args.nq * args.n * (m + 4) / (ms * 1e-3) / 1e9
-        lookups = args.nq * args.n * m / (ms * 1e-3)
-        print(json.dumps({
-            "metric": "adc_scan_queries_per_sec", "value": args.nq / (ms * 1e-3), "unit": "queries/s", "m": m,
-            "n": args.n, "nq": args.nq, "nn": args.nn, "ms": ms, "exact_vs_reference": exact,
-            "effective_scan_GBps": eff, "effective_frac_of_hbm_peak": eff / peak,
-            "lookups_per_s": lookups, "lookup_frac_of_smem_bound": lookups / (148 * 32 * 1.965e9),
-            "cpu_baseline": {"kind": "reference" if oracle.ref_available() else "port", "cores": oracle.num_threads(),
-                             "queries_per_s": args.cpu_queries / cpu_s,
-                             "sample": f"{args.cpu_queries} queries x {args.n} codes"},
-        }))
+        r = adc_measure(m, args.n, args.nq, args.nn, args.d, args.reps, args.cpu_queries, args.check_queries)
+        r.update({"metric": "adc_scan_queries_per_sec", "value": r["queries_per_s"], "unit": "queries/s"})
+        print(json.dumps(r))
 
 
 # Chain (Viterbi / ChainQ) encoder: resident-data timing of the kernel, the whole host call, and the CPU
@@ -363,26 +390,159 @@ def run_legacy(argv, n=1_000_000, m=8, d=128, ils=16, icmiter=4):
     }))
 
 
+def _ev():
+    import torch
+    return torch.cuda.Event(enable_timing=True)
+
+
+def _max_over_ranks(x, world, dev):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(x)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
+def train_step_block(rank, world, dev, n_per_gpu, ilsiter=8, steps=2):
+    """One outer iteration of train_lsq on BASELINE configs[3]'s shape (10 M vectors over 8 GPUs = 1.25 M per GPU,
+    sharded): local statistics -> ONE all-reduce of the integer statistics (NCCL) -> replicated solve -> tables +
+    unaries -> `ilsiter` ILS iterations.  Each phase is timed with CUDA events on the launching stream; the
+    figures are the max over ranks of the per-step mean."""
+    import torch
+    import torch.distributed as dist
+    import lsq_b200
+    from lsq_b200 import device as lsqdev, parallel as par
+    from util import make_problem, sift_like
+    _, C_h, _ = make_problem(0, 16, D, M)
+    rng = np.random.default_rng(2000 + rank)
+    X = torch.from_numpy(sift_like(rng, n_per_gpu, D)).to(dev)
+    codes = torch.from_numpy(rng.integers(0, H, size=(n_per_gpu, M)).astype(np.uint8)).to(dev)
+    sess = lsqdev.EncodeSession(X, torch.from_numpy(C_h).to(dev), codes, g0=rank * n_per_gpu)
+    scale_exp = par.global_scale_exp(X)
+    stats = torch.zeros(int(lsq_b200.lib().lsq_cb_stats_len(M, D)), dtype=torch.int64, device=dev)
+    # outputs of finalize / solve are allocated once: no allocator call inside the timed phases
+    import ctypes as ct
+    L = lsq_b200.lib()
+    gram = torch.empty((M * H, M * H), dtype=torch.float64, device=dev)
+    rhs = torch.empty((M * H, D), dtype=torch.float64, device=dev)
+    C = torch.empty((M, H, D), dtype=torch.float32, device=dev)
+    cg = ct.c_int(0)
+    stream = lambda: ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+    phases = {k: [] for k in ("cb_accumulate_ms", "allreduce_ms", "finalize_solve_ms", "tables_unaries_ms", "ils_ms", "total_ms")}
+    it = 0
+    warm = 2
+    for s in range(steps + warm):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        e = [_ev() for _ in range(6)]
+        e[0].record()
+        stats.zero_()
+        lsqdev.cb_accumulate(X, codes, M, scale_exp, stats=stats)
+        e[1].record()
+        if world > 1:
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        e[2].record()
+        lsq_b200.api._check(L.lsq_dev_cb_finalize(ct_ptr(stats), M, D, scale_exp, ct_ptr(gram), ct_ptr(rhs), stream()))
+        lsq_b200.api._check(L.lsq_dev_cb_solve(ct_ptr(gram), ct_ptr(rhs), M, D, ct_ptr(C), 0, ct.c_double(0.0), ct.byref(cg), stream()))
+        cg_iters = cg.value
+        e[3].record()
+        sess.set_codebooks(C)
+        e[4].record()
+        sess.ils(ilsiter, ICMITER, NPERT, True, seed=3, ils_iter0=it)
+        e[5].record()
+        it += ilsiter
+        torch.cuda.synchronize()
+        if s >= warm:
+            for k, i in zip(list(phases)[:5], range(5)):
+                phases[k].append(e[i].elapsed_time(e[i + 1]))
+            phases["total_ms"].append(e[0].elapsed_time(e[5]))
+    out = {k: _max_over_ranks(statistics.mean(v), world, dev) for k, v in phases.items()}
+    out.update({"workload": f"train_lsq outer iteration, m={M}, {n_per_gpu} vectors per GPU x {world} GPUs, ilsiter={ilsiter} "
+                            f"(BASELINE configs[3] shape: 10 M over 8 GPUs)",
+                "allreduce": (f"torch.distributed NCCL all_reduce(SUM) of {stats.numel() * 8 / 1e6:.1f} MB int64" if world > 1 else None),
+                "cg_iterations": cg_iters, "qerror_after": sess.qerror(),
+                "vectors_per_s": world * n_per_gpu / (out["total_ms"] * 1e-3)})
+    return out
+
+
+def trained_codebooks_block(dev, X, codes0, ils, steps=3, ntrain=100_000):
+    """BASELINE configs[1] literally: codebooks from a short train_lsq on 100 K training vectors (same
+    distribution), then the resident-data encode of the base shard with THOSE codebooks.  The skip rate of the
+    ICM kernel is a property of the data, so this is reported beside the random-codebook headline."""
+    import torch
+    import lsq_b200
+    from lsq_b200 import device as lsqdev
+    from util import sift_like
+    rng = np.random.default_rng(4242)
+    Xt = sift_like(rng, ntrain, D)
+    Bt = lsq_b200.randinit(ntrain, M, H, rng)
+    t0 = time.perf_counter()
+    Ct, _, _, _, obj = lsq_b200.train_lsq(Xt, M, H, None, Bt, None, 4, 4, ICMITER, True, NPERT, seed=5)
+    train_s = time.perf_counter() - t0
+    C = torch.from_numpy(Ct).to(dev)
+    codes = codes0.clone()
+    sess = lsqdev.EncodeSession(X, C, codes)
+    n = X.shape[0]
+    orders = np.stack([lsq_b200.make_to_look(1, i, M, True) for i in range(ils)])
+    visits = torch.zeros(1, dtype=torch.int64, device=dev)
+    ms, kms = [], []
+    for s in range(steps + 1):
+        codes.copy_(codes0)
+        torch.cuda.synchronize()
+        a, b, c = _ev(), _ev(), _ev()
+        a.record()
+        sess.set_codebooks(C)
+        b.record()
+        if s == 0:
+            lsq_b200.lib().lsq_dev_icm_visit_counter(ct_ptr(visits))
+        sess.ils(ils, ICMITER, NPERT, True, seed=1, ils_iter0=0, orders=orders)
+        if s == 0:
+            lsq_b200.lib().lsq_dev_icm_visit_counter(None)
+        c.record()
+        torch.cuda.synchronize()
+        if s > 0:
+            ms.append(a.elapsed_time(c)); kms.append(b.elapsed_time(c))
+    peak, _ = measured_peak()
+    k = statistics.mean(kms)
+    return {"value_per_gpu": n / (statistics.mean(ms) * 1e-3), "unit": "vectors/s", "n_per_gpu": n, "ms_per_step": statistics.mean(ms),
+            "kernel_ms": k, "roofline_frac": algorithmic_bytes_per_vec_iter() * n * ils / (k * 1e-3) / 1e9 / peak,
+            "visits_per_vector_iter": visits.item() / (n * ils), "qerror": sess.qerror(),
+            "codebooks": f"lsq_train_lsq on {ntrain} vectors, 4 outer x 4 ILS iterations ({train_s:.2f} s, objective {float(obj[0]):.1f} -> {float(obj[-1]):.1f})"}
+
+
+def ct_ptr(t):
+    import ctypes as ct
+    return ct.c_void_p(t.data_ptr())
+
+
 def main():
     pre = argparse.ArgumentParser(add_help=False)
     pre.add_argument("--workload", default="icm", choices=["icm", "adc", "chain", "legacy"])
     ns, rest = pre.parse_known_args()
     if ns.workload != "icm":
         return {"adc": run_adc, "chain": run_chain, "legacy": run_legacy}[ns.workload](rest)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="icm", help="icm (headline, default) | adc | chain | legacy")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000, help="base vectors per GPU (weak) or in total (strong)")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak: --n vectors per GPU (the contract's default); strong: --n vectors split over the GPUs")
+    ap.add_argument("--n", type=int, default=1_000_000, help="base vectors in total (strong) or per GPU (weak)")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="strong (default): --n vectors split over the GPUs, the north-star's 1 M-vector encode; "
+                         "weak: --n vectors per GPU.  Identical at 1 GPU.")
     ap.add_argument("--ils", type=int, default=16, help="ILS iterations per encode (LSQ-16)")
     ap.add_argument("--cpu-sample", type=int, default=400000)
-    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-recall", action="store_true", help="skip the untimed recall@1 probe of the full flow")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the secondary blocks (adc, train_step, trained_codebooks, weak, in-library multi-GPU)")
+    ap.add_argument("--train-n", type=int, default=1_250_000, help="vectors per GPU of the train_step block (configs[3])")
     ap.add_argument("--m", type=int, default=8, help="codebooks (BASELINE configs[2] uses 16)")
     ap.add_argument("--unary", default="exact", choices=["exact", "tc"],
                     help="exact = parity path (sequential fp32 chain); tc = tcgen05 3xTF32 fast mode (tolerance-checked)")
@@ -396,52 +556,30 @@ def main():
     import torch.distributed as dist
     import lsq_b200
     from lsq_b200 import device as lsqdev
-    from util import make_problem
+    from util import make_problem, sift_like
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")   # host-side barrier for the leg where rank 0 drives every GPU
     lsq_b200.init(local)
     dev = torch.device("cuda", local)
-    n, ils = args.n, args.ils
-    if args.scaling == "strong":  # fixed total, contiguous splitarray shards (utils.jl:152-177)
-        lo, hi = lsq_b200.splitarray(args.n, world)[rank]
-        n, g0 = hi - lo, lo
-    else:
-        g0 = rank * n  # global index of this shard's first vector
-    n_total = args.n if args.scaling == "strong" else world * n
+    ils = args.ils
 
-    # synthetic SIFT-shaped shard; codebooks identical on every rank
-    _, C_h, _ = make_problem(0, 16, D, M)
-    rng = np.random.default_rng(1000 + rank)
-    from util import sift_like
-    X_h = sift_like(rng, n, D)
-    B_h = rng.integers(1, H + 1, size=(n, M)).astype(np.int16)
-    X = torch.from_numpy(X_h).to(dev)
+    def shard_of(n_arg, scaling):
+        if scaling == "strong":  # fixed total, contiguous splitarray shards (utils.jl:152-177)
+            lo, hi = lsq_b200.splitarray(n_arg, world)[rank]
+            return hi - lo, lo, n_arg
+        return n_arg, rank * n_arg, world * n_arg
+
+    _, C_h, _ = make_problem(0, 16, D, M)   # codebooks identical on every rank
     C = torch.from_numpy(C_h).to(dev)
-    codes0 = torch.from_numpy((B_h - 1).astype(np.uint8)).to(dev)
-    codes = codes0.clone()
-    sess = lsqdev.EncodeSession(X, C, codes, g0=g0, unary=args.unary)
+    orders = np.stack([lsq_b200.make_to_look(1, i, M, True) for i in range(ils)])
     if args.unary == "tc":
         os.environ["LSQ_B200_UNARY"] = "tc"  # the host-API (e2e) leg follows the same mode
-    orders = np.stack([lsq_b200.make_to_look(1, i, M, True) for i in range(ils)])
-
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    kern_ms = []
-
-    def step(timed):
-        codes.copy_(codes0)
-        sess.set_codebooks(C)              # pair tables + norms + unaries + cost of the initial codes
-        if timed:
-            a, b = ev(), ev()
-            a.record()
-        sess.ils(ils, ICMITER, NPERT, True, seed=1, ils_iter0=0, orders=orders)
-        if timed:
-            b.record()
-            kern_ms.append((a, b))
 
     def sync():
         torch.cuda.synchronize()
@@ -449,69 +587,153 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step(False)
-    sync()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    t0, t1 = ev(), ev()
-    t0.record()
-    for _ in range(args.steps):
-        step(True)
-    t1.record()
-    sync()
-    clocks = sampler.stop() if rank == 0 else None
-    total_ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
-    k_ms = torch.tensor([statistics.mean(a.elapsed_time(b) for a, b in kern_ms)], device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = total_ms.item() / args.steps
+    def measure(n, g0, warmup, steps, sampler=None):
+        """Resident-data steps on this rank's shard: returns (ms_per_step, kernel_ms, state)."""
+        rng = np.random.default_rng(1000 + rank)
+        X_h = sift_like(rng, n, D)
+        B_h = rng.integers(1, H + 1, size=(n, M)).astype(np.int16)
+        X = torch.from_numpy(X_h).to(dev)
+        codes0 = torch.from_numpy((B_h - 1).astype(np.uint8)).to(dev)
+        codes = codes0.clone()
+        sess = lsqdev.EncodeSession(X, C, codes, g0=g0, unary=args.unary)
+        kern = []
+
+        def step(timed):
+            codes.copy_(codes0)
+            sess.set_codebooks(C)              # pair tables + norms + unaries + cost of the initial codes
+            if timed:
+                a, b = _ev(), _ev()
+                a.record()
+            sess.ils(ils, ICMITER, NPERT, True, seed=1, ils_iter0=0, orders=orders)
+            if timed:
+                b.record()
+                kern.append((a, b))
+
+        for _ in range(warmup):
+            step(False)
+        sync()
+        if sampler is not None:
+            sampler.start()
+        l0 = lsq_b200.launch_count()
+        t0, t1 = _ev(), _ev()
+        t0.record()
+        for _ in range(steps):
+            step(True)
+        t1.record()
+        sync()
+        launches = lsq_b200.launch_count() - l0
+        clocks = sampler.stop() if sampler is not None else None
+        total = _max_over_ranks(t0.elapsed_time(t1), world, dev)
+        k_ms = _max_over_ranks(statistics.mean(a.elapsed_time(b) for a, b in kern), world, dev)
+        return total / steps, k_ms, dict(X_h=X_h, B_h=B_h, X=X, codes0=codes0, codes=codes, sess=sess, launches=launches,
+                                         clocks=clocks, step=step)
+
+    n, g0, n_total = shard_of(args.n, args.scaling)
+    ms_per_step, k_ms, S = measure(n, g0, args.warmup, args.steps, ClockSampler(local) if rank == 0 else None)
     value = n_total / (ms_per_step * 1e-3)
+    sess, X_h, B_h, codes = S["sess"], S["X_h"], S["B_h"], S["codes"]
     qerr = sess.qerror()
 
-    # ---- e2e: the C-ABI host call with pinned host buffers, copies inside the timed region ----
-    Xp = torch.from_numpy(X_h).pin_memory()
-    Bp = torch.from_numpy(B_h).pin_memory()
-    its = np.array([ils], np.int64)
-    e2e_t = []
-    e2e_out = None
-    for i in range(1 + args.e2e_steps if args.e2e_steps > 0 else 0):
-        sync()
-        w0 = time.perf_counter()
-        e2e_out, _ = lsq_b200.encode_icm_cuda(Xp.numpy(), Bp.numpy(), C_h, its, ICMITER, NPERT, True, 1, seed=1, g0=g0)
-        if i > 0:
-            e2e_t.append(time.perf_counter() - w0)
-    e2e_ms = torch.tensor([1e3 * statistics.median(e2e_t) if e2e_t else float("nan")], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    same = bool(np.array_equal(e2e_out[0], codes.cpu().numpy().astype(np.int16) + 1)) if e2e_out else None
+    # executed node visits per vector and ILS iteration (device counter; one extra untimed step)
+    visits = torch.zeros(1, dtype=torch.int64, device=dev)
+    lsq_b200.lib().lsq_dev_icm_visit_counter(ct_ptr(visits))
+    S["step"](False)
+    torch.cuda.synchronize()
+    lsq_b200.lib().lsq_dev_icm_visit_counter(None)
+    visits_pvi = visits.item() / (n * ils)
 
+    # ---- e2e: the C-ABI host call, host<->device copies inside the timed region; pinned and pageable sources ----
+    its = np.array([ils], np.int64)
+
+    def e2e_leg(Xsrc, Bsrc):
+        ts, out = [], None
+        for i in range(1 + args.e2e_steps if args.e2e_steps > 0 else 0):
+            sync()
+            w0 = time.perf_counter()
+            out, _ = lsq_b200.encode_icm_cuda(Xsrc, Bsrc, C_h, its, ICMITER, NPERT, True, 1, seed=1, g0=g0)
+            if i > 0:
+                ts.append(time.perf_counter() - w0)
+        ms = _max_over_ranks(1e3 * statistics.median(ts) if ts else float("nan"), world, dev)
+        return ms, out, [round(1e3 * t, 2) for t in ts]
+
+    Xp, Bp = torch.from_numpy(X_h).pin_memory(), torch.from_numpy(B_h).pin_memory()
+    e2e_ms, e2e_out, e2e_all = e2e_leg(Xp.numpy(), Bp.numpy())
+    same = bool(np.array_equal(e2e_out[0], codes.cpu().numpy().astype(np.int16) + 1)) if e2e_out else None
+    e2e_pg_ms, pg_out, e2e_pg_all = e2e_leg(X_h, B_h)      # plain numpy arrays: pageable, like Julia's
+    same_pg = bool(np.array_equal(pg_out[0], e2e_out[0])) if pg_out else None
+    del Xp, Bp
+
+    out = None
     if rank == 0:
         peak, peak_src = measured_peak()
         abytes = algorithmic_bytes_per_vec_iter() * n * ils
-        achieved = abytes / (k_ms.item() * 1e-3) / 1e9
+        achieved = abytes / (k_ms * 1e-3) / 1e9
         out = {
             "metric": "icm_encode_vectors_per_sec", "value": value, "unit": "vectors/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"LSQ ICM encode m={M} h={H} d={D}, {ils} ILS iters x icmiter={ICMITER}, npert={NPERT} (BASELINE configs[1] base-set encode)",
-                       "n_per_gpu": n, "parallelism": f"shard{world}", "l2": f"inputs larger than L2 ({M * n * 1024 / 1e9:.0f} GB unaries per GPU)",
-                       "step": "pair tables + unaries + cost + all ILS iterations",
-                       "unary_mode": "exact fp32 chain (parity)" if args.unary == "exact" else "tcgen05 3xTF32 (fast mode, not bit-exact)"},
+            "config": workload_config(args, world),
             "vector_ils_iters_per_sec": value * ils,
-            "qerror": qerr, "e2e_codes_equal_resident_codes": same,
+            "qerror": qerr, "e2e_codes_equal_resident_codes": same, "pageable_codes_equal_pinned_codes": same_pg,
+            "visits_per_vector_iter": visits_pvi, "nominal_visits_per_vector_iter": ICMITER * M,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(f"icm_ils_warp_kernel<{M}>", n, ils), "kernel": f"icm_ils_warp_kernel<{M}>", "kernel_ms": k_ms.item(),
+                         "traffic": ncu_traffic(f"icm_ils_warp_kernel<{M}>", n, ils), "kernel": f"icm_ils_warp_kernel<{M}>", "kernel_ms": k_ms,
                          "peak_source": peak_src, "bytes_per_vector_iter": algorithmic_bytes_per_vec_iter(),
-                         "algorithmic_bytes_per_launch": abytes},
-            "e2e": {"value": n_total / (e2e_ms.item() * 1e-3), "unit": "vectors/s",
+                         "algorithmic_bytes_per_launch": abytes,
+                         "note": "effective figure (SURVEY.md 8d streamed-unary model); the physical limiter is the SM<->L2 gather path, see profiles/"},
+            "e2e": {"value": n_total / (e2e_ms * 1e-3), "unit": "vectors/s",
                     "h2d_bytes_per_step": int(X_h.nbytes + B_h.nbytes + C_h.nbytes), "d2h_bytes_per_step": int(B_h.nbytes),
-                    "ms_per_step": e2e_ms.item(), "api": "lsq_encode_icm_cuda (host pointers)"},
-            "gpu_launches": 5 * args.steps,
-            "clocks": clocks,
+                    "ms_per_step": e2e_ms, "ms_each_call_rank0": e2e_all,
+                    "api": "lsq_encode_icm_cuda (host pointers, pinned source), median of the timed calls, max over ranks"},
+            "e2e_pageable": {"value": n_total / (e2e_pg_ms * 1e-3), "unit": "vectors/s", "ms_per_step": e2e_pg_ms, "ms_each_call_rank0": e2e_pg_all,
+                             "api": "lsq_encode_icm_cuda (plain pageable numpy arrays, as a Julia caller passes them)",
+                             "h2d": os.environ.get("LSQ_B200_H2D", "staged")},
+            "gpu_launches": S["launches"],
+            "clocks": S["clocks"],
         }
+
+    # free the headline shard before the secondary blocks
+    codes0_keep, X_keep = S["codes0"], S["X"]
+    del sess, S
+    torch.cuda.empty_cache()
+
+    if not args.no_extras:
+        # the same base shard with codebooks trained on 100 K vectors (configs[1] as written); rank 0's figure
+        tr = trained_codebooks_block(dev, X_keep, codes0_keep, ils)
+        if rank == 0:
+            out["trained_codebooks"] = tr
+    del codes0_keep, X_keep
+    torch.cuda.empty_cache()
+
+    if not args.no_extras:
+        if world > 1 and args.scaling == "strong":
+            # the weak-scaling figure (fixed work per GPU), kept as an extra key
+            wn, wg0, wtot = shard_of(args.n, "weak")
+            wms, wk, WS = measure(wn, wg0, 1, 2)
+            del WS
+            torch.cuda.empty_cache()
+            if rank == 0:
+                out["weak"] = {"value": wtot / (wms * 1e-3), "unit": "vectors/s", "n_per_gpu": wn, "ms_per_step": wms, "kernel_ms": wk}
+        # train_lsq outer iteration at the configs[3] shape, with the all-reduce timed
+        ts = train_step_block(rank, world, dev, args.train_n)
+        torch.cuda.empty_cache()
+        if rank == 0:
+            out["train_step"] = ts
+        # ADC scan, configs[4]; with several ranks the queries are partitioned
+        adc = [adc_measure(m_, 1_000_000, 10_000, 1000, rank=rank, world=world, cpu_leg=not args.no_cpu) for m_ in (8, 16)]
+        torch.cuda.empty_cache()
+        if rank == 0:
+            out["adc"] = adc
+        # one process driving ALL GPUs through the C ABI (lsq_init_devices): what a Julia caller gets.  Rank 0 runs
+        # it while the other ranks wait at a HOST barrier (no kernel of theirs is resident).
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier(group=cpu_group)
+            if rank == 0:
+                out["inlib_multi_gpu"] = inlib_block(world, args.n, ils, C_h, args.e2e_steps)
+            dist.barrier(group=cpu_group)
+
+    if rank == 0:
         if not args.no_recall:
             out["recall"] = recall_probe(lsq_b200)
         if not args.no_cpu:
@@ -520,7 +742,38 @@ def main():
                                    "sample": f"{args.cpu_sample} vectors x 1 ILS iteration ({dt:.1f} s), scaled to {ils} iterations"}
         print(json.dumps(out))
     if world > 1:
+        dist.barrier(group=cpu_group)
         dist.destroy_process_group()
+
+
+def inlib_block(ndev, n, ils, C_h, e2e_steps):
+    """lsq_init_devices(0..ndev-1) in THIS process, then the same host-pointer encode of all n vectors: the library
+    shards it over the devices from the one calling thread.  Wall-clock, copies included."""
+    import lsq_b200
+    from util import sift_like
+    rng = np.random.default_rng(999)
+    X = sift_like(rng, n, D)
+    B = rng.integers(1, H + 1, size=(n, M)).astype(np.int16)
+    its = np.array([ils], np.int64)
+    res = {"devices": ndev, "n": n}
+    for label, devs in (("one_device", [0]), ("all_devices", list(range(ndev)))):
+        lsq_b200.finalize()
+        lsq_b200.init_devices(devs)
+        ts, outc = [], None
+        for i in range(1 + max(1, e2e_steps)):
+            w0 = time.perf_counter()
+            outc, _ = lsq_b200.encode_icm_cuda(X, B, C_h, its, ICMITER, NPERT, True, 1, seed=1)
+            if i > 0:
+                ts.append(time.perf_counter() - w0)
+        res[label] = {"ms": 1e3 * statistics.median(ts), "vectors_per_s": n / statistics.median(ts)}
+        res.setdefault("codes", outc[0])
+        res["codes_equal"] = bool(np.array_equal(res["codes"], outc[0]))
+    del res["codes"]
+    res["speedup"] = res["one_device"]["ms"] / res["all_devices"]["ms"]
+    res["source"] = "pageable numpy arrays"
+    lsq_b200.finalize()
+    lsq_b200.init(0)
+    return res
 
 
 if __name__ == "__main__":

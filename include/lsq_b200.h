@@ -48,6 +48,9 @@ int lsq_num_bound_devices(void);
 int lsq_finalize(void);
 const char* lsq_last_error(void);
 int lsq_device_count(void);
+/* number of CUDA kernels this library has launched so far in the process (measurement aid: bench.py reports
+ * the difference over its timed region as gpu_launches) */
+unsigned long long lsq_launch_count(void);
 const char* lsq_version(void);
 
 /* ---- a10: splitarray (utils.jl:152-177): part p of nparts over 0..n-1 -> [lo, hi) ------------- */

@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 __all__ = [
-    "LsqError", "lib", "lib_path", "have_library", "init", "init_devices", "num_bound_devices", "finalize", "device_count", "version",
+    "LsqError", "lib", "lib_path", "have_library", "init", "init_devices", "num_bound_devices", "finalize", "device_count", "launch_count", "version",
     "splitarray", "make_to_look", "make_perturb", "get_unaries", "get_binaries", "veccost", "qerror",
     "reconstruct", "quantize_norms", "encoding_icm", "reset_ils_counter", "encoding_icm_sched", "encode_icm_cuda",
     "update_codebooks", "linscan_lsq", "linscan_pq", "linscan_opq", "eval_recall", "randinit", "train_lsq",
@@ -19,7 +19,7 @@ _lib = None
 
 # every symbol include/lsq_b200.h declares (tests check the .so exports exactly these)
 EXPORTED_SYMBOLS = [
-    "lsq_init", "lsq_init_devices", "lsq_num_bound_devices", "lsq_finalize", "lsq_last_error", "lsq_device_count", "lsq_version", "lsq_splitarray",
+    "lsq_init", "lsq_init_devices", "lsq_num_bound_devices", "lsq_finalize", "lsq_last_error", "lsq_device_count", "lsq_launch_count", "lsq_version", "lsq_splitarray",
     "lsq_make_to_look", "lsq_make_perturb", "lsq_get_unaries", "lsq_get_binaries", "lsq_veccost",
     "lsq_qerror", "lsq_reconstruct", "lsq_encoding_icm", "lsq_encoding_icm_sched", "lsq_encode_icm_cuda",
     "lsq_update_codebooks", "linscan_aqd_query_extra_byte", "linscan_aqd_query", "lsq_linscan_lsq",
@@ -62,6 +62,7 @@ def lib():
         L.lsq_dev_tables_bytes.restype = ct.c_int64
         L.lsq_dev_sliced_tables_bytes.restype = ct.c_int64
         L.lsq_cb_stats_len.restype = ct.c_int64
+        L.lsq_launch_count.restype = ct.c_uint64
         L.linscan_aqd_query_extra_byte.restype = None
         L.linscan_aqd_query.restype = None
         _lib = L
@@ -125,6 +126,11 @@ def finalize():
 
 def device_count():
     return int(lib().lsq_device_count())
+
+
+def launch_count():
+    """CUDA kernels launched by the library so far in this process."""
+    return int(lib().lsq_launch_count())
 
 
 def version():

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ X
 int cb_absmax(const float* dX, int64_t count, float* dmax, cudaStream_t st) {
   if (count == 0) return LSQ_OK;
   const int64_t blocks = std::min<int64_t>(ceil_div(count, 256 * 8), (int64_t)LSQ_NUM_SMS_HINT * 8);
+  note_launch();
   absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(dX, count, reinterpret_cast<unsigned*>(dmax));
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
@@ -96,6 +97,7 @@ int cb_accumulate(const float* dX, int d, int64_t n, const uint8_t* dcodes, int 
                   cudaStream_t st) {
   if (n == 0) return LSQ_OK;
   const int64_t blocks = std::min<int64_t>(ceil_div(n, 8), (int64_t)LSQ_NUM_SMS_HINT * 8);
+  note_launch();
   cb_accumulate_kernel<<<(unsigned)blocks, 256, 0, st>>>(dX, d, n, dcodes, m, scale_exp,
                                                          reinterpret_cast<unsigned long long*>(dS));
   LSQ_CUDA(cudaGetLastError());
@@ -114,6 +116,7 @@ __global__ void cb_finalize_kernel(const int64_t* __restrict__ S, int64_t ngram,
 int cb_finalize(const int64_t* dS, int m, int d, int scale_exp, double* dGram, double* dRhs, cudaStream_t st) {
   const int64_t mh = (int64_t)m * LSQ_H;
   const int64_t total = mh * (mh + d);
+  note_launch();
   cb_finalize_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(dS, mh * mh, total, scale_exp, dGram, dRhs);
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
@@ -289,13 +292,16 @@ int cb_solve(const double* dGram, const double* dRhs, int m, int d, float* dCout
   LSQ_CUDA(rs.alloc(d));
   LSQ_CUDA(rs0.alloc(d));
   LSQ_CUDA(done.alloc(d));
+  note_launch();
   cg_init_kernel<<<d, 256, 0, st>>>(dRhs, mh, d, Xt.p, Rt.p, Pt.p, rs.p, rs0.p, done.p);
   LSQ_CUDA(cudaGetLastError());
   std::vector<int> hdone(d);
   dim3 ggrid(mh / 64, (unsigned)ceil_div(d, 32), ksplit);
   int it = 0;
   for (; it < max_iter; it++) {
+    note_launch();
     cg_gemm_kernel<<<ggrid, 256, 0, st>>>(dGram, Pt.p, mh, d, APt.p);
+    note_launch();
     cg_step_kernel<<<d, 256, 0, st>>>(mh, tol * tol, Xt.p, Rt.p, Pt.p, APt.p, ksplit, d, rs.p, rs0.p, done.p);
     if ((it & 15) == 15) {
       LSQ_CUDA(cudaMemcpyAsync(hdone.data(), done.p, (size_t)d * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -306,6 +312,7 @@ int cb_solve(const double* dGram, const double* dRhs, int m, int d, float* dCout
     }
   }
   LSQ_CUDA(cudaGetLastError());
+  note_launch();
   cg_finish_kernel<<<(unsigned)ceil_div((int64_t)mh * d, 256), 256, 0, st>>>(Xt.p, mh, d, dCout);
   LSQ_CUDA(cudaGetLastError());
   LSQ_CUDA(cudaStreamSynchronize(st));

@@ -305,6 +305,7 @@ int launch_viterbi(float* dU, int64_t n, int m, const float* dT, uint8_t* dcodes
     LSQ_CUDA(cudaFuncSetAttribute(viterbi_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VC_SMEM));
     const int64_t passes = ceil_div(n, VC_WARPS * VC_VPW);
     const unsigned grid = (unsigned)std::min<int64_t>(passes, sms);
+    note_launch();
     viterbi_tma_kernel<<<grid, (VC_WARPS + 1) * 32, VC_SMEM, st>>>(dU, dT, n, m, dcodes);
     LSQ_CUDA(cudaGetLastError());
     return LSQ_OK;
@@ -314,6 +315,7 @@ int launch_viterbi(float* dU, int64_t n, int m, const float* dT, uint8_t* dcodes
   if (per_sm < 1) per_sm = 1;
   const int64_t need = ceil_div(ceil_div(n, VPW), VIT_WARPS);
   const unsigned grid = (unsigned)std::min<int64_t>(need, (int64_t)sms * per_sm);
+  note_launch();
   viterbi_kernel<VPW><<<grid, VIT_WARPS * 32, 0, st>>>(dU, dT, n, m, dcodes);
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;

@@ -15,6 +15,7 @@
 namespace lsq {
 
 void set_error(const std::string& msg);
+void note_launch();  // counts the kernel launches this library issues (lsq_launch_count)
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define LSQ_CUDA(call)                                                     \

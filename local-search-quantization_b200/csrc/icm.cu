@@ -270,8 +270,10 @@ static int launch_icm_warp_m(const IcmParams& p, cudaStream_t st) {
   }
   if (usmem) {
     LSQ_CUDA(cudaFuncSetAttribute(icm_ils_warp_kernel<M, kCanUsmem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    note_launch();
     icm_ils_warp_kernel<M, kCanUsmem><<<grid, 256, smem, st>>>(q);
   } else {
+    note_launch();
     icm_ils_warp_kernel<M, false><<<grid, 256, 0, st>>>(q);
   }
   if (window) {
@@ -329,6 +331,7 @@ static unsigned warp_grid(int64_t n) {
 int launch_veccost(const float* dX, int d, int64_t n, const uint8_t* dcodes, const float* dC, int m,
                    float* dcost, cudaStream_t st) {
   if (n == 0) return LSQ_OK;
+  note_launch();
   veccost_kernel<<<warp_grid(n), 256, 0, st>>>(dX, d, n, dcodes, dC, m, dcost);
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
@@ -353,6 +356,7 @@ __global__ void __launch_bounds__(256) reconstruct_kernel(const uint8_t* __restr
 int launch_reconstruct(const uint8_t* dcodes, int64_t n, const float* dC, int d, int m, float* dCB,
                        cudaStream_t st) {
   if (n == 0) return LSQ_OK;
+  note_launch();
   reconstruct_kernel<<<warp_grid(n), 256, 0, st>>>(dcodes, n, dC, d, m, dCB);
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
@@ -389,7 +393,9 @@ __global__ void sum_final_kernel(const double* __restrict__ partial, int np, dou
 
 // dout: [1 + 1024] doubles; dout[0] receives the sum, the rest is scratch
 int launch_sum_f32_to_f64(const float* dv, int64_t n, double* dout, cudaStream_t st) {
+  note_launch();
   sum_partial_kernel<<<1024, 256, 0, st>>>(dv, n, dout + 1);
+  note_launch();
   sum_final_kernel<<<1, 1024, 0, st>>>(dout + 1, 1024, dout);
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
@@ -423,6 +429,7 @@ __global__ void __launch_bounds__(128) quantize_norms_kernel(const uint8_t* __re
 int launch_quantize_norms(const uint8_t* dcodes, int64_t n, const float* dC, int d, int m,
                           const float* dcbnorms, int hn, int16_t* dout1, cudaStream_t st) {
   if (n == 0) return LSQ_OK;
+  note_launch();
   quantize_norms_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, st>>>(dcodes, n, dC, d, m, dcbnorms, hn, dout1);
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
@@ -444,12 +451,14 @@ __global__ void u8_to_i16_kernel(const uint8_t* __restrict__ s, int16_t* __restr
 
 int launch_codes_i16_to_u8(const int16_t* d16, uint8_t* d8, int64_t count, int* derr, cudaStream_t st) {
   if (count == 0) return LSQ_OK;
+  note_launch();
   i16_to_u8_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(d16, d8, count, derr);
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
 }
 int launch_codes_u8_to_i16(const uint8_t* d8, int16_t* d16, int64_t count, cudaStream_t st) {
   if (count == 0) return LSQ_OK;
+  note_launch();
   u8_to_i16_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(d8, d16, count);
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;

@@ -392,6 +392,7 @@ static int launch_icm_slice_m(const IcmParams& p, cudaStream_t st) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const size_t smem = (size_t)(M - 1) * LSQ_H * ICM_SLICE_W * 4;
   LSQ_CUDA(cudaFuncSetAttribute(icm_ils_slice_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  note_launch();
   icm_ils_slice_kernel<M><<<sms, SLICE_THREADS, smem, st>>>(p);
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;

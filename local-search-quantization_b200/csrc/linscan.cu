@@ -606,9 +606,11 @@ static int launch_scan_m(const ScanParams& p, int ntiles, int nsplit, cudaStream
   dim3 grid(ntiles, nsplit, 1);
   if (p.norms != nullptr) {
     LSQ_CUDA(cudaFuncSetAttribute(scan_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    note_launch();
     scan_kernel<M, true><<<grid, SCAN_THREADS, smem, st>>>(p);
   } else {
     LSQ_CUDA(cudaFuncSetAttribute(scan_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    note_launch();
     scan_kernel<M, false><<<grid, SCAN_THREADS, smem, st>>>(p);
   }
   LSQ_CUDA(cudaGetLastError());
@@ -643,6 +645,7 @@ static int launch_lut(int lut_kind, const float* dq, int nq, int qstride, const 
                       float* dlut, cudaStream_t st) {
   const int ntiles = (int)ceil_div(nq, QT);
   dim3 grid(ntiles, m * LSQ_H / (8 * LUT_JPT), 1), block(32, 8, 1);
+  note_launch();
   if (lut_kind == LUT_LSQ) lut_kernel<LUT_LSQ><<<grid, block, 0, st>>>(dq, nq, qstride, dcb, m, kd, QT, dlut);
   else lut_kernel<LUT_PQ><<<grid, block, 0, st>>>(dq, nq, qstride, dcb, m, kd, QT, dlut);
   LSQ_CUDA(cudaGetLastError());
@@ -691,9 +694,11 @@ static int scan_exhaustive(const ScanCtx& S, const float* dq, int nqc, const int
     LSQ_TRY(launch_scan(S.m, p, ntiles, S.st));
     // outputs of this batch: rows q0.. (or scattered)
     if (dscatter) {
+      note_launch();
       topk_kernel<SORT_CAP, 1024><<<nb, 1024, SORT_CAP * 8, S.st>>>(dcand.p, S.n, nullptr, S.n, S.nn, dscatter + q0,
                                                                      S.ddists, S.dids, dstatus.p, 0, nullptr, nullptr);
     } else {
+      note_launch();
       topk_kernel<SORT_CAP, 1024><<<nb, 1024, SORT_CAP * 8, S.st>>>(dcand.p, S.n, nullptr, S.n, S.nn, nullptr,
                                                                      S.ddists + (size_t)q0 * S.nn,
                                                                      S.dids + (size_t)q0 * S.nn, dstatus.p, 0, nullptr, nullptr);
@@ -768,6 +773,7 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
     // sample pass -> thresholds
     p.mode = MODE_SAMPLE; p.stride = stride; p.count = s;
     LSQ_TRY(launch_scan(m, p, ntiles, st));
+    note_launch();
     threshold_kernel<<<ntiles, 1024, 0, st>>>(dsbuf.p, s, (int)r, dtau.p);
     LSQ_CUDA(cudaGetLastError());
     // main pass
@@ -777,8 +783,10 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
     LSQ_TRY(launch_scan(m, p, ntiles, st));
     // most queries end up with a few thousand candidates and nn <= 1024: select + sort of the survivors
     // in 40 KB of shared memory (5 CTAs per SM); the 128 KB sorter only runs for the queries it flags
+    note_launch();
     topk_select_kernel<SEL_CAP, SEL_SORT, 256><<<nb, 256, (SEL_CAP + SEL_SORT) * 8, st>>>(
         dcand.p, cap, dcnt.p, nn, ddists + (size_t)q0 * nn, dids + (size_t)q0 * nn, dstatus.p, dbig.p, dbig.p + qbatch);
+    note_launch();
     topk_kernel<SORT_CAP, 1024><<<std::min(nb, LSQ_NUM_SMS_HINT), 1024, SORT_CAP * 8, st>>>(dcand.p, cap, dcnt.p, -1, nn, nullptr,
                                                                  ddists + (size_t)q0 * nn, dids + (size_t)q0 * nn,
                                                                  dstatus.p, 2, dbig.p, dbig.p + qbatch);
@@ -797,6 +805,7 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
     LSQ_CUDA(drows.alloc(nr));
     LSQ_CUDA(dqsel.alloc((size_t)nr * d));
     LSQ_CUDA(cudaMemcpyAsync(drows.p, redo.data(), (size_t)nr * sizeof(int), cudaMemcpyHostToDevice, st));
+    note_launch();
     gather_rows_kernel<<<(unsigned)ceil_div((int64_t)nr * d, 256), 256, 0, st>>>(dqueries, drows.p, nr, d, dqsel.p);
     LSQ_CUDA(cudaGetLastError());
     LSQ_TRY(scan_exhaustive(S, dqsel.p, nr, drows.p));

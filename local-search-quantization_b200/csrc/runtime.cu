@@ -19,6 +19,9 @@ static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
 const char* last_error_cstr() { return g_err.c_str(); }
 
+static std::atomic<unsigned long long> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 static thread_local cudaStream_t g_alloc_stream = nullptr;
 cudaStream_t alloc_stream() { return g_alloc_stream; }
 void set_alloc_stream(cudaStream_t st) { g_alloc_stream = st; }
@@ -469,6 +472,7 @@ int rt_allreduce_sum_i64(AllReduceGroup* g, int rank, int64_t* dbuf, int64_t* ds
     if (j != rank && e == cudaSuccess) e = cudaStreamWaitEvent(st, g->ready[j], 0);
   }
   if (e == cudaSuccess) {
+    note_launch();
     reduce_peers_kernel<<<LSQ_NUM_SMS_HINT * 4, 256, 0, st>>>(pp, g->k, count, dscratch);
     e = cudaGetLastError();
   }
@@ -502,6 +506,8 @@ int lsq_device_count(void) {
   if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); return 0; }
   return cnt;
 }
+
+unsigned long long lsq_launch_count(void) { return g_launches.load(); }
 
 const char* lsq_version(void) { return "lsq_b200 0.2 (sm_100a)"; }
 

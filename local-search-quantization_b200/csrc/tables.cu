@@ -163,6 +163,7 @@ __global__ void norms_kernel(const float* __restrict__ C, int rows, int d, float
 
 int build_norms(const float* dC, int d, int m, float* dnorms, cudaStream_t st) {
   const int rows = m * LSQ_H;
+  note_launch();
   norms_kernel<<<(rows + 127) / 128, 128, 0, st>>>(dC, rows, d, dnorms);
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
@@ -177,12 +178,14 @@ int build_unaries(const float* dX, int d, int64_t n, const float* dC, int m, con
     const int64_t rows = (n - r0 < max_rows) ? (n - r0) : max_rows;
     if (r0 == 0 && rows == n) {
       dim3 grid(LSQ_H / TM, (unsigned)ceil_div(rows, TN), m);
+      note_launch();
       gemm_tables_kernel<EPI_UNARY><<<grid, 256, 0, st>>>(dC, dX, dnorms, dU, n, d, m, sliced, n);
     } else {
       // one launch per codebook when the launch is chunked, since U's z-stride is n*256
       for (int j = 0; j < m; j++) {
         dim3 grid(LSQ_H / TM, (unsigned)ceil_div(rows, TN), 1);
         float* o = dU + (size_t)j * n * LSQ_H + (sliced ? (size_t)r0 * ICM_SLICE_W : (size_t)r0 * LSQ_H);
+        note_launch();
         gemm_tables_kernel<EPI_UNARY><<<grid, 256, 0, st>>>(dC + (size_t)j * LSQ_H * d, dX + (size_t)r0 * d,
                                                             dnorms + j * LSQ_H, o, rows, d, m, sliced, n);
       }
@@ -194,6 +197,7 @@ int build_unaries(const float* dX, int d, int64_t n, const float* dC, int m, con
 
 int build_tables(const float* dC, int d, int m, float* dT, cudaStream_t st) {
   dim3 grid(LSQ_H / TM, LSQ_H / TN, m * m);
+  note_launch();
   gemm_tables_kernel<EPI_BINARY><<<grid, 256, 0, st>>>(dC, dC, nullptr, dT, LSQ_H, d, m, 0, LSQ_H);
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
@@ -217,6 +221,7 @@ __global__ void slice_tables_kernel(const float* __restrict__ T, int m, float* _
 
 int build_sliced_tables(const float* dT, int m, float* dTs, cudaStream_t st) {
   if (m < 2) return LSQ_OK;
+  note_launch();
   slice_tables_kernel<<<LSQ_NUM_SMS_HINT * 8, 256, 0, st>>>(dT, m, dTs);
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;

@@ -55,6 +55,7 @@ static int launch_rows_times_matrix(const float* in, int64_t rows, int d, const 
   if (rows == 0) return LSQ_OK;
   const int64_t b = ceil_div(rows, 8);
   const unsigned grid = (unsigned)std::min<int64_t>(b, (int64_t)LSQ_NUM_SMS_HINT * 8);
+  note_launch();
   rows_times_matrix_kernel<<<grid, 256, (size_t)8 * d * sizeof(float), st>>>(in, rows, d, Mx, sj, si, out);
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
@@ -141,16 +142,19 @@ static int kmeans1d_device(const float* dvals, int64_t n, int h, float* dcent, i
   LSQ_CUDA(dtmp.alloc(tmp_bytes));
   LSQ_CUDA(cub::DeviceRadixSort::SortKeys(dtmp.p, tmp_bytes, dvals, dsorted.p, (int)n, 0, 32, st));
   const unsigned gb = (unsigned)ceil_div(h + 1, 128);
+  note_launch();
   kmeans1d_seed_kernel<<<gb, 128, 0, st>>>(dsorted.p, n, h, dcent, dbounds.p);
   LSQ_CUDA(cudaGetLastError());
   int it = 0;
   for (; it < maxiter; it++) {
     LSQ_CUDA(cudaMemsetAsync(dchanged.p, 0, sizeof(int), st));
+    note_launch();
     kmeans1d_bounds_kernel<<<gb, 128, 0, st>>>(dsorted.p, n, dcent, h, dbounds.p, dchanged.p);
     int hchanged = 0;
     LSQ_CUDA(cudaMemcpyAsync(&hchanged, dchanged.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     LSQ_CUDA(cudaStreamSynchronize(st));
     if (!hchanged) break;  // assignments are a fixed point: the means would not move either
+    note_launch();
     kmeans1d_means_kernel<<<h, 256, 0, st>>>(dsorted.p, dbounds.p, dcent);
     LSQ_CUDA(cudaGetLastError());
   }
@@ -416,6 +420,7 @@ int lsq_train_lsq(const float* X, int d, int64_t n, int m, int h, const float* R
       STEP_CUDA(dvn.alloc(nl));
       STEP_CUDA(dcent.alloc(h));
       if (rc == LSQ_OK) {
+        note_launch();
         decoded_norms_kernel<<<(unsigned)ceil_div(nl, 128), 128, 0, st>>>(dcodes.p, nl, dC.p, d, m, dvn.p);
         STEP_CUDA(cudaGetLastError());
       }
@@ -482,7 +487,9 @@ int lsq_dev_eval_recall(const int32_t* dgnd, const int32_t* dpred, int nq, int l
   DevBuf<int> dhist;
   LSQ_CUDA(dhist.alloc(k + 1));
   LSQ_CUDA(cudaMemsetAsync(dhist.p, 0, (size_t)(k + 1) * sizeof(int), st));
+  note_launch();
   recall_rank_kernel<<<(unsigned)ceil_div(nq, 8), 256, 0, st>>>(dgnd, dpred, nq, ld, k, dhist.p);
+  note_launch();
   recall_curve_kernel<<<1, 32, 0, st>>>(dhist.p, k, nq, drecall);
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;

@@ -207,9 +207,11 @@ int build_unaries_tc(const float* dX, int d, int64_t n, const float* dC, int m, 
   set_alloc_stream(st);
   DevBuf<float> csplit;
   LSQ_CUDA(csplit.alloc((size_t)ntile * 2 * a_bytes / 4));
+  note_launch();
   split_codebooks_kernel<<<ntile, 256, 0, st>>>(dC, m, d, csplit.p);
   const size_t smem = 2 * (size_t)a_bytes + 2 * (size_t)b_bytes;
   LSQ_CUDA(cudaFuncSetAttribute(unary_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  note_launch();
   unary_tc_kernel<<<ntile * per, TC_THREADS, smem, st>>>(dX, d, n, csplit.p, dnorms, m, dU, per);
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
