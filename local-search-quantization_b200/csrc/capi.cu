@@ -143,7 +143,7 @@ static int run_encode_job(const EncodeJob& J, int devidx, double* obj_sum) {
   // LSQ_B200_PIPELINE_PARTS=k forces k equal parts (k = 1: no pipelining).
   std::vector<int64_t> cuts;  // part p = [cuts[p], cuts[p+1])
   const char* pe = getenv("LSQ_B200_PIPELINE_PARTS");
-  bool geometric = (pe == nullptr) && n >= 262144 && nparts <= 4 && (n * 8 / 15 + 1) <= cap;
+  bool geometric = (pe == nullptr) && n >= 65536 && nparts <= 4 && (n * 8 / 15 + 1) <= cap;
   if (geometric) {
     cuts = {0, n / 15, n / 15 + 2 * n / 15, n / 15 + 2 * n / 15 + 4 * n / 15, n};
     nparts = 4;

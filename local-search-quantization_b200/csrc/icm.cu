@@ -222,15 +222,18 @@ static int launch_icm_warp_m(const IcmParams& p, cudaStream_t st) {
   int dev = 0, sms = LSQ_NUM_SMS_HINT;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t blocks_needed = ceil_div(p.n, 8);
-  constexpr bool kCanUsmem = (M <= 8);
+  constexpr bool kCanUsmem = true;
   // Measured (1 M x 16 iterations, m = 8): staging the unary rows in shared memory removes 1/8 of the L2
   // traffic but caps residency at 24 warps/SM: 140.3 ms vs 136.6 ms with 32 warps and everything from
   // L2.  Occupancy wins, so the staged variant is opt-in (LSQ_B200_ICM_USMEM=1).
   const char* ue = getenv("LSQ_B200_ICM_USMEM");
   const bool usmem = kCanUsmem && ue != nullptr && atoi(ue) != 0;
-  const size_t smem = usmem ? 128 + (size_t)8 * M * 1024 : 0;
-  int per_sm = usmem ? (int)std::min<size_t>(8, (size_t)(224 * 1024) / (smem + 1024)) : 8;
+  // warps per block: 8, or 4 when the staged rows of 8 warps would leave room for a single block per SM (m > 8)
+  int wpb = (usmem && M > 8) ? 4 : 8;
+  if (const char* we = getenv("LSQ_B200_ICM_WARPS_PER_BLOCK")) wpb = std::max(1, std::min(8, atoi(we)));
+  const int64_t blocks_needed = ceil_div(p.n, wpb);
+  const size_t smem = usmem ? 128 + (size_t)wpb * M * 1024 : 0;
+  int per_sm = usmem ? (int)std::min<size_t>(64 / wpb, (size_t)(227 * 1024) / (smem + 1024)) : 64 / wpb;
   if (const char* e = getenv("LSQ_B200_ICM_BLOCKS_PER_SM")) per_sm = std::max(1, atoi(e));  // tuning override
   const int64_t cap = (int64_t)sms * per_sm;
   const unsigned grid = (unsigned)(blocks_needed < cap ? blocks_needed : cap);
@@ -271,10 +274,10 @@ static int launch_icm_warp_m(const IcmParams& p, cudaStream_t st) {
   if (usmem) {
     LSQ_CUDA(cudaFuncSetAttribute(icm_ils_warp_kernel<M, kCanUsmem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     note_launch();
-    icm_ils_warp_kernel<M, kCanUsmem><<<grid, 256, smem, st>>>(q);
+    icm_ils_warp_kernel<M, kCanUsmem><<<grid, 32 * wpb, smem, st>>>(q);
   } else {
     note_launch();
-    icm_ils_warp_kernel<M, false><<<grid, 256, 0, st>>>(q);
+    icm_ils_warp_kernel<M, false><<<grid, 32 * wpb, 0, st>>>(q);
   }
   if (window) {
     cudaStreamAttrValue attr;

@@ -278,6 +278,20 @@ int rt_ensure_init() {
     set_error("no CUDA device available: liblsq_b200 has no CPU fallback");
     return LSQ_ERR_CUDA;
   }
+  // LSQ_B200_DEVICES=all | 0,1,2,...: device set of a process that never calls lsq_init / lsq_init_devices (so an
+  // unchanged Julia program can use every GPU of the box); unset: the current device, like the reference
+  if (const char* e = getenv("LSQ_B200_DEVICES")) {
+    if (strcmp(e, "all") == 0) return bind_devices_locked(nullptr, 0);
+    std::vector<int> devs;
+    for (const char* p = e; *p;) {
+      char* end = nullptr;
+      const long v = strtol(p, &end, 10);
+      if (end == p) break;
+      devs.push_back((int)v);
+      p = (*end == ',') ? end + 1 : end;
+    }
+    if (!devs.empty()) return bind_devices_locked(devs.data(), (int)devs.size());
+  }
   int dev = 0;
   cudaGetDevice(&dev);
   return bind_devices_locked(&dev, 1);

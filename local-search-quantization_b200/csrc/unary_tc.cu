@@ -193,7 +193,222 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unary_tc_kernel(const float* __
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)TC_N) : "memory");
 }
 
-// U[m][n][256] (plain layout) with the tensor-core kernel.  d must be a multiple of 8 and <= 128.
+// ------------------------------------------------------------------------------------------------
+// Pipelined, warp-specialised version (the default).  Same arithmetic as the serial kernel above, but:
+//   * the stationary operand (the CTA's 128-candidate codebook tile, hi and lo) lives in TENSOR MEMORY for
+//     the whole kernel (tcgen05.st once; tcgen05.mma takes A from TMEM), so shared memory only holds the
+//     streaming operand: 3 stages of a 64-vector X tile (hi + lo, 64 KB each);
+//   * one thread streams the raw X tiles (64 vectors = one contiguous 32 KB block of X) into a 3-slot ring
+//     with TMA bulk copies (cp.async.bulk + mbarrier expect_tx), running up to 3 tiles ahead, so no warp
+//     ever waits on a global load; 4 producer warps read a raw slot, split it into hi / lo and write the two
+//     operand images of a stage (generic-proxy stores + fence.proxy.async + an mbarrier arrive per thread);
+//     one thread issues the 3 x K/8 MMAs per tile and commits twice — onto the stage's "empty" barrier
+//     (releases shared memory) and onto the accumulator's "full" barrier;
+//   * two TMEM accumulators (2 x 64 columns) alternate, so the MMAs of tile t+1 run while 4 epilogue warps
+//     drain tile t (tcgen05.ld 32x32b.x32 -> -2*acc + ||c||^2 -> 128-byte row segments of U).
+// TMEM columns: [0, 128) hi(C), [128, 256) lo(C), [256, 320) and [320, 384) accumulators (512 allocated).
+// ------------------------------------------------------------------------------------------------
+constexpr int TCP_STAGES = 2;     // operand-image stages
+constexpr int TCP_RAW = 3;        // raw X-tile ring slots
+constexpr int TCP_THREADS = 320;  // warps 0-3 epilogue (TMEM lane quadrant = warp id), 4-7 producers, 8 MMA issuer, 9 TMA
+constexpr uint32_t TCP_COL_AHI = 0, TCP_COL_ALO = 128, TCP_COL_ACC = 256;
+
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(TCP_THREADS, 1) unary_tc_pipe_kernel(const float* __restrict__ X, int d, int64_t n,
+                                                                       const float* __restrict__ C,
+                                                                       const float* __restrict__ norms, int m,
+                                                                       float* __restrict__ U, int ctas_per_tile) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t bar_full[TCP_STAGES], bar_empty[TCP_STAGES], bar_acc_full[2], bar_acc_empty[2];
+  __shared__ uint64_t bar_raw_full[TCP_RAW], bar_raw_empty[TCP_RAW];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int jah = blockIdx.x / ctas_per_tile;       // which 128-candidate tile
+  const int sub = blockIdx.x % ctas_per_tile;       // which stride class of vector tiles
+  const int j = jah >> 1, a0 = (jah & 1) * TC_M;
+  const uint32_t b_bytes = tc_operand_bytes(TC_N, d);            // one of hi / lo of a stage
+  const uint32_t stage_bytes = 2 * b_bytes;
+  const uint32_t lboB = tc_lbo(TC_N);
+
+  if (tid == 0) {
+    for (int s = 0; s < TCP_STAGES; s++) { mbar_init(&bar_full[s], 128); mbar_init(&bar_empty[s], 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_empty[b], 4); }
+    for (int s = 0; s < TCP_RAW; s++) { mbar_init(&bar_raw_full[s], 1); mbar_init(&bar_raw_empty[s], 128); }
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_slot;
+
+  // ---- stationary operand -> TMEM: thread = candidate row (lane of its warp's quadrant), 32 k per store ----
+  if (warp < 4) {
+    const float* crow = C + ((size_t)j * LSQ_H + a0 + warp * 32 + lane) * d;
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int k0 = 0; k0 < d; k0 += 32) {
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        const float x = (k0 + i < d) ? __ldg(crow + k0 + i) : 0.0f;
+        const float h = tf32_hi(x);
+        hi[i] = __float_as_uint(h);
+        lo[i] = __float_as_uint(tf32_hi(x - h));
+      }
+      tc_st32(lane_base + TCP_COL_AHI + (uint32_t)k0, hi);
+      tc_st32(lane_base + TCP_COL_ALO + (uint32_t)k0, lo);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  const int64_t ntiles = (n + TC_N - 1) / TC_N;
+  const int64_t my_tiles = (ntiles > sub) ? (ntiles - sub + ctas_per_tile - 1) / ctas_per_tile : 0;
+
+  const uint32_t raw_bytes = (uint32_t)TC_N * (uint32_t)d * 4u;               // one raw tile: 64 rows of X, contiguous
+  unsigned char* raw_base = smem_raw + (size_t)TCP_STAGES * stage_bytes;
+
+  if (warp == 9) {
+    // ===================== TMA: raw X tiles, up to TCP_RAW tiles ahead =====================
+    if (lane == 0) {
+      for (int64_t t = 0; t < my_tiles; t++) {
+        const int slot = (int)(t % TCP_RAW);
+        mbar_wait(&bar_raw_empty[slot], (uint32_t)((t / TCP_RAW) & 1) ^ 1u);
+        const int64_t v0 = (sub + t * ctas_per_tile) * TC_N;
+        const int64_t valid = (n - v0 < TC_N) ? (n - v0) : TC_N;
+        bulk_load_issue(raw_base + (size_t)slot * raw_bytes, X + (size_t)v0 * d, (uint32_t)valid * (uint32_t)d * 4u,
+                        &bar_raw_full[slot]);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== producers: raw X tile -> hi / lo operand images =====================
+    const int ptid = tid - 128;
+    const int chunks = d / 4;
+    for (int64_t t = 0; t < my_tiles; t++) {
+      const int s = (int)(t % TCP_STAGES);
+      const int slot = (int)(t % TCP_RAW);
+      const int64_t v0 = (sub + t * ctas_per_tile) * TC_N;
+      const int valid = (int)((n - v0 < TC_N) ? (n - v0) : TC_N);
+      mbar_wait(&bar_raw_full[slot], (uint32_t)((t / TCP_RAW) & 1));
+      mbar_wait(&bar_empty[s], (uint32_t)((t / TCP_STAGES) & 1) ^ 1u);
+      unsigned char* sB = smem_raw + (size_t)s * stage_bytes;
+      const float4* raw = reinterpret_cast<const float4*>(raw_base + (size_t)slot * raw_bytes);
+      auto put = [&](int r, int kc) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < valid) x = raw[r * chunks + kc];
+        float4 hi, lo;
+        hi.x = tf32_hi(x.x); hi.y = tf32_hi(x.y); hi.z = tf32_hi(x.z); hi.w = tf32_hi(x.w);
+        lo.x = tf32_hi(x.x - hi.x); lo.y = tf32_hi(x.y - hi.y); lo.z = tf32_hi(x.z - hi.z); lo.w = tf32_hi(x.w - hi.w);
+        const uint32_t off = (uint32_t)kc * lboB + (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u;
+        *reinterpret_cast<float4*>(sB + off) = hi;
+        *reinterpret_cast<float4*>(sB + b_bytes + off) = lo;
+      };
+      if (chunks == 32) {  // d = 128: a warp walks one 512-byte row, no division
+#pragma unroll 4
+        for (int i = 0; i < TC_N / 4; i++) put((ptid >> 5) + 4 * i, ptid & 31);
+      } else {
+        for (int e = ptid; e < TC_N * chunks; e += 128) put(e / chunks, e % chunks);
+      }
+      fence_proxy_async();       // this thread's generic-proxy stores -> visible to the tensor core
+      mbar_arrive(&bar_full[s]);
+      mbar_arrive(&bar_raw_empty[slot]);
+    }
+  } else if (warp == 8) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+      const int ksteps = d / 8;
+      const uint32_t sB_u = smem_u32(smem_raw);
+      for (int64_t t = 0; t < my_tiles; t++) {
+        const int s = (int)(t % TCP_STAGES);
+        const uint32_t use = (uint32_t)(t / TCP_STAGES);
+        const int b = (int)(t & 1);
+        mbar_wait(&bar_acc_empty[b], (uint32_t)((t >> 1) & 1) ^ 1u);
+        mbar_wait(&bar_full[s], use & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t dcol = tmem + TCP_COL_ACC + (uint32_t)b * TC_N;
+        const uint32_t stage_u = sB_u + (uint32_t)s * stage_bytes;
+        uint32_t acc = 0;
+#pragma unroll 1
+        for (int pass = 0; pass < 3; pass++) {
+          const uint32_t acol = tmem + ((pass == 0) ? TCP_COL_ALO : TCP_COL_AHI);   // pass 0: lo(C)
+          const uint32_t boff = (pass == 1) ? b_bytes : 0u;                         // pass 1: lo(X)
+          for (int k = 0; k < ksteps; k++) {
+            const uint64_t bd = tc_smem_desc(stage_u + boff + (uint32_t)(2 * k) * lboB, lboB, tc_sbo());
+            tc_mma_tf32_ts(dcol, acol + (uint32_t)(8 * k), bd, idesc, acc);
+            acc = 1;
+          }
+        }
+        tc_commit(&bar_empty[s]);      // shared-memory stage may be refilled once these MMAs have read it
+        tc_commit(&bar_acc_full[b]);   // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue: warp w drains TMEM lanes 32w .. 32w+31 =====================
+    const float nrm = norms[j * LSQ_H + a0 + warp * 32 + lane];
+    for (int64_t t = 0; t < my_tiles; t++) {
+      const int b = (int)(t & 1);
+      mbar_wait(&bar_acc_full[b], (uint32_t)((t >> 1) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t v0 = (sub + t * ctas_per_tile) * TC_N;
+      const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + TCP_COL_ACC + (uint32_t)b * TC_N;
+      float* ubase = U + ((size_t)j * n + v0) * LSQ_H + a0 + warp * 32 + lane;
+      uint32_t r0[32], r1[32];
+      tc_ld32(taddr, r0);
+      tc_ld32(taddr + 32u, r1);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_acc_empty[b]);   // the values are in registers: the accumulator is free
+#pragma unroll
+      for (int i = 0; i < 32; i++)
+        if (v0 + i < n) ubase[(size_t)i * LSQ_H] = __fadd_rn(__fmul_rn(-2.0f, __uint_as_float(r0[i])), nrm);
+#pragma unroll
+      for (int i = 0; i < 32; i++)
+        if (v0 + 32 + i < n) ubase[(size_t)(32 + i) * LSQ_H] = __fadd_rn(__fmul_rn(-2.0f, __uint_as_float(r1[i])), nrm);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// U[m][n][256] (plain layout) with the tensor-core kernels.  d must be a multiple of 8 and <= 128.
+// LSQ_B200_UNARY_TC=serial selects the unpipelined kernel (A/B comparison).
 int build_unaries_tc(const float* dX, int d, int64_t n, const float* dC, int m, const float* dnorms, float* dU,
                      cudaStream_t st) {
   if (n == 0) return LSQ_OK;
@@ -204,6 +419,15 @@ int build_unaries_tc(const float* dX, int d, int64_t n, const float* dC, int m, 
   const int ntile = 2 * m;                                   // 128-candidate tiles
   const int per = sms / ntile > 0 ? sms / ntile : 1;          // CTAs per candidate tile
   const uint32_t a_bytes = tc_operand_bytes(TC_M, d), b_bytes = tc_operand_bytes(TC_N, d);
+  const char* mode = getenv("LSQ_B200_UNARY_TC");
+  if (mode == nullptr || strcmp(mode, "serial") != 0) {
+    const size_t smem = (size_t)TCP_STAGES * 2 * b_bytes + (size_t)TCP_RAW * TC_N * d * 4;
+    LSQ_CUDA(cudaFuncSetAttribute(unary_tc_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    note_launch();
+    unary_tc_pipe_kernel<<<ntile * per, TCP_THREADS, smem, st>>>(dX, d, n, dC, dnorms, m, dU, per);
+    LSQ_CUDA(cudaGetLastError());
+    return LSQ_OK;
+  }
   set_alloc_stream(st);
   DevBuf<float> csplit;
   LSQ_CUDA(csplit.alloc((size_t)ntile * 2 * a_bytes / 4));

@@ -23,6 +23,15 @@ end
 # Replaces CudaUtilsModule.init / finit (cudaUtilsModule.jl:37-43)
 lsq_init(gpuid::Integer=0) = lsq_check( ccall((:lsq_init, LSQ_B200_LIB), Cint, (Cint,), gpuid) )
 lsq_finit()                = lsq_check( ccall((:lsq_finalize, LSQ_B200_LIB), Cint, ()) )
+# Several GPUs of the box (the reference is hard-wired to device 0, encode_icm_cuda.jl:59-64): after this call
+# encoding_icm / encode_icm_cuda / update_codebooks / train_lsq / linscan_* split their input over the listed
+# devices inside the library; results do not depend on the device set.  An empty list binds every visible GPU.
+# Without any Julia change the same is selected by the environment: LSQ_B200_DEVICES=all (or 0,1,2,...).
+function lsq_init_devices(gpuids::Vector{Int}=Int[])
+  devs = convert(Vector{Cint}, gpuids)
+  lsq_check( ccall((:lsq_init_devices, LSQ_B200_LIB), Cint, (Ptr{Cint}, Cint), devs, length(devs)) )
+  return Int( ccall((:lsq_num_bound_devices, LSQ_B200_LIB), Cint, ()) )
+end
 
 # d-by-h-by-m stack of the codebooks: exactly what Linscan.jl:22 already builds for the PQ scan
 lsq_pack_codebooks{T <: AbstractFloat}(C::Vector{Matrix{T}}) = convert(Array{Cfloat,3}, cat(3, C...))

@@ -345,11 +345,15 @@ def test_slice_kernel_large_n_matches_warp_kernel(gpu, monkeypatch):
 
 
 # ---------------------------------------------------------------- tensor-core unaries (fast mode)
-@pytest.mark.parametrize("n,d,m", [(3000, 128, 8), (1000, 64, 7), (129, 128, 16), (5, 8, 2)])
-def test_unaries_tensor_core_tolerance(gpu, oracle, n, d, m):
-    """tcgen05 3xTF32 build of the unary tables: NOT bit-exact by construction; |dU| <= 4e-6 * max|U|."""
+@pytest.mark.parametrize("kernel", ["pipelined", "serial"])
+@pytest.mark.parametrize("n,d,m", [(3000, 128, 8), (1000, 64, 7), (129, 128, 16), (5, 8, 2), (70000, 128, 8), (64, 40, 3)])
+def test_unaries_tensor_core_tolerance(gpu, oracle, monkeypatch, n, d, m, kernel):
+    """tcgen05 3xTF32 build of the unary tables: NOT bit-exact by construction; |dU| <= 4e-6 * max|U|.
+    Both kernels: the warp-specialised pipeline (codebook operand in TMEM, 3 shared-memory stages, two
+    accumulators; n = 70000 makes every CTA walk many tiles and wrap all its barriers) and the serial one."""
     import ctypes as ct
     import torch
+    monkeypatch.setenv("LSQ_B200_UNARY_TC", kernel)
     X, C, _ = make_problem(1900 + n, n, d, m, kind="gauss")
     X *= 37.0
     Xd, Cd = torch.from_numpy(X).cuda(), torch.from_numpy(C).cuda()
