@@ -513,6 +513,35 @@ def trained_codebooks_block(dev, X, codes0, ils, steps=3, ntrain=100_000):
             "codebooks": f"lsq_train_lsq on {ntrain} vectors, 4 outer x 4 ILS iterations ({train_s:.2f} s, objective {float(obj[0]):.1f} -> {float(obj[-1]):.1f})"}
 
 
+def fast_mode_block(dev, X, codes0, C, ils, orders, qerr_exact, codes_exact, steps=3):
+    """The same step with the unary tables built on the tensor cores (tcgen05 kind::tf32, 3xTF32 split, fp32
+    accumulation in TMEM): not bit-exact with the sequential fp32 chain of the parity path, so it is opt-in
+    (LSQ_B200_UNARY=tc) and held to the north-star's tolerance (quantisation error within 1e-5 relative)."""
+    import torch
+    from lsq_b200 import device as lsqdev
+    codes = codes0.clone()
+    sess = lsqdev.EncodeSession(X, C, codes, unary="tc")
+    ms, ums = [], []
+    for s in range(steps + 1):
+        codes.copy_(codes0)
+        torch.cuda.synchronize()
+        a, b, c = _ev(), _ev(), _ev()
+        a.record()
+        sess.set_codebooks(C)
+        b.record()
+        sess.ils(ils, ICMITER, NPERT, True, seed=1, ils_iter0=0, orders=orders)
+        c.record()
+        torch.cuda.synchronize()
+        if s > 0:
+            ms.append(a.elapsed_time(c)); ums.append(a.elapsed_time(b))
+    n = X.shape[0]
+    q = sess.qerror()
+    return {"value_per_gpu": n / (statistics.mean(ms) * 1e-3), "unit": "vectors/s", "ms_per_step": statistics.mean(ms),
+            "tables_unaries_cost_ms": statistics.mean(ums), "qerror": q, "qerror_rel_diff_vs_exact": abs(q - qerr_exact) / qerr_exact,
+            "codes_equal_to_exact_frac": float((codes == codes_exact).all(dim=1).float().mean().item()),
+            "unary": "tcgen05 kind::tf32 3xTF32, codebook operand in TMEM, TMA raw-tile ring (csrc/unary_tc.cu)"}
+
+
 def ct_ptr(t):
     import ctypes as ct
     return ct.c_void_p(t.data_ptr())
@@ -702,6 +731,10 @@ def main():
         tr = trained_codebooks_block(dev, X_keep, codes0_keep, ils)
         if rank == 0:
             out["trained_codebooks"] = tr
+        if args.unary == "exact" and D % 8 == 0:
+            fm = fast_mode_block(dev, X_keep, codes0_keep, C, ils, orders, qerr, codes)
+            if rank == 0:
+                out["fast_mode"] = fm
     del codes0_keep, X_keep
     torch.cuda.empty_cache()
 

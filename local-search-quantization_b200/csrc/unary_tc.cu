@@ -225,20 +225,31 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32])
       : "memory");
 }
 
-// D[tmem] (+)= A[tmem] * B[smem]
+// D[tmem] (+)= A[tmem] * B[smem].  Called by ALL lanes of the issuing warp in uniform control flow; the
+// instruction itself runs on one elected lane (elect.sync inside the asm block).  Keeping the election out of
+// the C++ control flow lets ptxas hold the descriptors in uniform registers — with `if (lane == 0)` around the
+// loop it wraps every UTCHMMA in an ELECT / BRA.U.ANY uniformising loop (~12 SASS instructions per MMA, the
+// issuing thread became the bottleneck of the pipeline).
 __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n"
-      ".reg .pred p;\n"
+      ".reg .pred p, e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void tc_commit_elected(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
 }
 
 __global__ void __launch_bounds__(TCP_THREADS, 1) unary_tc_pipe_kernel(const float* __restrict__ X, int d, int64_t n,
@@ -347,34 +358,36 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) unary_tc_pipe_kernel(const flo
       mbar_arrive(&bar_raw_empty[slot]);
     }
   } else if (warp == 8) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-      const int ksteps = d / 8;
-      const uint32_t sB_u = smem_u32(smem_raw);
-      for (int64_t t = 0; t < my_tiles; t++) {
-        const int s = (int)(t % TCP_STAGES);
-        const uint32_t use = (uint32_t)(t / TCP_STAGES);
-        const int b = (int)(t & 1);
-        mbar_wait(&bar_acc_empty[b], (uint32_t)((t >> 1) & 1) ^ 1u);
-        mbar_wait(&bar_full[s], use & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t dcol = tmem + TCP_COL_ACC + (uint32_t)b * TC_N;
-        const uint32_t stage_u = sB_u + (uint32_t)s * stage_bytes;
-        uint32_t acc = 0;
-#pragma unroll 1
-        for (int pass = 0; pass < 3; pass++) {
-          const uint32_t acol = tmem + ((pass == 0) ? TCP_COL_ALO : TCP_COL_AHI);   // pass 0: lo(C)
-          const uint32_t boff = (pass == 1) ? b_bytes : 0u;                         // pass 1: lo(X)
-          for (int k = 0; k < ksteps; k++) {
-            const uint64_t bd = tc_smem_desc(stage_u + boff + (uint32_t)(2 * k) * lboB, lboB, tc_sbo());
-            tc_mma_tf32_ts(dcol, acol + (uint32_t)(8 * k), bd, idesc, acc);
-            acc = 1;
-          }
-        }
-        tc_commit(&bar_empty[s]);      // shared-memory stage may be refilled once these MMAs have read it
-        tc_commit(&bar_acc_full[b]);   // accumulator complete
-      }
+    // ===================== MMA issuer (whole warp, uniform; one elected lane issues) =====================
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+    const int ksteps = d / 8;
+    const uint32_t sB_u = smem_u32(smem_raw);
+    // shared-memory descriptor = constant high word (SBO, version) + low word (start >> 4 | LBO << 16); the
+    // start field advances by 2 K-chunks per MMA and never carries out of its 14 bits (addresses < 256 KB)
+    const uint64_t desc_hi = (uint64_t)((tc_sbo() >> 4) | (1u << 14)) << 32;
+    const uint32_t desc_lbo = (lboB >> 4) << 16;
+    const uint32_t kstep_enc = (2u * lboB) >> 4;
+    for (int64_t t = 0; t < my_tiles; t++) {
+      const int s = (int)(t % TCP_STAGES);
+      const int b = (int)(t & 1);
+      mbar_wait(&bar_acc_empty[b], (uint32_t)((t >> 1) & 1) ^ 1u);
+      mbar_wait(&bar_full[s], (uint32_t)((t / TCP_STAGES) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t dcol = tmem + TCP_COL_ACC + (uint32_t)b * TC_N;
+      const uint32_t stage_u = sB_u + (uint32_t)s * stage_bytes;
+      const uint32_t lo_hiX = desc_lbo | (stage_u >> 4), lo_loX = desc_lbo | ((stage_u + b_bytes) >> 4);
+      // pass 0: lo(C).hi(X)   pass 1: hi(C).lo(X)   pass 2: hi(C).hi(X)   (small terms first)
+#pragma unroll 4
+      for (int k = 0; k < ksteps; k++)
+        tc_mma_tf32_ts(dcol, tmem + TCP_COL_ALO + (uint32_t)(8 * k), desc_hi | (lo_hiX + (uint32_t)k * kstep_enc), idesc, k > 0);
+#pragma unroll 4
+      for (int k = 0; k < ksteps; k++)
+        tc_mma_tf32_ts(dcol, tmem + TCP_COL_AHI + (uint32_t)(8 * k), desc_hi | (lo_loX + (uint32_t)k * kstep_enc), idesc, 1u);
+#pragma unroll 4
+      for (int k = 0; k < ksteps; k++)
+        tc_mma_tf32_ts(dcol, tmem + TCP_COL_AHI + (uint32_t)(8 * k), desc_hi | (lo_hiX + (uint32_t)k * kstep_enc), idesc, 1u);
+      tc_commit_elected(&bar_empty[s]);      // shared-memory stage may be refilled once these MMAs have read it
+      tc_commit_elected(&bar_acc_full[b]);   // accumulator complete
     }
   } else {
     // ===================== epilogue: warp w drains TMEM lanes 32w .. 32w+31 =====================
