@@ -190,7 +190,7 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------
 # Secondary workloads (python bench.py --workload adc|chain|legacy ...): they live in this file because
 # their CPU legs run the oracle / the reference's own binaries, which only bench.py and tests/ may do.
-# benchmarks/bench_adc.py, bench_chain.py and legacy_kernel.py are thin shims onto these.
+
 # ----------------------------------------------------------------------------------------------------
 # ADC linear scan (BASELINE configs[4]): n base codes x nq queries, top-nn.  Reports queries/s, the effective
 # scan bandwidth nq*n*(m+4)/t against the measured HBM peak (an *effective* figure — the
@@ -804,6 +804,40 @@ def inlib_block(ndev, n, ils, C_h, e2e_steps):
     del res["codes"]
     res["speedup"] = res["one_device"]["ms"] / res["all_devices"]["ms"]
     res["source"] = "pageable numpy arrays"
+    # the same call from pinned host memory (what the pageable path is up against)
+    import torch
+    Xp, Bp = torch.from_numpy(X).pin_memory(), torch.from_numpy(B).pin_memory()
+    ts = []
+    for i in range(1 + max(1, e2e_steps)):
+        w0 = time.perf_counter()
+        lsq_b200.encode_icm_cuda(Xp.numpy(), Bp.numpy(), C_h, its, ICMITER, NPERT, True, 1, seed=1)
+        if i > 0:
+            ts.append(time.perf_counter() - w0)
+    res["all_devices_pinned_source"] = {"ms": 1e3 * statistics.median(ts), "vectors_per_s": n / statistics.median(ts),
+                                        "speedup_vs_one_device_pageable": res["one_device"]["ms"] / (1e3 * statistics.median(ts))}
+    del Xp, Bp
+    # lsq_train_lsq sharded inside the library: the statistics exchange by NCCL (ncclAllReduce on the clique built with
+    # ncclCommInitAll) and by the library's own fused peer-memory kernel (the finalize kernel reads every device's
+    # statistics over NVLink and sums them itself); identical results, device-timed on the primary GPU
+    tr = {}
+    ref_out = None
+    for backend in ("nccl", "p2p"):
+        os.environ["LSQ_B200_ALLREDUCE"] = backend
+        lsq_b200.finalize()
+        lsq_b200.init_devices(list(range(ndev)))
+        ts = []
+        for i in range(2):
+            w0 = time.perf_counter()
+            Ct, Bt, _, _, obj = lsq_b200.train_lsq(X, M, H, None, B, None, 2, 2, ICMITER, True, NPERT, seed=3)
+            ts.append(time.perf_counter() - w0)
+        tr[backend] = {"train_lsq_ms": 1e3 * min(ts), "exchange_plus_finalize_ms": float(lsq_b200.lib().lsq_last_collective_ms())}
+        if ref_out is None:
+            ref_out = (Ct, Bt)
+        else:
+            tr["backends_bit_identical"] = bool(np.array_equal(ref_out[0], Ct) and np.array_equal(ref_out[1], Bt))
+    os.environ.pop("LSQ_B200_ALLREDUCE", None)
+    tr["workload"] = f"lsq_train_lsq on {n} vectors, 2 outer iterations x 2 ILS iterations, {ndev} devices, host call incl. copies"
+    res["train_lsq"] = tr
     lsq_b200.finalize()
     lsq_b200.init(0)
     return res

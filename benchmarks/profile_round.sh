@@ -8,8 +8,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:icm_ils -c 1 -o gpurun_out/icm_${TAG} \
     python bench.py --steps 1 --warmup 0 --no-cpu --e2e-steps 0 >> gpurun_out/ncu_icm_${TAG}.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/launches_adc_${TAG}.csv \
-    python benchmarks/bench_adc.py --m 8 --reps 1 --cpu-queries 2 --check-queries 2 > gpurun_out/ncu_adc_${TAG}.log 2>&1
+    python bench.py --workload adc --m 8 --reps 1 --cpu-queries 2 --check-queries 2 > gpurun_out/ncu_adc_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:scan_kernel -s 3 -c 1 -o gpurun_out/scan_${TAG} \
-    python benchmarks/bench_adc.py --m 8 --reps 1 --cpu-queries 2 --check-queries 2 >> gpurun_out/ncu_adc_${TAG}.log 2>&1
+    python bench.py --workload adc --m 8 --reps 1 --cpu-queries 2 --check-queries 2 >> gpurun_out/ncu_adc_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:viterbi -s 1 -c 1 -o gpurun_out/viterbi_${TAG} \
-    python benchmarks/bench_chain.py --m 8 --n 400000 --reps 1 --cpu-n 10 > gpurun_out/ncu_vit_${TAG}.log 2>&1
+    python bench.py --workload chain --m 8 --n 400000 --reps 1 --cpu-n 10 > gpurun_out/ncu_vit_${TAG}.log 2>&1

@@ -51,6 +51,9 @@ int lsq_device_count(void);
 /* number of CUDA kernels this library has launched so far in the process (measurement aid: bench.py reports
  * the difference over its timed region as gpu_launches) */
 unsigned long long lsq_launch_count(void);
+/* device time (ms, primary device) of the most recent statistics exchange + finalize inside lsq_train_lsq
+ * (NCCL all-reduce, or the fused peer-memory kernel); -1 if none happened yet.  Measurement aid. */
+float lsq_last_collective_ms(void);
 const char* lsq_version(void);
 
 /* ---- a10: splitarray (utils.jl:152-177): part p of nparts over 0..n-1 -> [lo, hi) ------------- */

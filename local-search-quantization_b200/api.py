@@ -19,7 +19,7 @@ _lib = None
 
 # every symbol include/lsq_b200.h declares (tests check the .so exports exactly these)
 EXPORTED_SYMBOLS = [
-    "lsq_init", "lsq_init_devices", "lsq_num_bound_devices", "lsq_finalize", "lsq_last_error", "lsq_device_count", "lsq_launch_count", "lsq_version", "lsq_splitarray",
+    "lsq_init", "lsq_init_devices", "lsq_num_bound_devices", "lsq_finalize", "lsq_last_error", "lsq_device_count", "lsq_launch_count", "lsq_last_collective_ms", "lsq_version", "lsq_splitarray",
     "lsq_make_to_look", "lsq_make_perturb", "lsq_get_unaries", "lsq_get_binaries", "lsq_veccost",
     "lsq_qerror", "lsq_reconstruct", "lsq_encoding_icm", "lsq_encoding_icm_sched", "lsq_encode_icm_cuda",
     "lsq_update_codebooks", "linscan_aqd_query_extra_byte", "linscan_aqd_query", "lsq_linscan_lsq",
@@ -63,6 +63,7 @@ def lib():
         L.lsq_dev_sliced_tables_bytes.restype = ct.c_int64
         L.lsq_cb_stats_len.restype = ct.c_int64
         L.lsq_launch_count.restype = ct.c_uint64
+        L.lsq_last_collective_ms.restype = ct.c_float
         L.linscan_aqd_query_extra_byte.restype = None
         L.linscan_aqd_query.restype = None
         _lib = L

@@ -122,6 +122,31 @@ int cb_finalize(const int64_t* dS, int m, int d, int scale_exp, double* dGram, d
   return LSQ_OK;
 }
 
+__global__ void __launch_bounds__(256) cb_finalize_peers_kernel(PeerPtrs peers, int k, int64_t ngram, int64_t total, int scale_exp,
+                                                               double* __restrict__ gram, double* __restrict__ rhs) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; 2 * i < total; i += stride) {
+    // two int64 per thread and peer: 16-byte loads over NVLink (total = mh*(mh+d) is even: mh is a multiple of 256)
+    longlong2 acc = make_longlong2(0, 0);
+    for (int j = 0; j < k; j++) {
+      const longlong2 v = *reinterpret_cast<const longlong2*>(peers.p[j] + 2 * i);
+      acc.x += v.x; acc.y += v.y;
+    }
+    const int64_t e0 = 2 * i, e1 = 2 * i + 1;
+    if (e0 < ngram) gram[e0] = (double)acc.x; else rhs[e0 - ngram] = scalbn((double)acc.x, -scale_exp);
+    if (e1 < ngram) gram[e1] = (double)acc.y; else rhs[e1 - ngram] = scalbn((double)acc.y, -scale_exp);
+  }
+}
+
+int cb_finalize_peers(const PeerPtrs& peers, int k, int m, int d, int scale_exp, double* dGram, double* dRhs, cudaStream_t st) {
+  const int64_t mh = (int64_t)m * LSQ_H;
+  const int64_t total = mh * (mh + d);
+  note_launch();
+  cb_finalize_peers_kernel<<<LSQ_NUM_SMS_HINT * 8, 256, 0, st>>>(peers, k, mh * mh, total, scale_exp, dGram, dRhs);
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
+}
+
 // single-shard convenience: scale from this X alone
 int cb_stats(const float* dX, int d, int64_t n, const uint8_t* dcodes, int m, double* dGram, double* dRhs,
              cudaStream_t st) {
@@ -357,7 +382,7 @@ static int update_codebooks_host(const float* X, int d, int64_t n, const int16_t
       LSQ_CUDA(d16.alloc((size_t)nl * m));
       LSQ_CUDA(dcodes.alloc((size_t)nl * m));
       LSQ_CUDA(dS.alloc(slen));
-      if (k > 1) LSQ_CUDA(dS2.alloc(slen));
+      if (k > 1 && !rt_allreduce_is_p2p(grp)) LSQ_CUDA(dS2.alloc(slen));
       LSQ_CUDA(dmax.alloc(1));
       LSQ_CUDA(derr.alloc(1));
       LSQ_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), st));
@@ -383,14 +408,18 @@ static int update_codebooks_host(const float* X, int d, int64_t n, const int16_t
     bar.wait();
     rc = cb_accumulate(dX.p, d, nl, dcodes.p, m, scale_exp, dS.p, st);
     if (!phase_ok(rc)) return rc != LSQ_OK ? rc : LSQ_ERR_CUDA;
-    if (k > 1) rc = rt_allreduce_sum_i64(grp, r, dS.p, dS2.p, slen, st, &bar);
+    const bool fused = (k > 1) && rt_allreduce_is_p2p(grp);
+    PeerPtrs peers;
+    if (fused) rc = rt_peer_begin(grp, r, dS.p, st, &bar, &peers);
+    else if (k > 1) rc = rt_allreduce_sum_i64(grp, r, dS.p, dS2.p, slen, st, &bar);
     auto stage3 = [&]() -> int {
       LSQ_TRY(rc);
       if (r == 0) {
         LSQ_CUDA(dG.alloc((size_t)mh * mh));
         LSQ_CUDA(dR.alloc((size_t)mh * d));
         LSQ_CUDA(dC.alloc((size_t)mh * d));
-        LSQ_TRY(cb_finalize(dS.p, m, d, scale_exp, dG.p, dR.p, st));
+        if (fused) LSQ_TRY(cb_finalize_peers(peers, k, m, d, scale_exp, dG.p, dR.p, st));
+        else LSQ_TRY(cb_finalize(dS.p, m, d, scale_exp, dG.p, dR.p, st));
         int iters = 0;
         LSQ_TRY(cb_solve(dG.p, dR.p, m, d, dC.p, 0, 0.0, &iters, st));
         if (verbose) fprintf(stderr, "[lsq_b200] codebook update: CG converged in %d iterations (%d device%s)\n", iters, k, k > 1 ? "s" : "");
@@ -400,6 +429,7 @@ static int update_codebooks_host(const float* X, int d, int64_t n, const int16_t
       return LSQ_OK;
     };
     rc = stage3();
+    if (fused) { const int rc2 = rt_peer_end(grp, r, st, &bar); if (rc == LSQ_OK) rc = rc2; cudaStreamSynchronize(st); }
     phase_ok(rc);  // nobody frees its statistics while a peer may still be reading them
     return rc;
   });

@@ -10,6 +10,10 @@ int cb_scale_exp(float absmax, int64_t n_total);                               /
 int cb_accumulate(const float* dX, int d, int64_t n, const uint8_t* dcodes, int m, int scale_exp, int64_t* dS,
                   cudaStream_t st);                                            // S += shard
 int cb_finalize(const int64_t* dS, int m, int d, int scale_exp, double* dGram, double* dRhs, cudaStream_t st);
+// fused peer-memory form of "all-reduce + finalize": Gram / Rhs from the statistics buffers of k devices, read in place
+// through NVLink peer memory and summed in rank order (exact integers: the order is irrelevant for the value)
+struct PeerPtrs;
+int cb_finalize_peers(const PeerPtrs& peers, int k, int m, int d, int scale_exp, double* dGram, double* dRhs, cudaStream_t st);
 // single shard: absmax + accumulate + finalize; OVERWRITES Gram[mh][mh] and Rhs[mh][d] (float64, device)
 int cb_stats(const float* dX, int d, int64_t n, const uint8_t* dcodes, int m, double* dGram, double* dRhs,
              cudaStream_t st);

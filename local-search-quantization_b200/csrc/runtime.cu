@@ -396,8 +396,6 @@ int rt_h2d(void* ddst, const void* hsrc, size_t bytes, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // the statistics all-reduce
 // ------------------------------------------------------------------------------------------------
-struct PeerPtrs { const int64_t* p[16]; };
-
 // out[i] = sum_j peers[j][i], j ascending: every device reads its peers' buffers through NVLink peer memory
 __global__ void __launch_bounds__(256) reduce_peers_kernel(PeerPtrs peers, int k, size_t count, int64_t* __restrict__ out) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -463,6 +461,35 @@ AllReduceGroup* rt_allreduce_group(int k) {
 }
 
 const char* rt_allreduce_backend(const AllReduceGroup* g) { return g->nccl ? "nccl" : "p2p"; }
+bool rt_allreduce_is_p2p(const AllReduceGroup* g) { return !g->nccl; }
+
+int rt_peer_begin(AllReduceGroup* g, int rank, const int64_t* dbuf, cudaStream_t st, HostBarrier* bar, PeerPtrs* peers) {
+  g->bufs[rank] = const_cast<int64_t*>(dbuf);
+  cudaError_t e = cudaEventRecord(g->ready[rank], st);
+  bar->wait();
+  for (int j = 0; j < g->k; j++) {
+    peers->p[j] = g->bufs[j];
+    if (j != rank && e == cudaSuccess) e = cudaStreamWaitEvent(st, g->ready[j], 0);
+  }
+  LSQ_CUDA(e);
+  return LSQ_OK;
+}
+
+int rt_peer_end(AllReduceGroup* g, int rank, cudaStream_t st, HostBarrier* bar) {
+  cudaError_t e = cudaEventRecord(g->done[rank], st);
+  bar->wait();
+  for (int j = 0; j < g->k; j++)
+    if (j != rank && e == cudaSuccess) e = cudaStreamWaitEvent(st, g->done[j], 0);
+  LSQ_CUDA(e);
+  return LSQ_OK;
+}
+
+static std::atomic<float> g_collective_ms{-1.0f};
+void rt_note_collective(cudaEvent_t a, cudaEvent_t b) {
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, a, b) == cudaSuccess) g_collective_ms.store(ms);
+  cudaGetLastError();
+}
 
 int rt_allreduce_sum_i64(AllReduceGroup* g, int rank, int64_t* dbuf, int64_t* dscratch, size_t count,
                          cudaStream_t st, HostBarrier* bar) {
@@ -522,6 +549,8 @@ int lsq_device_count(void) {
 }
 
 unsigned long long lsq_launch_count(void) { return g_launches.load(); }
+
+float lsq_last_collective_ms(void) { return g_collective_ms.load(); }
 
 const char* lsq_version(void) { return "lsq_b200 0.2 (sm_100a)"; }
 

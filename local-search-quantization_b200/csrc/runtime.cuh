@@ -85,6 +85,16 @@ int rt_h2d(void* ddst, const void* hsrc, size_t bytes, cudaStream_t st);
 //                   LSQ_B200_ALLREDUCE=p2p.
 struct AllReduceGroup;
 AllReduceGroup* rt_allreduce_group(int k);   // nullptr + lsq_last_error() on failure; owned by the runtime
+// p2p backend, fused form: instead of materialising the sum, the CONSUMER kernel reads every peer's buffer itself
+// (cb_finalize_peers: sum over the peers in rank order + conversion to float64 in one pass, no intermediate copy).
+//   rt_peer_begin : publish `dbuf`, wait (stream-side) until every peer's buffer is complete, return their pointers
+//   rt_peer_end   : after the consumer kernel was queued: nobody overwrites its buffer while a peer still reads it
+struct PeerPtrs { const int64_t* p[16]; };
+bool rt_allreduce_is_p2p(const AllReduceGroup* g);
+int rt_peer_begin(AllReduceGroup* g, int rank, const int64_t* dbuf, cudaStream_t st, HostBarrier* bar, PeerPtrs* peers);
+int rt_peer_end(AllReduceGroup* g, int rank, cudaStream_t st, HostBarrier* bar);
+// device-time of the most recent statistics exchange on the primary device (measurement aid, lsq_last_collective_ms)
+void rt_note_collective(cudaEvent_t a, cudaEvent_t b);
 int rt_allreduce_sum_i64(AllReduceGroup* g, int rank, int64_t* dbuf, int64_t* dscratch, size_t count,
                          cudaStream_t st, HostBarrier* bar);
 const char* rt_allreduce_backend(const AllReduceGroup* g);

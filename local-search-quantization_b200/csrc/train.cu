@@ -316,7 +316,7 @@ int lsq_train_lsq(const float* X, int d, int64_t n, int m, int h, const float* R
     STEP_CUDA(d16.alloc((size_t)nl * m));
     STEP_CUDA(dcodes.alloc((size_t)nl * m));
     STEP_CUDA(dS.alloc(slen));
-    if (k > 1) STEP_CUDA(dS2.alloc(slen));
+    if (k > 1 && !rt_allreduce_is_p2p(grp)) STEP_CUDA(dS2.alloc(slen));
     STEP_CUDA(dG.alloc((size_t)mh * mh));
     STEP_CUDA(dRhs.alloc((size_t)mh * d));
     STEP_CUDA(dsum.alloc(1025));
@@ -343,6 +343,10 @@ int lsq_train_lsq(const float* X, int d, int64_t n, int m, int h, const float* R
     T.dC = dC.p; T.dnorms = dnorms.p; T.dT = dT.p; T.dU = dU.p; T.chunk = chunk;
     T.icmiter = icmiter; T.npert = npert; T.randord = randord; T.seed = seed;
 
+    const bool fused = (k > 1) && rt_allreduce_is_p2p(grp);
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;   // device time of the exchange + finalize on the primary device
+    struct EvGuard { cudaEvent_t& a; cudaEvent_t& b; ~EvGuard() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evg{ev_a, ev_b};
+    if (r == 0) { STEP_CUDA(cudaEventCreate(&ev_a)); STEP_CUDA(cudaEventCreate(&ev_b)); }
     // scale exponent of the fixed-point statistics for data source `src` (global max|x| over the shards)
     int scale_exp = 0;
     auto exchange_scale = [&](const float* src) -> int {
@@ -361,11 +365,24 @@ int lsq_train_lsq(const float* X, int d, int64_t n, int m, int h, const float* R
       STEP_CUDA(cudaMemsetAsync(dS.p, 0, slen * sizeof(int64_t), st));
       STEP(cb_accumulate(src, d, nl, dcodes.p, m, scale_exp, dS.p, st));
       SYNC();
-      if (k > 1) rc = rt_allreduce_sum_i64(grp, r, dS.p, dS2.p, slen, st, &sync.bar);
-      STEP(cb_finalize(dS.p, m, d, scale_exp, dG.p, dRhs.p, st));
+      // the one exchange per outer iteration: NCCL all-reduce + finalize, or the fused peer-memory form in which
+      // the finalize kernel itself reads and sums every device's statistics (no intermediate buffer or copy)
+      if (r == 0) STEP_CUDA(cudaEventRecord(ev_a, st));
+      if (fused) {
+        PeerPtrs peers;
+        rc = rt_peer_begin(grp, r, dS.p, st, &sync.bar, &peers);
+        STEP(cb_finalize_peers(peers, k, m, d, scale_exp, dG.p, dRhs.p, st));
+        const int rc2 = rt_peer_end(grp, r, st, &sync.bar);
+        if (rc == LSQ_OK) rc = rc2;
+      } else {
+        if (k > 1) rc = rt_allreduce_sum_i64(grp, r, dS.p, dS2.p, slen, st, &sync.bar);
+        STEP(cb_finalize(dS.p, m, d, scale_exp, dG.p, dRhs.p, st));
+      }
+      if (r == 0) STEP_CUDA(cudaEventRecord(ev_b, st));
       int iters = 0;
       STEP(cb_solve(dG.p, dRhs.p, m, d, dC.p, 0, 0.0, &iters, st));
       if (verbose && r == 0 && rc == LSQ_OK) fprintf(stderr, "[lsq_b200] codebook update: CG converged in %d iterations\n", iters);
+      if (r == 0 && rc == LSQ_OK) rt_note_collective(ev_a, ev_b);   // (cb_solve synchronised the stream)
       SYNC();
       return LSQ_OK;
     };
