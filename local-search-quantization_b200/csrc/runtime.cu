@@ -35,57 +35,97 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// copy pool: a few persistent threads that split one large memcpy
+// staging pool: host -> device copies of PAGEABLE caller memory.  The copy is cut into 4 MB chunks; the calling
+// thread and a few persistent helpers each grab the next chunk, memcpy it into one of their own two pinned
+// buffers and queue the DMA on the caller's stream.  Chunk-level work stealing: no per-chunk rendezvous, so a
+// helper that is scheduled late only does less of the work.
 // ------------------------------------------------------------------------------------------------
-class CopyPool {
+constexpr size_t STAGE_BYTES = (size_t)4 << 20;
+
+class StagePool {
  public:
-  explicit CopyPool(int helpers) {
-    for (int i = 0; i < helpers; i++) th_.emplace_back([this, i] { run(i); });
+  StagePool(int dev, int helpers) : dev_(dev), slots_(helpers + 1) {
+    for (int i = 0; i < helpers; i++) th_.emplace_back([this, i] { run(i + 1); });
   }
-  ~CopyPool() {
+  ~StagePool() {
     { std::lock_guard<std::mutex> lk(mu_); stop_ = true; gen_++; }
     cv_.notify_all();
     for (auto& t : th_) t.join();
+    for (auto& S : slots_)
+      for (int s = 0; s < 2; s++) {
+        if (S.ev[s]) cudaEventDestroy(S.ev[s]);
+        if (S.buf[s]) cudaFreeHost(S.buf[s]);
+      }
   }
-  void copy(void* dst, const void* src, size_t bytes) {
-    const int parts = (int)th_.size() + 1;
-    if (parts == 1 || bytes < ((size_t)1 << 20)) { memcpy(dst, src, bytes); return; }
-    const size_t per = ((bytes / parts) + 4095) & ~(size_t)4095;
+  // returns once every chunk's cudaMemcpyAsync has been queued on `st` (the staging buffers are recycled
+  // behind their own events, so the caller may go on queuing work on `st` immediately)
+  cudaError_t copy(void* ddst, const void* hsrc, size_t bytes, cudaStream_t st) {
     {
       std::lock_guard<std::mutex> lk(mu_);
-      dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes; per_ = per; pending_ = (int)th_.size(); gen_++;
+      dst_ = (char*)ddst; src_ = (const char*)hsrc; bytes_ = bytes; st_ = st;
+      nchunks_ = (bytes + STAGE_BYTES - 1) / STAGE_BYTES;
+      next_.store(0);
+      err_.store((int)cudaSuccess);
+      pending_ = (int)th_.size();
+      gen_++;
     }
     cv_.notify_all();
-    memcpy(dst, src, std::min(per, bytes));
+    work(0);
     std::unique_lock<std::mutex> lk(mu_);
     done_cv_.wait(lk, [&] { return pending_ == 0; });
+    return (cudaError_t)err_.load();
   }
+
  private:
-  void run(int idx) {
+  struct Slots { void* buf[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr}; bool busy[2] = {false, false}; int next = 0; };
+  void fail(cudaError_t e) { int ok = (int)cudaSuccess; err_.compare_exchange_strong(ok, (int)e); }
+  void work(int me) {
+    Slots& S = slots_[me];
+    for (;;) {
+      const size_t c = next_.fetch_add(1);
+      if (c >= nchunks_ || err_.load() != (int)cudaSuccess) return;
+      const size_t off = c * STAGE_BYTES, sz = std::min(STAGE_BYTES, bytes_ - off);
+      const int s = S.next;
+      S.next ^= 1;
+      cudaError_t e = cudaSuccess;
+      if (S.buf[s] == nullptr) {
+        e = cudaHostAlloc(&S.buf[s], STAGE_BYTES, cudaHostAllocPortable);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&S.ev[s], cudaEventDisableTiming);
+      }
+      if (e == cudaSuccess && S.busy[s]) e = cudaEventSynchronize(S.ev[s]);  // its previous DMA has drained
+      if (e != cudaSuccess) { fail(e); return; }
+      memcpy(S.buf[s], src_ + off, sz);
+      e = cudaMemcpyAsync(dst_ + off, S.buf[s], sz, cudaMemcpyHostToDevice, st_);
+      if (e == cudaSuccess) e = cudaEventRecord(S.ev[s], st_);
+      if (e != cudaSuccess) { fail(e); return; }
+      S.busy[s] = true;
+    }
+  }
+  void run(int me) {
+    cudaSetDevice(dev_);
     unsigned seen = 0;
     for (;;) {
-      char* d; const char* s; size_t bytes, per;
       {
         std::unique_lock<std::mutex> lk(mu_);
         cv_.wait(lk, [&] { return gen_ != seen; });
         seen = gen_;
         if (stop_) return;
-        d = dst_; s = src_; bytes = bytes_; per = per_;
       }
-      const size_t off = per * (size_t)(idx + 1);
-      if (off < bytes) memcpy(d + off, s + off, std::min(per, bytes - off));
-      {
-        std::lock_guard<std::mutex> lk(mu_);
-        pending_--;
-      }
+      work(me);
+      { std::lock_guard<std::mutex> lk(mu_); pending_--; }
       done_cv_.notify_one();
     }
   }
+  int dev_;
+  std::vector<Slots> slots_;
   std::vector<std::thread> th_;
   std::mutex mu_;
   std::condition_variable cv_, done_cv_;
   char* dst_ = nullptr; const char* src_ = nullptr;
-  size_t bytes_ = 0, per_ = 0;
+  size_t bytes_ = 0, nchunks_ = 0;
+  cudaStream_t st_ = nullptr;
+  std::atomic<size_t> next_{0};
+  std::atomic<int> err_{0};
   int pending_ = 0;
   unsigned gen_ = 0;
   bool stop_ = false;
@@ -94,17 +134,9 @@ class CopyPool {
 // ------------------------------------------------------------------------------------------------
 // bound devices
 // ------------------------------------------------------------------------------------------------
-constexpr int STAGE_SLOTS = 4;
-constexpr size_t STAGE_BYTES = (size_t)8 << 20;
-
 struct DevState {
   DevCtx ctx;
-  // pinned staging ring for pageable sources (allocated at first use)
-  void* stage[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t stage_ev[STAGE_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
-  bool stage_busy[STAGE_SLOTS] = {false, false, false, false};
-  int stage_next = 0;
-  CopyPool* pool = nullptr;
+  StagePool* pool = nullptr;   // pinned staging for pageable sources (buffers allocated at first use)
 };
 
 struct AllReduceGroup {
@@ -179,10 +211,6 @@ static void release_devices_locked() {
     cudaSetDevice(D->ctx.dev);
     if (D->ctx.st) { cudaStreamSynchronize(D->ctx.st); cudaStreamDestroy(D->ctx.st); }
     if (D->ctx.st2) { cudaStreamSynchronize(D->ctx.st2); cudaStreamDestroy(D->ctx.st2); }
-    for (int s = 0; s < STAGE_SLOTS; s++) {
-      if (D->stage_ev[s]) cudaEventDestroy(D->stage_ev[s]);
-      if (D->stage[s]) cudaFreeHost(D->stage[s]);
-    }
     delete D->pool;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, D->ctx.dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
@@ -232,7 +260,7 @@ static int bind_devices_locked(const int* devs, int n) {
     keep_pool_memory(want[i]);
     int helpers = hw / (int)want.size() - 1;
     if (const char* he = getenv("LSQ_B200_COPY_THREADS")) helpers = atoi(he) - 1;
-    D->pool = new CopyPool(std::max(0, std::min(helpers, 5)));
+    D->pool = new StagePool(want[i], std::max(0, std::min(helpers, 3)));
   }
   // peer access for the device set (P2P all-reduce backend; also lets NCCL pick its P2P transport)
   for (size_t i = 0; i < want.size(); i++)
@@ -376,20 +404,7 @@ int rt_h2d(void* ddst, const void* hsrc, size_t bytes, cudaStream_t st) {
     LSQ_CUDA(cudaMemcpyAsync(ddst, hsrc, bytes, cudaMemcpyHostToDevice, st));
     return LSQ_OK;
   }
-  for (size_t off = 0; off < bytes; off += STAGE_BYTES) {
-    const size_t sz = std::min(STAGE_BYTES, bytes - off);
-    const int s = D->stage_next;
-    D->stage_next = (s + 1) % STAGE_SLOTS;
-    if (D->stage[s] == nullptr) {
-      LSQ_CUDA(cudaHostAlloc(&D->stage[s], STAGE_BYTES, cudaHostAllocPortable));
-      LSQ_CUDA(cudaEventCreateWithFlags(&D->stage_ev[s], cudaEventDisableTiming));
-    }
-    if (D->stage_busy[s]) LSQ_CUDA(cudaEventSynchronize(D->stage_ev[s]));  // its previous DMA has drained
-    D->pool->copy(D->stage[s], (const char*)hsrc + off, sz);
-    LSQ_CUDA(cudaMemcpyAsync((char*)ddst + off, D->stage[s], sz, cudaMemcpyHostToDevice, st));
-    LSQ_CUDA(cudaEventRecord(D->stage_ev[s], st));
-    D->stage_busy[s] = true;
-  }
+  LSQ_CUDA(D->pool->copy(ddst, hsrc, bytes, st));
   return LSQ_OK;
 }
 

@@ -70,9 +70,10 @@ class PhaseSync {
 int rt_devices_for(int64_t n, int64_t min_per_device);
 
 // Host -> device copy of caller memory, ordered on `st`.  Pinned / registered sources go straight to
-// cudaMemcpyAsync.  Pageable sources are staged through a ring of pinned buffers owned by the calling
-// thread, filled by a small pool of copy threads, so the DMA of chunk i overlaps the host memcpy of chunk
-// i+1 and the copy is not limited to one core's memcpy rate (LSQ_B200_H2D=direct|staged, default staged).
+// cudaMemcpyAsync.  Pageable sources (Julia arrays) are cut into 4 MB chunks; the calling thread and a few
+// persistent helper threads of the device each grab the next chunk, memcpy it into one of their own two pinned
+// buffers and queue its DMA, so the DMA of one chunk overlaps the host copies of the others and the copy is not
+// limited to one core's memcpy rate (LSQ_B200_H2D=direct|staged, default staged; LSQ_B200_COPY_THREADS=k).
 int rt_h2d(void* ddst, const void* hsrc, size_t bytes, cudaStream_t st);
 
 // ---- the collective: in-place sum of `count` int64 over the k bound devices ---------------------------
