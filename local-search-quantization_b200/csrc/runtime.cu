@@ -437,9 +437,19 @@ AllReduceGroup* rt_allreduce_group(int k) {
   if (k > 16 || k > (int)g_dev.size()) { set_error("all-reduce group larger than the bound device set"); return nullptr; }
   AllReduceGroup* g = new AllReduceGroup();
   g->k = k;
+  // Default backend, from measurements on B200 (35.7 MB of statistics, exchange + finalize on the primary device):
+  // 2 GPUs: fused peer-memory kernel 0.074 ms vs NCCL 0.107 ms; 8 GPUs: 0.47 ms (every device reads all 8 buffers)
+  // vs NCCL 0.17 ms (reduce-scatter + all-gather).  So: two devices -> own kernel, more -> NCCL.
+  bool p2p_ok = true;
+  for (int i = 0; i < k; i++)
+    for (int j = 0; j < k; j++) {
+      int can = (g_dev[i]->ctx.dev == g_dev[j]->ctx.dev);
+      if (!can) cudaDeviceCanAccessPeer(&can, g_dev[i]->ctx.dev, g_dev[j]->ctx.dev);
+      p2p_ok = p2p_ok && can;
+    }
   const char* be = getenv("LSQ_B200_ALLREDUCE");
-  const bool want_p2p = (be != nullptr && strcmp(be, "p2p") == 0);
-  if (!want_p2p && load_nccl()) {
+  const bool prefer_p2p = (be != nullptr) ? (strcmp(be, "p2p") == 0) : (k <= 2);
+  if (!(prefer_p2p && p2p_ok) && load_nccl()) {
     std::vector<int> devs(k);
     for (int i = 0; i < k; i++) devs[i] = g_dev[i]->ctx.dev;
     g->comms.resize(k);
@@ -451,16 +461,11 @@ AllReduceGroup* rt_allreduce_group(int k) {
     }
   }
   if (!g->nccl) {
-    for (int i = 0; i < k; i++)
-      for (int j = 0; j < k; j++) {
-        int can = (g_dev[i]->ctx.dev == g_dev[j]->ctx.dev);
-        if (!can) cudaDeviceCanAccessPeer(&can, g_dev[i]->ctx.dev, g_dev[j]->ctx.dev);
-        if (!can) {
-          set_error("statistics all-reduce: NCCL unavailable and the devices have no peer access");
-          delete g;
-          return nullptr;
-        }
-      }
+    if (!p2p_ok) {
+      set_error("statistics all-reduce: NCCL unavailable and the devices have no peer access");
+      delete g;
+      return nullptr;
+    }
     g->bufs.assign(k, nullptr);
     g->ready.resize(k);
     g->done.resize(k);
