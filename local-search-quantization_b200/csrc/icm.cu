@@ -74,13 +74,19 @@ __device__ __forceinline__ float4 lds128_u(uint32_t addr) {
 // (cp.async.bulk + one mbarrier per warp) and re-read from there on every node visit of every ILS
 // iteration, which takes the unary share (1/m-th... 1 KB of every 8 KB visit at m = 8) off the saturated
 // SM<->L2 path.  Used for m <= 8 (m KB per warp must leave room for >= 24 warps per SM).
+// rows of a vector's unary table kept in shared memory by the staged variant: all of them up to m = 6, else 6 —
+// 8 warps x 6 KB per block still lets 4 blocks (32 warps) share an SM, which full staging (m KB per warp) did not
+template <int M>
+__host__ __device__ constexpr int icm_staged_rows() { return M < 6 ? M : 6; }
+
 template <int M, bool USMEM>
 __global__ void __launch_bounds__(256, 4) icm_ils_warp_kernel(const __grid_constant__ IcmParams p) {
+  constexpr int UR = icm_staged_rows<M>();
   extern __shared__ __align__(128) unsigned char icm_smem[];
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;                                  // warp in block
   uint64_t* ubar = reinterpret_cast<uint64_t*>(icm_smem) + wib;      // 8 barriers, then 8 x M KB of rows
-  const uint32_t urow = smem_u32(icm_smem + 128 + (size_t)wib * M * 1024) + (uint32_t)lane * 16u;
+  const uint32_t urow = smem_u32(icm_smem + 128 + (size_t)wib * UR * 1024) + (uint32_t)lane * 16u;
   uint32_t uphase = 0;
   if (USMEM) {
     if (lane == 0) { mbar_init(ubar, 1); fence_mbar_init(); }
@@ -104,10 +110,10 @@ __global__ void __launch_bounds__(256, 4) icm_ils_warp_kernel(const __grid_const
     if (USMEM) {
       __syncwarp();  // every lane is done with the previous vector's rows
       if (lane == 0) {
-        mbar_expect_tx(ubar, (uint32_t)M * 1024u);
+        mbar_expect_tx(ubar, (uint32_t)UR * 1024u);
 #pragma unroll
-        for (int j = 0; j < M; j++)
-          bulk_g2s(icm_smem + 128 + ((size_t)wib * M + j) * 1024, p.U + ((size_t)j * p.n + v) * LSQ_H, 1024u, ubar);
+        for (int j = 0; j < UR; j++)
+          bulk_g2s(icm_smem + 128 + ((size_t)wib * UR + j) * 1024, p.U + ((size_t)j * p.n + v) * LSQ_H, 1024u, ubar);
       }
       mbar_wait(ubar, uphase);
       uphase ^= 1u;
@@ -142,9 +148,23 @@ __global__ void __launch_bounds__(256, 4) icm_ils_warp_kernel(const __grid_const
         for (int jj = 0; jj < M; jj++) {
           const int j = p.orders[it][jj];
           if ((wclean >> j) & 1u) continue;
+          // Every OTHER node already carries its accepted code and the accepted state is known to be minimal at
+          // node j: the visit would compute exactly what it computed then — the accepted code of j (the update is
+          // a deterministic function of the other codes).  Typical case: the last perturbed node of a relaxing
+          // perturbation.  No memory traffic; afterwards the working codes equal the accepted ones.
+          if ((clean >> j) & 1u) {
+            const int sh = 8 * (j & 7);
+            const uint64_t mlo = (M <= 8 || j < 8) ? ~(0xFFull << sh) : ~0ull;
+            const uint64_t mhi = (M <= 8 || j < 8) ? ~0ull : ~(0xFFull << sh);
+            if (((wlo ^ lo) & mlo) == 0 && ((whi ^ hi) & mhi) == 0) {
+              wlo = lo; whi = hi;
+              wclean = clean;
+              continue;
+            }
+          }
           nvis++;
           float4 a0, a1;
-          if (USMEM) {
+          if (USMEM && j < UR) {
             a0 = lds128_u(urow + (uint32_t)j * 1024u);
             a1 = lds128_u(urow + (uint32_t)j * 1024u + 512u);
           } else {
@@ -229,10 +249,10 @@ static int launch_icm_warp_m(const IcmParams& p, cudaStream_t st) {
   const char* ue = getenv("LSQ_B200_ICM_USMEM");
   const bool usmem = kCanUsmem && ue != nullptr && atoi(ue) != 0;
   // warps per block: 8, or 4 when the staged rows of 8 warps would leave room for a single block per SM (m > 8)
-  int wpb = (usmem && M > 8) ? 4 : 8;
+  int wpb = 8;
   if (const char* we = getenv("LSQ_B200_ICM_WARPS_PER_BLOCK")) wpb = std::max(1, std::min(8, atoi(we)));
   const int64_t blocks_needed = ceil_div(p.n, wpb);
-  const size_t smem = usmem ? 128 + (size_t)wpb * M * 1024 : 0;
+  const size_t smem = usmem ? 128 + (size_t)wpb * icm_staged_rows<M>() * 1024 : 0;
   int per_sm = usmem ? (int)std::min<size_t>(64 / wpb, (size_t)(227 * 1024) / (smem + 1024)) : 64 / wpb;
   if (const char* e = getenv("LSQ_B200_ICM_BLOCKS_PER_SM")) per_sm = std::max(1, atoi(e));  // tuning override
   const int64_t cap = (int64_t)sms * per_sm;
