@@ -261,7 +261,8 @@ static int launch_icm_warp_m(const IcmParams& p, cudaStream_t st) {
   // (hit rate 77 % measured); pin them with a persisting access-policy window for this launch.
   const size_t tbytes = (size_t)M * M * LSQ_H * LSQ_H * sizeof(float);
   bool window = false;
-  if (M > 8) {
+  const char* we2 = getenv("LSQ_B200_ICM_L2WINDOW");   // A/B switch (default on for m > 8)
+  if (M > 8 && !(we2 != nullptr && atoi(we2) == 0)) {
     int max_persist = 0, max_window = 0;
     cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
     cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
