@@ -77,6 +77,53 @@ def test_inlibrary_sharding_matches_single_device(lsq, monkeypatch):
         lsq.init(0)
 
 
+def test_error_on_one_shard_fails_the_call_without_deadlock(lsq, monkeypatch):
+    """An invalid code in the LAST shard: every sharded call must return the error (no worker may be left at a
+    barrier or inside the collective), and the library must stay usable afterwards."""
+    ngpu = lsq.device_count()
+    devs = [0, 1] if ngpu >= 2 else [0, 0]
+    lsq.finalize()
+    if ngpu < 2:
+        monkeypatch.setenv("LSQ_B200_ALLOW_DUPLICATE_DEVICES", "1")
+    try:
+        assert lsq.init_devices(devs) == 2
+        n, d, m = 20000, 32, 4
+        X, C, B = make_problem(91, n, d, m)
+        bad = B.copy()
+        bad[n - 7, 2] = 300
+        for call in (lambda: lsq.encoding_icm(X, bad, C, 2, True, 2, seed=1, ils_iter=0),
+                     lambda: lsq.encode_icm_cuda(X, bad, C, [2], 2, 2, True, 1, seed=1),
+                     lambda: lsq.update_codebooks(X, bad, 256),
+                     lambda: lsq.train_lsq(X, m, 256, None, bad, None, 1, 1, 2, True, 2, seed=1)):
+            with pytest.raises(lsq.LsqError, match="1-based"):
+                call()
+        # still healthy: the same calls with valid codes
+        good = lsq.encoding_icm(X, B, C, 2, True, 2, seed=1, ils_iter=0)
+        Cn = lsq.update_codebooks(X, good, 256)
+        assert lsq.qerror(X, good, Cn) <= lsq.qerror(X, good, C) * (1 + 1e-6)
+    finally:
+        lsq.finalize()
+        lsq.init(0)
+
+
+def test_device_set_from_environment(lsq, monkeypatch):
+    """LSQ_B200_DEVICES selects the device set of a process that never calls lsq_init (an unchanged Julia program)."""
+    lsq.finalize()
+    monkeypatch.setenv("LSQ_B200_ALLOW_DUPLICATE_DEVICES", "1")
+    monkeypatch.setenv("LSQ_B200_DEVICES", "0,0" if lsq.device_count() < 2 else "all")
+    try:
+        X, C, B = make_problem(92, 9000, 32, 4)
+        out = lsq.encoding_icm(X, B, C, 2, True, 2, seed=1, ils_iter=0)      # binds lazily
+        assert lsq.num_bound_devices() == max(2, lsq.device_count())
+        monkeypatch.delenv("LSQ_B200_DEVICES")
+        lsq.finalize()
+        lsq.init(0)
+        assert np.array_equal(out, lsq.encoding_icm(X, B, C, 2, True, 2, seed=1, ils_iter=0))
+    finally:
+        lsq.finalize()
+        lsq.init(0)
+
+
 def test_update_codebooks_is_deterministic_and_chunk_invariant(lsq):
     """Exact integer statistics: run-to-run identical bits, and accumulating a shard in pieces (what sharding over
     GPUs does) gives the same integers as one pass — on non-integer data, where float64 atomics would not."""
