@@ -1,7 +1,7 @@
 """Host-side copy diagnostics on the multi-GPU box (scratch, not product)."""
 import os, sys, time, threading, ctypes as ct
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repository root
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch
 import lsq_b200

@@ -17,6 +17,10 @@
 
 #include <algorithm>
 
+#ifndef LSQ_ICM_SHORTCUT
+#define LSQ_ICM_SHORTCUT(M) ((M) <= 8)
+#endif
+
 namespace lsq {
 
 template <int M>
@@ -79,7 +83,10 @@ __device__ __forceinline__ float4 lds128_u(uint32_t addr) {
 template <int M>
 __host__ __device__ constexpr int icm_staged_rows() { return M < 6 ? M : 6; }
 
-template <int M, bool USMEM>
+// COUNT: the measurement variant that adds the executed node visits to *p.visits.  It is a separate
+// instantiation on purpose: the kernel sits exactly at its 64-register budget (4 blocks per SM), and one more
+// live counter in the visit loop cost 2 % at m = 8 and 10 % at m = 16 (measured against the same build without it).
+template <int M, bool USMEM, bool COUNT = false>
 __global__ void __launch_bounds__(256, 4) icm_ils_warp_kernel(const __grid_constant__ IcmParams p) {
   constexpr int UR = icm_staged_rows<M>();
   extern __shared__ __align__(128) unsigned char icm_smem[];
@@ -125,7 +132,7 @@ __global__ void __launch_bounds__(256, 4) icm_ils_warp_kernel(const __grid_const
     // reaches a fixed point after about two sweeps.  Any code change clears every other node's bit.
     constexpr uint32_t ALL_CLEAN = (M == 32) ? 0xFFFFFFFFu : ((1u << M) - 1u);
     uint32_t clean = 0;
-    uint32_t nvis = 0;  // node visits executed for this vector
+    uint32_t nvis = 0;  // node visits executed for this vector (COUNT variant only)
     for (int it = 0; it < p.niters; it++) {
       uint64_t wlo = lo, whi = hi;
       uint32_t wclean = clean;
@@ -152,7 +159,7 @@ __global__ void __launch_bounds__(256, 4) icm_ils_warp_kernel(const __grid_const
           // node j: the visit would compute exactly what it computed then — the accepted code of j (the update is
           // a deterministic function of the other codes).  Typical case: the last perturbed node of a relaxing
           // perturbation.  No memory traffic; afterwards the working codes equal the accepted ones.
-          if ((clean >> j) & 1u) {
+          if (LSQ_ICM_SHORTCUT(M) && ((clean >> j) & 1u)) {
             const int sh = 8 * (j & 7);
             const uint64_t mlo = (M <= 8 || j < 8) ? ~(0xFFull << sh) : ~0ull;
             const uint64_t mhi = (M <= 8 || j < 8) ? ~0ull : ~(0xFFull << sh);
@@ -162,7 +169,7 @@ __global__ void __launch_bounds__(256, 4) icm_ils_warp_kernel(const __grid_const
               continue;
             }
           }
-          nvis++;
+          if (COUNT) nvis++;
           float4 a0, a1;
           if (USMEM && j < UR) {
             a0 = lds128_u(urow + (uint32_t)j * 1024u);
@@ -223,7 +230,7 @@ __global__ void __launch_bounds__(256, 4) icm_ils_warp_kernel(const __grid_const
     }
     if (lane < M) p.codes[v * M + lane] = (uint8_t)get_code<M>(lo, hi, lane);
     if (lane == 0) p.cost[v] = prev;
-    if (p.visits != nullptr && lane == 0) atomicAdd(p.visits, (unsigned long long)nvis);
+    if (COUNT && lane == 0) atomicAdd(p.visits, (unsigned long long)nvis);
     if (p.next_vector != nullptr) {
       unsigned long long t = 0;
       if (lane == 0) t = atomicAdd(p.next_vector, 1ull);
@@ -242,7 +249,7 @@ static int launch_icm_warp_m(const IcmParams& p, cudaStream_t st) {
   int dev = 0, sms = LSQ_NUM_SMS_HINT;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  constexpr bool kCanUsmem = true;
+  constexpr bool kCanUsmem = (M <= 8);
   // Measured (1 M x 16 iterations, m = 8): staging the unary rows in shared memory removes 1/8 of the L2
   // traffic but caps residency at 24 warps/SM: 140.3 ms vs 136.6 ms with 32 warps and everything from
   // L2.  Occupancy wins, so the staged variant is opt-in (LSQ_B200_ICM_USMEM=1).
@@ -296,6 +303,9 @@ static int launch_icm_warp_m(const IcmParams& p, cudaStream_t st) {
     LSQ_CUDA(cudaFuncSetAttribute(icm_ils_warp_kernel<M, kCanUsmem>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     note_launch();
     icm_ils_warp_kernel<M, kCanUsmem><<<grid, 32 * wpb, smem, st>>>(q);
+  } else if (q.visits != nullptr) {
+    note_launch();
+    icm_ils_warp_kernel<M, false, true><<<grid, 32 * wpb, 0, st>>>(q);
   } else {
     note_launch();
     icm_ils_warp_kernel<M, false><<<grid, 32 * wpb, 0, st>>>(q);
