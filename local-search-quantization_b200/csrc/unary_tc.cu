@@ -210,7 +210,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) unary_tc_kernel(const float* __
 // ------------------------------------------------------------------------------------------------
 constexpr int TCP_STAGES = 2;     // operand-image stages
 constexpr int TCP_RAW = 3;        // raw X-tile ring slots
-constexpr int TCP_THREADS = 320;  // warps 0-3 epilogue (TMEM lane quadrant = warp id), 4-7 producers, 8 MMA issuer, 9 TMA
+constexpr int TCP_PRODUCERS = 256; // threads that split raw tiles into operand images (ncu: with 128 they were busy 90 % of the time)
+constexpr int TCP_THREADS = 128 + TCP_PRODUCERS + 64;  // warps 0-3 epilogue (TMEM lane quadrant = warp id), producers, MMA issuer, TMA
 constexpr uint32_t TCP_COL_AHI = 0, TCP_COL_ALO = 128, TCP_COL_ACC = 256;
 
 __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -270,9 +271,9 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) unary_tc_pipe_kernel(const flo
   const uint32_t lboB = tc_lbo(TC_N);
 
   if (tid == 0) {
-    for (int s = 0; s < TCP_STAGES; s++) { mbar_init(&bar_full[s], 128); mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < TCP_STAGES; s++) { mbar_init(&bar_full[s], TCP_PRODUCERS); mbar_init(&bar_empty[s], 1); }
     for (int b = 0; b < 2; b++) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_empty[b], 4); }
-    for (int s = 0; s < TCP_RAW; s++) { mbar_init(&bar_raw_full[s], 1); mbar_init(&bar_raw_empty[s], 128); }
+    for (int s = 0; s < TCP_RAW; s++) { mbar_init(&bar_raw_full[s], 1); mbar_init(&bar_raw_empty[s], TCP_PRODUCERS); }
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -312,7 +313,8 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) unary_tc_pipe_kernel(const flo
   const uint32_t raw_bytes = (uint32_t)TC_N * (uint32_t)d * 4u;               // one raw tile: 64 rows of X, contiguous
   unsigned char* raw_base = smem_raw + (size_t)TCP_STAGES * stage_bytes;
 
-  if (warp == 9) {
+  constexpr int W_MMA = (128 + TCP_PRODUCERS) / 32, W_TMA = W_MMA + 1;
+  if (warp == W_TMA) {
     // ===================== TMA: raw X tiles, up to TCP_RAW tiles ahead =====================
     if (lane == 0) {
       for (int64_t t = 0; t < my_tiles; t++) {
@@ -324,7 +326,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) unary_tc_pipe_kernel(const flo
                         &bar_raw_full[slot]);
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < W_MMA) {
     // ===================== producers: raw X tile -> hi / lo operand images =====================
     const int ptid = tid - 128;
     const int chunks = d / 4;
@@ -348,16 +350,16 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) unary_tc_pipe_kernel(const flo
         *reinterpret_cast<float4*>(sB + b_bytes + off) = lo;
       };
       if (chunks == 32) {  // d = 128: a warp walks one 512-byte row, no division
-#pragma unroll 4
-        for (int i = 0; i < TC_N / 4; i++) put((ptid >> 5) + 4 * i, ptid & 31);
+#pragma unroll
+        for (int i = 0; i < TC_N * 32 / TCP_PRODUCERS; i++) put((ptid >> 5) + (TCP_PRODUCERS / 32) * i, ptid & 31);
       } else {
-        for (int e = ptid; e < TC_N * chunks; e += 128) put(e / chunks, e % chunks);
+        for (int e = ptid; e < TC_N * chunks; e += TCP_PRODUCERS) put(e / chunks, e % chunks);
       }
       fence_proxy_async();       // this thread's generic-proxy stores -> visible to the tensor core
       mbar_arrive(&bar_full[s]);
       mbar_arrive(&bar_raw_empty[slot]);
     }
-  } else if (warp == 8) {
+  } else if (warp == W_MMA) {
     // ===================== MMA issuer (whole warp, uniform; one elected lane issues) =====================
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
     const int ksteps = d / 8;
