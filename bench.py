@@ -566,7 +566,7 @@ def main():
                          "weak: --n vectors per GPU.  Identical at 1 GPU.")
     ap.add_argument("--ils", type=int, default=16, help="ILS iterations per encode (LSQ-16)")
     ap.add_argument("--cpu-sample", type=int, default=400000)
-    ap.add_argument("--e2e-steps", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=12)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-recall", action="store_true", help="skip the untimed recall@1 probe of the full flow")
     ap.add_argument("--no-extras", action="store_true",

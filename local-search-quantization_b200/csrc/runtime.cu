@@ -35,12 +35,12 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// staging pool: host -> device copies of PAGEABLE caller memory.  The copy is cut into 4 MB chunks; the calling
+// staging pool: host -> device copies of PAGEABLE caller memory.  The copy is cut into 2 MB chunks; the calling
 // thread and a few persistent helpers each grab the next chunk, memcpy it into one of their own two pinned
 // buffers and queue the DMA on the caller's stream.  Chunk-level work stealing: no per-chunk rendezvous, so a
 // helper that is scheduled late only does less of the work.
 // ------------------------------------------------------------------------------------------------
-constexpr size_t STAGE_BYTES = (size_t)4 << 20;
+constexpr size_t STAGE_BYTES = (size_t)2 << 20;
 
 class StagePool {
  public:

@@ -70,7 +70,7 @@ class PhaseSync {
 int rt_devices_for(int64_t n, int64_t min_per_device);
 
 // Host -> device copy of caller memory, ordered on `st`.  Pinned / registered sources go straight to
-// cudaMemcpyAsync.  Pageable sources (Julia arrays) are cut into 4 MB chunks; the calling thread and a few
+// cudaMemcpyAsync.  Pageable sources (Julia arrays) are cut into 2 MB chunks; the calling thread and a few
 // persistent helper threads of the device each grab the next chunk, memcpy it into one of their own two pinned
 // buffers and queue its DMA, so the DMA of one chunk overlaps the host copies of the others and the copy is not
 // limited to one core's memcpy rate (LSQ_B200_H2D=direct|staged, default staged; LSQ_B200_COPY_THREADS=k).
