@@ -176,7 +176,7 @@ int lsq_dev_build_unaries(const float* dX, int d, int64_t n, const float* dC, in
 /* FAST MODE: the same table (plain layout) on the tensor cores — tcgen05.mma kind::tf32 with a 3xTF32
  * operand split, fp32 accumulation in TMEM.  Not bit-exact with the sequential fp32 chain of the
  * parity path (|dU|/|U| ~ 1e-6; quantisation error within 1e-5 relative).  Needs d % 8 == 0, d <= 128.
- * The host-pointer encode calls use it when the environment has LSQ_B200_UNARY=tc. */
+ * The host-pointer encode calls and lsq_train_lsq use it when the environment has LSQ_B200_UNARY=tc. */
 int lsq_dev_build_unaries_tc(const float* dX, int d, int64_t n, const float* dC, int m, float* dU,
                              void* stream);
 int lsq_dev_veccost(const float* dX, int d, int64_t n, const uint8_t* dcodes, const float* dC, int m,

@@ -218,7 +218,12 @@ static int train_encode(const TrainCtx& T, uint32_t ils_iter0, int niters) {
   LSQ_TRY(launch_veccost(T.dX, T.d, T.n, T.dcodes, T.dC, T.m, T.dcost, T.st));  // prevcost, encode_icm.jl:147
   for (int64_t lo = 0; lo < T.n; lo += T.chunk) {
     const int64_t nc = std::min<int64_t>(T.chunk, T.n - lo);
-    LSQ_TRY(build_unaries(T.dX + (size_t)lo * T.d, T.d, nc, T.dC, T.m, T.dnorms, T.dU, 0, T.st));
+    // LSQ_B200_UNARY=tc: tensor-core unaries (fast mode), exactly as the host encode path does (capi.cu)
+    const char* um = getenv("LSQ_B200_UNARY");
+    if (um != nullptr && strcmp(um, "tc") == 0 && T.d % 8 == 0 && T.d <= 128)
+      LSQ_TRY(build_unaries_tc(T.dX + (size_t)lo * T.d, T.d, nc, T.dC, T.m, T.dnorms, T.dU, T.st));
+    else
+      LSQ_TRY(build_unaries(T.dX + (size_t)lo * T.d, T.d, nc, T.dC, T.m, T.dnorms, T.dU, 0, T.st));
     for (int it0 = 0; it0 < niters; it0 += ICM_MAX_ITERS_PER_LAUNCH) {
       const int nit = std::min(ICM_MAX_ITERS_PER_LAUNCH, niters - it0);
       IcmParams p;

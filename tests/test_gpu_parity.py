@@ -438,6 +438,27 @@ def test_train_lsq_equals_public_calls(gpu, use_R):
     assert np.array_equal(Bn, gpu.quantize_norms(B1, C1, cbn))
 
 
+def test_train_lsq_fast_mode_equals_public_calls(gpu, monkeypatch):
+    """LSQ_B200_UNARY=tc (tensor-core unaries) applies to the resident training loop and to the host encode calls
+    alike: in fast mode the one-call train_lsq still equals the loop of public calls bit for bit, and its
+    objective stays within the north-star's 1e-5 of the exact mode (Gaussian data, so the modes really differ)."""
+    n, d, m, niter, ilsiter = 8000, 128, 8, 2, 2
+    X, C, B = make_problem(2350, n, d, m, kind="gauss")
+    X *= 20.0
+    _, _, _, _, obj_exact = gpu.train_lsq(X, m, 256, None, B, None, niter, ilsiter, 4, True, 4, seed=5)
+    monkeypatch.setenv("LSQ_B200_UNARY", "tc")
+    C1, B1, _, _, obj = gpu.train_lsq(X, m, 256, None, B, None, niter, ilsiter, 4, True, 4, seed=5)
+    Bc, Cc, count = B.copy(), gpu.update_codebooks(X, B, 256), 0
+    for it in range(niter + 1):
+        if it > 0:
+            Cc = gpu.update_codebooks(X, Bc, 256)
+        for i in range(ilsiter):
+            Bc = gpu.encoding_icm(X, Bc, Cc, 4, True, 4, seed=5, ils_iter=count)
+            count += 1
+    assert np.array_equal(B1, Bc) and np.array_equal(C1, Cc)
+    assert np.allclose(obj, obj_exact, rtol=1e-5, atol=0)
+
+
 def test_train_lsq_vs_oracle_objective(gpu, oracle):
     """Against the restated train_lsq (oracle): the codebook update is parity-unpinned (IterativeSolvers),
     so codes may part ways after the first update; the objective trajectory must agree to 1e-3 relative."""
