@@ -28,7 +28,8 @@ def build(force=False, verbose=False):
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for s in SOURCES:
         o = os.path.join(HERE, "build", s.replace(".cu", ".o"))
-        cmd = [NVCC] + [f for f in FLAGS if f != "-shared"] + ["-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [NVCC] + [f for f in FLAGS if f != "-shared"] + os.environ.get("LSQ_B200_NVCC_FLAGS", "").split() + \
+              ["-c", os.path.join(CSRC, s), "-o", o]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -17,6 +17,17 @@
 
 #include <algorithm>
 
+// Occupancy of the warp kernel (measured on B200, kernel ms for 1 M vectors x 16 ILS iterations, m = 8 / m = 16):
+//   32 warps per SM, 64 registers (round 1): 103.4 / 465      36 warps, 56 registers: 97.9 / 460
+//   40 warps, 48 registers: 99.0 / 430                         48 warps, 40 registers: 104.4 / 448     64 warps, 32: 134 / 530
+// The dependent chain of a visit is hidden by resident warps, not by loads in flight per warp, until the register
+// budget starts to spill inside the visit loop.  Blocks of 4 warps; 9 per SM for m <= 8, 10 beyond.
+#ifndef LSQ_ICM_LB_THREADS
+#define LSQ_ICM_LB_THREADS 128
+#endif
+#ifndef LSQ_ICM_LB_BLOCKS
+#define LSQ_ICM_LB_BLOCKS(M) ((M) <= 8 ? 9 : 10)
+#endif
 #ifndef LSQ_ICM_SHORTCUT
 #define LSQ_ICM_SHORTCUT(M) ((M) <= 8)
 #endif
@@ -87,7 +98,7 @@ __host__ __device__ constexpr int icm_staged_rows() { return M < 6 ? M : 6; }
 // instantiation on purpose: the kernel sits exactly at its 64-register budget (4 blocks per SM), and one more
 // live counter in the visit loop cost 2 % at m = 8 and 10 % at m = 16 (measured against the same build without it).
 template <int M, bool USMEM, bool COUNT = false>
-__global__ void __launch_bounds__(256, 4) icm_ils_warp_kernel(const __grid_constant__ IcmParams p) {
+__global__ void __launch_bounds__(LSQ_ICM_LB_THREADS, LSQ_ICM_LB_BLOCKS(M)) icm_ils_warp_kernel(const __grid_constant__ IcmParams p) {
   constexpr int UR = icm_staged_rows<M>();
   extern __shared__ __align__(128) unsigned char icm_smem[];
   const int lane = threadIdx.x & 31;
@@ -256,11 +267,11 @@ static int launch_icm_warp_m(const IcmParams& p, cudaStream_t st) {
   const char* ue = getenv("LSQ_B200_ICM_USMEM");
   const bool usmem = kCanUsmem && ue != nullptr && atoi(ue) != 0;
   // warps per block: 8, or 4 when the staged rows of 8 warps would leave room for a single block per SM (m > 8)
-  int wpb = 8;
+  int wpb = LSQ_ICM_LB_THREADS / 32;
   if (const char* we = getenv("LSQ_B200_ICM_WARPS_PER_BLOCK")) wpb = std::max(1, std::min(8, atoi(we)));
   const int64_t blocks_needed = ceil_div(p.n, wpb);
   const size_t smem = usmem ? 128 + (size_t)wpb * icm_staged_rows<M>() * 1024 : 0;
-  int per_sm = usmem ? (int)std::min<size_t>(64 / wpb, (size_t)(227 * 1024) / (smem + 1024)) : 64 / wpb;
+  int per_sm = usmem ? (int)std::min<size_t>(64 / wpb, (size_t)(227 * 1024) / (smem + 1024)) : 2 * LSQ_ICM_LB_BLOCKS(M);
   if (const char* e = getenv("LSQ_B200_ICM_BLOCKS_PER_SM")) per_sm = std::max(1, atoi(e));  // tuning override
   const int64_t cap = (int64_t)sms * per_sm;
   const unsigned grid = (unsigned)(blocks_needed < cap ? blocks_needed : cap);
