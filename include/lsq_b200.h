@@ -225,6 +225,12 @@ int lsq_dev_linscan(const uint8_t* dcodes, int64_t n, int m, const float* dqueri
                     const float* dcodebooks, const float* dbnorms, int lut_kind, int subdim, int nn,
                     float* ddists, int32_t* dids, void* stream);
 
+/* Test hook of the tensor-core ADC prefilter (csrc/adc_tc.cu): the filter values dbnorm[v] - 2<q, xhat_v> as the
+ * bf16 hi/lo tcgen05 GEMM computes them, for every (query, base vector) pair.  dout: float [nq][ld],
+ * ld >= 128*ceil(n/128); columns >= n are padding (+inf).  Needs d % 16 == 0, 16 <= d <= 128. */
+int lsq_dev_adc_filter_values(const uint8_t* dcodes, int64_t n, int m, const float* dqueries, int nq, int d,
+                              const float* dcodebooks, const float* dbnorms, float* dout, int64_t ld, void* stream);
+
 /* chain encoder on device buffers: dU = U[m][n][256] (lsq_dev_build_unaries, plain layout) is CONSUMED
  * (the forward messages overwrite it in place); dT from lsq_dev_build_tables; dcodes uint8 [n][m] out. */
 int lsq_dev_viterbi(float* dU, int64_t n, int m, const float* dT, uint8_t* dcodes, void* stream);

@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "lsq_dev_build_unaries", "lsq_dev_build_unaries_tc", "lsq_dev_veccost", "lsq_dev_icm_ils", "lsq_dev_icm_visit_counter",
     "lsq_cb_stats_len", "lsq_cb_scale_exp", "lsq_dev_absmax", "lsq_dev_cb_accumulate", "lsq_dev_cb_finalize",
     "lsq_dev_cb_stats", "lsq_dev_cb_solve",
-    "lsq_dev_linscan", "lsq_train_lsq", "lsq_kmeans1d", "lsq_eval_recall", "lsq_dev_eval_recall",
+    "lsq_dev_linscan", "lsq_dev_adc_filter_values", "lsq_train_lsq", "lsq_kmeans1d", "lsq_eval_recall", "lsq_dev_eval_recall",
     "lsq_encoding_viterbi", "lsq_dev_viterbi",
 ]
 

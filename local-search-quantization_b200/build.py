@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liblsq_b200.so")
-SOURCES = ["runtime.cu", "capi.cu", "icm.cu", "icm_slice.cu", "tables.cu", "unary_tc.cu", "linscan.cu", "cbupdate.cu", "train.cu", "chain.cu"]
+SOURCES = ["runtime.cu", "capi.cu", "icm.cu", "icm_slice.cu", "tables.cu", "unary_tc.cu", "linscan.cu", "adc_tc.cu", "cbupdate.cu", "train.cu", "chain.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--fmad=true", "-ccbin", "/usr/bin/g++"]

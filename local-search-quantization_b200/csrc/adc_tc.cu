@@ -1,0 +1,567 @@
+// adc_tc.cu — tensor-core PREFILTER for the exact ADC scan (linscan_lsq, linscan_aqd_pairwise_byte.cpp:14-93).
+//
+// The reference scores every (query, base vector) pair with m table lookups.  On B200 that scan is bound by
+// shared-memory wavefronts and, for m >= 9, by shared-memory CAPACITY (only 14 query LUTs of 16 KB fit one SM at
+// m = 16).  But the quantity the lookups add up is an inner product:
+//     dist(q, v) = dbnorm[v] - 2 <q, xhat_v>,   xhat_v = sum_k C_k[code_vk]
+// so the pass that decides WHICH pairs can be among a query's nn nearest is GEMM-shaped, and the result only has
+// to be bit-exact for the pairs that survive.  This file therefore splits the main pass of linscan.cu in two:
+//
+//   1. adc_decode_kernel   xhat_v in fp32, split into bf16 hi + lo, written as ready-made UMMA operand images
+//                          (K-major, no swizzle; one 64 KB block per 128 base vectors), plus max ||xhat||.
+//   2. adc_filter_kernel   tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), 3 products
+//                          lo(q).hi(x) + hi(q).lo(x) + hi(q).hi(x).  A CTA keeps 256 queries (two 128-row A
+//                          tiles, hi and lo) resident in TENSOR MEMORY, streams base tiles through a 3-stage
+//                          TMA ring, and its epilogue warps compare  dbnorm - 2*acc  with  tau_q + margin_q
+//                          straight out of TMEM: only the ids of the pairs that pass are written.
+//   3. adc_rescore_kernel  the survivors (a few thousand per query) are scored EXACTLY like the reference —
+//                          ((0 + LUT_0[c0]) + LUT_1[c1]) + ... + dbnorm, fp32 adds in that order, from the same
+//                          LUT the scan kernel uses — and appended as keys iff dist <= tau_q.
+//
+// The keys that reach the top-k kernels are therefore the same SET the thresholded scan produces, provided
+// margin_q bounds |filter value - reference value|.  Bound used (u = 2^-24):
+//     reference:  |d_ref - D| <= (d+m+2) u (2 ||q|| m cmax + max|dbnorm|)           (fp32 chains, Cauchy-Schwarz)
+//     filter:     |d_tc  - D| <= 2^-12 * 2 ||q|| max_v||xhat_v||  — the bf16 hi+lo split is good to 2^-16 per
+//                 operand, the dropped lo.lo term to 2^-17, fp32 accumulation of 3d products to well under
+//                 2^-13 (measured 3e-7 relative, tests/test_gpu_adc_tc.py), so 2^-12 leaves > 10x headroom.
+//     margin_q = 2^-12 * 2 ||q|| xmax + 2 (d+m+2) u (2 ||q|| m cmax + nmax)
+// A wider margin only lets a few more pairs through to the exact rescoring; it never changes the result.
+// Anything unusual (NaN, candidate overflow, fewer than nn survivors) ends on linscan.cu's exhaustive path,
+// exactly as before.  tests/: bit-identical ids and distances against the reference's own .so and against the
+// lookup scan (LSQ_B200_ADC=scan).
+#include <cuda_bf16.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "adc_tc.cuh"
+
+namespace lsq {
+
+constexpr int AT_M = 128;         // queries per A tile (UMMA M)
+constexpr int AT_NA = 2;          // A tiles resident in tensor memory per CTA
+constexpr int AT_N = 128;         // base vectors per tile (UMMA N)
+constexpr int AT_STAGES = 3;      // shared-memory ring of base tiles (hi + lo image = 64 KB each at d = 128)
+constexpr int AT_EPI_WARPS = 4 * AT_NA;
+constexpr int AT_W_TMA = AT_EPI_WARPS, AT_W_MMA = AT_EPI_WARPS + 1;
+constexpr int AT_THREADS = 32 * (AT_EPI_WARPS + 2);
+// K-major, no swizzle, 2-byte elements: core matrix = 8 rows x 8 elements (16 B per row, 128 B, contiguous);
+// 8-row groups are SBO apart, K-adjacent core matrices LBO apart
+constexpr uint32_t AT_SBO = 128u;
+constexpr uint32_t AT_LBO = (AT_N / 8) * 128u;
+// tensor-memory columns: A tile a, part p (0 = hi, 1 = lo) at (2a + p) * 64 (128 bf16 = 64 columns);
+// accumulator of A tile a at 256 + 128 a
+constexpr uint32_t AT_COL_A = 0u, AT_COL_ACC = 256u;
+
+__host__ __device__ inline uint32_t at_part_bytes(int d) { return (uint32_t)(d / 8) * AT_LBO; }
+
+__device__ __forceinline__ void bf16_split(float x, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(x);
+  const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+  hi = (uint32_t)__bfloat16_as_ushort(h);
+  lo = (uint32_t)__bfloat16_as_ushort(l);
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 0. largest squared codeword norm (for the reference-rounding part of the margin)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adc_cbnorm_kernel(const float* __restrict__ C, int rows, int d, AdcStats* stats) {
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  float s = 0.0f;
+  if (r < rows)
+    for (int k = 0; k < d; k++) { const float c = C[(size_t)r * d + k]; s = fmaf(c, c, s); }
+  s = warp_max(s);
+  if ((threadIdx.x & 31) == 0) atomicMax(&stats->cmax2_bits, __float_as_uint(s));
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1. decode + split.  CTA = one tile of 128 base vectors; thread = (vector r, K half).  Consecutive lanes hold
+//    consecutive vectors, so a warp's 16-byte stores of one K chunk fill 512 contiguous bytes of the image.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adc_decode_kernel(const uint8_t* __restrict__ codes, int64_t n, int m,
+                                                         const float* __restrict__ C, int d,
+                                                         const float* __restrict__ norms, unsigned char* __restrict__ img,
+                                                         float* __restrict__ normpad, AdcStats* stats) {
+  __shared__ float part2[256];
+  const int t = threadIdx.x, r = t & 127, half = t >> 7;
+  const int64_t tile = blockIdx.x;
+  const int64_t v = tile * AT_N + r;
+  const bool valid = v < n;
+  const int nch = d / 8;
+  const uint32_t part_bytes = at_part_bytes(d);
+  unsigned char* base = img + (size_t)tile * 2 * part_bytes;
+  uint32_t code[LSQ_MAXM];
+#pragma unroll
+  for (int k = 0; k < LSQ_MAXM; k++) code[k] = (valid && k < m) ? (uint32_t)codes[(size_t)v * m + k] : 0u;
+  float n2 = 0.0f;
+  for (int kc = half; kc < nch; kc += 2) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.0f;
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < LSQ_MAXM; k++) {
+        if (k < m) {
+          const float4* row = reinterpret_cast<const float4*>(C + ((size_t)k * LSQ_H + code[k]) * d + kc * 8);
+          const float4 a = __ldg(row), b = __ldg(row + 1);
+          acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+          acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+        }
+      }
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      uint32_t h0, l0, h1, l1;
+      bf16_split(acc[2 * i], h0, l0);
+      bf16_split(acc[2 * i + 1], h1, l1);
+      hi[i] = h0 | (h1 << 16);   // element k in the low half, k+1 in the high half (little endian)
+      lo[i] = l0 | (l1 << 16);
+      n2 = fmaf(acc[2 * i], acc[2 * i], n2);
+      n2 = fmaf(acc[2 * i + 1], acc[2 * i + 1], n2);
+    }
+    const uint32_t off = (uint32_t)kc * AT_LBO + (uint32_t)(r >> 3) * AT_SBO + (uint32_t)(r & 7) * 16u;
+    *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(base + part_bytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  part2[t] = n2;
+  __syncthreads();
+  if (t < 128) {
+    float tot = part2[t] + part2[t + 128];
+    float an = 0.0f;
+    if (valid) {
+      const float nv = norms[v];
+      normpad[v] = nv;
+      an = fabsf(nv);
+    } else {
+      normpad[v] = INFINITY;  // padding columns of the last tile never pass the filter
+      tot = 0.0f;
+    }
+    // max over the warp on the bit patterns (non-negative floats order like unsigned integers; a NaN is the
+    // largest pattern, so it survives and poisons the margin, which sends the query to the exhaustive path)
+    uint32_t tb = __float_as_uint(tot), ab = __float_as_uint(an);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tb = max(tb, __shfl_xor_sync(0xFFFFFFFFu, tb, o));
+      ab = max(ab, __shfl_xor_sync(0xFFFFFFFFu, ab, o));
+    }
+    if ((t & 31) == 0) {
+      atomicMax(&stats->xmax2_bits, tb);
+      atomicMax(&stats->nmax_bits, ab);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. the filter GEMM
+// ------------------------------------------------------------------------------------------------
+struct AdcFilterParams {
+  const float* queries;      // [nq][d]
+  const unsigned char* img;  // [ntiles][2][part_bytes]
+  const float* normpad;      // [ntiles*128]
+  const float* tau;          // [qtile*32 + slot], qtile = q / QT, slot = q % QT  (threshold_kernel's layout)
+  const AdcStats* stats;
+  uint32_t* candidx;         // [nq][ccap] 0-based base indices that passed
+  int* ccnt;                 // [nq]
+  float* dbg;                // optional: [nq][dbg_ld] filter values (tests)
+  int64_t n, ntiles, ccap, dbg_ld;
+  int nq, d, m, QT, npass;
+};
+
+__device__ __forceinline__ void at_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void at_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem], bf16 operands.  Called by every lane of the issuing warp in uniform control
+// flow; one elected lane issues (see unary_tc.cu: keeping the election inside the asm keeps the descriptors in
+// uniform registers).
+__device__ __forceinline__ void at_mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p, e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void at_commit_elected(uint64_t* bar) {
+  asm volatile(
+      "{\n"
+      ".reg .pred e;\n"
+      "elect.sync _|e, 0xffffffff;\n"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n"
+      "}\n" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
+// bit i of the result = (norm_i - 2 * acc_i <= thr) for the 32 accumulator columns in r; nrm4 -> their norms
+__device__ __forceinline__ uint32_t at_scan32(const uint32_t (&r)[32], const float4* __restrict__ nrm4, float thr,
+                                              float* __restrict__ dbg) {
+  uint32_t mask = 0u;
+#pragma unroll
+  for (int i4 = 0; i4 < 8; i4++) {
+    const float4 nv = __ldg(nrm4 + i4);   // the same address in every lane: one broadcast load
+    const float d0 = fmaf(-2.0f, __uint_as_float(r[4 * i4 + 0]), nv.x);
+    const float d1 = fmaf(-2.0f, __uint_as_float(r[4 * i4 + 1]), nv.y);
+    const float d2 = fmaf(-2.0f, __uint_as_float(r[4 * i4 + 2]), nv.z);
+    const float d3 = fmaf(-2.0f, __uint_as_float(r[4 * i4 + 3]), nv.w);
+    if (d0 <= thr) mask |= 1u << (4 * i4 + 0);
+    if (d1 <= thr) mask |= 1u << (4 * i4 + 1);
+    if (d2 <= thr) mask |= 1u << (4 * i4 + 2);
+    if (d3 <= thr) mask |= 1u << (4 * i4 + 3);
+    if (dbg) { dbg[4 * i4 + 0] = d0; dbg[4 * i4 + 1] = d1; dbg[4 * i4 + 2] = d2; dbg[4 * i4 + 3] = d3; }
+  }
+  return mask;
+}
+
+__global__ void __launch_bounds__(AT_THREADS, 1) adc_filter_kernel(const __grid_constant__ AdcFilterParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ uint64_t bar_full[AT_STAGES], bar_empty[AT_STAGES], bar_acc_full[AT_NA], bar_acc_empty[AT_NA];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int d = p.d, ksteps = d / 16;
+  const uint32_t part_bytes = at_part_bytes(d), stage_bytes = 2u * part_bytes;
+  const int qbase = blockIdx.x * (AT_NA * AT_M);
+  const int na = (p.nq - qbase > AT_M) ? 2 : 1;   // A tiles in use
+  // this CTA's slice of the base tiles
+  const int64_t per = (p.ntiles + gridDim.y - 1) / gridDim.y;
+  const int64_t t_lo = (int64_t)blockIdx.y * per;
+  const int64_t t_hi = (t_lo + per < p.ntiles) ? (t_lo + per) : p.ntiles;
+  const int64_t my_tiles = (t_hi > t_lo) ? (t_hi - t_lo) : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < AT_STAGES; s++) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    for (int a = 0; a < AT_NA; a++) { mbar_init(&bar_acc_full[a], 1); mbar_init(&bar_acc_empty[a], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = tmem_base_slot;
+
+  // ---- stationary operand -> tensor memory: thread = query row (lane of its warp's quadrant); hi and lo bf16,
+  //      two K elements per 32-bit column.  The same threads keep ||q|| and the threshold for the epilogue. ----
+  const int a_mine = warp >> 2, quad = warp & 3;
+  const int q = qbase + a_mine * AT_M + quad * 32 + lane;
+  const bool q_valid = (warp < AT_EPI_WARPS) && (a_mine < na) && (q < p.nq);
+  float thr = -INFINITY;   // rows without a query never pass `value <= thr`
+  if (warp < AT_EPI_WARPS && a_mine < na) {
+    const float* qrow = p.queries + (size_t)(q_valid ? q : 0) * d;
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16) + AT_COL_A + (uint32_t)(a_mine * 2) * 64u;
+    float qn2 = 0.0f;
+    for (int k0 = 0; k0 < d; k0 += 64) {
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int i4 = 0; i4 < 16; i4++) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (q_valid && k0 + 4 * i4 < d) x = __ldg(reinterpret_cast<const float4*>(qrow + k0) + i4);
+        uint32_t h0, l0, h1, l1;
+        bf16_split(x.x, h0, l0);
+        bf16_split(x.y, h1, l1);
+        hi[2 * i4] = h0 | (h1 << 16);
+        lo[2 * i4] = l0 | (l1 << 16);
+        bf16_split(x.z, h0, l0);
+        bf16_split(x.w, h1, l1);
+        hi[2 * i4 + 1] = h0 | (h1 << 16);
+        lo[2 * i4 + 1] = l0 | (l1 << 16);
+        qn2 = fmaf(x.x, x.x, qn2); qn2 = fmaf(x.y, x.y, qn2); qn2 = fmaf(x.z, x.z, qn2); qn2 = fmaf(x.w, x.w, qn2);
+      }
+      at_st32(lane_base + (uint32_t)(k0 >> 1), hi);
+      at_st32(lane_base + 64u + (uint32_t)(k0 >> 1), lo);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    if (q_valid) {
+      const float tau = p.tau[(q / p.QT) * 32 + (q % p.QT)];
+      const float qn = sqrtf(qn2) * 1.000001f;
+      const float xmax = sqrtf(__uint_as_float(p.stats->xmax2_bits)) * 1.000001f;
+      const float cmax = sqrtf(__uint_as_float(p.stats->cmax2_bits)) * 1.000001f;
+      const float nmax = __uint_as_float(p.stats->nmax_bits);
+      const float eps_f = 1.0f / 4096.0f;                                   // 2^-12, see the header
+      const float eps_r = 2.0f * (float)(d + p.m + 2) * 5.9604645e-8f;      // 2 (d+m+2) u
+      const float margin = eps_f * 2.0f * qn * xmax + eps_r * (2.0f * qn * (float)p.m * cmax + nmax);
+      thr = tau + margin;   // NaN anywhere -> no pair passes -> the query is re-run exhaustively
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  if (warp == AT_W_TMA) {
+    // ===================== TMA: base tiles (hi + lo operand images), up to AT_STAGES ahead =====================
+    if (lane == 0) {
+      for (int64_t t = 0; t < my_tiles; t++) {
+        const int s = (int)(t % AT_STAGES);
+        mbar_wait(&bar_empty[s], (uint32_t)((t / AT_STAGES) & 1) ^ 1u);
+        bulk_load_issue(smem_raw + (size_t)s * stage_bytes, p.img + (size_t)(t_lo + t) * stage_bytes, stage_bytes,
+                        &bar_full[s]);
+      }
+    }
+  } else if (warp == AT_W_MMA) {
+    // ===================== MMA issuer (whole warp, uniform; one elected lane issues) =====================
+    // instruction descriptor: D = f32 (1 << 4), A = B = bf16 (1 << 7, 1 << 10), K-major both, N >> 3 at bit 17,
+    // M >> 4 at bit 24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_N >> 3) << 17) | ((uint32_t)(AT_M >> 4) << 24);
+    const uint32_t sB_u = smem_u32(smem_raw);
+    const uint64_t desc_hi = (uint64_t)((AT_SBO >> 4) | (1u << 14)) << 32;   // SBO, descriptor version 1
+    const uint32_t desc_lbo = (AT_LBO >> 4) << 16;
+    const uint32_t kstep_enc = (2u * AT_LBO) >> 4;                           // one MMA consumes K = 16 = 2 core matrices
+    const int npass = p.npass;
+    for (int64_t t = 0; t < my_tiles; t++) {
+      const int s = (int)(t % AT_STAGES);
+      mbar_wait(&bar_full[s], (uint32_t)((t / AT_STAGES) & 1));
+      const uint32_t stage_u = sB_u + (uint32_t)s * stage_bytes;
+      const uint32_t lo_hiX = desc_lbo | (stage_u >> 4), lo_loX = desc_lbo | ((stage_u + part_bytes) >> 4);
+      for (int a = 0; a < na; a++) {
+        mbar_wait(&bar_acc_empty[a], (uint32_t)(t & 1) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t dcol = tmem + AT_COL_ACC + (uint32_t)a * AT_N;
+        const uint32_t a_hi = tmem + AT_COL_A + (uint32_t)(a * 2) * 64u, a_lo = a_hi + 64u;
+        uint32_t accum = 0u;
+        if (npass >= 3) {   // lo(q).hi(x)  (small terms first)
+#pragma unroll 4
+          for (int k = 0; k < ksteps; k++) {
+            at_mma_bf16_ts(dcol, a_lo + (uint32_t)(8 * k), desc_hi | (lo_hiX + (uint32_t)k * kstep_enc), idesc, accum);
+            accum = 1u;
+          }
+        }
+        if (npass >= 2) {   // hi(q).lo(x)
+#pragma unroll 4
+          for (int k = 0; k < ksteps; k++) {
+            at_mma_bf16_ts(dcol, a_hi + (uint32_t)(8 * k), desc_hi | (lo_loX + (uint32_t)k * kstep_enc), idesc, accum);
+            accum = 1u;
+          }
+        }
+#pragma unroll 4
+        for (int k = 0; k < ksteps; k++) {   // hi(q).hi(x)
+          at_mma_bf16_ts(dcol, a_hi + (uint32_t)(8 * k), desc_hi | (lo_hiX + (uint32_t)k * kstep_enc), idesc, accum);
+          accum = 1u;
+        }
+        if (a == na - 1) at_commit_elected(&bar_empty[s]);   // the stage may be refilled once these MMAs have read it
+        at_commit_elected(&bar_acc_full[a]);
+      }
+    }
+  } else if (a_mine < na) {
+    // ===================== epilogue: warps 4a .. 4a+3 drain the accumulator of A tile a =====================
+    const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + AT_COL_ACC + (uint32_t)a_mine * AT_N;
+    int* my_cnt = p.ccnt + (q_valid ? q : 0);
+    uint32_t* my_list = p.candidx + (size_t)(q_valid ? q : 0) * p.ccap;
+    for (int64_t t = 0; t < my_tiles; t++) {
+      mbar_wait(&bar_acc_full[a_mine], (uint32_t)(t & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t v0 = (t_lo + t) * AT_N;
+      const float4* nrm4 = reinterpret_cast<const float4*>(p.normpad + v0);
+      float* dbg = (p.dbg != nullptr && q_valid) ? (p.dbg + (size_t)q * p.dbg_ld + v0) : nullptr;
+      uint32_t mask[4];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        uint32_t r0[32], r1[32];
+        at_ld32(taddr + (uint32_t)(h * 64), r0);
+        at_ld32(taddr + (uint32_t)(h * 64 + 32), r1);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (h == 1) {   // every column is in registers: the accumulator may be overwritten
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_acc_empty[a_mine]);
+        }
+        mask[2 * h] = at_scan32(r0, nrm4 + h * 16, thr, dbg ? dbg + h * 64 : nullptr);
+        mask[2 * h + 1] = at_scan32(r1, nrm4 + h * 16 + 8, thr, dbg ? dbg + h * 64 + 32 : nullptr);
+      }
+      const int hits = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]);
+      if (hits > 0) {   // thr = -inf for rows without a query, so q is valid here
+        int64_t pos = (int64_t)atomicAdd(my_cnt, hits);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+          uint32_t mk = mask[c];
+          while (mk) {
+            const int b = __ffs(mk) - 1;
+            mk &= mk - 1u;
+            if (pos < p.ccap) my_list[pos] = (uint32_t)(v0 + c * 32 + b);
+            pos++;
+          }
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3. exact rescoring of the survivors: one CTA per query, its LUT column in shared memory.
+//    dist = ((0 + LUT_0[c0]) + LUT_1[c1]) + ... + dbnorm  — the reference's order (:69-73) — appended iff <= tau,
+//    i.e. exactly what scan_kernel's MODE_MAIN appends.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) adc_rescore_kernel(const uint8_t* __restrict__ codes, int64_t n, int m,
+                                                          const float* __restrict__ norms, const float* __restrict__ lut,
+                                                          int QT, const float* __restrict__ tau,
+                                                          const uint32_t* __restrict__ candidx, const int* __restrict__ ccnt,
+                                                          int64_t ccap, unsigned long long* __restrict__ cand,
+                                                          int* __restrict__ cnt, int64_t cap, int id_base) {
+  __shared__ float lutq[LSQ_MAXM * LSQ_H];
+  __shared__ int sh_n;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int qtile = q / QT, slot = q % QT;
+  const float* lsrc = lut + (size_t)qtile * m * LSQ_H * QT + slot;
+  for (int j = tid; j < m * LSQ_H; j += 256) lutq[j] = lsrc[(size_t)j * QT];
+  if (tid == 0) sh_n = 0;
+  __syncthreads();
+  const float tq = tau[qtile * 32 + slot];
+  const int64_t c_all = ccnt[q];
+  const int64_t c = (c_all < ccap) ? c_all : ccap;
+  const uint32_t* list = candidx + (size_t)q * ccap;
+  unsigned long long* out = cand + (size_t)q * cap;
+  for (int64_t i = tid; i < c; i += 256) {
+    const uint32_t v = list[i];
+    if ((int64_t)v >= n) continue;
+    const uint8_t* cp = codes + (size_t)v * m;
+    float acc = 0.0f;
+    for (int k = 0; k < m; k++) acc = __fadd_rn(acc, lutq[k * LSQ_H + cp[k]]);
+    acc = __fadd_rn(acc, norms[v]);
+    if (acc <= tq) {
+      const int pos = atomicAdd(&sh_n, 1);
+      if (pos < cap) out[pos] = ((unsigned long long)float_to_ordered(acc) << 32) | (uint32_t)(v + (uint32_t)id_base);
+    }
+  }
+  __syncthreads();
+  // a filter list that overflowed may have lost true neighbours: report "too many" so that the query is re-run
+  if (tid == 0) cnt[q] = (c_all > ccap) ? (int)((cap + 1 < 0x7FFFFFFF) ? cap + 1 : 0x7FFFFFFF) : sh_n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+bool adc_tc_applicable(int64_t n, int m, int d, const float* dqueries, const float* dcodebooks, const float* dbnorms) {
+  const char* mode = getenv("LSQ_B200_ADC");
+  if (mode != nullptr && strcmp(mode, "scan") == 0) return false;
+  if (dbnorms == nullptr || d % 16 != 0 || d > 128 || m < 1 || m > LSQ_MAXM) return false;
+  if ((reinterpret_cast<uintptr_t>(dqueries) & 15) || (reinterpret_cast<uintptr_t>(dcodebooks) & 15)) return false;
+  const bool forced = (mode != nullptr && strcmp(mode, "tc") == 0);
+  // below ~64 K base vectors the lookup scan is launch-bound anyway; above the memory gate the images would
+  // crowd out the caller (4 d bytes per base vector)
+  if (!forced && n < 65536) return false;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+  const size_t need = (size_t)ceil_div(n, AT_N) * 2 * at_part_bytes(d);
+  return need < free_b / 4;
+}
+
+int adc_tc_prepare(const uint8_t* dcodes, int64_t n, int m, const float* dcodebooks, int d, const float* dbnorms,
+                   cudaStream_t st, AdcTcBase& B) {
+  B.ntiles = ceil_div(n, AT_N);
+  LSQ_CUDA(B.img.alloc((size_t)B.ntiles * 2 * at_part_bytes(d)));
+  LSQ_CUDA(B.normpad.alloc((size_t)B.ntiles * AT_N));
+  LSQ_CUDA(B.stats.alloc(1));
+  LSQ_CUDA(cudaMemsetAsync(B.stats.p, 0, sizeof(AdcStats), st));
+  note_launch();
+  adc_cbnorm_kernel<<<(unsigned)ceil_div((int64_t)m * LSQ_H, 256), 256, 0, st>>>(dcodebooks, m * LSQ_H, d, B.stats.p);
+  note_launch();
+  adc_decode_kernel<<<(unsigned)B.ntiles, 256, 0, st>>>(dcodes, n, m, dcodebooks, d, dbnorms, B.img.p, B.normpad.p, B.stats.p);
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
+}
+
+static int filter_slices(int groups, int64_t ntiles) {
+  // every CTA does the same work: the pass takes ceil(CTAs / SMs) waves of 1/slices each; slices of >= 32 tiles
+  int dev = 0, sms = LSQ_NUM_SMS_HINT;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t max_s = std::max<int64_t>(1, std::min<int64_t>(65535, ntiles / 32));
+  int best_s = 1;
+  double best = 1e30;
+  for (int64_t s = 1; s <= max_s; s++) {
+    const double cost = (double)ceil_div((int64_t)groups * s, sms) / (double)s + 2e-4 * (double)s;  // + per-CTA set-up
+    if (cost < best - 1e-12) { best = cost; best_s = (int)s; }
+  }
+  return best_s;
+}
+
+int adc_tc_main_pass(const AdcTcBase& B, const uint8_t* dcodes, int64_t n, int m, const float* dq, int nb, int d,
+                     const float* dbnorms, const float* dlut, int QT, const float* dtau, uint32_t* dcandidx,
+                     int* dccnt, int64_t ccap, unsigned long long* dcand, int* dcnt, int64_t cap, int id_base,
+                     float* ddbg, int64_t dbg_ld, cudaStream_t st) {
+  AdcFilterParams p;
+  memset(&p, 0, sizeof(p));
+  p.queries = dq; p.img = B.img.p; p.normpad = B.normpad.p; p.tau = dtau; p.stats = B.stats.p;
+  p.candidx = dcandidx; p.ccnt = dccnt; p.dbg = ddbg; p.n = n; p.ntiles = B.ntiles; p.ccap = ccap; p.dbg_ld = dbg_ld;
+  p.nq = nb; p.d = d; p.m = m; p.QT = QT;
+  p.npass = 3;
+  if (const char* e = getenv("LSQ_B200_ADC_PASSES")) { const int v = atoi(e); if (v >= 1 && v <= 3) p.npass = v; }
+  LSQ_CHECK_ARG(p.npass == 3, "the filter margin is derived for the 3-product split");
+  const int groups = (int)ceil_div(nb, AT_NA * AT_M);
+  const int slices = filter_slices(groups, B.ntiles);
+  const size_t smem = (size_t)AT_STAGES * 2 * at_part_bytes(d);
+  LSQ_CUDA(cudaFuncSetAttribute(adc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LSQ_CUDA(cudaMemsetAsync(dccnt, 0, (size_t)nb * sizeof(int), st));
+  note_launch();
+  adc_filter_kernel<<<dim3(groups, slices, 1), AT_THREADS, smem, st>>>(p);
+  LSQ_CUDA(cudaGetLastError());
+  if (dcand != nullptr) {
+    note_launch();
+    adc_rescore_kernel<<<nb, 256, 0, st>>>(dcodes, n, m, dbnorms, dlut, QT, dtau, dcandidx, dccnt, ccap, dcand, dcnt, cap, id_base);
+    LSQ_CUDA(cudaGetLastError());
+  }
+  return LSQ_OK;
+}
+
+}  // namespace lsq
+
+using namespace lsq;
+
+// Test hook: the filter values  dbnorm[v] - 2 <q, xhat_v>  as the tensor cores compute them, for every pair.
+// dout: device float [nq][ld], ld >= 128 * ceil(n / 128).  Nothing passes the filter (NaN thresholds).
+extern "C" int lsq_dev_adc_filter_values(const uint8_t* dcodes, int64_t n, int m, const float* dqueries, int nq, int d,
+                                         const float* dcodebooks, const float* dbnorms, float* dout, int64_t ld,
+                                         void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  set_alloc_stream(st);
+  LSQ_CHECK_ARG(n >= 1 && nq >= 1 && m >= 1 && m <= LSQ_MAXM && d % 16 == 0 && d >= 16 && d <= 128, "adc filter: bad sizes");
+  LSQ_CHECK_ARG(ld >= 128 * ceil_div(n, 128), "adc filter: ld too small");
+  AdcTcBase B;
+  LSQ_TRY(adc_tc_prepare(dcodes, n, m, dcodebooks, d, dbnorms, st, B));
+  const int nt = (int)ceil_div(nq, 32) * 32;
+  DevBuf<float> dtau;
+  DevBuf<int> dccnt;
+  LSQ_CUDA(dtau.alloc(nt));
+  LSQ_CUDA(dccnt.alloc(nq));
+  LSQ_CUDA(cudaMemsetAsync(dtau.p, 0xFF, (size_t)nt * sizeof(float), st));  // NaN thresholds: nothing passes
+  return adc_tc_main_pass(B, dcodes, n, m, dqueries, nq, d, dbnorms, nullptr, 32, dtau.p, nullptr, dccnt.p, 0, nullptr,
+                          nullptr, 0, 0, dout, ld, st);
+}

@@ -22,6 +22,7 @@
 //                      pass appends only candidates with dist <= tau; a per-query CTA then sorts the
 //                      64-bit keys (ordered(dist) << 32 | id) in shared memory (bitonic), or, when the
 //                      candidate list is longer than the sorter, radix-selects the nn-th key first.
+#include "adc_tc.cuh"
 #include "linscan.cuh"
 #include "runtime.cuh"
 
@@ -755,6 +756,17 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
   DevBuf<uint32_t> dsbuf;
   DevBuf<unsigned long long> dcand;
   DevBuf<int> dcnt, dstatus, dbig;  // dbig: worklist of the queries the select kernel flags + its length
+  // LSQ tables of an inner product: the main pass runs as a tensor-core filter + exact rescoring of the
+  // survivors (adc_tc.cu); everything around it (LUT, sample pass, thresholds, top-k, re-runs) is unchanged
+  const bool use_tc = (lut_kind == LUT_LSQ) && adc_tc_applicable(n, m, d, dqueries, dcodebooks, dbnorms);
+  AdcTcBase tcbase;
+  DevBuf<uint32_t> dcandidx;
+  DevBuf<int> dccnt;
+  if (use_tc) {
+    LSQ_TRY(adc_tc_prepare(dcodes, n, m, dcodebooks, d, dbnorms, st, tcbase));
+    LSQ_CUDA(dcandidx.alloc((size_t)qbatch * cap));
+    LSQ_CUDA(dccnt.alloc(qbatch));
+  }
   LSQ_CUDA(dbig.alloc(qbatch + 1));
   LSQ_CUDA(dlut.alloc((size_t)max_tiles * m * LSQ_H * QT));
   LSQ_CUDA(dtau.alloc((size_t)max_tiles * 32));
@@ -783,7 +795,12 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
     LSQ_CUDA(cudaMemsetAsync(dcnt.p, 0, (size_t)nb * sizeof(int), st));
     LSQ_CUDA(cudaMemsetAsync(dbig.p + qbatch, 0, sizeof(int), st));
     p.mode = MODE_MAIN; p.stride = 1; p.count = n;
-    LSQ_TRY(launch_scan(m, p, ntiles, st));
+    if (use_tc) {
+      LSQ_TRY(adc_tc_main_pass(tcbase, dcodes, n, m, dq, nb, d, dbnorms, dlut.p, QT, dtau.p, dcandidx.p, dccnt.p, cap,
+                               dcand.p, dcnt.p, cap, S.id_base, nullptr, 0, st));
+    } else {
+      LSQ_TRY(launch_scan(m, p, ntiles, st));
+    }
     // most queries end up with a few thousand candidates and nn <= 1024: select + sort of the survivors
     // in 40 KB of shared memory (5 CTAs per SM); the 128 KB sorter only runs for the queries it flags
     note_launch();

@@ -131,6 +131,18 @@ def linscan(codes, queries, codebooks, dbnorms, nn, lut_kind=0, subdim=0):
     return dists, ids
 
 
+def adc_filter_values(codes, queries, codebooks, dbnorms):
+    """Test hook for the tensor-core ADC prefilter (csrc/adc_tc.cu): the values dbnorm[v] - 2<q, xhat_v> as the
+    bf16 hi/lo tcgen05 GEMM computes them, (nq, 128*ceil(n/128)) float32 (columns >= n are padding)."""
+    n, m = codes.shape
+    nq, d = queries.shape
+    ld = 128 * ((n + 127) // 128)
+    out = torch.full((nq, ld), float("nan"), dtype=torch.float32, device=codes.device)
+    api._check(api.lib().lsq_dev_adc_filter_values(_ptr(codes), ct.c_int64(n), m, _ptr(queries), nq, d, _ptr(codebooks),
+                                                   _ptr(dbnorms), _ptr(out), ct.c_int64(ld), _stream()))
+    return out
+
+
 def viterbi(X, C):
     """Chain (ChainQ) encoder with device tensors: builds the tables and unaries, runs the DP
     (encode_chain.jl:95-127); returns uint8 0-based codes (n, m).  The unary buffer is scratch."""

@@ -1,0 +1,107 @@
+"""Tensor-core ADC prefilter (csrc/adc_tc.cu): the filter values against float64, and the whole linscan through
+the filter against the reference's own .so and against the lookup scan — ids and distances bit for bit."""
+import os
+
+import numpy as np
+import pytest
+
+from util import make_scan_problem
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu(lsq):
+    assert lsq.device_count() > 0, "no CUDA device: these tests must run on the GPU box"
+    lsq.init(0)
+    return lsq
+
+
+def gauss_scan_problem(seed, n, nq, d, m, h=256):
+    """Signed, non-representable data: every operand has a non-zero bf16 lo part; norms = ||xhat||^2."""
+    rng = np.random.default_rng(seed)
+    codes = rng.integers(0, h, size=(n, m)).astype(np.uint8)
+    queries = (rng.standard_normal((nq, d)) * 3.0).astype(np.float32)
+    codebooks = rng.standard_normal((m * h, d)).astype(np.float32)
+    xhat = np.zeros((n, d), np.float32)
+    for k in range(m):
+        xhat += codebooks[k * h + codes[:, k].astype(np.int64)]
+    norms = (xhat.astype(np.float64) ** 2).sum(1).astype(np.float32)
+    return codes, queries, codebooks, norms
+
+
+def _ref(oracle, *a):
+    return oracle.ref_linscan_lsq(*a) if oracle.ref_available() else oracle.linscan_lsq(*a)
+
+
+@pytest.mark.parametrize("n,nq,d,m,kind", [
+    (1000, 5, 128, 8, "gauss"),      # one A tile, tail tile (1000 = 7*128 + 104)
+    (3000, 300, 128, 16, "gauss"),   # two query groups, second one with a single A tile
+    (640, 256, 64, 3, "gauss"),      # both A tiles full, d = 64
+    (257, 130, 16, 1, "gauss"),      # d = 16: a single MMA K step
+    (5000, 200, 96, 12, "sift"),     # d = 96: K not a multiple of 64
+])
+def test_filter_values_match_float64(gpu, n, nq, d, m, kind):
+    import torch
+    from lsq_b200 import device as dev
+    mk = gauss_scan_problem if kind == "gauss" else make_scan_problem
+    codes, queries, codebooks, norms = mk(7000 + n, n, nq, d, m)
+    out = dev.adc_filter_values(torch.from_numpy(codes).cuda(), torch.from_numpy(queries).cuda(),
+                                torch.from_numpy(codebooks).cuda(), torch.from_numpy(norms).cuda()).cpu().numpy()
+    xhat = np.zeros((n, d), np.float64)
+    for k in range(m):
+        xhat += codebooks[k * 256 + codes[:, k].astype(np.int64)].astype(np.float64)
+    D = norms.astype(np.float64)[None, :] - 2.0 * queries.astype(np.float64) @ xhat.T
+    got = out[:, :n].astype(np.float64)
+    assert np.all(np.isfinite(got)), "filter values missing (an epilogue warp skipped a tile?)"
+    assert np.all(np.isinf(out[:, n:])), "padding columns must carry +inf"
+    scale = 2.0 * np.linalg.norm(queries.astype(np.float64), axis=1)[:, None] * np.linalg.norm(xhat, axis=1).max()
+    rel = np.abs(got - D) / scale
+    print(f"filter: max |d_tc - D| / (2 |q| max|xhat|) = {rel.max():.3e}")
+    # the margin in adc_tc.cu allows 2^-12; the split + fp32 accumulation must stay far below it
+    assert rel.max() < 2.0 ** -15, rel.max()
+
+
+CASES = [
+    (200000, 300, 128, 8, 1000, "sift"),
+    (150000, 257, 128, 16, 500, "gauss"),
+    (70000, 40, 64, 12, 200, "gauss"),
+    (66000, 129, 32, 15, 100, "sift"),
+    (20000, 30, 16, 4, 50, "gauss"),     # forced below the size gate
+    (100000, 64, 128, 8, 3000, "gauss"),
+]
+
+
+@pytest.mark.parametrize("n,nq,d,m,nn,kind", CASES)
+def test_linscan_through_the_filter_is_exact(gpu, oracle, n, nq, d, m, nn, kind, monkeypatch):
+    mk = gauss_scan_problem if kind == "gauss" else make_scan_problem
+    codes, queries, codebooks, norms = mk(7100 + m + nn, n, nq, d, m)
+    R = np.eye(d, dtype=np.float32)
+    monkeypatch.setenv("LSQ_B200_ADC", "tc")
+    l0 = gpu.launch_count()
+    dt, it = gpu.linscan_lsq(codes, queries, codebooks.reshape(m, 256, d), norms, R, nn)
+    launches_tc = gpu.launch_count() - l0
+    monkeypatch.setenv("LSQ_B200_ADC", "scan")
+    l0 = gpu.launch_count()
+    ds, is_ = gpu.linscan_lsq(codes, queries, codebooks.reshape(m, 256, d), norms, R, nn)
+    launches_scan = gpu.launch_count() - l0
+    assert launches_tc > launches_scan, "the tensor-core path did not run"
+    assert np.array_equal(it, is_) and np.array_equal(dt, ds)
+    k = min(nq, 24)
+    dr, ir = _ref(oracle, codes, queries[:k], codebooks, norms, nn)
+    assert np.array_equal(it[:k], ir) and np.array_equal(dt[:k], dr)
+
+
+def test_filter_ties_and_clustered_neighbours(gpu, oracle, monkeypatch):
+    """Duplicates (ties -> lower id first) and a base set whose near neighbours all sit at the end: the sampled
+    threshold misses, the filter lists overflow or come up short, and the exhaustive path must take over."""
+    n, nq, d, m, nn = 80000, 20, 32, 8, 500
+    codes, queries, codebooks, norms = make_scan_problem(7300, n, nq, d, m)
+    codes[n // 2:] = codes[: n // 2]
+    norms[n // 2:] = norms[: n // 2]
+    R = np.eye(d, dtype=np.float32)
+    monkeypatch.setenv("LSQ_B200_ADC", "tc")
+    for nrm in (norms, np.concatenate([norms[:-600], norms[-600:] - 1e6]).astype(np.float32)):
+        dr, ir = _ref(oracle, codes, queries, codebooks, nrm, nn)
+        dg, ig = gpu.linscan_lsq(codes, queries, codebooks.reshape(m, 256, d), nrm, R, nn)
+        assert np.array_equal(ig, ir) and np.array_equal(dg, dr)
