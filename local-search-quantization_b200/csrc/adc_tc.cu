@@ -50,9 +50,10 @@ constexpr int AT_THREADS = 32 * (AT_EPI_WARPS + 2);
 // 8-row groups are SBO apart, K-adjacent core matrices LBO apart
 constexpr uint32_t AT_SBO = 128u;
 constexpr uint32_t AT_LBO = (AT_N / 8) * 128u;
-// tensor-memory columns: A tile a, part p (0 = hi, 1 = lo) at (2a + p) * 64 (128 bf16 = 64 columns);
-// accumulator of A tile a at 256 + 128 a
-constexpr uint32_t AT_COL_A = 0u, AT_COL_ACC = 256u;
+// tensor-memory columns: hi(q) of A tile a at 64 a (128 bf16 = 64 columns); three accumulators of 128 columns at
+// 128 + 128 b, used round-robin by the (base tile, A tile) products
+constexpr int AT_NACC = 3;
+constexpr uint32_t AT_COL_A = 0u, AT_COL_ACC = 128u;
 
 __host__ __device__ inline uint32_t at_part_bytes(int d) { return (uint32_t)(d / 8) * AT_LBO; }
 
@@ -82,79 +83,133 @@ __global__ void __launch_bounds__(256) adc_cbnorm_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// 1. decode + split.  CTA = one tile of 128 base vectors; thread = (vector r, K half).  Consecutive lanes hold
-//    consecutive vectors, so a warp's 16-byte stores of one K chunk fill 512 contiguous bytes of the image.
+// 1. decode + split.  CTA = one tile of 128 base vectors, 8 warps x 16 vectors.  A warp sums one vector at a
+//    time: lane = 16-byte piece of the d-float row, so every codeword row is ONE coalesced 512-byte load (the
+//    first version gathered 32-byte pieces per lane and was bound by the LSU: 1.8 ms at m = 16).
+//    Vector `sidx` of the image is base vector sidx * stride (stride > 1: the strided sample for the thresholds).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) adc_decode_kernel(const uint8_t* __restrict__ codes, int64_t n, int m,
+__global__ void __launch_bounds__(256) adc_decode_kernel(const uint8_t* __restrict__ codes, int m,
                                                          const float* __restrict__ C, int d,
                                                          const float* __restrict__ norms, unsigned char* __restrict__ img,
-                                                         float* __restrict__ normpad, AdcStats* stats) {
-  __shared__ float part2[256];
-  const int t = threadIdx.x, r = t & 127, half = t >> 7;
+                                                         float* __restrict__ normpad, AdcStats* stats, int64_t count,
+                                                         int64_t stride) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t tile = blockIdx.x;
-  const int64_t v = tile * AT_N + r;
-  const bool valid = v < n;
-  const int nch = d / 8;
+  const bool lane_on = lane < d / 4;
   const uint32_t part_bytes = at_part_bytes(d);
   unsigned char* base = img + (size_t)tile * 2 * part_bytes;
-  uint32_t code[LSQ_MAXM];
-#pragma unroll
-  for (int k = 0; k < LSQ_MAXM; k++) code[k] = (valid && k < m) ? (uint32_t)codes[(size_t)v * m + k] : 0u;
-  float n2 = 0.0f;
-  for (int kc = half; kc < nch; kc += 2) {
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] = 0.0f;
+  uint32_t xb = 0u, nb = 0u;   // running maxima (bit patterns of non-negative floats)
+#pragma unroll 2
+  for (int i = 0; i < 16; i++) {
+    const int r = warp * 16 + i;
+    const int64_t sidx = tile * AT_N + r;
+    const bool valid = sidx < count;
+    const int64_t v = sidx * stride;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
+      const uint8_t* cp = codes + (size_t)v * m;   // the same bytes in every lane: broadcast loads
 #pragma unroll
       for (int k = 0; k < LSQ_MAXM; k++) {
         if (k < m) {
-          const float4* row = reinterpret_cast<const float4*>(C + ((size_t)k * LSQ_H + code[k]) * d + kc * 8);
-          const float4 a = __ldg(row), b = __ldg(row + 1);
-          acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-          acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+          const uint32_t c = cp[k];
+          if (lane_on) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(C + ((size_t)k * LSQ_H + c) * d) + lane);
+            acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+          }
         }
       }
     }
-    uint32_t hi[4], lo[4];
+    float n2 = fmaf(acc.x, acc.x, fmaf(acc.y, acc.y, fmaf(acc.z, acc.z, acc.w * acc.w)));
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      uint32_t h0, l0, h1, l1;
-      bf16_split(acc[2 * i], h0, l0);
-      bf16_split(acc[2 * i + 1], h1, l1);
-      hi[i] = h0 | (h1 << 16);   // element k in the low half, k+1 in the high half (little endian)
-      lo[i] = l0 | (l1 << 16);
-      n2 = fmaf(acc[2 * i], acc[2 * i], n2);
-      n2 = fmaf(acc[2 * i + 1], acc[2 * i + 1], n2);
+    for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xFFFFFFFFu, n2, o);
+    if (lane_on) {
+      uint32_t h0, l0, h1, l1, h2, l2, h3, l3;
+      bf16_split(acc.x, h0, l0);
+      bf16_split(acc.y, h1, l1);
+      bf16_split(acc.z, h2, l2);
+      bf16_split(acc.w, h3, l3);
+      // elements 4*lane .. 4*lane+3 of row r: K chunk lane/2, bytes (lane&1)*8 .. +7 of the 16-byte core-matrix row
+      const uint32_t off = (uint32_t)(lane >> 1) * AT_LBO + (uint32_t)(r >> 3) * AT_SBO + (uint32_t)(r & 7) * 16u + (uint32_t)(lane & 1) * 8u;
+      *reinterpret_cast<uint2*>(base + off) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));   // element k in the low half
+      *reinterpret_cast<uint2*>(base + part_bytes + off) = make_uint2(l0 | (l1 << 16), l2 | (l3 << 16));
     }
-    const uint32_t off = (uint32_t)kc * AT_LBO + (uint32_t)(r >> 3) * AT_SBO + (uint32_t)(r & 7) * 16u;
-    *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(base + part_bytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    if (lane == 0) {
+      float nv = INFINITY;   // padding columns of the last tile never pass the filter
+      if (valid) {
+        nv = norms[v];
+        nb = max(nb, __float_as_uint(fabsf(nv)));   // a NaN is the largest pattern: it survives and poisons the margin
+        xb = max(xb, __float_as_uint(n2));
+      }
+      normpad[sidx] = nv;
+    }
   }
-  part2[t] = n2;
+  if (stats != nullptr && lane == 0) {
+    atomicMax(&stats->xmax2_bits, xb);
+    atomicMax(&stats->nmax_bits, nb);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1b. exact LUT rows for the rescoring: lutq[q][j] = -(2 q).c_j accumulated like the reference
+//     (t -= (2*q[k])*c[k], k ascending, separate multiply and subtract, linscan_aqd_pairwise_byte.cpp:42-48).
+//     Register tile 4 queries x 8 rows per thread, both operands of the 64 x 128 block tile in shared memory,
+//     k-major, so every k step is 3 LDS.128 for 64 multiply-subtract pairs.
+// ------------------------------------------------------------------------------------------------
+constexpr int LR_Q = 64, LR_J = 128;
+
+__global__ void __launch_bounds__(256) adc_lut_rows_kernel(const float* __restrict__ queries, int nq, int d,
+                                                           const float* __restrict__ cb, int rows,
+                                                           float* __restrict__ lutq) {
+  extern __shared__ __align__(16) float lr_smem[];
+  float* qs = lr_smem;                 // [d][LR_Q]   (2 * q)
+  float* cs = lr_smem + d * LR_Q;      // [d][LR_J]
+  const int tid = threadIdx.x;
+  const int q0 = blockIdx.x * LR_Q, j0 = blockIdx.y * LR_J;
+  const int d4 = d / 4;
+  for (int e = tid; e < LR_Q * d4; e += 256) {
+    const int qq = e % LR_Q, k4 = e / LR_Q;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + qq < nq) x = __ldg(reinterpret_cast<const float4*>(queries + (size_t)(q0 + qq) * d) + k4);
+    qs[(4 * k4 + 0) * LR_Q + qq] = __fmul_rn(2.0f, x.x);   // the factor (2*q[k]) of :45-47, exact
+    qs[(4 * k4 + 1) * LR_Q + qq] = __fmul_rn(2.0f, x.y);
+    qs[(4 * k4 + 2) * LR_Q + qq] = __fmul_rn(2.0f, x.z);
+    qs[(4 * k4 + 3) * LR_Q + qq] = __fmul_rn(2.0f, x.w);
+  }
+  for (int e = tid; e < LR_J * d4; e += 256) {
+    const int jj = e % LR_J, k4 = e / LR_J;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j0 + jj < rows) x = __ldg(reinterpret_cast<const float4*>(cb + (size_t)(j0 + jj) * d) + k4);
+    cs[(4 * k4 + 0) * LR_J + jj] = x.x;
+    cs[(4 * k4 + 1) * LR_J + jj] = x.y;
+    cs[(4 * k4 + 2) * LR_J + jj] = x.z;
+    cs[(4 * k4 + 3) * LR_J + jj] = x.w;
+  }
   __syncthreads();
-  if (t < 128) {
-    float tot = part2[t] + part2[t + 128];
-    float an = 0.0f;
-    if (valid) {
-      const float nv = norms[v];
-      normpad[v] = nv;
-      an = fabsf(nv);
-    } else {
-      normpad[v] = INFINITY;  // padding columns of the last tile never pass the filter
-      tot = 0.0f;
-    }
-    // max over the warp on the bit patterns (non-negative floats order like unsigned integers; a NaN is the
-    // largest pattern, so it survives and poisons the margin, which sends the query to the exhaustive path)
-    uint32_t tb = __float_as_uint(tot), ab = __float_as_uint(an);
+  const int tq = tid & 15, tj = tid >> 4;
+  float acc[4][8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      tb = max(tb, __shfl_xor_sync(0xFFFFFFFFu, tb, o));
-      ab = max(ab, __shfl_xor_sync(0xFFFFFFFFu, ab, o));
-    }
-    if ((t & 31) == 0) {
-      atomicMax(&stats->xmax2_bits, tb);
-      atomicMax(&stats->nmax_bits, ab);
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 8; b++) acc[a][b] = 0.0f;
+#pragma unroll 4
+  for (int k = 0; k < d; k++) {
+    const float4 qv = *reinterpret_cast<const float4*>(qs + k * LR_Q + 4 * tq);
+    const float4 c0 = *reinterpret_cast<const float4*>(cs + k * LR_J + 8 * tj);
+    const float4 c1 = *reinterpret_cast<const float4*>(cs + k * LR_J + 8 * tj + 4);
+    const float qa[4] = {qv.x, qv.y, qv.z, qv.w};
+    const float ca[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int b = 0; b < 8; b++) acc[a][b] = __fsub_rn(acc[a][b], __fmul_rn(qa[a], ca[b]));
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const int q = q0 + 4 * tq + a;
+    if (q < nq && j0 + 8 * tj < rows) {
+      float4* dst = reinterpret_cast<float4*>(lutq + (size_t)q * rows + j0 + 8 * tj);
+      dst[0] = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+      dst[1] = make_float4(acc[a][4], acc[a][5], acc[a][6], acc[a][7]);
     }
   }
 }
@@ -166,13 +221,14 @@ struct AdcFilterParams {
   const float* queries;      // [nq][d]
   const unsigned char* img;  // [ntiles][2][part_bytes]
   const float* normpad;      // [ntiles*128]
-  const float* tau;          // [qtile*32 + slot], qtile = q / QT, slot = q % QT  (threshold_kernel's layout)
+  const float* tau;          // [nq] (threshold_kernel's layout with 32-query tiles)
   const AdcStats* stats;
   uint32_t* candidx;         // [nq][ccap] 0-based base indices that passed
   int* ccnt;                 // [nq]
   float* dbg;                // optional: [nq][dbg_ld] filter values (tests)
-  int64_t n, ntiles, ccap, dbg_ld;
-  int nq, d, m, QT, npass;
+  uint32_t* sbuf;            // sample mode: ordered filter values, threshold_kernel's layout [(q/32 * scount + t) * 32 + q%32]
+  int64_t n, ntiles, ccap, dbg_ld, scount;
+  int nq, d, m, exp;
 };
 
 __device__ __forceinline__ void at_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -225,10 +281,11 @@ __device__ __forceinline__ void at_commit_elected(uint64_t* bar) {
       : "memory");
 }
 
-// bit i of the result = (norm_i - 2 * acc_i <= thr) for the 32 accumulator columns in r; nrm4 -> their norms
+// bit i of the result = (norm_i - 2 * acc_i <= thr) for the 32 accumulator columns in r; nrm4 -> their norms.
+// Four independent partial masks: one serial chain of 32 predicated ORs was a third of the epilogue's latency.
 __device__ __forceinline__ uint32_t at_scan32(const uint32_t (&r)[32], const float4* __restrict__ nrm4, float thr,
                                               float* __restrict__ dbg) {
-  uint32_t mask = 0u;
+  uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
 #pragma unroll
   for (int i4 = 0; i4 < 8; i4++) {
     const float4 nv = __ldg(nrm4 + i4);   // the same address in every lane: one broadcast load
@@ -236,18 +293,18 @@ __device__ __forceinline__ uint32_t at_scan32(const uint32_t (&r)[32], const flo
     const float d1 = fmaf(-2.0f, __uint_as_float(r[4 * i4 + 1]), nv.y);
     const float d2 = fmaf(-2.0f, __uint_as_float(r[4 * i4 + 2]), nv.z);
     const float d3 = fmaf(-2.0f, __uint_as_float(r[4 * i4 + 3]), nv.w);
-    if (d0 <= thr) mask |= 1u << (4 * i4 + 0);
-    if (d1 <= thr) mask |= 1u << (4 * i4 + 1);
-    if (d2 <= thr) mask |= 1u << (4 * i4 + 2);
-    if (d3 <= thr) mask |= 1u << (4 * i4 + 3);
-    if (dbg) { dbg[4 * i4 + 0] = d0; dbg[4 * i4 + 1] = d1; dbg[4 * i4 + 2] = d2; dbg[4 * i4 + 3] = d3; }
+    if (d0 <= thr) m0 |= 1u << (4 * i4 + 0);
+    if (d1 <= thr) m1 |= 1u << (4 * i4 + 1);
+    if (d2 <= thr) m2 |= 1u << (4 * i4 + 2);
+    if (d3 <= thr) m3 |= 1u << (4 * i4 + 3);
+    if (dbg != nullptr) { dbg[4 * i4 + 0] = d0; dbg[4 * i4 + 1] = d1; dbg[4 * i4 + 2] = d2; dbg[4 * i4 + 3] = d3; }
   }
-  return mask;
+  return (m0 | m1) | (m2 | m3);
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 1) adc_filter_kernel(const __grid_constant__ AdcFilterParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ uint64_t bar_full[AT_STAGES], bar_empty[AT_STAGES], bar_acc_full[AT_NA], bar_acc_empty[AT_NA];
+  __shared__ uint64_t bar_full[AT_STAGES], bar_empty[AT_STAGES], bar_acc_full[AT_NACC], bar_acc_empty[AT_NACC];
   __shared__ uint32_t tmem_base_slot;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -263,7 +320,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) adc_filter_kernel(const __grid_
 
   if (tid == 0) {
     for (int s = 0; s < AT_STAGES; s++) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
-    for (int a = 0; a < AT_NA; a++) { mbar_init(&bar_acc_full[a], 1); mbar_init(&bar_acc_empty[a], 4); }
+    for (int b = 0; b < AT_NACC; b++) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_empty[b], 4); }
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -275,46 +332,43 @@ __global__ void __launch_bounds__(AT_THREADS, 1) adc_filter_kernel(const __grid_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = tmem_base_slot;
 
-  // ---- stationary operand -> tensor memory: thread = query row (lane of its warp's quadrant); hi and lo bf16,
-  //      two K elements per 32-bit column.  The same threads keep ||q|| and the threshold for the epilogue. ----
+  // ---- stationary operand -> tensor memory: thread = query row (lane of its warp's quadrant); hi(q) in bf16,
+  //      two K elements per 32-bit column.  The same threads keep the threshold for the epilogue. ----
   const int a_mine = warp >> 2, quad = warp & 3;
   const int q = qbase + a_mine * AT_M + quad * 32 + lane;
   const bool q_valid = (warp < AT_EPI_WARPS) && (a_mine < na) && (q < p.nq);
   float thr = -INFINITY;   // rows without a query never pass `value <= thr`
   if (warp < AT_EPI_WARPS && a_mine < na) {
     const float* qrow = p.queries + (size_t)(q_valid ? q : 0) * d;
-    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16) + AT_COL_A + (uint32_t)(a_mine * 2) * 64u;
-    float qn2 = 0.0f;
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16) + AT_COL_A + (uint32_t)a_mine * 64u;
+    float qn2 = 0.0f, ql2 = 0.0f;   // ||q||^2 and ||q - hi(q)||^2
     for (int k0 = 0; k0 < d; k0 += 64) {
-      uint32_t hi[32], lo[32];
+      uint32_t hi[32];
 #pragma unroll
       for (int i4 = 0; i4 < 16; i4++) {
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q_valid && k0 + 4 * i4 < d) x = __ldg(reinterpret_cast<const float4*>(qrow + k0) + i4);
-        uint32_t h0, l0, h1, l1;
-        bf16_split(x.x, h0, l0);
-        bf16_split(x.y, h1, l1);
-        hi[2 * i4] = h0 | (h1 << 16);
-        lo[2 * i4] = l0 | (l1 << 16);
-        bf16_split(x.z, h0, l0);
-        bf16_split(x.w, h1, l1);
-        hi[2 * i4 + 1] = h0 | (h1 << 16);
-        lo[2 * i4 + 1] = l0 | (l1 << 16);
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y);
+        const __nv_bfloat16 h2 = __float2bfloat16_rn(x.z), h3 = __float2bfloat16_rn(x.w);
+        hi[2 * i4] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        hi[2 * i4 + 1] = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+        const float r0 = x.x - __bfloat162float(h0), r1 = x.y - __bfloat162float(h1);   // exact in fp32
+        const float r2 = x.z - __bfloat162float(h2), r3 = x.w - __bfloat162float(h3);
+        ql2 = fmaf(r0, r0, ql2); ql2 = fmaf(r1, r1, ql2); ql2 = fmaf(r2, r2, ql2); ql2 = fmaf(r3, r3, ql2);
         qn2 = fmaf(x.x, x.x, qn2); qn2 = fmaf(x.y, x.y, qn2); qn2 = fmaf(x.z, x.z, qn2); qn2 = fmaf(x.w, x.w, qn2);
       }
       at_st32(lane_base + (uint32_t)(k0 >> 1), hi);
-      at_st32(lane_base + 64u + (uint32_t)(k0 >> 1), lo);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    if (q_valid) {
-      const float tau = p.tau[(q / p.QT) * 32 + (q % p.QT)];
-      const float qn = sqrtf(qn2) * 1.000001f;
-      const float xmax = sqrtf(__uint_as_float(p.stats->xmax2_bits)) * 1.000001f;
-      const float cmax = sqrtf(__uint_as_float(p.stats->cmax2_bits)) * 1.000001f;
+    if (q_valid && p.sbuf == nullptr) {
+      const float tau = p.tau[q];
+      const float qn = sqrtf(qn2) * 1.00001f, ql = sqrtf(ql2) * 1.00001f;
+      const float xmax = sqrtf(__uint_as_float(p.stats->xmax2_bits)) * 1.00001f;
+      const float cmax = sqrtf(__uint_as_float(p.stats->cmax2_bits)) * 1.00001f;
       const float nmax = __uint_as_float(p.stats->nmax_bits);
-      const float eps_f = 1.0f / 4096.0f;                                   // 2^-12, see the header
+      const float eps_f = 1.0f / 8192.0f;                                   // 2^-13, see the header
       const float eps_r = 2.0f * (float)(d + p.m + 2) * 5.9604645e-8f;      // 2 (d+m+2) u
-      const float margin = eps_f * 2.0f * qn * xmax + eps_r * (2.0f * qn * (float)p.m * cmax + nmax);
+      const float margin = 2.0f * ql * xmax + eps_f * 2.0f * qn * xmax + eps_r * (2.0f * qn * (float)p.m * cmax + nmax);
       thr = tau + margin;   // NaN anywhere -> no pair passes -> the query is re-run exhaustively
     }
   }
@@ -341,53 +395,72 @@ __global__ void __launch_bounds__(AT_THREADS, 1) adc_filter_kernel(const __grid_
     const uint64_t desc_hi = (uint64_t)((AT_SBO >> 4) | (1u << 14)) << 32;   // SBO, descriptor version 1
     const uint32_t desc_lbo = (AT_LBO >> 4) << 16;
     const uint32_t kstep_enc = (2u * AT_LBO) >> 4;                           // one MMA consumes K = 16 = 2 core matrices
-    const int npass = p.npass;
+    int64_t j = 0;        // product index: (base tile t, A tile a) -> accumulator j % 3, its (j / 3)-th use
     for (int64_t t = 0; t < my_tiles; t++) {
       const int s = (int)(t % AT_STAGES);
       mbar_wait(&bar_full[s], (uint32_t)((t / AT_STAGES) & 1));
       const uint32_t stage_u = sB_u + (uint32_t)s * stage_bytes;
       const uint32_t lo_hiX = desc_lbo | (stage_u >> 4), lo_loX = desc_lbo | ((stage_u + part_bytes) >> 4);
       for (int a = 0; a < na; a++) {
-        mbar_wait(&bar_acc_empty[a], (uint32_t)(t & 1) ^ 1u);
+        const int b = (int)(j % AT_NACC);
+        const uint32_t bu = (uint32_t)((j / AT_NACC) & 1);
+        mbar_wait(&bar_acc_empty[b], bu ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t dcol = tmem + AT_COL_ACC + (uint32_t)a * AT_N;
-        const uint32_t a_hi = tmem + AT_COL_A + (uint32_t)(a * 2) * 64u, a_lo = a_hi + 64u;
-        uint32_t accum = 0u;
-        if (npass >= 3) {   // lo(q).hi(x)  (small terms first)
+        const uint32_t dcol = tmem + AT_COL_ACC + (uint32_t)b * AT_N;
+        const uint32_t a_hi = tmem + AT_COL_A + (uint32_t)a * 64u;
 #pragma unroll 4
-          for (int k = 0; k < ksteps; k++) {
-            at_mma_bf16_ts(dcol, a_lo + (uint32_t)(8 * k), desc_hi | (lo_hiX + (uint32_t)k * kstep_enc), idesc, accum);
-            accum = 1u;
-          }
-        }
-        if (npass >= 2) {   // hi(q).lo(x)
+        for (int k = 0; k < ksteps; k++)     // hi(q).lo(x)  (small terms first)
+          at_mma_bf16_ts(dcol, a_hi + (uint32_t)(8 * k), desc_hi | (lo_loX + (uint32_t)k * kstep_enc), idesc, k > 0);
 #pragma unroll 4
-          for (int k = 0; k < ksteps; k++) {
-            at_mma_bf16_ts(dcol, a_hi + (uint32_t)(8 * k), desc_hi | (lo_loX + (uint32_t)k * kstep_enc), idesc, accum);
-            accum = 1u;
-          }
-        }
-#pragma unroll 4
-        for (int k = 0; k < ksteps; k++) {   // hi(q).hi(x)
-          at_mma_bf16_ts(dcol, a_hi + (uint32_t)(8 * k), desc_hi | (lo_hiX + (uint32_t)k * kstep_enc), idesc, accum);
-          accum = 1u;
-        }
+        for (int k = 0; k < ksteps; k++)     // hi(q).hi(x)
+          at_mma_bf16_ts(dcol, a_hi + (uint32_t)(8 * k), desc_hi | (lo_hiX + (uint32_t)k * kstep_enc), idesc, 1u);
         if (a == na - 1) at_commit_elected(&bar_empty[s]);   // the stage may be refilled once these MMAs have read it
-        at_commit_elected(&bar_acc_full[a]);
+        at_commit_elected(&bar_acc_full[b]);
+        j++;
       }
     }
   } else if (a_mine < na) {
-    // ===================== epilogue: warps 4a .. 4a+3 drain the accumulator of A tile a =====================
-    const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + AT_COL_ACC + (uint32_t)a_mine * AT_N;
+    // ===================== epilogue: warps 4a .. 4a+3 drain the products of A tile a =====================
     int* my_cnt = p.ccnt + (q_valid ? q : 0);
     uint32_t* my_list = p.candidx + (size_t)(q_valid ? q : 0) * p.ccap;
+    uint32_t* my_sbuf = (p.sbuf != nullptr && q_valid) ? (p.sbuf + ((size_t)(q >> 5) * p.scount) * 32 + (q & 31)) : nullptr;
+    // The list position of a tile's hits comes from an atomicAdd whose round trip (~1 us) must not sit in the
+    // per-tile dependency chain: the add is issued at the end of tile t and its result is consumed, together
+    // with the saved hit masks, after the scans of tile t + 1.
+    uint32_t pmask[4] = {0u, 0u, 0u, 0u};
+    int64_t ppos = 0, pv0 = 0;
+    auto flush = [&]() {
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        uint32_t mk = pmask[c];
+        while (mk) {
+          const int bit = __ffs(mk) - 1;
+          mk &= mk - 1u;
+          if (ppos < p.ccap) my_list[ppos] = (uint32_t)(pv0 + c * 32 + bit);
+          ppos++;
+        }
+      }
+    };
+    if (lane < 4 && my_tiles > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.normpad + t_lo * AT_N + lane * 32));
     for (int64_t t = 0; t < my_tiles; t++) {
-      mbar_wait(&bar_acc_full[a_mine], (uint32_t)(t & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t j = t * na + a_mine;   // product index -> accumulator j % 3, its (j / 3)-th use
+      const int b = (int)(j % AT_NACC);
+      const uint32_t bu = (uint32_t)((j / AT_NACC) & 1);
       const int64_t v0 = (t_lo + t) * AT_N;
+      // the next tile's norms (512 B) into L1 while this tile is processed
+      if (lane < 4 && t + 1 < my_tiles) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.normpad + v0 + AT_N + lane * 32));
+      mbar_wait(&bar_acc_full[b], bu);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + AT_COL_ACC + (uint32_t)b * AT_N;
       const float4* nrm4 = reinterpret_cast<const float4*>(p.normpad + v0);
       float* dbg = (p.dbg != nullptr && q_valid) ? (p.dbg + (size_t)q * p.dbg_ld + v0) : nullptr;
-      uint32_t mask[4];
+      uint32_t mask[4] = {0u, 0u, 0u, 0u};
+      if (p.exp == 1) {   // experiment: no drain at all
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+        continue;
+      }
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         uint32_t r0[32], r1[32];
@@ -397,26 +470,34 @@ __global__ void __launch_bounds__(AT_THREADS, 1) adc_filter_kernel(const __grid_
         if (h == 1) {   // every column is in registers: the accumulator may be overwritten
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_acc_empty[a_mine]);
+          if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
+        }
+        if (my_sbuf != nullptr) {   // sample mode: keep the values, ordered for the radix select
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const int64_t c0 = v0 + h * 64 + i, c1 = c0 + 32;
+            if (c0 < p.scount) my_sbuf[(size_t)c0 * 32] = float_to_ordered(fmaf(-2.0f, __uint_as_float(r0[i]), p.normpad[c0]));
+            if (c1 < p.scount) my_sbuf[(size_t)c1 * 32] = float_to_ordered(fmaf(-2.0f, __uint_as_float(r1[i]), p.normpad[c1]));
+          }
+        }
+        if (p.exp == 2) {   // experiment: drain only (one cheap use of every register keeps the loads alive)
+          uint32_t x = 0u;
+#pragma unroll
+          for (int i = 0; i < 32; i++) x |= r0[i] & r1[i];
+          mask[h] = (x == 0x7FC12345u) ? 1u : 0u;
+          continue;
         }
         mask[2 * h] = at_scan32(r0, nrm4 + h * 16, thr, dbg ? dbg + h * 64 : nullptr);
         mask[2 * h + 1] = at_scan32(r1, nrm4 + h * 16 + 8, thr, dbg ? dbg + h * 64 + 32 : nullptr);
       }
+      flush();   // hits of the previous tile: their atomicAdd has had a whole tile to return
       const int hits = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]);
-      if (hits > 0) {   // thr = -inf for rows without a query, so q is valid here
-        int64_t pos = (int64_t)atomicAdd(my_cnt, hits);
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-          uint32_t mk = mask[c];
-          while (mk) {
-            const int b = __ffs(mk) - 1;
-            mk &= mk - 1u;
-            if (pos < p.ccap) my_list[pos] = (uint32_t)(v0 + c * 32 + b);
-            pos++;
-          }
-        }
-      }
+      for (int c = 0; c < 4; c++) pmask[c] = mask[c];
+      pv0 = v0;
+      if (hits > 0) ppos = (int64_t)atomicAdd(my_cnt, hits);   // thr = -inf for rows without a query, so q is valid here
     }
+    flush();
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -430,20 +511,19 @@ __global__ void __launch_bounds__(AT_THREADS, 1) adc_filter_kernel(const __grid_
 //    i.e. exactly what scan_kernel's MODE_MAIN appends.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) adc_rescore_kernel(const uint8_t* __restrict__ codes, int64_t n, int m,
-                                                          const float* __restrict__ norms, const float* __restrict__ lut,
-                                                          int QT, const float* __restrict__ tau,
+                                                          const float* __restrict__ norms, const float* __restrict__ lutq,
+                                                          const float* __restrict__ tau,
                                                           const uint32_t* __restrict__ candidx, const int* __restrict__ ccnt,
                                                           int64_t ccap, unsigned long long* __restrict__ cand,
                                                           int* __restrict__ cnt, int64_t cap, int id_base) {
-  __shared__ float lutq[LSQ_MAXM * LSQ_H];
+  __shared__ __align__(16) float lut[LSQ_MAXM * LSQ_H];
   __shared__ int sh_n;
   const int q = blockIdx.x, tid = threadIdx.x;
-  const int qtile = q / QT, slot = q % QT;
-  const float* lsrc = lut + (size_t)qtile * m * LSQ_H * QT + slot;
-  for (int j = tid; j < m * LSQ_H; j += 256) lutq[j] = lsrc[(size_t)j * QT];
+  const float4* lsrc = reinterpret_cast<const float4*>(lutq + (size_t)q * m * LSQ_H);
+  for (int j = tid; j < m * LSQ_H / 4; j += 256) reinterpret_cast<float4*>(lut)[j] = __ldg(lsrc + j);
   if (tid == 0) sh_n = 0;
   __syncthreads();
-  const float tq = tau[qtile * 32 + slot];
+  const float tq = tau[q];
   const int64_t c_all = ccnt[q];
   const int64_t c = (c_all < ccap) ? c_all : ccap;
   const uint32_t* list = candidx + (size_t)q * ccap;
@@ -453,7 +533,17 @@ __global__ void __launch_bounds__(256) adc_rescore_kernel(const uint8_t* __restr
     if ((int64_t)v >= n) continue;
     const uint8_t* cp = codes + (size_t)v * m;
     float acc = 0.0f;
-    for (int k = 0; k < m; k++) acc = __fadd_rn(acc, lutq[k * LSQ_H + cp[k]]);
+    if ((m & 3) == 0) {
+      for (int k4 = 0; k4 < m; k4 += 4) {
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(cp + k4);
+        acc = __fadd_rn(acc, lut[(k4 + 0) * LSQ_H + (w & 0xFFu)]);
+        acc = __fadd_rn(acc, lut[(k4 + 1) * LSQ_H + ((w >> 8) & 0xFFu)]);
+        acc = __fadd_rn(acc, lut[(k4 + 2) * LSQ_H + ((w >> 16) & 0xFFu)]);
+        acc = __fadd_rn(acc, lut[(k4 + 3) * LSQ_H + (w >> 24)]);
+      }
+    } else {
+      for (int k = 0; k < m; k++) acc = __fadd_rn(acc, lut[k * LSQ_H + cp[k]]);
+    }
     acc = __fadd_rn(acc, norms[v]);
     if (acc <= tq) {
       const int pos = atomicAdd(&sh_n, 1);
@@ -468,11 +558,14 @@ __global__ void __launch_bounds__(256) adc_rescore_kernel(const uint8_t* __restr
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-bool adc_tc_applicable(int64_t n, int m, int d, const float* dqueries, const float* dcodebooks, const float* dbnorms) {
+bool adc_tc_applicable(const uint8_t* dcodes, int64_t n, int m, int d, const float* dqueries, const float* dcodebooks,
+                       const float* dbnorms) {
   const char* mode = getenv("LSQ_B200_ADC");
   if (mode != nullptr && strcmp(mode, "scan") == 0) return false;
   if (dbnorms == nullptr || d % 16 != 0 || d > 128 || m < 1 || m > LSQ_MAXM) return false;
-  if ((reinterpret_cast<uintptr_t>(dqueries) & 15) || (reinterpret_cast<uintptr_t>(dcodebooks) & 15)) return false;
+  if ((reinterpret_cast<uintptr_t>(dqueries) & 15) || (reinterpret_cast<uintptr_t>(dcodebooks) & 15) ||
+      (reinterpret_cast<uintptr_t>(dcodes) & 3))
+    return false;
   const bool forced = (mode != nullptr && strcmp(mode, "tc") == 0);
   // below ~64 K base vectors the lookup scan is launch-bound anyway; above the memory gate the images would
   // crowd out the caller (4 d bytes per base vector)
@@ -484,26 +577,35 @@ bool adc_tc_applicable(int64_t n, int m, int d, const float* dqueries, const flo
 }
 
 int adc_tc_prepare(const uint8_t* dcodes, int64_t n, int m, const float* dcodebooks, int d, const float* dbnorms,
-                   cudaStream_t st, AdcTcBase& B) {
+                   int64_t scount, int64_t sstride, cudaStream_t st, AdcTcBase& B) {
   B.ntiles = ceil_div(n, AT_N);
+  B.scount = scount;
+  B.stiles = ceil_div(scount, AT_N);
   LSQ_CUDA(B.img.alloc((size_t)B.ntiles * 2 * at_part_bytes(d)));
   LSQ_CUDA(B.normpad.alloc((size_t)B.ntiles * AT_N));
+  LSQ_CUDA(B.simg.alloc((size_t)B.stiles * 2 * at_part_bytes(d)));
+  LSQ_CUDA(B.snormpad.alloc((size_t)B.stiles * AT_N));
   LSQ_CUDA(B.stats.alloc(1));
   LSQ_CUDA(cudaMemsetAsync(B.stats.p, 0, sizeof(AdcStats), st));
   note_launch();
   adc_cbnorm_kernel<<<(unsigned)ceil_div((int64_t)m * LSQ_H, 256), 256, 0, st>>>(dcodebooks, m * LSQ_H, d, B.stats.p);
   note_launch();
-  adc_decode_kernel<<<(unsigned)B.ntiles, 256, 0, st>>>(dcodes, n, m, dcodebooks, d, dbnorms, B.img.p, B.normpad.p, B.stats.p);
+  adc_decode_kernel<<<(unsigned)B.ntiles, 256, 0, st>>>(dcodes, m, dcodebooks, d, dbnorms, B.img.p, B.normpad.p, B.stats.p, n, 1);
+  if (B.stiles > 0) {
+    note_launch();
+    adc_decode_kernel<<<(unsigned)B.stiles, 256, 0, st>>>(dcodes, m, dcodebooks, d, dbnorms, B.simg.p, B.snormpad.p, nullptr,
+                                                         scount, sstride);
+  }
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
 }
 
 static int filter_slices(int groups, int64_t ntiles) {
-  // every CTA does the same work: the pass takes ceil(CTAs / SMs) waves of 1/slices each; slices of >= 32 tiles
+  // every CTA does the same work: the pass takes ceil(CTAs / SMs) waves of 1/slices each; slices of >= 16 tiles
   int dev = 0, sms = LSQ_NUM_SMS_HINT;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t max_s = std::max<int64_t>(1, std::min<int64_t>(65535, ntiles / 32));
+  const int64_t max_s = std::max<int64_t>(1, std::min<int64_t>(65535, ntiles / 16));
   int best_s = 1;
   double best = 1e30;
   for (int64_t s = 1; s <= max_s; s++) {
@@ -513,29 +615,51 @@ static int filter_slices(int groups, int64_t ntiles) {
   return best_s;
 }
 
+static int launch_filter(AdcFilterParams& p, cudaStream_t st) {
+  const int groups = (int)ceil_div(p.nq, AT_NA * AT_M);
+  const int slices = filter_slices(groups, p.ntiles);
+  const size_t smem = (size_t)AT_STAGES * 2 * at_part_bytes(p.d);
+  LSQ_CUDA(cudaFuncSetAttribute(adc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  note_launch();
+  adc_filter_kernel<<<dim3(groups, slices, 1), AT_THREADS, smem, st>>>(p);
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
+}
+
+// filter values of the strided sample -> dsbuf in threshold_kernel's layout (32-query tiles, `scount` steps)
+int adc_tc_sample(const AdcTcBase& B, const float* dq, int nb, int d, int m, uint32_t* dsbuf, cudaStream_t st) {
+  AdcFilterParams p;
+  memset(&p, 0, sizeof(p));
+  p.queries = dq; p.img = B.simg.p; p.normpad = B.snormpad.p; p.sbuf = dsbuf; p.scount = B.scount;
+  p.n = B.scount; p.ntiles = B.stiles; p.nq = nb; p.d = d; p.m = m;
+  return launch_filter(p, st);
+}
+
+int adc_tc_lut_rows(const float* dq, int nb, int d, const float* dcodebooks, int m, float* dlutq, cudaStream_t st) {
+  const size_t smem = (size_t)d * (LR_Q + LR_J) * sizeof(float);
+  LSQ_CUDA(cudaFuncSetAttribute(adc_lut_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  note_launch();
+  adc_lut_rows_kernel<<<dim3((unsigned)ceil_div(nb, LR_Q), (unsigned)ceil_div((int64_t)m * LSQ_H, LR_J), 1), 256, smem, st>>>(
+      dq, nb, d, dcodebooks, m * LSQ_H, dlutq);
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
+}
+
 int adc_tc_main_pass(const AdcTcBase& B, const uint8_t* dcodes, int64_t n, int m, const float* dq, int nb, int d,
-                     const float* dbnorms, const float* dlut, int QT, const float* dtau, uint32_t* dcandidx,
-                     int* dccnt, int64_t ccap, unsigned long long* dcand, int* dcnt, int64_t cap, int id_base,
-                     float* ddbg, int64_t dbg_ld, cudaStream_t st) {
+                     const float* dbnorms, const float* dlutq, const float* dtau, uint32_t* dcandidx, int* dccnt,
+                     int64_t ccap, unsigned long long* dcand, int* dcnt, int64_t cap, int id_base, float* ddbg,
+                     int64_t dbg_ld, cudaStream_t st) {
   AdcFilterParams p;
   memset(&p, 0, sizeof(p));
   p.queries = dq; p.img = B.img.p; p.normpad = B.normpad.p; p.tau = dtau; p.stats = B.stats.p;
   p.candidx = dcandidx; p.ccnt = dccnt; p.dbg = ddbg; p.n = n; p.ntiles = B.ntiles; p.ccap = ccap; p.dbg_ld = dbg_ld;
-  p.nq = nb; p.d = d; p.m = m; p.QT = QT;
-  p.npass = 3;
-  if (const char* e = getenv("LSQ_B200_ADC_PASSES")) { const int v = atoi(e); if (v >= 1 && v <= 3) p.npass = v; }
-  LSQ_CHECK_ARG(p.npass == 3, "the filter margin is derived for the 3-product split");
-  const int groups = (int)ceil_div(nb, AT_NA * AT_M);
-  const int slices = filter_slices(groups, B.ntiles);
-  const size_t smem = (size_t)AT_STAGES * 2 * at_part_bytes(d);
-  LSQ_CUDA(cudaFuncSetAttribute(adc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  p.nq = nb; p.d = d; p.m = m;
+  if (const char* e = getenv("LSQ_B200_ADC_EXP")) p.exp = atoi(e);   // timing experiments only (results invalid)
   LSQ_CUDA(cudaMemsetAsync(dccnt, 0, (size_t)nb * sizeof(int), st));
-  note_launch();
-  adc_filter_kernel<<<dim3(groups, slices, 1), AT_THREADS, smem, st>>>(p);
-  LSQ_CUDA(cudaGetLastError());
+  LSQ_TRY(launch_filter(p, st));
   if (dcand != nullptr) {
     note_launch();
-    adc_rescore_kernel<<<nb, 256, 0, st>>>(dcodes, n, m, dbnorms, dlut, QT, dtau, dcandidx, dccnt, ccap, dcand, dcnt, cap, id_base);
+    adc_rescore_kernel<<<nb, 256, 0, st>>>(dcodes, n, m, dbnorms, dlutq, dtau, dcandidx, dccnt, ccap, dcand, dcnt, cap, id_base);
     LSQ_CUDA(cudaGetLastError());
   }
   return LSQ_OK;
@@ -555,13 +679,12 @@ extern "C" int lsq_dev_adc_filter_values(const uint8_t* dcodes, int64_t n, int m
   LSQ_CHECK_ARG(n >= 1 && nq >= 1 && m >= 1 && m <= LSQ_MAXM && d % 16 == 0 && d >= 16 && d <= 128, "adc filter: bad sizes");
   LSQ_CHECK_ARG(ld >= 128 * ceil_div(n, 128), "adc filter: ld too small");
   AdcTcBase B;
-  LSQ_TRY(adc_tc_prepare(dcodes, n, m, dcodebooks, d, dbnorms, st, B));
-  const int nt = (int)ceil_div(nq, 32) * 32;
+  LSQ_TRY(adc_tc_prepare(dcodes, n, m, dcodebooks, d, dbnorms, 0, 1, st, B));
   DevBuf<float> dtau;
   DevBuf<int> dccnt;
-  LSQ_CUDA(dtau.alloc(nt));
+  LSQ_CUDA(dtau.alloc(nq));
   LSQ_CUDA(dccnt.alloc(nq));
-  LSQ_CUDA(cudaMemsetAsync(dtau.p, 0xFF, (size_t)nt * sizeof(float), st));  // NaN thresholds: nothing passes
-  return adc_tc_main_pass(B, dcodes, n, m, dqueries, nq, d, dbnorms, nullptr, 32, dtau.p, nullptr, dccnt.p, 0, nullptr,
+  LSQ_CUDA(cudaMemsetAsync(dtau.p, 0xFF, (size_t)nq * sizeof(float), st));  // NaN thresholds: nothing passes
+  return adc_tc_main_pass(B, dcodes, n, m, dqueries, nq, d, dbnorms, nullptr, dtau.p, nullptr, dccnt.p, 0, nullptr,
                           nullptr, 0, 0, dout, ld, st);
 }

@@ -12,22 +12,29 @@ struct AdcStats {
   unsigned int pad;
 };
 
-// per-call image of the base set: bf16 hi/lo UMMA operand tiles of the decoded vectors, padded norms, maxima
+// per-call image of the base set: bf16 hi/lo UMMA operand tiles of the decoded vectors, padded norms, maxima;
+// the same for the strided sample the thresholds are estimated on
 struct AdcTcBase {
-  DevBuf<unsigned char> img;
-  DevBuf<float> normpad;
+  DevBuf<unsigned char> img, simg;
+  DevBuf<float> normpad, snormpad;
   DevBuf<AdcStats> stats;
-  int64_t ntiles = 0;
+  int64_t ntiles = 0, stiles = 0, scount = 0;
 };
 
-bool adc_tc_applicable(int64_t n, int m, int d, const float* dqueries, const float* dcodebooks, const float* dbnorms);
+bool adc_tc_applicable(const uint8_t* dcodes, int64_t n, int m, int d, const float* dqueries, const float* dcodebooks,
+                       const float* dbnorms);
+// base image + image of the sample {i * sstride : i < scount}
 int adc_tc_prepare(const uint8_t* dcodes, int64_t n, int m, const float* dcodebooks, int d, const float* dbnorms,
-                   cudaStream_t st, AdcTcBase& B);
-// filter (-> dcandidx / dccnt) + exact rescoring (-> dcand / dcnt, the buffers the top-k kernels read).
+                   int64_t scount, int64_t sstride, cudaStream_t st, AdcTcBase& B);
+// filter values of the sample, ordered, in threshold_kernel's layout with 32-query tiles: [(q/32 * scount + t) * 32 + q%32]
+int adc_tc_sample(const AdcTcBase& B, const float* dq, int nb, int d, int m, uint32_t* dsbuf, cudaStream_t st);
+// exact LUT rows lutq[q][m*256] (the reference's fp32 chain) for the rescoring
+int adc_tc_lut_rows(const float* dq, int nb, int d, const float* dcodebooks, int m, float* dlutq, cudaStream_t st);
+// filter (-> dcandidx / dccnt) + exact rescoring (-> dcand / dcnt, the buffers the top-k kernels read); dtau[q].
 // dcand == nullptr: filter only.  ddbg (optional): [nb][dbg_ld] filter values.
 int adc_tc_main_pass(const AdcTcBase& B, const uint8_t* dcodes, int64_t n, int m, const float* dq, int nb, int d,
-                     const float* dbnorms, const float* dlut, int QT, const float* dtau, uint32_t* dcandidx,
-                     int* dccnt, int64_t ccap, unsigned long long* dcand, int* dcnt, int64_t cap, int id_base,
-                     float* ddbg, int64_t dbg_ld, cudaStream_t st);
+                     const float* dbnorms, const float* dlutq, const float* dtau, uint32_t* dcandidx, int* dccnt,
+                     int64_t ccap, unsigned long long* dcand, int* dcnt, int64_t cap, int id_base, float* ddbg,
+                     int64_t dbg_ld, cudaStream_t st);
 
 }  // namespace lsq

@@ -30,6 +30,8 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <string>
+#include <utility>
 #include <vector>
 
 namespace lsq {
@@ -663,6 +665,38 @@ static int configure_topk() {
   return LSQ_OK;
 }
 
+// LSQ_B200_ADC_TIMING=1: device time of every phase of a linscan call (CUDA events on the call's stream), printed
+// to stderr at the end of the call.  Measurement aid; off by default (no events, no extra synchronisation).
+struct PhaseTimer {
+  bool on;
+  cudaStream_t st;
+  std::vector<std::pair<const char*, cudaEvent_t>> ev;
+  PhaseTimer(cudaStream_t s) : on(getenv("LSQ_B200_ADC_TIMING") != nullptr), st(s) { mark("start"); }
+  void mark(const char* name) {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    ev.emplace_back(name, e);
+  }
+  ~PhaseTimer() {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    std::string line = "linscan phases (ms):";
+    for (size_t i = 1; i < ev.size(); i++) {
+      float ms = 0.0f;
+      cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
+      char buf[96];
+      snprintf(buf, sizeof(buf), " %s %.3f", ev[i].first, ms);
+      line += buf;
+    }
+    float tot = 0.0f;
+    if (ev.size() > 1) cudaEventElapsedTime(&tot, ev.front().second, ev.back().second);
+    fprintf(stderr, "%s | total %.3f\n", line.c_str(), tot);
+    for (auto& e : ev) cudaEventDestroy(e.second);
+  }
+};
+
 struct ScanCtx {
   const uint8_t* dcodes; int64_t n; int m;
   const float* dcb; const float* dnorms;
@@ -752,20 +786,22 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
   qbatch = ceil_div(qbatch, QT) * QT;
   const int max_tiles = (int)ceil_div(qbatch, QT);
 
+  PhaseTimer timer(st);
   DevBuf<float> dlut, dtau;
   DevBuf<uint32_t> dsbuf;
   DevBuf<unsigned long long> dcand;
   DevBuf<int> dcnt, dstatus, dbig;  // dbig: worklist of the queries the select kernel flags + its length
   // LSQ tables of an inner product: the main pass runs as a tensor-core filter + exact rescoring of the
   // survivors (adc_tc.cu); everything around it (LUT, sample pass, thresholds, top-k, re-runs) is unchanged
-  const bool use_tc = (lut_kind == LUT_LSQ) && adc_tc_applicable(n, m, d, dqueries, dcodebooks, dbnorms);
+  const bool use_tc = (lut_kind == LUT_LSQ) && adc_tc_applicable(dcodes, n, m, d, dqueries, dcodebooks, dbnorms);
   AdcTcBase tcbase;
   DevBuf<uint32_t> dcandidx;
   DevBuf<int> dccnt;
   if (use_tc) {
-    LSQ_TRY(adc_tc_prepare(dcodes, n, m, dcodebooks, d, dbnorms, st, tcbase));
+    LSQ_TRY(adc_tc_prepare(dcodes, n, m, dcodebooks, d, dbnorms, s, stride, st, tcbase));
     LSQ_CUDA(dcandidx.alloc((size_t)qbatch * cap));
     LSQ_CUDA(dccnt.alloc(qbatch));
+    timer.mark("decode");
   }
   LSQ_CUDA(dbig.alloc(qbatch + 1));
   LSQ_CUDA(dlut.alloc((size_t)max_tiles * m * LSQ_H * QT));
@@ -780,26 +816,41 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
     const int nb = (int)std::min<int64_t>(qbatch, nq - q0);
     const int ntiles = (int)ceil_div(nb, QT);
     const float* dq = dqueries + (size_t)q0 * d;
-    LSQ_TRY(launch_lut(lut_kind, dq, nb, d, dcodebooks, m, S.kd, QT, dlut.p, st));
-    ScanParams p;
-    memset(&p, 0, sizeof(p));
-    p.codes = dcodes; p.norms = S.dnorms; p.lut = dlut.p; p.tau = dtau.p; p.cand = dcand.p; p.cnt = dcnt.p;
-    p.sbuf = dsbuf.p; p.cap = cap; p.nq = nb; p.id_base = S.id_base;
-    // sample pass -> thresholds
-    p.mode = MODE_SAMPLE; p.stride = stride; p.count = s;
-    LSQ_TRY(launch_scan(m, p, ntiles, st));
-    note_launch();
-    threshold_kernel<<<ntiles, 1024, 0, st>>>(dsbuf.p, s, (int)r, dtau.p);
-    LSQ_CUDA(cudaGetLastError());
-    // main pass
-    LSQ_CUDA(cudaMemsetAsync(dcnt.p, 0, (size_t)nb * sizeof(int), st));
-    LSQ_CUDA(cudaMemsetAsync(dbig.p + qbatch, 0, sizeof(int), st));
-    p.mode = MODE_MAIN; p.stride = 1; p.count = n;
     if (use_tc) {
-      LSQ_TRY(adc_tc_main_pass(tcbase, dcodes, n, m, dq, nb, d, dbnorms, dlut.p, QT, dtau.p, dcandidx.p, dccnt.p, cap,
+      // thresholds from the tensor-core values of the sample (any tau is valid: a query whose candidate count
+      // ends up < nn or > capacity is re-run), exact LUT rows, filter + exact rescoring of the survivors
+      const int tiles32 = (int)ceil_div(nb, 32);
+      LSQ_TRY(adc_tc_sample(tcbase, dq, nb, d, m, dsbuf.p, st));
+      timer.mark("sample");
+      note_launch();
+      threshold_kernel<<<tiles32, 1024, 0, st>>>(dsbuf.p, s, (int)r, dtau.p);
+      LSQ_CUDA(cudaGetLastError());
+      timer.mark("threshold");
+      LSQ_TRY(adc_tc_lut_rows(dq, nb, d, dcodebooks, m, dlut.p, st));
+      timer.mark("lut");
+      LSQ_CUDA(cudaMemsetAsync(dbig.p + qbatch, 0, sizeof(int), st));
+      LSQ_TRY(adc_tc_main_pass(tcbase, dcodes, n, m, dq, nb, d, dbnorms, dlut.p, dtau.p, dcandidx.p, dccnt.p, cap,
                                dcand.p, dcnt.p, cap, S.id_base, nullptr, 0, st));
+      timer.mark("filter+rescore");
     } else {
+      LSQ_TRY(launch_lut(lut_kind, dq, nb, d, dcodebooks, m, S.kd, QT, dlut.p, st));
+      ScanParams p;
+      memset(&p, 0, sizeof(p));
+      p.codes = dcodes; p.norms = S.dnorms; p.lut = dlut.p; p.tau = dtau.p; p.cand = dcand.p; p.cnt = dcnt.p;
+      p.sbuf = dsbuf.p; p.cap = cap; p.nq = nb; p.id_base = S.id_base;
+      // sample pass -> thresholds
+      p.mode = MODE_SAMPLE; p.stride = stride; p.count = s;
       LSQ_TRY(launch_scan(m, p, ntiles, st));
+      note_launch();
+      threshold_kernel<<<ntiles, 1024, 0, st>>>(dsbuf.p, s, (int)r, dtau.p);
+      LSQ_CUDA(cudaGetLastError());
+      // main pass
+      LSQ_CUDA(cudaMemsetAsync(dcnt.p, 0, (size_t)nb * sizeof(int), st));
+      LSQ_CUDA(cudaMemsetAsync(dbig.p + qbatch, 0, sizeof(int), st));
+      timer.mark("lut+sample+threshold");
+      p.mode = MODE_MAIN; p.stride = 1; p.count = n;
+      LSQ_TRY(launch_scan(m, p, ntiles, st));
+      timer.mark("scan");
     }
     // most queries end up with a few thousand candidates and nn <= 1024: select + sort of the survivors
     // in 40 KB of shared memory (5 CTAs per SM); the 128 KB sorter only runs for the queries it flags
@@ -811,6 +862,7 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
                                                                  ddists + (size_t)q0 * nn, dids + (size_t)q0 * nn,
                                                                  dstatus.p, 2, dbig.p, dbig.p + qbatch);
     LSQ_CUDA(cudaGetLastError());
+    timer.mark("topk");
     LSQ_CUDA(cudaMemcpyAsync(hstatus.data(), dstatus.p, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, st));
     LSQ_CUDA(cudaStreamSynchronize(st));
     for (int i = 0; i < nb; i++)
