@@ -227,7 +227,7 @@ int lsq_dev_linscan(const uint8_t* dcodes, int64_t n, int m, const float* dqueri
 
 /* Test hook of the tensor-core ADC prefilter (csrc/adc_tc.cu): the filter values dbnorm[v] - 2<q, xhat_v> as the
  * bf16 hi/lo tcgen05 GEMM computes them, for every (query, base vector) pair.  dout: float [nq][ld],
- * ld >= 128*ceil(n/128); columns >= n are padding (+inf).  Needs d % 16 == 0, 16 <= d <= 128. */
+ * ld >= 128*ceil(n/128); columns >= n are padding (> 1e37).  Needs d % 16 == 0, 16 <= d <= 128. */
 int lsq_dev_adc_filter_values(const uint8_t* dcodes, int64_t n, int m, const float* dqueries, int nq, int d,
                               const float* dcodebooks, const float* dbnorms, float* dout, int64_t ld, void* stream);
 

@@ -8,27 +8,34 @@
 // to be bit-exact for the pairs that survive.  This file therefore splits the main pass of linscan.cu in two:
 //
 //   1. adc_decode_kernel   xhat_v in fp32, split into bf16 hi + lo, written as ready-made UMMA operand images
-//                          (K-major, no swizzle; one 64 KB block per 128 base vectors), plus max ||xhat||.
-//   2. adc_filter_kernel   tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), 3 products
-//                          lo(q).hi(x) + hi(q).lo(x) + hi(q).hi(x).  A CTA keeps 256 queries (two 128-row A
-//                          tiles, hi and lo) resident in TENSOR MEMORY, streams base tiles through a 3-stage
-//                          TMA ring, and its epilogue warps compare  dbnorm - 2*acc  with  tau_q + margin_q
-//                          straight out of TMEM: only the ids of the pairs that pass are written.
+//                          (K-major, no swizzle; one block per 128 base vectors), plus max ||xhat||.  The hi image
+//                          carries 16 extra K elements per vector: the 3-term bf16 split of -dbnorm/2 and three 1s.
+//   2. adc_filter_kernel   tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM): hi(q).lo(x) + hi(q).hi(x).  A CTA
+//                          keeps 256 queries (two 128-row A tiles) resident in TENSOR MEMORY for its whole life —
+//                          each row extended by three 1s and the 3-term split of (tau_q + margin_q)/2 — and streams
+//                          base tiles through a 3-stage TMA ring.  With the extra K elements the accumulator IS
+//                              <hi(q), x> - dbnorm/2 + (tau_q + margin_q)/2  =  ((tau_q + margin_q) - dist) / 2,
+//                          so "this pair may be among the nn nearest" is its SIGN BIT: the epilogue warps gather
+//                          sign bits straight out of TMEM (one funnel shift per pair, no load, no compare) and only
+//                          the ids of the pairs that pass are written.
 //   3. adc_rescore_kernel  the survivors (a few thousand per query) are scored EXACTLY like the reference —
-//                          ((0 + LUT_0[c0]) + LUT_1[c1]) + ... + dbnorm, fp32 adds in that order, from the same
-//                          LUT the scan kernel uses — and appended as keys iff dist <= tau_q.
+//                          ((0 + LUT_0[c0]) + LUT_1[c1]) + ... + dbnorm, fp32 adds in that order — and appended as
+//                          keys iff dist <= tau_q.
 //
 // The keys that reach the top-k kernels are therefore the same SET the thresholded scan produces, provided
-// margin_q bounds |filter value - reference value|.  Bound used (u = 2^-24):
-//     reference:  |d_ref - D| <= (d+m+2) u (2 ||q|| m cmax + max|dbnorm|)           (fp32 chains, Cauchy-Schwarz)
-//     filter:     |d_tc  - D| <= 2^-12 * 2 ||q|| max_v||xhat_v||  — the bf16 hi+lo split is good to 2^-16 per
-//                 operand, the dropped lo.lo term to 2^-17, fp32 accumulation of 3d products to well under
-//                 2^-13 (measured 3e-7 relative, tests/test_gpu_adc_tc.py), so 2^-12 leaves > 10x headroom.
-//     margin_q = 2^-12 * 2 ||q|| xmax + 2 (d+m+2) u (2 ||q|| m cmax + nmax)
+// margin_q bounds |filter value - reference value|.  Bound used (u = 2^-24; all norms Euclidean):
+//     reference:  |d_ref - D| <= (d+m+2) u (2 ||q|| m cmax + max|dbnorm|)        (fp32 chains, Cauchy-Schwarz)
+//     dropped lo(q) = q - bf16(q):      2 ||lo(q)|| xmax          (||lo(q)|| computed exactly per query; 0 for
+//                                                                  8-bit data such as SIFT descriptors)
+//     one-product mode drops hi(q).lo(x) as well:  2 ||q|| max_v ||lo(xhat_v)||   (computed exactly at decode)
+//     bf16 hi+lo split of xhat (2^-16), 3-term splits of the scalars (2^-24), fp32 accumulation in the tensor
+//     core:       2^-13 (2 ||q|| xmax + max|dbnorm| + |tau|)    — measured 1e-6 .. 3e-6 relative
+//                 (tests/test_gpu_adc_tc.py), i.e. > 40x headroom
 // A wider margin only lets a few more pairs through to the exact rescoring; it never changes the result.
 // Anything unusual (NaN, candidate overflow, fewer than nn survivors) ends on linscan.cu's exhaustive path,
-// exactly as before.  tests/: bit-identical ids and distances against the reference's own .so and against the
-// lookup scan (LSQ_B200_ADC=scan).
+// exactly as before.  The thresholds tau_q themselves come from the same kernel run on a strided sample of the
+// base set (any tau is valid, see linscan.cu).  tests/: bit-identical ids and distances against the reference's
+// own .so and against the lookup scan (LSQ_B200_ADC=scan).
 #include <cuda_bf16.h>
 #include <math.h>
 #include <stdlib.h>
@@ -43,19 +50,34 @@ constexpr int AT_M = 128;         // queries per A tile (UMMA M)
 constexpr int AT_NA = 2;          // A tiles resident in tensor memory per CTA
 constexpr int AT_N = 128;         // base vectors per tile (UMMA N)
 constexpr int AT_STAGES = 3;      // shared-memory ring of base tiles (hi + lo image = 64 KB each at d = 128)
-constexpr int AT_EPI_WARPS = 4 * AT_NA;
-constexpr int AT_W_TMA = AT_EPI_WARPS, AT_W_MMA = AT_EPI_WARPS + 1;
-constexpr int AT_THREADS = 32 * (AT_EPI_WARPS + 2);
+// epilogue warps: SPLIT warp sets share the 128 columns of a product (4 warps per set = the 4 lane quadrants)
+__host__ __device__ constexpr int at_epi_warps(int split) { return 4 * AT_NA * split; }
+__host__ __device__ constexpr int at_threads(int split) { return 32 * (at_epi_warps(split) + 2); }
 // K-major, no swizzle, 2-byte elements: core matrix = 8 rows x 8 elements (16 B per row, 128 B, contiguous);
 // 8-row groups are SBO apart, K-adjacent core matrices LBO apart
 constexpr uint32_t AT_SBO = 128u;
 constexpr uint32_t AT_LBO = (AT_N / 8) * 128u;
-// tensor-memory columns: hi(q) of A tile a at 64 a (128 bf16 = 64 columns); three accumulators of 128 columns at
-// 128 + 128 b, used round-robin by the (base tile, A tile) products
-constexpr int AT_NACC = 3;
-constexpr uint32_t AT_COL_A = 0u, AT_COL_ACC = 128u;
+// tensor-memory columns: A tile a at 72 a (d <= 128 bf16 of hi(q) = 64 columns, then 8 columns = 16 extra K
+// elements); two accumulators of 128 columns at 144 + 128 b, used alternately by the (base tile, A tile) products
+constexpr int AT_NACC = 2;
+constexpr uint32_t AT_COL_A = 0u, AT_A_STRIDE = 72u, AT_COL_ACC = 144u;
+constexpr float AT_BIG = 1.5e38f;   // "never passes": -AT_BIG as the folded norm of padding vectors / threshold of padding rows
 
-__host__ __device__ inline uint32_t at_part_bytes(int d) { return (uint32_t)(d / 8) * AT_LBO; }
+// operand images of one base tile: hi part = d/8 + 2 K chunks (the last two carry the 16 extra K elements), lo part = d/8
+__host__ __device__ inline uint32_t at_hi_bytes(int d) { return (uint32_t)(d / 8 + 2) * AT_LBO; }
+__host__ __device__ inline uint32_t at_lo_bytes(int d) { return (uint32_t)(d / 8) * AT_LBO; }
+__host__ __device__ inline uint32_t at_tile_bytes(int d) { return at_hi_bytes(d) + at_lo_bytes(d); }
+
+// x = a + b + c with a, b, c bf16 (24 significant bits: exact for normal fp32 values)
+__device__ __forceinline__ void bf16_split3(float x, uint32_t& a, uint32_t& b, uint32_t& c) {
+  const __nv_bfloat16 ha = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(ha);
+  const __nv_bfloat16 hb = __float2bfloat16_rn(r1);
+  const __nv_bfloat16 hc = __float2bfloat16_rn(r1 - __bfloat162float(hb));
+  a = (uint32_t)__bfloat16_as_ushort(ha);
+  b = (uint32_t)__bfloat16_as_ushort(hb);
+  c = (uint32_t)__bfloat16_as_ushort(hc);
+}
 
 __device__ __forceinline__ void bf16_split(float x, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat16 h = __float2bfloat16_rn(x);
@@ -87,18 +109,18 @@ __global__ void __launch_bounds__(256) adc_cbnorm_kernel(const float* __restrict
 //    time: lane = 16-byte piece of the d-float row, so every codeword row is ONE coalesced 512-byte load (the
 //    first version gathered 32-byte pieces per lane and was bound by the LSU: 1.8 ms at m = 16).
 //    Vector `sidx` of the image is base vector sidx * stride (stride > 1: the strided sample for the thresholds).
+//    Lane 0 adds the 16 extra K elements of the row to the hi image.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) adc_decode_kernel(const uint8_t* __restrict__ codes, int m,
                                                          const float* __restrict__ C, int d,
                                                          const float* __restrict__ norms, unsigned char* __restrict__ img,
-                                                         float* __restrict__ normpad, AdcStats* stats, int64_t count,
-                                                         int64_t stride) {
+                                                         AdcStats* stats, int64_t count, int64_t stride) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t tile = blockIdx.x;
   const bool lane_on = lane < d / 4;
-  const uint32_t part_bytes = at_part_bytes(d);
-  unsigned char* base = img + (size_t)tile * 2 * part_bytes;
-  uint32_t xb = 0u, nb = 0u;   // running maxima (bit patterns of non-negative floats)
+  const uint32_t hi_bytes = at_hi_bytes(d);
+  unsigned char* base = img + (size_t)tile * at_tile_bytes(d);
+  uint32_t xb = 0u, nb = 0u, lb = 0u;   // running maxima (bit patterns of non-negative floats)
 #pragma unroll 2
   for (int i = 0; i < 16; i++) {
     const int r = warp * 16 + i;
@@ -120,32 +142,49 @@ __global__ void __launch_bounds__(256) adc_decode_kernel(const uint8_t* __restri
       }
     }
     float n2 = fmaf(acc.x, acc.x, fmaf(acc.y, acc.y, fmaf(acc.z, acc.z, acc.w * acc.w)));
+    uint32_t h0, l0, h1, l1, h2, l2, h3, l3;
+    bf16_split(acc.x, h0, l0);
+    bf16_split(acc.y, h1, l1);
+    bf16_split(acc.z, h2, l2);
+    bf16_split(acc.w, h3, l3);
+    // ||x - hi(x)||^2 (bounds the product a one-pass filter drops); x - hi(x) is exact in fp32
+    const float e0 = acc.x - __uint_as_float(h0 << 16), e1 = acc.y - __uint_as_float(h1 << 16);
+    const float e2 = acc.z - __uint_as_float(h2 << 16), e3 = acc.w - __uint_as_float(h3 << 16);
+    float lo2 = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2, e2, e3 * e3)));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xFFFFFFFFu, n2, o);
+    for (int o = 16; o > 0; o >>= 1) {
+      n2 += __shfl_xor_sync(0xFFFFFFFFu, n2, o);
+      lo2 += __shfl_xor_sync(0xFFFFFFFFu, lo2, o);
+    }
+    const uint32_t row_off = (uint32_t)(r >> 3) * AT_SBO + (uint32_t)(r & 7) * 16u;
     if (lane_on) {
-      uint32_t h0, l0, h1, l1, h2, l2, h3, l3;
-      bf16_split(acc.x, h0, l0);
-      bf16_split(acc.y, h1, l1);
-      bf16_split(acc.z, h2, l2);
-      bf16_split(acc.w, h3, l3);
       // elements 4*lane .. 4*lane+3 of row r: K chunk lane/2, bytes (lane&1)*8 .. +7 of the 16-byte core-matrix row
-      const uint32_t off = (uint32_t)(lane >> 1) * AT_LBO + (uint32_t)(r >> 3) * AT_SBO + (uint32_t)(r & 7) * 16u + (uint32_t)(lane & 1) * 8u;
+      const uint32_t off = (uint32_t)(lane >> 1) * AT_LBO + row_off + (uint32_t)(lane & 1) * 8u;
       *reinterpret_cast<uint2*>(base + off) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));   // element k in the low half
-      *reinterpret_cast<uint2*>(base + part_bytes + off) = make_uint2(l0 | (l1 << 16), l2 | (l3 << 16));
+      *reinterpret_cast<uint2*>(base + hi_bytes + off) = make_uint2(l0 | (l1 << 16), l2 | (l3 << 16));
     }
     if (lane == 0) {
-      float nv = INFINITY;   // padding columns of the last tile never pass the filter
+      float half_neg = -AT_BIG;   // padding columns of the last tile never pass the filter
       if (valid) {
-        nv = norms[v];
+        const float nv = norms[v];
+        half_neg = -0.5f * nv;
         nb = max(nb, __float_as_uint(fabsf(nv)));   // a NaN is the largest pattern: it survives and poisons the margin
         xb = max(xb, __float_as_uint(n2));
+        lb = max(lb, __float_as_uint(lo2));
       }
-      normpad[sidx] = nv;
+      // extra K elements d .. d+15 of the hi image: -dbnorm/2 as three bf16 terms, three 1s (they meet the
+      // threshold terms of the query rows), zeros
+      uint32_t ca, cb, cc;
+      bf16_split3(half_neg, ca, cb, cc);
+      const uint32_t one = 0x3F80u;
+      *reinterpret_cast<uint4*>(base + (uint32_t)(d / 8) * AT_LBO + row_off) = make_uint4(ca | (cb << 16), cc | (one << 16), one | (one << 16), 0u);
+      *reinterpret_cast<uint4*>(base + (uint32_t)(d / 8 + 1) * AT_LBO + row_off) = make_uint4(0u, 0u, 0u, 0u);
     }
   }
   if (stats != nullptr && lane == 0) {
     atomicMax(&stats->xmax2_bits, xb);
     atomicMax(&stats->nmax_bits, nb);
+    atomicMax(&stats->xlo2_bits, lb);
   }
 }
 
@@ -219,16 +258,15 @@ __global__ void __launch_bounds__(256) adc_lut_rows_kernel(const float* __restri
 // ------------------------------------------------------------------------------------------------
 struct AdcFilterParams {
   const float* queries;      // [nq][d]
-  const unsigned char* img;  // [ntiles][2][part_bytes]
-  const float* normpad;      // [ntiles*128]
+  const unsigned char* img;  // [ntiles][at_tile_bytes(d)]
   const float* tau;          // [nq] (threshold_kernel's layout with 32-query tiles)
   const AdcStats* stats;
   uint32_t* candidx;         // [nq][ccap] 0-based base indices that passed
   int* ccnt;                 // [nq]
-  float* dbg;                // optional: [nq][dbg_ld] filter values (tests)
+  float* dbg;                // values mode: [nq][dbg_ld] filter values (tests)
   uint32_t* sbuf;            // sample mode: ordered filter values, threshold_kernel's layout [(q/32 * scount + t) * 32 + q%32]
   int64_t n, ntiles, ccap, dbg_ld, scount;
-  int nq, d, m, exp;
+  int nq, d, m, exp, npass;
 };
 
 __device__ __forceinline__ void at_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -256,6 +294,12 @@ __device__ __forceinline__ void at_st32(uint32_t taddr, const uint32_t (&r)[32])
       : "memory");
 }
 
+__device__ __forceinline__ void at_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
 // D[tmem] (+)= A[tmem] * B[smem], bf16 operands.  Called by every lane of the issuing warp in uniform control
 // flow; one elected lane issues (see unary_tc.cu: keeping the election inside the asm keeps the descriptors in
 // uniform registers).
@@ -281,35 +325,35 @@ __device__ __forceinline__ void at_commit_elected(uint64_t* bar) {
       : "memory");
 }
 
-// bit i of the result = (norm_i - 2 * acc_i <= thr) for the 32 accumulator columns in r; nrm4 -> their norms.
-// Four independent partial masks: one serial chain of 32 predicated ORs was a third of the epilogue's latency.
-__device__ __forceinline__ uint32_t at_scan32(const uint32_t (&r)[32], const float4* __restrict__ nrm4, float thr,
-                                              float* __restrict__ dbg) {
-  uint32_t m0 = 0u, m1 = 0u, m2 = 0u, m3 = 0u;
+// bit i of the result = SIGN bit of accumulator column i (set = the pair does NOT pass).  One funnel shift per
+// value, four independent chains of eight.
+__device__ __forceinline__ uint32_t at_signs32(const uint32_t (&r)[32]) {
+  uint32_t s[4];
 #pragma unroll
-  for (int i4 = 0; i4 < 8; i4++) {
-    const float4 nv = __ldg(nrm4 + i4);   // the same address in every lane: one broadcast load
-    const float d0 = fmaf(-2.0f, __uint_as_float(r[4 * i4 + 0]), nv.x);
-    const float d1 = fmaf(-2.0f, __uint_as_float(r[4 * i4 + 1]), nv.y);
-    const float d2 = fmaf(-2.0f, __uint_as_float(r[4 * i4 + 2]), nv.z);
-    const float d3 = fmaf(-2.0f, __uint_as_float(r[4 * i4 + 3]), nv.w);
-    if (d0 <= thr) m0 |= 1u << (4 * i4 + 0);
-    if (d1 <= thr) m1 |= 1u << (4 * i4 + 1);
-    if (d2 <= thr) m2 |= 1u << (4 * i4 + 2);
-    if (d3 <= thr) m3 |= 1u << (4 * i4 + 3);
-    if (dbg != nullptr) { dbg[4 * i4 + 0] = d0; dbg[4 * i4 + 1] = d1; dbg[4 * i4 + 2] = d2; dbg[4 * i4 + 3] = d3; }
+  for (int c = 0; c < 4; c++) {
+    uint32_t x = 0u;
+#pragma unroll
+    for (int i = 7; i >= 0; i--) x = __funnelshift_l(r[8 * c + i], x, 1);   // x = (x << 1) | sign(r)
+    s[c] = x;
   }
-  return (m0 | m1) | (m2 | m3);
+  return (s[0] | (s[1] << 8)) | ((s[2] << 16) | (s[3] << 24));
 }
 
-__global__ void __launch_bounds__(AT_THREADS, 1) adc_filter_kernel(const __grid_constant__ AdcFilterParams p) {
+enum { AT_FILTER = 0, AT_SAMPLE = 1, AT_VALUES = 2 };   // what the epilogue does with the products
+
+template <int SPLIT, int MODE>
+__global__ void __launch_bounds__(at_threads(SPLIT), 1) adc_filter_kernel(const __grid_constant__ AdcFilterParams p) {
+  constexpr int EPI_WARPS = at_epi_warps(SPLIT), W_TMA = EPI_WARPS, W_MMA = EPI_WARPS + 1;
+  constexpr int HPW = 2 / SPLIT;   // 64-column halves of a product drained by one warp
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ uint64_t bar_full[AT_STAGES], bar_empty[AT_STAGES], bar_acc_full[AT_NACC], bar_acc_empty[AT_NACC];
   __shared__ uint32_t tmem_base_slot;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = p.d, ksteps = d / 16;
-  const uint32_t part_bytes = at_part_bytes(d), stage_bytes = 2u * part_bytes;
+  const int npass = p.npass;
+  const uint32_t hi_bytes = at_hi_bytes(d), tile_bytes = at_tile_bytes(d);
+  const uint32_t load_bytes = (npass == 2) ? tile_bytes : hi_bytes;   // one product: the lo image stays in HBM
   const int qbase = blockIdx.x * (AT_NA * AT_M);
   const int na = (p.nq - qbase > AT_M) ? 2 : 1;   // A tiles in use
   // this CTA's slice of the base tiles
@@ -320,7 +364,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) adc_filter_kernel(const __grid_
 
   if (tid == 0) {
     for (int s = 0; s < AT_STAGES; s++) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
-    for (int b = 0; b < AT_NACC; b++) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_empty[b], 4); }
+    for (int b = 0; b < AT_NACC; b++) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_empty[b], 4 * SPLIT); }
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -333,14 +377,16 @@ __global__ void __launch_bounds__(AT_THREADS, 1) adc_filter_kernel(const __grid_
   const uint32_t tmem = tmem_base_slot;
 
   // ---- stationary operand -> tensor memory: thread = query row (lane of its warp's quadrant); hi(q) in bf16,
-  //      two K elements per 32-bit column.  The same threads keep the threshold for the epilogue. ----
-  const int a_mine = warp >> 2, quad = warp & 3;
-  const int q = qbase + a_mine * AT_M + quad * 32 + lane;
-  const bool q_valid = (warp < AT_EPI_WARPS) && (a_mine < na) && (q < p.nq);
-  float thr = -INFINITY;   // rows without a query never pass `value <= thr`
-  if (warp < AT_EPI_WARPS && a_mine < na) {
+  //      two K elements per 32-bit column, then the 16 extra K elements: 1, 1, 1, the three bf16 terms of
+  //      (tau + margin) / 2, zeros.  Done once per CTA by the first warp set. ----
+  const int a_mine = (warp >> 2) & 1, quad = warp & 3, half0 = (warp >> 3) * HPW;
+  const int row = a_mine * AT_M + quad * 32 + lane;
+  const int q = qbase + row;
+  const bool is_epi = warp < EPI_WARPS && a_mine < na;
+  const bool q_valid = is_epi && (q < p.nq);
+  if (warp < 8 && a_mine < na) {
     const float* qrow = p.queries + (size_t)(q_valid ? q : 0) * d;
-    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16) + AT_COL_A + (uint32_t)a_mine * 64u;
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16) + AT_COL_A + (uint32_t)a_mine * AT_A_STRIDE;
     float qn2 = 0.0f, ql2 = 0.0f;   // ||q||^2 and ||q - hi(q)||^2
     for (int k0 = 0; k0 < d; k0 += 64) {
       uint32_t hi[32];
@@ -357,36 +403,60 @@ __global__ void __launch_bounds__(AT_THREADS, 1) adc_filter_kernel(const __grid_
         ql2 = fmaf(r0, r0, ql2); ql2 = fmaf(r1, r1, ql2); ql2 = fmaf(r2, r2, ql2); ql2 = fmaf(r3, r3, ql2);
         qn2 = fmaf(x.x, x.x, qn2); qn2 = fmaf(x.y, x.y, qn2); qn2 = fmaf(x.z, x.z, qn2); qn2 = fmaf(x.w, x.w, qn2);
       }
-      at_st32(lane_base + (uint32_t)(k0 >> 1), hi);
+      if (d - k0 >= 64) {
+        at_st32(lane_base + (uint32_t)(k0 >> 1), hi);
+      } else {   // d % 64 != 0: the tail in 8-column pieces, so that the extra columns right behind it stay free
+        for (int c0 = 0; c0 < (d - k0) / 2; c0 += 8) {
+          uint32_t part[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) part[i] = hi[c0 + i];
+          at_st8(lane_base + (uint32_t)(k0 >> 1) + (uint32_t)c0, part);
+        }
+      }
     }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-    if (q_valid && p.sbuf == nullptr) {
+    // threshold: the filter accumulates <hi(q), x> - dbnorm/2 + half_thr, which is >= 0 iff dist <= tau + margin
+    float half_thr = (MODE == AT_FILTER) ? -AT_BIG : 0.0f;   // rows without a query never pass; sample / values: plain values
+    if (q_valid && MODE == AT_FILTER) {
       const float tau = p.tau[q];
       const float qn = sqrtf(qn2) * 1.00001f, ql = sqrtf(ql2) * 1.00001f;
       const float xmax = sqrtf(__uint_as_float(p.stats->xmax2_bits)) * 1.00001f;
       const float cmax = sqrtf(__uint_as_float(p.stats->cmax2_bits)) * 1.00001f;
       const float nmax = __uint_as_float(p.stats->nmax_bits);
+      // one product only (hi(q).hi(x)): the dropped hi(q).lo(x) is bounded by 2 ||q|| max||lo(x)||, exactly like lo(q)
+      const float xlo = (npass == 1) ? sqrtf(__uint_as_float(p.stats->xlo2_bits)) * 1.00001f : 0.0f;
       const float eps_f = 1.0f / 8192.0f;                                   // 2^-13, see the header
       const float eps_r = 2.0f * (float)(d + p.m + 2) * 5.9604645e-8f;      // 2 (d+m+2) u
-      const float margin = 2.0f * ql * xmax + eps_f * 2.0f * qn * xmax + eps_r * (2.0f * qn * (float)p.m * cmax + nmax);
-      thr = tau + margin;   // NaN anywhere -> no pair passes -> the query is re-run exhaustively
+      float margin = 2.0f * ql * xmax + 2.0f * qn * xlo + eps_f * 2.0f * qn * xmax +
+                     eps_r * (2.0f * qn * (float)p.m * cmax + nmax);
+      margin += 1.01f * eps_f * (nmax + fabsf(tau) + margin);
+      half_thr = 0.5f * (tau + margin);
+      if (!(fabsf(half_thr) < AT_BIG)) half_thr = __uint_as_float(0x7FC00000u);   // NaN / overflow: poison the row -> exhaustive re-run
     }
+    {
+      uint32_t ta, tb, tc, ext[8];
+      bf16_split3(half_thr, ta, tb, tc);
+      const uint32_t one = 0x3F80u;
+      ext[0] = one | (one << 16); ext[1] = one | (ta << 16); ext[2] = tb | (tc << 16);
+#pragma unroll
+      for (int i = 3; i < 8; i++) ext[i] = 0u;
+      at_st8(lane_base + (uint32_t)(d >> 1), ext);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  if (warp == AT_W_TMA) {
-    // ===================== TMA: base tiles (hi + lo operand images), up to AT_STAGES ahead =====================
+  if (warp == W_TMA) {
+    // ===================== TMA: base tiles (operand images), up to AT_STAGES ahead =====================
     if (lane == 0) {
       for (int64_t t = 0; t < my_tiles; t++) {
         const int s = (int)(t % AT_STAGES);
         mbar_wait(&bar_empty[s], (uint32_t)((t / AT_STAGES) & 1) ^ 1u);
-        bulk_load_issue(smem_raw + (size_t)s * stage_bytes, p.img + (size_t)(t_lo + t) * stage_bytes, stage_bytes,
-                        &bar_full[s]);
+        bulk_load_issue(smem_raw + (size_t)s * tile_bytes, p.img + (size_t)(t_lo + t) * tile_bytes, load_bytes, &bar_full[s]);
       }
     }
-  } else if (warp == AT_W_MMA) {
+  } else if (warp == W_MMA) {
     // ===================== MMA issuer (whole warp, uniform; one elected lane issues) =====================
     // instruction descriptor: D = f32 (1 << 4), A = B = bf16 (1 << 7, 1 << 10), K-major both, N >> 3 at bit 17,
     // M >> 4 at bit 24
@@ -395,66 +465,76 @@ __global__ void __launch_bounds__(AT_THREADS, 1) adc_filter_kernel(const __grid_
     const uint64_t desc_hi = (uint64_t)((AT_SBO >> 4) | (1u << 14)) << 32;   // SBO, descriptor version 1
     const uint32_t desc_lbo = (AT_LBO >> 4) << 16;
     const uint32_t kstep_enc = (2u * AT_LBO) >> 4;                           // one MMA consumes K = 16 = 2 core matrices
-    int64_t j = 0;        // product index: (base tile t, A tile a) -> accumulator j % 3, its (j / 3)-th use
+    int64_t j = 0;        // product index: (base tile t, A tile a) -> accumulator j % 2, its (j / 2)-th use
     for (int64_t t = 0; t < my_tiles; t++) {
       const int s = (int)(t % AT_STAGES);
       mbar_wait(&bar_full[s], (uint32_t)((t / AT_STAGES) & 1));
-      const uint32_t stage_u = sB_u + (uint32_t)s * stage_bytes;
-      const uint32_t lo_hiX = desc_lbo | (stage_u >> 4), lo_loX = desc_lbo | ((stage_u + part_bytes) >> 4);
+      const uint32_t stage_u = sB_u + (uint32_t)s * tile_bytes;
+      const uint32_t lo_hiX = desc_lbo | (stage_u >> 4), lo_loX = desc_lbo | ((stage_u + hi_bytes) >> 4);
       for (int a = 0; a < na; a++) {
         const int b = (int)(j % AT_NACC);
         const uint32_t bu = (uint32_t)((j / AT_NACC) & 1);
         mbar_wait(&bar_acc_empty[b], bu ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t dcol = tmem + AT_COL_ACC + (uint32_t)b * AT_N;
-        const uint32_t a_hi = tmem + AT_COL_A + (uint32_t)a * 64u;
+        const uint32_t a_hi = tmem + AT_COL_A + (uint32_t)a * AT_A_STRIDE;
+        uint32_t accum = 0u;
+        if (npass == 2) {
 #pragma unroll 4
-        for (int k = 0; k < ksteps; k++)     // hi(q).lo(x)  (small terms first)
-          at_mma_bf16_ts(dcol, a_hi + (uint32_t)(8 * k), desc_hi | (lo_loX + (uint32_t)k * kstep_enc), idesc, k > 0);
-#pragma unroll 4
-        for (int k = 0; k < ksteps; k++)     // hi(q).hi(x)
-          at_mma_bf16_ts(dcol, a_hi + (uint32_t)(8 * k), desc_hi | (lo_hiX + (uint32_t)k * kstep_enc), idesc, 1u);
+          for (int k = 0; k < ksteps; k++) {   // hi(q).lo(x)  (small terms first)
+            at_mma_bf16_ts(dcol, a_hi + (uint32_t)(8 * k), desc_hi | (lo_loX + (uint32_t)k * kstep_enc), idesc, accum);
+            accum = 1u;
+          }
+        }
+#pragma unroll 3
+        for (int k = 0; k <= ksteps; k++) {    // hi(q).hi(x), and the extra K step: - dbnorm/2 + (tau + margin)/2
+          at_mma_bf16_ts(dcol, a_hi + (uint32_t)(8 * k), desc_hi | (lo_hiX + (uint32_t)k * kstep_enc), idesc, accum);
+          accum = 1u;
+        }
         if (a == na - 1) at_commit_elected(&bar_empty[s]);   // the stage may be refilled once these MMAs have read it
         at_commit_elected(&bar_acc_full[b]);
         j++;
       }
     }
-  } else if (a_mine < na) {
-    // ===================== epilogue: warps 4a .. 4a+3 drain the products of A tile a =====================
+  } else if (is_epi) {
+    // ===================== epilogue: 4 * SPLIT warps drain each product of their A tile =====================
     int* my_cnt = p.ccnt + (q_valid ? q : 0);
     uint32_t* my_list = p.candidx + (size_t)(q_valid ? q : 0) * p.ccap;
-    uint32_t* my_sbuf = (p.sbuf != nullptr && q_valid) ? (p.sbuf + ((size_t)(q >> 5) * p.scount) * 32 + (q & 31)) : nullptr;
+    uint32_t* my_sbuf = (MODE == AT_SAMPLE && q_valid) ? (p.sbuf + ((size_t)(q >> 5) * p.scount) * 32 + (q & 31)) : nullptr;
+    float* my_dbg = (MODE == AT_VALUES && q_valid) ? (p.dbg + (size_t)q * p.dbg_ld) : nullptr;
     // The list position of a tile's hits comes from an atomicAdd whose round trip (~1 us) must not sit in the
     // per-tile dependency chain: the add is issued at the end of tile t and its result is consumed, together
-    // with the saved hit masks, after the scans of tile t + 1.
-    uint32_t pmask[4] = {0u, 0u, 0u, 0u};
-    int64_t ppos = 0, pv0 = 0;
-    auto flush = [&]() {
+    // with the saved hit masks, after tile t + 1 has been drained.
+    uint32_t pmask[2 * HPW];
 #pragma unroll
-      for (int c = 0; c < 4; c++) {
+    for (int c = 0; c < 2 * HPW; c++) pmask[c] = 0u;
+    int ppos = 0;
+    int64_t pv0 = 0;
+    const int ccap32 = (int)((p.ccap < 0x7FFFFFFF) ? p.ccap : 0x7FFFFFFF);
+    auto flush = [&]() {
+      asm volatile("" : "+r"(ppos));   // the first use of the atomic's result stays HERE (not right behind the add)
+#pragma unroll
+      for (int c = 0; c < 2 * HPW; c++) {
         uint32_t mk = pmask[c];
         while (mk) {
           const int bit = __ffs(mk) - 1;
           mk &= mk - 1u;
-          if (ppos < p.ccap) my_list[ppos] = (uint32_t)(pv0 + c * 32 + bit);
+          if (ppos < ccap32) my_list[ppos] = (uint32_t)(pv0 + c * 32 + bit);
           ppos++;
         }
       }
     };
-    if (lane < 4 && my_tiles > 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.normpad + t_lo * AT_N + lane * 32));
     for (int64_t t = 0; t < my_tiles; t++) {
-      const int64_t j = t * na + a_mine;   // product index -> accumulator j % 3, its (j / 3)-th use
+      const int64_t j = t * na + a_mine;   // product index -> accumulator j % 2, its (j / 2)-th use
       const int b = (int)(j % AT_NACC);
       const uint32_t bu = (uint32_t)((j / AT_NACC) & 1);
-      const int64_t v0 = (t_lo + t) * AT_N;
-      // the next tile's norms (512 B) into L1 while this tile is processed
-      if (lane < 4 && t + 1 < my_tiles) asm volatile("prefetch.global.L1 [%0];" ::"l"(p.normpad + v0 + AT_N + lane * 32));
+      const int64_t v0 = (t_lo + t) * AT_N + half0 * 64;   // first base vector of this warp's columns
       mbar_wait(&bar_acc_full[b], bu);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + AT_COL_ACC + (uint32_t)b * AT_N;
-      const float4* nrm4 = reinterpret_cast<const float4*>(p.normpad + v0);
-      float* dbg = (p.dbg != nullptr && q_valid) ? (p.dbg + (size_t)q * p.dbg_ld + v0) : nullptr;
-      uint32_t mask[4] = {0u, 0u, 0u, 0u};
+      const uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + AT_COL_ACC + (uint32_t)b * AT_N + (uint32_t)(half0 * 64);
+      uint32_t mask[2 * HPW];
+#pragma unroll
+      for (int c = 0; c < 2 * HPW; c++) mask[c] = 0u;
       if (p.exp == 1) {   // experiment: no drain at all
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
@@ -462,42 +542,44 @@ __global__ void __launch_bounds__(AT_THREADS, 1) adc_filter_kernel(const __grid_
         continue;
       }
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
+      for (int h = 0; h < HPW; h++) {
         uint32_t r0[32], r1[32];
         at_ld32(taddr + (uint32_t)(h * 64), r0);
         at_ld32(taddr + (uint32_t)(h * 64 + 32), r1);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (h == 1) {   // every column is in registers: the accumulator may be overwritten
+        if (h == HPW - 1) {   // every column of this warp is in registers: its share of the accumulator is free
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
         }
-        if (my_sbuf != nullptr) {   // sample mode: keep the values, ordered for the radix select
+        if (MODE == AT_FILTER) {
+          mask[2 * h] = ~at_signs32(r0);
+          mask[2 * h + 1] = ~at_signs32(r1);
+        } else {
+          // the accumulator is <hi(q), x> - dbnorm/2: the filter's estimate of the distance is -2 * acc
 #pragma unroll
           for (int i = 0; i < 32; i++) {
             const int64_t c0 = v0 + h * 64 + i, c1 = c0 + 32;
-            if (c0 < p.scount) my_sbuf[(size_t)c0 * 32] = float_to_ordered(fmaf(-2.0f, __uint_as_float(r0[i]), p.normpad[c0]));
-            if (c1 < p.scount) my_sbuf[(size_t)c1 * 32] = float_to_ordered(fmaf(-2.0f, __uint_as_float(r1[i]), p.normpad[c1]));
+            const float d0 = -2.0f * __uint_as_float(r0[i]), d1 = -2.0f * __uint_as_float(r1[i]);
+            if (MODE == AT_SAMPLE) {   // ordered for the radix select of threshold_kernel
+              if (my_sbuf != nullptr && c0 < p.scount) my_sbuf[(size_t)c0 * 32] = float_to_ordered(d0);
+              if (my_sbuf != nullptr && c1 < p.scount) my_sbuf[(size_t)c1 * 32] = float_to_ordered(d1);
+            } else if (my_dbg != nullptr) {
+              my_dbg[c0] = d0;
+              my_dbg[c1] = d1;
+            }
           }
         }
-        if (p.exp == 2) {   // experiment: drain only (one cheap use of every register keeps the loads alive)
-          uint32_t x = 0u;
-#pragma unroll
-          for (int i = 0; i < 32; i++) x |= r0[i] & r1[i];
-          mask[h] = (x == 0x7FC12345u) ? 1u : 0u;
-          continue;
-        }
-        mask[2 * h] = at_scan32(r0, nrm4 + h * 16, thr, dbg ? dbg + h * 64 : nullptr);
-        mask[2 * h + 1] = at_scan32(r1, nrm4 + h * 16 + 8, thr, dbg ? dbg + h * 64 + 32 : nullptr);
       }
+      if (MODE != AT_FILTER) continue;
       flush();   // hits of the previous tile: their atomicAdd has had a whole tile to return
-      const int hits = __popc(mask[0]) + __popc(mask[1]) + __popc(mask[2]) + __popc(mask[3]);
+      int hits = 0;
 #pragma unroll
-      for (int c = 0; c < 4; c++) pmask[c] = mask[c];
+      for (int c = 0; c < 2 * HPW; c++) { hits += __popc(mask[c]); pmask[c] = mask[c]; }
       pv0 = v0;
-      if (hits > 0) ppos = (int64_t)atomicAdd(my_cnt, hits);   // thr = -inf for rows without a query, so q is valid here
+      if (hits > 0) ppos = atomicAdd(my_cnt, hits);   // rows without a query carry -AT_BIG: never here
     }
-    flush();
+    if (MODE == AT_FILTER) flush();
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -572,7 +654,7 @@ bool adc_tc_applicable(const uint8_t* dcodes, int64_t n, int m, int d, const flo
   if (!forced && n < 65536) return false;
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
-  const size_t need = (size_t)ceil_div(n, AT_N) * 2 * at_part_bytes(d);
+  const size_t need = (size_t)ceil_div(n, AT_N) * at_tile_bytes(d);
   return need < free_b / 4;
 }
 
@@ -581,19 +663,17 @@ int adc_tc_prepare(const uint8_t* dcodes, int64_t n, int m, const float* dcodebo
   B.ntiles = ceil_div(n, AT_N);
   B.scount = scount;
   B.stiles = ceil_div(scount, AT_N);
-  LSQ_CUDA(B.img.alloc((size_t)B.ntiles * 2 * at_part_bytes(d)));
-  LSQ_CUDA(B.normpad.alloc((size_t)B.ntiles * AT_N));
-  LSQ_CUDA(B.simg.alloc((size_t)B.stiles * 2 * at_part_bytes(d)));
-  LSQ_CUDA(B.snormpad.alloc((size_t)B.stiles * AT_N));
+  LSQ_CUDA(B.img.alloc((size_t)B.ntiles * at_tile_bytes(d)));
+  LSQ_CUDA(B.simg.alloc((size_t)B.stiles * at_tile_bytes(d)));
   LSQ_CUDA(B.stats.alloc(1));
   LSQ_CUDA(cudaMemsetAsync(B.stats.p, 0, sizeof(AdcStats), st));
   note_launch();
   adc_cbnorm_kernel<<<(unsigned)ceil_div((int64_t)m * LSQ_H, 256), 256, 0, st>>>(dcodebooks, m * LSQ_H, d, B.stats.p);
   note_launch();
-  adc_decode_kernel<<<(unsigned)B.ntiles, 256, 0, st>>>(dcodes, m, dcodebooks, d, dbnorms, B.img.p, B.normpad.p, B.stats.p, n, 1);
+  adc_decode_kernel<<<(unsigned)B.ntiles, 256, 0, st>>>(dcodes, m, dcodebooks, d, dbnorms, B.img.p, B.stats.p, n, 1);
   if (B.stiles > 0) {
     note_launch();
-    adc_decode_kernel<<<(unsigned)B.stiles, 256, 0, st>>>(dcodes, m, dcodebooks, d, dbnorms, B.simg.p, B.snormpad.p, nullptr,
+    adc_decode_kernel<<<(unsigned)B.stiles, 256, 0, st>>>(dcodes, m, dcodebooks, d, dbnorms, B.simg.p, nullptr,
                                                          scount, sstride);
   }
   LSQ_CUDA(cudaGetLastError());
@@ -618,10 +698,21 @@ static int filter_slices(int groups, int64_t ntiles) {
 static int launch_filter(AdcFilterParams& p, cudaStream_t st) {
   const int groups = (int)ceil_div(p.nq, AT_NA * AT_M);
   const int slices = filter_slices(groups, p.ntiles);
-  const size_t smem = (size_t)AT_STAGES * 2 * at_part_bytes(p.d);
-  LSQ_CUDA(cudaFuncSetAttribute(adc_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t smem = (size_t)AT_STAGES * at_tile_bytes(p.d);
+  int split = 1;
+  if (const char* e = getenv("LSQ_B200_ADC_SPLIT")) split = (atoi(e) == 2) ? 2 : 1;   // A/B switch of the epilogue width
+  const int mode = (p.sbuf != nullptr) ? AT_SAMPLE : (p.dbg != nullptr) ? AT_VALUES : AT_FILTER;
   note_launch();
-  adc_filter_kernel<<<dim3(groups, slices, 1), AT_THREADS, smem, st>>>(p);
+#define LSQ_AT_LAUNCH(SP, MD)                                                                                      \
+  do {                                                                                                             \
+    LSQ_CUDA(cudaFuncSetAttribute(adc_filter_kernel<SP, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    adc_filter_kernel<SP, MD><<<dim3(groups, slices, 1), at_threads(SP), smem, st>>>(p);                           \
+  } while (0)
+  if (mode == AT_SAMPLE) LSQ_AT_LAUNCH(1, AT_SAMPLE);
+  else if (mode == AT_VALUES) LSQ_AT_LAUNCH(1, AT_VALUES);
+  else if (split == 2) LSQ_AT_LAUNCH(2, AT_FILTER);
+  else LSQ_AT_LAUNCH(1, AT_FILTER);
+#undef LSQ_AT_LAUNCH
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
 }
@@ -630,8 +721,8 @@ static int launch_filter(AdcFilterParams& p, cudaStream_t st) {
 int adc_tc_sample(const AdcTcBase& B, const float* dq, int nb, int d, int m, uint32_t* dsbuf, cudaStream_t st) {
   AdcFilterParams p;
   memset(&p, 0, sizeof(p));
-  p.queries = dq; p.img = B.simg.p; p.normpad = B.snormpad.p; p.sbuf = dsbuf; p.scount = B.scount;
-  p.n = B.scount; p.ntiles = B.stiles; p.nq = nb; p.d = d; p.m = m;
+  p.queries = dq; p.img = B.simg.p; p.sbuf = dsbuf; p.scount = B.scount;
+  p.n = B.scount; p.ntiles = B.stiles; p.nq = nb; p.d = d; p.m = m; p.npass = 2;
   return launch_filter(p, st);
 }
 
@@ -651,10 +742,12 @@ int adc_tc_main_pass(const AdcTcBase& B, const uint8_t* dcodes, int64_t n, int m
                      int64_t dbg_ld, cudaStream_t st) {
   AdcFilterParams p;
   memset(&p, 0, sizeof(p));
-  p.queries = dq; p.img = B.img.p; p.normpad = B.normpad.p; p.tau = dtau; p.stats = B.stats.p;
+  p.queries = dq; p.img = B.img.p; p.tau = dtau; p.stats = B.stats.p;
   p.candidx = dcandidx; p.ccnt = dccnt; p.dbg = ddbg; p.n = n; p.ntiles = B.ntiles; p.ccap = ccap; p.dbg_ld = dbg_ld;
   p.nq = nb; p.d = d; p.m = m;
   if (const char* e = getenv("LSQ_B200_ADC_EXP")) p.exp = atoi(e);   // timing experiments only (results invalid)
+  p.npass = 2;
+  if (const char* e = getenv("LSQ_B200_ADC_PASSES")) p.npass = (atoi(e) == 1) ? 1 : 2;
   LSQ_CUDA(cudaMemsetAsync(dccnt, 0, (size_t)nb * sizeof(int), st));
   LSQ_TRY(launch_filter(p, st));
   if (dcand != nullptr) {

@@ -9,14 +9,13 @@ struct AdcStats {
   unsigned int xmax2_bits;  // max_v ||xhat_v||^2
   unsigned int nmax_bits;   // max_v |dbnorm_v|
   unsigned int cmax2_bits;  // max codeword ||c||^2
-  unsigned int pad;
+  unsigned int xlo2_bits;   // max_v ||xhat_v - bf16(xhat_v)||^2
 };
 
-// per-call image of the base set: bf16 hi/lo UMMA operand tiles of the decoded vectors, padded norms, maxima;
+// per-call image of the base set: bf16 hi/lo UMMA operand tiles of the decoded vectors (norms folded in), maxima;
 // the same for the strided sample the thresholds are estimated on
 struct AdcTcBase {
   DevBuf<unsigned char> img, simg;
-  DevBuf<float> normpad, snormpad;
   DevBuf<AdcStats> stats;
   int64_t ntiles = 0, stiles = 0, scount = 0;
 };

@@ -58,7 +58,7 @@ def test_filter_values_match_float64(gpu, n, nq, d, m, kind):
     D = norms.astype(np.float64)[None, :] - 2.0 * q_hi.astype(np.float64) @ xhat.T
     got = out[:, :n].astype(np.float64)
     assert np.all(np.isfinite(got)), "filter values missing (an epilogue warp skipped a tile?)"
-    assert np.all(np.isinf(out[:, n:])), "padding columns must carry +inf"
+    assert np.all(out[:, n:] > 1e37), "padding columns must carry a huge distance (they never pass the filter)"
     scale = 2.0 * np.linalg.norm(queries.astype(np.float64), axis=1)[:, None] * np.linalg.norm(xhat, axis=1).max()
     rel = np.abs(got - D) / scale
     print(f"filter: max |d_tc - D| / (2 |q| max|xhat|) = {rel.max():.3e}")
