@@ -49,7 +49,7 @@ namespace lsq {
 constexpr int AT_M = 128;         // queries per A tile (UMMA M)
 constexpr int AT_NA = 2;          // A tiles resident in tensor memory per CTA
 constexpr int AT_N = 128;         // base vectors per tile (UMMA N)
-constexpr int AT_STAGES = 3;      // shared-memory ring of base tiles (hi + lo image = 64 KB each at d = 128)
+constexpr int AT_STAGES = 6;      // max depth of the shared-memory ring of base tiles (as many as fit ~200 KB: 5 x 36 KB in one-product mode)
 // epilogue warps: SPLIT warp sets share the 128 columns of a product (4 warps per set = the 4 lane quadrants)
 __host__ __device__ constexpr int at_epi_warps(int split) { return 4 * AT_NA * split; }
 __host__ __device__ constexpr int at_threads(int split) { return 32 * (at_epi_warps(split) + 2); }
@@ -266,7 +266,7 @@ struct AdcFilterParams {
   float* dbg;                // values mode: [nq][dbg_ld] filter values (tests)
   uint32_t* sbuf;            // sample mode: ordered filter values, threshold_kernel's layout [(q/32 * scount + t) * 32 + q%32]
   int64_t n, ntiles, ccap, dbg_ld, scount;
-  int nq, d, m, exp, npass;
+  int nq, d, m, exp, npass, nstages;
 };
 
 __device__ __forceinline__ void at_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -354,6 +354,7 @@ __global__ void __launch_bounds__(at_threads(SPLIT), 1) adc_filter_kernel(const 
   const int npass = p.npass;
   const uint32_t hi_bytes = at_hi_bytes(d), tile_bytes = at_tile_bytes(d);
   const uint32_t load_bytes = (npass == 2) ? tile_bytes : hi_bytes;   // one product: the lo image stays in HBM
+  const int nstages = p.nstages;
   const int qbase = blockIdx.x * (AT_NA * AT_M);
   const int na = (p.nq - qbase > AT_M) ? 2 : 1;   // A tiles in use
   // this CTA's slice of the base tiles
@@ -451,9 +452,9 @@ __global__ void __launch_bounds__(at_threads(SPLIT), 1) adc_filter_kernel(const 
     // ===================== TMA: base tiles (operand images), up to AT_STAGES ahead =====================
     if (lane == 0) {
       for (int64_t t = 0; t < my_tiles; t++) {
-        const int s = (int)(t % AT_STAGES);
-        mbar_wait(&bar_empty[s], (uint32_t)((t / AT_STAGES) & 1) ^ 1u);
-        bulk_load_issue(smem_raw + (size_t)s * tile_bytes, p.img + (size_t)(t_lo + t) * tile_bytes, load_bytes, &bar_full[s]);
+        const int s = (int)(t % nstages);
+        mbar_wait(&bar_empty[s], (uint32_t)((t / nstages) & 1) ^ 1u);
+        bulk_load_issue(smem_raw + (size_t)s * load_bytes, p.img + (size_t)(t_lo + t) * tile_bytes, load_bytes, &bar_full[s]);
       }
     }
   } else if (warp == W_MMA) {
@@ -467,9 +468,9 @@ __global__ void __launch_bounds__(at_threads(SPLIT), 1) adc_filter_kernel(const 
     const uint32_t kstep_enc = (2u * AT_LBO) >> 4;                           // one MMA consumes K = 16 = 2 core matrices
     int64_t j = 0;        // product index: (base tile t, A tile a) -> accumulator j % 2, its (j / 2)-th use
     for (int64_t t = 0; t < my_tiles; t++) {
-      const int s = (int)(t % AT_STAGES);
-      mbar_wait(&bar_full[s], (uint32_t)((t / AT_STAGES) & 1));
-      const uint32_t stage_u = sB_u + (uint32_t)s * tile_bytes;
+      const int s = (int)(t % nstages);
+      mbar_wait(&bar_full[s], (uint32_t)((t / nstages) & 1));
+      const uint32_t stage_u = sB_u + (uint32_t)s * load_bytes;
       const uint32_t lo_hiX = desc_lbo | (stage_u >> 4), lo_loX = desc_lbo | ((stage_u + hi_bytes) >> 4);
       for (int a = 0; a < na; a++) {
         const int b = (int)(j % AT_NACC);
@@ -698,9 +699,11 @@ static int filter_slices(int groups, int64_t ntiles) {
 static int launch_filter(AdcFilterParams& p, cudaStream_t st) {
   const int groups = (int)ceil_div(p.nq, AT_NA * AT_M);
   const int slices = filter_slices(groups, p.ntiles);
-  const size_t smem = (size_t)AT_STAGES * at_tile_bytes(p.d);
-  int split = 1;
-  if (const char* e = getenv("LSQ_B200_ADC_SPLIT")) split = (atoi(e) == 2) ? 2 : 1;   // A/B switch of the epilogue width
+  const size_t stage = (p.npass == 2) ? at_tile_bytes(p.d) : at_hi_bytes(p.d);
+  p.nstages = (int)std::min<size_t>(AT_STAGES, (size_t)(210 * 1024) / stage);
+  const size_t smem = (size_t)p.nstages * stage;
+  int split = 2;
+  if (const char* e = getenv("LSQ_B200_ADC_SPLIT")) split = (atoi(e) == 1) ? 1 : 2;   // A/B switch of the epilogue width
   const int mode = (p.sbuf != nullptr) ? AT_SAMPLE : (p.dbg != nullptr) ? AT_VALUES : AT_FILTER;
   note_launch();
 #define LSQ_AT_LAUNCH(SP, MD)                                                                                      \
@@ -746,6 +749,10 @@ int adc_tc_main_pass(const AdcTcBase& B, const uint8_t* dcodes, int64_t n, int m
   p.candidx = dcandidx; p.ccnt = dccnt; p.dbg = ddbg; p.n = n; p.ntiles = B.ntiles; p.ccap = ccap; p.dbg_ld = dbg_ld;
   p.nq = nb; p.d = d; p.m = m;
   if (const char* e = getenv("LSQ_B200_ADC_EXP")) p.exp = atoi(e);   // timing experiments only (results invalid)
+  // two products hi(q).lo(x) + hi(q).hi(x) by default.  LSQ_B200_ADC_PASSES=1 drops the first (9 instead of 17 MMAs
+  // per product, half the TMA bytes) for a margin wider by 2 ||q|| max||lo(x)||: measured 2.9 + 0.8 ms (filter +
+  // rescoring of 1.5x the candidates) against 3.05 + 0.5 ms on the 1 M x 10 K benchmark — no gain, so the tighter
+  // filter is the default.
   p.npass = 2;
   if (const char* e = getenv("LSQ_B200_ADC_PASSES")) p.npass = (atoi(e) == 1) ? 1 : 2;
   LSQ_CUDA(cudaMemsetAsync(dccnt, 0, (size_t)nb * sizeof(int), st));

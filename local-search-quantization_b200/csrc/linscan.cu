@@ -350,13 +350,91 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
 // 3a. per-query threshold: the r-th smallest (1-based) of the tile's sample, lane = query.
 //     MSB-first radix select, 4 passes of 8 bits over the ordered-uint distances.
 // ------------------------------------------------------------------------------------------------
+constexpr int THR_SMALL_R = 56;   // fast path of threshold_kernel: r <= 56 (of the 64 kept minima)
+constexpr int THR_LCAP = 191;     // per-query list it may collect (about 70 at r = 49) before falling back to the radix select
+
 __global__ void __launch_bounds__(1024) threshold_kernel(const uint32_t* __restrict__ sbuf, int64_t s, int r,
-                                                         float* __restrict__ tau) {
-  __shared__ int hist[32][257];
+                                                         float* __restrict__ tau, int qt) {
+  __shared__ int hist[32][257];       // radix path; the fast path reuses it as mins[64][32] + list[32][256]
   __shared__ uint32_t prefix[32];
   __shared__ int rank[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x;
+  const uint32_t* src = sbuf + (size_t)tile * s * 32 + lane;
+
+  if (r <= THR_SMALL_R) {
+    static_assert(8 * 257 >= 64 * 32 && 8 * 257 + 32 * (THR_LCAP + 1) <= 32 * 257, "fast-path buffers must fit the histogram");
+    // r is tiny against s (49 of 16384 for top-1000 of 1 M): two passes instead of four, no histogram.
+    // Pass 1: every (warp, query) keeps the 2 smallest of its 1/32 of the sample; the r-th smallest of those 64
+    // values bounds the r-th smallest of the whole sample from above (they are 64 distinct sample elements).
+    // Pass 2: the few values <= that bound are collected per query and ranked exactly.
+    uint32_t (*mins)[32] = reinterpret_cast<uint32_t (*)[32]>(&hist[0][0]);                   // [64][32]
+    uint32_t (*list)[THR_LCAP + 1] = reinterpret_cast<uint32_t (*)[THR_LCAP + 1]>(&hist[8][0]);   // [32][192], behind mins
+    uint32_t a = 0xFFFFFFFFu, b = 0xFFFFFFFFu;   // a <= b: the two smallest so far
+    const int64_t steps = (lane < qt) ? (s - warp + 31) / 32 : 0;   // lanes past the tile's queries hold no data
+    auto keep2 = [&](uint32_t v) {
+      if (v < b) {
+        if (v < a) { b = a; a = v; } else { b = v; }
+      }
+    };
+    int64_t i = 0;
+    for (; i + 8 <= steps; i += 8) {   // eight independent loads in flight per thread
+      uint32_t v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = __ldg(src + (warp + 32 * (i + u)) * 32);
+#pragma unroll
+      for (int u = 0; u < 8; u++) keep2(v[u]);
+    }
+    for (; i < steps; i++) keep2(__ldg(src + (warp + 32 * i) * 32));
+    mins[2 * warp][lane] = a;
+    mins[2 * warp + 1][lane] = b;
+    if (tid < 32) rank[tid] = 0;   // list fill counters
+    __syncthreads();
+    {
+      int ra = 0, rb = 0;   // ranks of a and b among the 64 values of this query (ties by position)
+      for (int j = 0; j < 64; j++) {
+        const uint32_t v = mins[j][lane];
+        ra += (v < a) || (v == a && j < 2 * warp);
+        rb += (v < b) || (v == b && j < 2 * warp + 1);
+      }
+      if (ra == r - 1) prefix[lane] = a;
+      if (rb == r - 1) prefix[lane] = b;
+    }
+    __syncthreads();
+    const uint32_t bound = prefix[lane];
+    __syncthreads();   // mins is dead from here on: list overlaps nothing of it, but keep the phases apart
+    auto collect = [&](uint32_t v) {
+      if (v <= bound) {
+        const int pos = atomicAdd(&rank[lane], 1);
+        if (pos <= THR_LCAP) list[lane][pos] = v;
+      }
+    };
+    for (i = 0; i + 8 <= steps; i += 8) {
+      uint32_t v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = __ldg(src + (warp + 32 * (i + u)) * 32);
+#pragma unroll
+      for (int u = 0; u < 8; u++) collect(v[u]);
+    }
+    for (; i < steps; i++) collect(__ldg(src + (warp + 32 * i) * 32));
+    __syncthreads();
+    const int c = rank[warp];   // warp w ranks the list of query w
+    const bool overflow = (warp < qt) && (c > THR_LCAP + 1);
+    if (!overflow) {
+      for (int e = lane; e < c; e += 32) {
+        const uint32_t v = list[warp][e];
+        int rk = 0;
+        for (int j = 0; j < c; j++) {
+          const uint32_t u = list[warp][j];
+          rk += (u < v) || (u == v && j < e);
+        }
+        if (rk == r - 1) tau[tile * 32 + warp] = ordered_to_float(v);
+      }
+    }
+    if (!__syncthreads_or(overflow)) return;
+    // a query collected more than the list holds (heavy ties, or the sample order defeated pass 1): radix select
+  }
+
   if (tid < 32) { prefix[tid] = 0; rank[tid] = r; }
   for (int pass = 0; pass < 4; pass++) {
     const int shift = 24 - 8 * pass;
@@ -823,7 +901,7 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
       LSQ_TRY(adc_tc_sample(tcbase, dq, nb, d, m, dsbuf.p, st));
       timer.mark("sample");
       note_launch();
-      threshold_kernel<<<tiles32, 1024, 0, st>>>(dsbuf.p, s, (int)r, dtau.p);
+      threshold_kernel<<<tiles32, 1024, 0, st>>>(dsbuf.p, s, (int)r, dtau.p, 32);
       LSQ_CUDA(cudaGetLastError());
       timer.mark("threshold");
       LSQ_TRY(adc_tc_lut_rows(dq, nb, d, dcodebooks, m, dlut.p, st));
@@ -842,7 +920,7 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
       p.mode = MODE_SAMPLE; p.stride = stride; p.count = s;
       LSQ_TRY(launch_scan(m, p, ntiles, st));
       note_launch();
-      threshold_kernel<<<ntiles, 1024, 0, st>>>(dsbuf.p, s, (int)r, dtau.p);
+      threshold_kernel<<<ntiles, 1024, 0, st>>>(dsbuf.p, s, (int)r, dtau.p, QT);
       LSQ_CUDA(cudaGetLastError());
       // main pass
       LSQ_CUDA(cudaMemsetAsync(dcnt.p, 0, (size_t)nb * sizeof(int), st));

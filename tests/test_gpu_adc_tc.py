@@ -41,21 +41,28 @@ def _ref(oracle, *a):
     (257, 130, 16, 1, "gauss"),      # d = 16: a single MMA K step
     (5000, 200, 96, 12, "sift"),     # d = 96: K not a multiple of 64
 ])
-def test_filter_values_match_float64(gpu, n, nq, d, m, kind):
+@pytest.mark.parametrize("passes", [2, 1])
+def test_filter_values_match_float64(gpu, n, nq, d, m, kind, passes, monkeypatch):
     import torch
+    monkeypatch.setenv("LSQ_B200_ADC_PASSES", str(passes))
     from lsq_b200 import device as dev
     mk = gauss_scan_problem if kind == "gauss" else make_scan_problem
     codes, queries, codebooks, norms = mk(7000 + n, n, nq, d, m)
     out = dev.adc_filter_values(torch.from_numpy(codes).cuda(), torch.from_numpy(queries).cuda(),
                                 torch.from_numpy(codebooks).cuda(), torch.from_numpy(norms).cuda()).cpu().numpy()
-    xhat = np.zeros((n, d), np.float64)
+    def bf16(x):   # round to nearest even, like __float2bfloat16_rn
+        b = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+        return (((b + 0x7FFF + ((b >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)).view(np.float32)
+
+    xhat32 = np.zeros((n, d), np.float32)   # the decode kernel sums the codewords in fp32, k ascending
     for k in range(m):
-        xhat += codebooks[k * 256 + codes[:, k].astype(np.int64)].astype(np.float64)
-    # the filter multiplies hi(q) = bf16(q) (round to nearest even) with hi(x) + lo(x); the dropped lo(q) part is
-    # covered by the 2 |lo(q)| max|xhat| term of the margin
-    qb = queries.view(np.uint32).astype(np.uint64)
-    q_hi = (((qb + 0x7FFF + ((qb >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)).view(np.float32)
-    D = norms.astype(np.float64)[None, :] - 2.0 * q_hi.astype(np.float64) @ xhat.T
+        xhat32 += codebooks[k * 256 + codes[:, k].astype(np.int64)]
+    xhat = xhat32.astype(np.float64)
+    # the filter multiplies hi(q) = bf16(q) with hi(x) + lo(x) (two products) or hi(x) alone (one product); what it
+    # drops is covered by the 2 |lo(q)| max|xhat| and 2 |q| max|lo(x)| terms of the margin
+    q_hi = bf16(queries)
+    x_used = xhat if passes == 2 else bf16(xhat32).astype(np.float64)
+    D = norms.astype(np.float64)[None, :] - 2.0 * q_hi.astype(np.float64) @ x_used.T
     got = out[:, :n].astype(np.float64)
     assert np.all(np.isfinite(got)), "filter values missing (an epilogue warp skipped a tile?)"
     assert np.all(out[:, n:] > 1e37), "padding columns must carry a huge distance (they never pass the filter)"
