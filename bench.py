@@ -228,10 +228,35 @@ def adc_measure(m, n, nq, nn, d=128, reps=3, cpu_queries=64, check_queries=16, r
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item()
     out = {"m": m, "n": n, "nq": nq, "nn": nn, "ms": ms, "queries_per_s": nq / (ms * 1e-3), "launches_per_call": launches}
+    tc = bool(lsq_b200.linscan_path(n, m, d))
+    out["path"] = ("tcgen05 bf16 filter GEMM (queries resident in TMEM, norm and threshold folded in, sign-bit epilogue) + "
+                   "exact rescoring of the survivors (csrc/adc_tc.cu)") if tc else "lookup-table scan (csrc/linscan.cu)"
     eff = nq * n * (m + 4) / (ms * 1e-3) / 1e9
     lookups = nq * n * m / (ms * 1e-3)
-    out.update({"effective_scan_GBps": eff, "effective_frac_of_hbm_peak": eff / peak / world,
-                "lookups_per_s": lookups, "lookup_frac_of_smem_bound": lookups / (world * 148 * 32 * 1.965e9)})
+    out.update({"pairs_per_s": nq * n / (ms * 1e-3), "effective_scan_GBps": eff, "effective_frac_of_hbm_peak": eff / peak / world})
+    if tc:
+        # two products of K = d plus one extra K step of 16 per (query, base vector) pair; the whole call is charged
+        flops = 2.0 * nq * n * (2 * d + 16)
+        bf16_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops_sustained", 1387.9)) \
+            if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1387.9
+        out.update({"filter_tflops_whole_call": flops / (ms * 1e-3) / 1e12,
+                    "frac_of_measured_bf16_peak_whole_call": flops / (ms * 1e-3) / 1e12 / bf16_peak / world,
+                    "equivalent_lookups_per_s": lookups})
+        # the lookup-table scan on the same problem (the path every shape took before this round's tensor-core filter)
+        os.environ["LSQ_B200_ADC"] = "scan"
+        try:
+            dev.linscan(dc, dq, dcb, dn, nn)
+            torch.cuda.synchronize()
+            a.record()
+            ds, is_ = dev.linscan(dc, dq, dcb, dn, nn)
+            b.record()
+            torch.cuda.synchronize()
+        finally:
+            del os.environ["LSQ_B200_ADC"]
+        out["lookup_scan_ms"] = a.elapsed_time(b)
+        out["equal_to_lookup_scan"] = bool(torch.equal(ds, dd) and torch.equal(is_, di))
+    else:
+        out.update({"lookups_per_s": lookups, "lookup_frac_of_smem_bound": lookups / (world * 148 * 32 * 1.965e9)})
     if cpu_leg and rank == 0:
         import oracle
         # exactness spot check against the reference .so (or the oracle restatement), which is also the CPU baseline

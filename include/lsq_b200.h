@@ -112,6 +112,10 @@ void linscan_aqd_query_extra_byte(float* dists, int* idx, unsigned char* codes, 
 void linscan_aqd_query(float* dists, unsigned int* res, unsigned char* codes, float* centers,
                        float* queries, int N, unsigned int NQ, int B, int K, int dim1codes,
                        int dim1queries, int subdim);
+/* which main pass linscan_lsq runs for this shape: 1 = tensor-core filter (tcgen05 bf16 GEMM over the decoded base
+ * vectors) + exact rescoring of the survivors (csrc/adc_tc.cu), 0 = lookup-table scan (csrc/linscan.cu).  Both give
+ * the reference's results bit for bit.  Environment override: LSQ_B200_ADC=scan|tc. */
+int lsq_linscan_path(int64_t n, int m, int d);
 /* status-returning twins of the two above (same arguments) */
 int lsq_linscan_lsq(float* dists, int* idx, const unsigned char* codes, const float* queries,
                     const float* codebooks, const float* dbnorms, int nqueries, int ncodes, int m, int h,

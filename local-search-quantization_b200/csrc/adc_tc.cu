@@ -451,10 +451,12 @@ __global__ void __launch_bounds__(at_threads(SPLIT), 1) adc_filter_kernel(const 
   if (warp == W_TMA) {
     // ===================== TMA: base tiles (operand images), up to AT_STAGES ahead =====================
     if (lane == 0) {
+      int s = 0;            // ring slot and the parity of its current use, kept incrementally (no division per tile)
+      uint32_t par = 0u;
       for (int64_t t = 0; t < my_tiles; t++) {
-        const int s = (int)(t % nstages);
-        mbar_wait(&bar_empty[s], (uint32_t)((t / nstages) & 1) ^ 1u);
+        mbar_wait(&bar_empty[s], par ^ 1u);
         bulk_load_issue(smem_raw + (size_t)s * load_bytes, p.img + (size_t)(t_lo + t) * tile_bytes, load_bytes, &bar_full[s]);
+        if (++s == nstages) { s = 0; par ^= 1u; }
       }
     }
   } else if (warp == W_MMA) {
@@ -467,9 +469,10 @@ __global__ void __launch_bounds__(at_threads(SPLIT), 1) adc_filter_kernel(const 
     const uint32_t desc_lbo = (AT_LBO >> 4) << 16;
     const uint32_t kstep_enc = (2u * AT_LBO) >> 4;                           // one MMA consumes K = 16 = 2 core matrices
     int64_t j = 0;        // product index: (base tile t, A tile a) -> accumulator j % 2, its (j / 2)-th use
+    int s = 0;            // ring slot and the parity of its current use
+    uint32_t par = 0u;
     for (int64_t t = 0; t < my_tiles; t++) {
-      const int s = (int)(t % nstages);
-      mbar_wait(&bar_full[s], (uint32_t)((t / nstages) & 1));
+      mbar_wait(&bar_full[s], par);
       const uint32_t stage_u = sB_u + (uint32_t)s * load_bytes;
       const uint32_t lo_hiX = desc_lbo | (stage_u >> 4), lo_loX = desc_lbo | ((stage_u + hi_bytes) >> 4);
       for (int a = 0; a < na; a++) {
@@ -496,6 +499,7 @@ __global__ void __launch_bounds__(at_threads(SPLIT), 1) adc_filter_kernel(const 
         at_commit_elected(&bar_acc_full[b]);
         j++;
       }
+      if (++s == nstages) { s = 0; par ^= 1u; }
     }
   } else if (is_epi) {
     // ===================== epilogue: 4 * SPLIT warps drain each product of their A tile =====================
@@ -607,6 +611,7 @@ __global__ void __launch_bounds__(256) adc_rescore_kernel(const uint8_t* __restr
   if (tid == 0) sh_n = 0;
   __syncthreads();
   const float tq = tau[q];
+  const bool vec16 = (reinterpret_cast<uintptr_t>(codes) & 15) == 0, vec8 = (reinterpret_cast<uintptr_t>(codes) & 7) == 0;
   const int64_t c_all = ccnt[q];
   const int64_t c = (c_all < ccap) ? c_all : ccap;
   const uint32_t* list = candidx + (size_t)q * ccap;
@@ -616,17 +621,26 @@ __global__ void __launch_bounds__(256) adc_rescore_kernel(const uint8_t* __restr
     if ((int64_t)v >= n) continue;
     const uint8_t* cp = codes + (size_t)v * m;
     float acc = 0.0f;
-    if ((m & 3) == 0) {
-      for (int k4 = 0; k4 < m; k4 += 4) {
-        const uint32_t w = *reinterpret_cast<const uint32_t*>(cp + k4);
-        acc = __fadd_rn(acc, lut[(k4 + 0) * LSQ_H + (w & 0xFFu)]);
-        acc = __fadd_rn(acc, lut[(k4 + 1) * LSQ_H + ((w >> 8) & 0xFFu)]);
-        acc = __fadd_rn(acc, lut[(k4 + 2) * LSQ_H + ((w >> 16) & 0xFFu)]);
-        acc = __fadd_rn(acc, lut[(k4 + 3) * LSQ_H + (w >> 24)]);
-      }
+    // the code row in ONE gather (16 / 8 / 4 bytes): the kernel is bound by L1 gather wavefronts, not by arithmetic
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+    if (m == 16 && vec16) {
+      const uint4 x = __ldg(reinterpret_cast<const uint4*>(cp));
+      w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
+    } else if (m == 8 && vec8) {
+      const uint2 x = __ldg(reinterpret_cast<const uint2*>(cp));
+      w[0] = x.x; w[1] = x.y;
+    } else if ((m & 3) == 0) {
+#pragma unroll
+      for (int k4 = 0; k4 < LSQ_MAXM; k4 += 4)
+        if (k4 < m) w[k4 >> 2] = *reinterpret_cast<const uint32_t*>(cp + k4);
     } else {
-      for (int k = 0; k < m; k++) acc = __fadd_rn(acc, lut[k * LSQ_H + cp[k]]);
+#pragma unroll
+      for (int k = 0; k < LSQ_MAXM; k++)
+        if (k < m) w[k >> 2] |= (uint32_t)cp[k] << (8 * (k & 3));
     }
+#pragma unroll
+    for (int k = 0; k < LSQ_MAXM; k++)
+      if (k < m) acc = __fadd_rn(acc, lut[k * LSQ_H + ((w[k >> 2] >> (8 * (k & 3))) & 0xFFu)]);
     acc = __fadd_rn(acc, norms[v]);
     if (acc <= tq) {
       const int pos = atomicAdd(&sh_n, 1);
@@ -641,18 +655,23 @@ __global__ void __launch_bounds__(256) adc_rescore_kernel(const uint8_t* __restr
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-bool adc_tc_applicable(const uint8_t* dcodes, int64_t n, int m, int d, const float* dqueries, const float* dcodebooks,
-                       const float* dbnorms) {
+// shape rule only (what lsq_linscan_path reports): LSQ tables, d a multiple of 16 up to 128, and enough base vectors
+// — below ~64 K the lookup scan is launch-bound anyway.  LSQ_B200_ADC=scan|tc overrides the size rule.
+bool adc_tc_shape_ok(int64_t n, int m, int d) {
   const char* mode = getenv("LSQ_B200_ADC");
   if (mode != nullptr && strcmp(mode, "scan") == 0) return false;
-  if (dbnorms == nullptr || d % 16 != 0 || d > 128 || m < 1 || m > LSQ_MAXM) return false;
+  if (d % 16 != 0 || d < 16 || d > 128 || m < 1 || m > LSQ_MAXM) return false;
+  const bool forced = (mode != nullptr && strcmp(mode, "tc") == 0);
+  return forced || n >= 65536;
+}
+
+bool adc_tc_applicable(const uint8_t* dcodes, int64_t n, int m, int d, const float* dqueries, const float* dcodebooks,
+                       const float* dbnorms) {
+  if (dbnorms == nullptr || !adc_tc_shape_ok(n, m, d)) return false;
   if ((reinterpret_cast<uintptr_t>(dqueries) & 15) || (reinterpret_cast<uintptr_t>(dcodebooks) & 15) ||
       (reinterpret_cast<uintptr_t>(dcodes) & 3))
     return false;
-  const bool forced = (mode != nullptr && strcmp(mode, "tc") == 0);
-  // below ~64 K base vectors the lookup scan is launch-bound anyway; above the memory gate the images would
-  // crowd out the caller (4 d bytes per base vector)
-  if (!forced && n < 65536) return false;
+  // above the memory gate the images would crowd out the caller (about 4 d bytes per base vector)
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
   const size_t need = (size_t)ceil_div(n, AT_N) * at_tile_bytes(d);
@@ -768,6 +787,8 @@ int adc_tc_main_pass(const AdcTcBase& B, const uint8_t* dcodes, int64_t n, int m
 }  // namespace lsq
 
 using namespace lsq;
+
+extern "C" int lsq_linscan_path(int64_t n, int m, int d) { return adc_tc_shape_ok(n, m, d) ? 1 : 0; }
 
 // Test hook: the filter values  dbnorm[v] - 2 <q, xhat_v>  as the tensor cores compute them, for every pair.
 // dout: device float [nq][ld], ld >= 128 * ceil(n / 128).  Nothing passes the filter (NaN thresholds).

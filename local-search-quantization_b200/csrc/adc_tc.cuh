@@ -20,6 +20,7 @@ struct AdcTcBase {
   int64_t ntiles = 0, stiles = 0, scount = 0;
 };
 
+bool adc_tc_shape_ok(int64_t n, int m, int d);
 bool adc_tc_applicable(const uint8_t* dcodes, int64_t n, int m, int d, const float* dqueries, const float* dcodebooks,
                        const float* dbnorms);
 // base image + image of the sample {i * sstride : i < scount}
