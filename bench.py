@@ -242,6 +242,20 @@ def adc_measure(m, n, nq, nn, d=128, reps=3, cpu_queries=64, check_queries=16, r
         out.update({"filter_tflops_whole_call": flops / (ms * 1e-3) / 1e12,
                     "frac_of_measured_bf16_peak_whole_call": flops / (ms * 1e-3) / 1e12 / bf16_peak / world,
                     "equivalent_lookups_per_s": lookups})
+        # device time of every phase of one more call (CUDA events inside the library), and the filter kernel alone
+        # against the tensor-core peak: 2 (2 d + 16) flop per (query, base vector) pair
+        os.environ["LSQ_B200_ADC_TIMING"] = "1"
+        try:
+            dev.linscan(dc, dq, dcb, dn, nn)
+            torch.cuda.synchronize()
+            ph = lsq_b200.linscan_last_phases()
+        finally:
+            del os.environ["LSQ_B200_ADC_TIMING"]
+        out["phases_ms"] = {k: round(v, 3) for k, v in ph.items()}
+        if ph.get("filter"):
+            ftf = 2.0 * (qhi - qlo) * n * (2 * d + 16) / (ph["filter"] * 1e-3) / 1e12
+            out["filter_kernel"] = {"ms": ph["filter"], "tflops": ftf, "frac_of_measured_bf16_peak": ftf / bf16_peak,
+                                    "frac_of_nominal_bf16_peak": ftf / 2250.0, "bound": "tensor (17 tcgen05.mma of 128x128x16 per 128 queries x 128 base vectors)"}
         # the lookup-table scan on the same problem (the path every shape took before this round's tensor-core filter)
         os.environ["LSQ_B200_ADC"] = "scan"
         try:

@@ -116,6 +116,10 @@ void linscan_aqd_query(float* dists, unsigned int* res, unsigned char* codes, fl
  * vectors) + exact rescoring of the survivors (csrc/adc_tc.cu), 0 = lookup-table scan (csrc/linscan.cu).  Both give
  * the reference's results bit for bit.  Environment override: LSQ_B200_ADC=scan|tc. */
 int lsq_linscan_path(int64_t n, int m, int d);
+/* Measurement aid: with LSQ_B200_ADC_TIMING set in the environment every linscan call times its phases with CUDA
+ * events (and prints them to stderr); this returns the device time (ms) and name of phase i of the calling thread's
+ * most recent call, and the number of phases. */
+int lsq_linscan_last_phases(int i, float* ms, const char** name);
 /* status-returning twins of the two above (same arguments) */
 int lsq_linscan_lsq(float* dists, int* idx, const unsigned char* codes, const float* queries,
                     const float* codebooks, const float* dbnorms, int nqueries, int ncodes, int m, int h,

@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 __all__ = [
-    "LsqError", "lib", "lib_path", "have_library", "init", "init_devices", "num_bound_devices", "finalize", "device_count", "launch_count", "linscan_path", "version",
+    "LsqError", "lib", "lib_path", "have_library", "init", "init_devices", "num_bound_devices", "finalize", "device_count", "launch_count", "linscan_path", "linscan_last_phases", "version",
     "splitarray", "make_to_look", "make_perturb", "get_unaries", "get_binaries", "veccost", "qerror",
     "reconstruct", "quantize_norms", "encoding_icm", "reset_ils_counter", "encoding_icm_sched", "encode_icm_cuda",
     "update_codebooks", "linscan_lsq", "linscan_pq", "linscan_opq", "eval_recall", "randinit", "train_lsq",
@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "lsq_dev_build_unaries", "lsq_dev_build_unaries_tc", "lsq_dev_veccost", "lsq_dev_icm_ils", "lsq_dev_icm_visit_counter",
     "lsq_cb_stats_len", "lsq_cb_scale_exp", "lsq_dev_absmax", "lsq_dev_cb_accumulate", "lsq_dev_cb_finalize",
     "lsq_dev_cb_stats", "lsq_dev_cb_solve",
-    "lsq_dev_linscan", "lsq_dev_adc_filter_values", "lsq_linscan_path", "lsq_train_lsq", "lsq_kmeans1d", "lsq_eval_recall", "lsq_dev_eval_recall",
+    "lsq_dev_linscan", "lsq_dev_adc_filter_values", "lsq_linscan_path", "lsq_linscan_last_phases", "lsq_train_lsq", "lsq_kmeans1d", "lsq_eval_recall", "lsq_dev_eval_recall",
     "lsq_encoding_viterbi", "lsq_dev_viterbi",
 ]
 
@@ -132,6 +132,18 @@ def device_count():
 def linscan_path(n, m, d):
     """1 if linscan_lsq runs the tensor-core filter + exact rescoring for this shape, 0 for the lookup-table scan."""
     return int(lib().lsq_linscan_path(ct.c_int64(n), int(m), int(d)))
+
+
+def linscan_last_phases():
+    """{phase name: device ms} of the calling thread's most recent linscan call (needs LSQ_B200_ADC_TIMING set)."""
+    L = lib()
+    out = {}
+    n = L.lsq_linscan_last_phases(-1, None, None)
+    for i in range(n):
+        ms, name = ct.c_float(0), ct.c_char_p()
+        L.lsq_linscan_last_phases(i, ct.byref(ms), ct.byref(name))
+        out[name.value.decode()] = ms.value
+    return out
 
 
 def launch_count():

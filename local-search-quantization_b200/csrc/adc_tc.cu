@@ -776,11 +776,16 @@ int adc_tc_main_pass(const AdcTcBase& B, const uint8_t* dcodes, int64_t n, int m
   if (const char* e = getenv("LSQ_B200_ADC_PASSES")) p.npass = (atoi(e) == 1) ? 1 : 2;
   LSQ_CUDA(cudaMemsetAsync(dccnt, 0, (size_t)nb * sizeof(int), st));
   LSQ_TRY(launch_filter(p, st));
-  if (dcand != nullptr) {
-    note_launch();
-    adc_rescore_kernel<<<nb, 256, 0, st>>>(dcodes, n, m, dbnorms, dlutq, dtau, dcandidx, dccnt, ccap, dcand, dcnt, cap, id_base);
-    LSQ_CUDA(cudaGetLastError());
-  }
+  if (dcand != nullptr) LSQ_TRY(adc_tc_rescore(dcodes, n, m, nb, dbnorms, dlutq, dtau, dcandidx, dccnt, ccap, dcand, dcnt, cap, id_base, st));
+  return LSQ_OK;
+}
+
+int adc_tc_rescore(const uint8_t* dcodes, int64_t n, int m, int nb, const float* dbnorms, const float* dlutq,
+                   const float* dtau, const uint32_t* dcandidx, const int* dccnt, int64_t ccap, unsigned long long* dcand,
+                   int* dcnt, int64_t cap, int id_base, cudaStream_t st) {
+  note_launch();
+  adc_rescore_kernel<<<nb, 256, 0, st>>>(dcodes, n, m, dbnorms, dlutq, dtau, dcandidx, dccnt, ccap, dcand, dcnt, cap, id_base);
+  LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
 }
 

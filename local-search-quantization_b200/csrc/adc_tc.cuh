@@ -37,4 +37,9 @@ int adc_tc_main_pass(const AdcTcBase& B, const uint8_t* dcodes, int64_t n, int m
                      int64_t ccap, unsigned long long* dcand, int* dcnt, int64_t cap, int id_base, float* ddbg,
                      int64_t dbg_ld, cudaStream_t st);
 
+// exact rescoring of the filter's survivors: dcandidx / dccnt -> keys in dcand / dcnt (the buffers the top-k kernels read)
+int adc_tc_rescore(const uint8_t* dcodes, int64_t n, int m, int nb, const float* dbnorms, const float* dlutq,
+                   const float* dtau, const uint32_t* dcandidx, const int* dccnt, int64_t ccap, unsigned long long* dcand,
+                   int* dcnt, int64_t cap, int id_base, cudaStream_t st);
+
 }  // namespace lsq

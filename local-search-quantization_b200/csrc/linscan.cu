@@ -745,6 +745,8 @@ static int configure_topk() {
 
 // LSQ_B200_ADC_TIMING=1: device time of every phase of a linscan call (CUDA events on the call's stream), printed
 // to stderr at the end of the call.  Measurement aid; off by default (no events, no extra synchronisation).
+static thread_local std::vector<std::pair<std::string, float>> g_last_phases;   // of the calling thread's last timed call
+
 struct PhaseTimer {
   bool on;
   cudaStream_t st;
@@ -771,6 +773,12 @@ struct PhaseTimer {
     float tot = 0.0f;
     if (ev.size() > 1) cudaEventElapsedTime(&tot, ev.front().second, ev.back().second);
     fprintf(stderr, "%s | total %.3f\n", line.c_str(), tot);
+    g_last_phases.clear();
+    for (size_t i = 1; i < ev.size(); i++) {
+      float ms = 0.0f;
+      cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second);
+      g_last_phases.emplace_back(ev[i].first, ms);
+    }
     for (auto& e : ev) cudaEventDestroy(e.second);
   }
 };
@@ -908,8 +916,11 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
       timer.mark("lut");
       LSQ_CUDA(cudaMemsetAsync(dbig.p + qbatch, 0, sizeof(int), st));
       LSQ_TRY(adc_tc_main_pass(tcbase, dcodes, n, m, dq, nb, d, dbnorms, dlut.p, dtau.p, dcandidx.p, dccnt.p, cap,
-                               dcand.p, dcnt.p, cap, S.id_base, nullptr, 0, st));
-      timer.mark("filter+rescore");
+                               nullptr, nullptr, cap, S.id_base, nullptr, 0, st));
+      timer.mark("filter");
+      LSQ_TRY(adc_tc_rescore(dcodes, n, m, nb, dbnorms, dlut.p, dtau.p, dcandidx.p, dccnt.p, cap, dcand.p, dcnt.p, cap,
+                             S.id_base, st));
+      timer.mark("rescore");
     } else {
       LSQ_TRY(launch_lut(lut_kind, dq, nb, d, dcodebooks, m, S.kd, QT, dlut.p, st));
       ScanParams p;
@@ -1044,6 +1055,16 @@ void linscan_aqd_query(float* dists, unsigned int* res, unsigned char* codes, fl
                        unsigned int NQ, int B, int K, int dim1codes, int dim1queries, int subdim) {
   if (lsq_linscan_pq(dists, res, codes, centers, queries, N, NQ, B, K, dim1codes, dim1queries, subdim) != LSQ_OK)
     die("linscan_aqd_query");
+}
+
+// Measurement aid (with LSQ_B200_ADC_TIMING set): device time of phase i of the calling thread's most recent
+// linscan call; name (may be NULL) receives a pointer valid until the next call.  Returns the number of phases.
+int lsq_linscan_last_phases(int i, float* ms, const char** name) {
+  if (i >= 0 && i < (int)g_last_phases.size()) {
+    if (ms) *ms = g_last_phases[i].second;
+    if (name) *name = g_last_phases[i].first.c_str();
+  }
+  return (int)g_last_phases.size();
 }
 
 int lsq_dev_linscan(const uint8_t* dcodes, int64_t n, int m, const float* dqueries, int nq, int d,
