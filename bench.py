@@ -196,7 +196,7 @@ def run_reference(args):
 # scan bandwidth nq*n*(m+4)/t against the measured HBM peak (an *effective* figure — the
 # query-tiled kernel re-serves the code array from L2), the LUT lookup rate against the shared-memory bound
 # 148 SMs x 32 banks x f_SM, and the reference's own C++ (oracle/_ref, OpenMP) on a query subsample.
-def adc_measure(m, n, nq, nn, d=128, reps=3, cpu_queries=64, check_queries=16, rank=0, world=1, cpu_leg=True):
+def adc_measure(m, n, nq, nn, d=128, reps=5, cpu_queries=64, check_queries=16, rank=0, world=1, cpu_leg=True):
     """One ADC configuration on the current device.  With world > 1 the QUERIES are partitioned over the ranks
     (codes replicated, no merge: SURVEY.md §8e) and the time is the max over ranks."""
     import torch
@@ -217,17 +217,20 @@ def adc_measure(m, n, nq, nn, d=128, reps=3, cpu_queries=64, check_queries=16, r
         torch.cuda.synchronize()
     l0 = lsq_b200.launch_count()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(reps):
+    each = []
+    for _ in range(reps):   # every call timed on its own: the median is immune to a host hiccup between launches
+        a.record()
         dd, di = dev.linscan(dc, dq, dcb, dn, nn)
-    b.record()
-    torch.cuda.synchronize()
+        b.record()
+        torch.cuda.synchronize()
+        each.append(a.elapsed_time(b))
     launches = (lsq_b200.launch_count() - l0) // reps
-    t = torch.tensor([a.elapsed_time(b) / reps], device="cuda")
+    t = torch.tensor([float(np.median(each))], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = t.item()
-    out = {"m": m, "n": n, "nq": nq, "nn": nn, "ms": ms, "queries_per_s": nq / (ms * 1e-3), "launches_per_call": launches}
+    out = {"m": m, "n": n, "nq": nq, "nn": nn, "ms": ms, "queries_per_s": nq / (ms * 1e-3), "launches_per_call": launches,
+           "ms_each_call": [round(x, 3) for x in each], "timing": "median of the calls, each bracketed by CUDA events"}
     tc = bool(lsq_b200.linscan_path(n, m, d))
     out["path"] = ("tcgen05 bf16 filter GEMM (queries resident in TMEM, norm and threshold folded in, sign-bit epilogue) + "
                    "exact rescoring of the survivors (csrc/adc_tc.cu)") if tc else "lookup-table scan (csrc/linscan.cu)"
@@ -292,7 +295,7 @@ def run_adc(argv):
     ap.add_argument("--nn", type=int, default=1000)
     ap.add_argument("--m", type=int, nargs="+", default=[8, 16])
     ap.add_argument("--d", type=int, default=128)
-    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--cpu-queries", type=int, default=64)
     ap.add_argument("--check-queries", type=int, default=16)
     args = ap.parse_args(argv)
