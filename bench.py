@@ -231,7 +231,7 @@ def adc_measure(m, n, nq, nn, d=128, reps=5, cpu_queries=64, check_queries=16, r
     ms = t.item()
     out = {"m": m, "n": n, "nq": nq, "nn": nn, "ms": ms, "queries_per_s": nq / (ms * 1e-3), "launches_per_call": launches,
            "ms_each_call": [round(x, 3) for x in each], "timing": "median of the calls, each bracketed by CUDA events"}
-    tc = bool(lsq_b200.linscan_path(n, m, d))
+    tc = bool(lsq_b200.linscan_path(n, qhi - qlo, m, d))
     out["path"] = ("tcgen05 bf16 filter GEMM (queries resident in TMEM, norm and threshold folded in, sign-bit epilogue) + "
                    "exact rescoring of the survivors (csrc/adc_tc.cu)") if tc else "lookup-table scan (csrc/linscan.cu)"
     eff = nq * n * (m + 4) / (ms * 1e-3) / 1e9

@@ -129,9 +129,10 @@ def device_count():
     return int(lib().lsq_device_count())
 
 
-def linscan_path(n, m, d):
-    """1 if linscan_lsq runs the tensor-core filter + exact rescoring for this shape, 0 for the lookup-table scan."""
-    return int(lib().lsq_linscan_path(ct.c_int64(n), int(m), int(d)))
+def linscan_path(n, nq, m, d):
+    """1 if linscan_lsq runs the tensor-core filter + exact rescoring for n base vectors and nq queries, 0 for the
+    lookup-table scan."""
+    return int(lib().lsq_linscan_path(ct.c_int64(n), ct.c_int64(nq), int(m), int(d)))
 
 
 def linscan_last_phases():

@@ -655,19 +655,21 @@ __global__ void __launch_bounds__(256) adc_rescore_kernel(const uint8_t* __restr
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-// shape rule only (what lsq_linscan_path reports): LSQ tables, d a multiple of 16 up to 128, and enough base vectors
-// — below ~64 K the lookup scan is launch-bound anyway.  LSQ_B200_ADC=scan|tc overrides the size rule.
-bool adc_tc_shape_ok(int64_t n, int m, int d) {
+// shape rule only (what lsq_linscan_path reports): LSQ tables, d a multiple of 16 up to 128, enough base vectors —
+// below ~64 K the lookup scan is launch-bound anyway — and enough queries to pay for decoding the base set
+// (0.6-0.9 ms per million vectors, once per call): measured break-even against the lookup kernel at 1 M base vectors is
+// ~940 queries at m = 8 and ~250 at m = 16, i.e. nq * m of 4-8 K.  LSQ_B200_ADC=scan|tc overrides the size rules.
+bool adc_tc_shape_ok(int64_t n, int64_t nq, int m, int d) {
   const char* mode = getenv("LSQ_B200_ADC");
   if (mode != nullptr && strcmp(mode, "scan") == 0) return false;
   if (d % 16 != 0 || d < 16 || d > 128 || m < 1 || m > LSQ_MAXM) return false;
   const bool forced = (mode != nullptr && strcmp(mode, "tc") == 0);
-  return forced || n >= 65536;
+  return forced || (n >= 65536 && nq * m >= 8000);
 }
 
-bool adc_tc_applicable(const uint8_t* dcodes, int64_t n, int m, int d, const float* dqueries, const float* dcodebooks,
-                       const float* dbnorms) {
-  if (dbnorms == nullptr || !adc_tc_shape_ok(n, m, d)) return false;
+bool adc_tc_applicable(const uint8_t* dcodes, int64_t n, int64_t nq, int m, int d, const float* dqueries,
+                       const float* dcodebooks, const float* dbnorms) {
+  if (dbnorms == nullptr || !adc_tc_shape_ok(n, nq, m, d)) return false;
   if ((reinterpret_cast<uintptr_t>(dqueries) & 15) || (reinterpret_cast<uintptr_t>(dcodebooks) & 15) ||
       (reinterpret_cast<uintptr_t>(dcodes) & 3))
     return false;
@@ -793,7 +795,7 @@ int adc_tc_rescore(const uint8_t* dcodes, int64_t n, int m, int nb, const float*
 
 using namespace lsq;
 
-extern "C" int lsq_linscan_path(int64_t n, int m, int d) { return adc_tc_shape_ok(n, m, d) ? 1 : 0; }
+extern "C" int lsq_linscan_path(int64_t n, int64_t nq, int m, int d) { return adc_tc_shape_ok(n, nq, m, d) ? 1 : 0; }
 
 // Test hook: the filter values  dbnorm[v] - 2 <q, xhat_v>  as the tensor cores compute them, for every pair.
 // dout: device float [nq][ld], ld >= 128 * ceil(n / 128).  Nothing passes the filter (NaN thresholds).

@@ -20,9 +20,9 @@ struct AdcTcBase {
   int64_t ntiles = 0, stiles = 0, scount = 0;
 };
 
-bool adc_tc_shape_ok(int64_t n, int m, int d);
-bool adc_tc_applicable(const uint8_t* dcodes, int64_t n, int m, int d, const float* dqueries, const float* dcodebooks,
-                       const float* dbnorms);
+bool adc_tc_shape_ok(int64_t n, int64_t nq, int m, int d);
+bool adc_tc_applicable(const uint8_t* dcodes, int64_t n, int64_t nq, int m, int d, const float* dqueries,
+                       const float* dcodebooks, const float* dbnorms);
 // base image + image of the sample {i * sstride : i < scount}
 int adc_tc_prepare(const uint8_t* dcodes, int64_t n, int m, const float* dcodebooks, int d, const float* dbnorms,
                    int64_t scount, int64_t sstride, cudaStream_t st, AdcTcBase& B);

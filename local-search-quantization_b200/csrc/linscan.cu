@@ -879,7 +879,7 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
   DevBuf<int> dcnt, dstatus, dbig;  // dbig: worklist of the queries the select kernel flags + its length
   // LSQ tables of an inner product: the main pass runs as a tensor-core filter + exact rescoring of the
   // survivors (adc_tc.cu); everything around it (LUT, sample pass, thresholds, top-k, re-runs) is unchanged
-  const bool use_tc = (lut_kind == LUT_LSQ) && adc_tc_applicable(dcodes, n, m, d, dqueries, dcodebooks, dbnorms);
+  const bool use_tc = (lut_kind == LUT_LSQ) && adc_tc_applicable(dcodes, n, nq, m, d, dqueries, dcodebooks, dbnorms);
   AdcTcBase tcbase;
   DevBuf<uint32_t> dcandidx;
   DevBuf<int> dccnt;

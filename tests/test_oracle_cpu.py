@@ -292,3 +292,17 @@ def test_vecs_wire_formats(lsq, tmp_path):
         assert np.array_equal(r(path), a)
         assert np.array_equal(r(path, 5), a[:5])
         assert np.array_equal(r(path, (3, 9)), a[2:9])
+
+
+def test_linscan_path_rule(lsq, monkeypatch):
+    """Which main pass linscan_lsq takes is a pure shape rule (no GPU needed to ask)."""
+    monkeypatch.delenv("LSQ_B200_ADC", raising=False)
+    assert lsq.linscan_path(1_000_000, 10_000, 8, 128) == 1      # BASELINE configs[4]
+    assert lsq.linscan_path(1_000_000, 10_000, 16, 64) == 1
+    assert lsq.linscan_path(1_000_000, 100, 8, 128) == 0         # too few queries to pay for decoding the base set
+    assert lsq.linscan_path(50_000, 10_000, 8, 128) == 0         # small base set
+    assert lsq.linscan_path(1_000_000, 10_000, 8, 100) == 0      # d not a multiple of 16
+    monkeypatch.setenv("LSQ_B200_ADC", "scan")
+    assert lsq.linscan_path(1_000_000, 10_000, 8, 128) == 0
+    monkeypatch.setenv("LSQ_B200_ADC", "tc")
+    assert lsq.linscan_path(1000, 1, 8, 128) == 1
