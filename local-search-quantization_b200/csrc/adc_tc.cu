@@ -105,65 +105,89 @@ __global__ void __launch_bounds__(256) adc_cbnorm_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
-// 1. decode + split.  CTA = one tile of 128 base vectors, 8 warps x 16 vectors.  A warp sums one vector at a
-//    time: lane = 16-byte piece of the d-float row, so every codeword row is ONE coalesced 512-byte load (the
-//    first version gathered 32-byte pieces per lane and was bound by the LSU: 1.8 ms at m = 16).
-//    Vector `sidx` of the image is base vector sidx * stride (stride > 1: the strided sample for the thresholds).
-//    Lane 0 adds the 16 extra K elements of the row to the hi image.
+// 1. decode + split.  CTA = one tile of 128 base vectors, 8 warps x 16 vectors.  A warp sums TWO vectors at a
+//    time (rows 2i and 2i+1 of the tile, one per half-warp): lane = 32-byte piece of the d-float row, so every
+//    codeword row is one coalesced 512-byte load per half-warp, the per-vector address arithmetic is shared by two
+//    vectors, and the two half-warps write ADJACENT 16-byte rows of the same core matrices (whole 32-byte sectors;
+//    the first version gathered 32-byte pieces per lane and was bound by the LSU: 1.8 ms at m = 16, the second
+//    wrote half sectors: 0.74 ms).  Vector `sidx` of the image is base vector sidx * stride (stride > 1: the
+//    strided sample for the thresholds).  The lane with K chunk 0 adds the 16 extra K elements of its row.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) adc_decode_kernel(const uint8_t* __restrict__ codes, int m,
                                                          const float* __restrict__ C, int d,
                                                          const float* __restrict__ norms, unsigned char* __restrict__ img,
                                                          AdcStats* stats, int64_t count, int64_t stride) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int half = lane >> 4, kc = lane & 15;   // which vector of the pair, which K chunk of 8 elements
   const int64_t tile = blockIdx.x;
-  const bool lane_on = lane < d / 4;
+  const bool lane_on = kc < d / 8;
   const uint32_t hi_bytes = at_hi_bytes(d);
   unsigned char* base = img + (size_t)tile * at_tile_bytes(d);
+  const bool vec16 = (m == 16) && ((reinterpret_cast<uintptr_t>(codes) & 15) == 0);
+  const bool vec8 = (m == 8) && ((reinterpret_cast<uintptr_t>(codes) & 7) == 0);
   uint32_t xb = 0u, nb = 0u, lb = 0u;   // running maxima (bit patterns of non-negative floats)
 #pragma unroll 2
-  for (int i = 0; i < 16; i++) {
-    const int r = warp * 16 + i;
+  for (int i = 0; i < 8; i++) {
+    const int r = warp * 16 + 2 * i + half;
     const int64_t sidx = tile * AT_N + r;
     const bool valid = sidx < count;
     const int64_t v = sidx * stride;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid) {
-      const uint8_t* cp = codes + (size_t)v * m;   // the same bytes in every lane: broadcast loads
+    float acc[8];
 #pragma unroll
-      for (int k = 0; k < LSQ_MAXM; k++) {
-        if (k < m) {
-          const uint32_t c = cp[k];
-          if (lane_on) {
-            const float4 x = __ldg(reinterpret_cast<const float4*>(C + ((size_t)k * LSQ_H + c) * d) + lane);
-            acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    for (int e = 0; e < 8; e++) acc[e] = 0.0f;
+    if (valid) {
+      const uint8_t* cp = codes + (size_t)v * m;   // the same bytes in the 16 lanes of a half-warp: broadcast loads
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+      if (vec16) {
+        const uint4 x = __ldg(reinterpret_cast<const uint4*>(cp));
+        w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w;
+      } else if (vec8) {
+        const uint2 x = __ldg(reinterpret_cast<const uint2*>(cp));
+        w[0] = x.x; w[1] = x.y;
+      } else {
+#pragma unroll
+        for (int k = 0; k < LSQ_MAXM; k++)
+          if (k < m) w[k >> 2] |= (uint32_t)cp[k] << (8 * (k & 3));
+      }
+      if (lane_on) {
+#pragma unroll
+        for (int k = 0; k < LSQ_MAXM; k++) {
+          if (k < m) {
+            const uint32_t c = (w[k >> 2] >> (8 * (k & 3))) & 0xFFu;
+            const float4* row = reinterpret_cast<const float4*>(C + ((size_t)k * LSQ_H + c) * d) + 2 * kc;
+            const float4 a = __ldg(row), b = __ldg(row + 1);
+            acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+            acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
           }
         }
       }
     }
-    float n2 = fmaf(acc.x, acc.x, fmaf(acc.y, acc.y, fmaf(acc.z, acc.z, acc.w * acc.w)));
-    uint32_t h0, l0, h1, l1, h2, l2, h3, l3;
-    bf16_split(acc.x, h0, l0);
-    bf16_split(acc.y, h1, l1);
-    bf16_split(acc.z, h2, l2);
-    bf16_split(acc.w, h3, l3);
-    // ||x - hi(x)||^2 (bounds the product a one-pass filter drops); x - hi(x) is exact in fp32
-    const float e0 = acc.x - __uint_as_float(h0 << 16), e1 = acc.y - __uint_as_float(h1 << 16);
-    const float e2 = acc.z - __uint_as_float(h2 << 16), e3 = acc.w - __uint_as_float(h3 << 16);
-    float lo2 = fmaf(e0, e0, fmaf(e1, e1, fmaf(e2, e2, e3 * e3)));
+    float n2 = 0.0f, lo2 = 0.0f;
+    uint32_t hi[4], lo[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int e = 0; e < 4; e++) {
+      uint32_t h0, l0, h1, l1;
+      bf16_split(acc[2 * e], h0, l0);
+      bf16_split(acc[2 * e + 1], h1, l1);
+      hi[e] = h0 | (h1 << 16);   // element k in the low half, k + 1 in the high half (little endian)
+      lo[e] = l0 | (l1 << 16);
+      // ||x - hi(x)||^2 bounds the product a one-pass filter drops; x - hi(x) is exact in fp32
+      const float e0 = acc[2 * e] - __uint_as_float(h0 << 16), e1 = acc[2 * e + 1] - __uint_as_float(h1 << 16);
+      n2 = fmaf(acc[2 * e], acc[2 * e], fmaf(acc[2 * e + 1], acc[2 * e + 1], n2));
+      lo2 = fmaf(e0, e0, fmaf(e1, e1, lo2));
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {   // over the 16 lanes of the half-warp
       n2 += __shfl_xor_sync(0xFFFFFFFFu, n2, o);
       lo2 += __shfl_xor_sync(0xFFFFFFFFu, lo2, o);
     }
     const uint32_t row_off = (uint32_t)(r >> 3) * AT_SBO + (uint32_t)(r & 7) * 16u;
     if (lane_on) {
-      // elements 4*lane .. 4*lane+3 of row r: K chunk lane/2, bytes (lane&1)*8 .. +7 of the 16-byte core-matrix row
-      const uint32_t off = (uint32_t)(lane >> 1) * AT_LBO + row_off + (uint32_t)(lane & 1) * 8u;
-      *reinterpret_cast<uint2*>(base + off) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));   // element k in the low half
-      *reinterpret_cast<uint2*>(base + hi_bytes + off) = make_uint2(l0 | (l1 << 16), l2 | (l3 << 16));
+      const uint32_t off = (uint32_t)kc * AT_LBO + row_off;   // elements 8 kc .. 8 kc + 7 of row r: one 16-byte core-matrix row
+      *reinterpret_cast<uint4*>(base + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(base + hi_bytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
-    if (lane == 0) {
+    if (kc == 0) {
       float half_neg = -AT_BIG;   // padding columns of the last tile never pass the filter
       if (valid) {
         const float nv = norms[v];
@@ -181,7 +205,7 @@ __global__ void __launch_bounds__(256) adc_decode_kernel(const uint8_t* __restri
       *reinterpret_cast<uint4*>(base + (uint32_t)(d / 8 + 1) * AT_LBO + row_off) = make_uint4(0u, 0u, 0u, 0u);
     }
   }
-  if (stats != nullptr && lane == 0) {
+  if (stats != nullptr && kc == 0) {
     atomicMax(&stats->xmax2_bits, xb);
     atomicMax(&stats->nmax_bits, nb);
     atomicMax(&stats->xlo2_bits, lb);

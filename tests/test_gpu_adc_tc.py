@@ -80,6 +80,7 @@ CASES = [
     (66000, 129, 32, 15, 100, "sift"),
     (20000, 30, 16, 4, 50, "gauss"),     # forced below the size gate
     (100000, 64, 128, 8, 3000, "gauss"),
+    (70000, 300, 96, 12, 100, "gauss"),  # d = 96: the K tail of the query rows is stored in 8-column pieces
 ]
 
 
@@ -116,3 +117,19 @@ def test_filter_ties_and_clustered_neighbours(gpu, oracle, monkeypatch):
         dr, ir = _ref(oracle, codes, queries, codebooks, nrm, nn)
         dg, ig = gpu.linscan_lsq(codes, queries, codebooks.reshape(m, 256, d), nrm, R, nn)
         assert np.array_equal(ig, ir) and np.array_equal(dg, dr)
+
+
+def test_filter_with_several_query_batches(gpu, oracle, monkeypatch):
+    """More queries than one batch of the candidate buffers holds (21845 at the 16 K-key capacity): the base image
+    is decoded once, every batch runs sample -> thresholds -> LUT rows -> filter -> rescoring -> top-k."""
+    n, nq, d, m, nn = 66000, 23000, 16, 4, 10
+    codes, queries, codebooks, norms = gauss_scan_problem(7400, n, nq, d, m)
+    R = np.eye(d, dtype=np.float32)
+    monkeypatch.setenv("LSQ_B200_ADC", "tc")
+    dt, it = gpu.linscan_lsq(codes, queries, codebooks.reshape(m, 256, d), norms, R, nn)
+    monkeypatch.setenv("LSQ_B200_ADC", "scan")
+    ds, is_ = gpu.linscan_lsq(codes, queries, codebooks.reshape(m, 256, d), norms, R, nn)
+    assert np.array_equal(it, is_) and np.array_equal(dt, ds)
+    sample = np.r_[0:8, 21840:21856, nq - 8:nq]   # first batch, the batch boundary, the last queries
+    dr, ir = _ref(oracle, codes, queries[sample], codebooks, norms, nn)
+    assert np.array_equal(it[sample], ir) and np.array_equal(dt[sample], dr)
