@@ -81,6 +81,7 @@ CASES = [
     (20000, 30, 16, 4, 50, "gauss"),     # forced below the size gate
     (100000, 64, 128, 8, 3000, "gauss"),
     (70000, 300, 96, 12, 100, "gauss"),  # d = 96: the K tail of the query rows is stored in 8-column pieces
+    (300000, 40, 64, 8, 5000, "gauss"),  # large nn: ~7000 survivors per query, the 128 KB sorter takes every query
 ]
 
 
