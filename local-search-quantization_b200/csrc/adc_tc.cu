@@ -677,6 +677,58 @@ __global__ void __launch_bounds__(256) adc_rescore_kernel(const uint8_t* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// 3b. thresholds without a sample buffer.  The filter kernel, run on the strided sample with a coarse bound from a
+//     1/8 sub-sample, leaves each query a short list of sample positions (a few hundred of 16 K); this kernel scores
+//     them exactly (same arithmetic as the rescoring) and returns the r-th smallest: the very tau the lookup-scan
+//     path derives from its exact sample pass.  A list that overflowed or holds fewer than r entries (the coarse
+//     bound was too tight: probability ~1e-10 per query) gives tau = +inf, which poisons the query's filter row
+//     and sends the query to the exhaustive path.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) adc_sample_tau_kernel(const uint8_t* __restrict__ codes, int m,
+                                                             const float* __restrict__ norms, const float* __restrict__ lutq,
+                                                             const uint32_t* __restrict__ list, const int* __restrict__ lcnt,
+                                                             int lcap, int64_t stride, int64_t scount, int r,
+                                                             float* __restrict__ tau) {
+  extern __shared__ __align__(16) unsigned char st_smem[];
+  float* lut = reinterpret_cast<float*>(st_smem);                                   // [m * 256]
+  uint32_t* dist = reinterpret_cast<uint32_t*>(st_smem + (size_t)m * LSQ_H * 4);    // [lcap] ordered distances
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const float4* lsrc = reinterpret_cast<const float4*>(lutq + (size_t)q * m * LSQ_H);
+  for (int j = tid; j < m * LSQ_H / 4; j += 128) reinterpret_cast<float4*>(lut)[j] = __ldg(lsrc + j);
+  const int c_all = lcnt[q];
+  const int c = (c_all < lcap) ? c_all : lcap;
+  __syncthreads();
+  const uint32_t* mine = list + (size_t)q * lcap;
+  for (int i = tid; i < c; i += 128) {
+    const uint32_t pos = mine[i];
+    uint32_t key = 0xFFFFFFFFu;   // padding positions of the last sample tile never pass; be safe anyway
+    if ((int64_t)pos < scount) {
+      const int64_t v = (int64_t)pos * stride;
+      const uint8_t* cp = codes + (size_t)v * m;
+      float acc = 0.0f;
+      for (int k = 0; k < m; k++) acc = __fadd_rn(acc, lut[k * LSQ_H + cp[k]]);
+      acc = __fadd_rn(acc, norms[v]);
+      key = float_to_ordered(acc);
+    }
+    dist[i] = key;
+  }
+  __syncthreads();
+  if (c_all > lcap || c < r) {
+    if (tid == 0) tau[q] = INFINITY;
+    return;
+  }
+  for (int e = tid; e < c; e += 128) {   // rank by counting (ties by position): exactly one element has rank r - 1
+    const uint32_t v = dist[e];
+    int rk = 0;
+    for (int j = 0; j < c; j++) {
+      const uint32_t u = dist[j];
+      rk += (u < v) || (u == v && j < e);
+    }
+    if (rk == r - 1) tau[q] = ordered_to_float(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 // shape rule only (what lsq_linscan_path reports): LSQ tables, d a multiple of 16 up to 128, enough base vectors —
@@ -709,8 +761,13 @@ int adc_tc_prepare(const uint8_t* dcodes, int64_t n, int m, const float* dcodebo
   B.ntiles = ceil_div(n, AT_N);
   B.scount = scount;
   B.stiles = ceil_div(scount, AT_N);
+  B.sstride = sstride;
+  // 1/8 sub-sample of the sample (coarse bounds for the list-based thresholds); off for small samples
+  B.s1count = (scount >= 8 * 1024) ? scount / 8 : 0;
+  B.s1tiles = ceil_div(B.s1count, AT_N);
   LSQ_CUDA(B.img.alloc((size_t)B.ntiles * at_tile_bytes(d)));
   LSQ_CUDA(B.simg.alloc((size_t)B.stiles * at_tile_bytes(d)));
+  LSQ_CUDA(B.s1img.alloc((size_t)std::max<int64_t>(B.s1tiles, 1) * at_tile_bytes(d)));
   LSQ_CUDA(B.stats.alloc(1));
   LSQ_CUDA(cudaMemsetAsync(B.stats.p, 0, sizeof(AdcStats), st));
   note_launch();
@@ -721,6 +778,11 @@ int adc_tc_prepare(const uint8_t* dcodes, int64_t n, int m, const float* dcodebo
     note_launch();
     adc_decode_kernel<<<(unsigned)B.stiles, 256, 0, st>>>(dcodes, m, dcodebooks, d, dbnorms, B.simg.p, nullptr,
                                                          scount, sstride);
+  }
+  if (B.s1tiles > 0) {
+    note_launch();
+    adc_decode_kernel<<<(unsigned)B.s1tiles, 256, 0, st>>>(dcodes, m, dcodebooks, d, dbnorms, B.s1img.p, nullptr,
+                                                          B.s1count, sstride * 8);
   }
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
@@ -766,12 +828,33 @@ static int launch_filter(AdcFilterParams& p, cudaStream_t st) {
 }
 
 // filter values of the strided sample -> dsbuf in threshold_kernel's layout (32-query tiles, `scount` steps)
-int adc_tc_sample(const AdcTcBase& B, const float* dq, int nb, int d, int m, uint32_t* dsbuf, cudaStream_t st) {
+int adc_tc_sample(const AdcTcBase& B, bool subsample, const float* dq, int nb, int d, int m, uint32_t* dsbuf,
+                  cudaStream_t st) {
   AdcFilterParams p;
   memset(&p, 0, sizeof(p));
-  p.queries = dq; p.img = B.simg.p; p.sbuf = dsbuf; p.scount = B.scount;
-  p.n = B.scount; p.ntiles = B.stiles; p.nq = nb; p.d = d; p.m = m; p.npass = 2;
+  p.queries = dq; p.sbuf = dsbuf; p.nq = nb; p.d = d; p.m = m; p.npass = 2;
+  if (subsample) { p.img = B.s1img.p; p.scount = B.s1count; p.ntiles = B.s1tiles; }
+  else { p.img = B.simg.p; p.scount = B.scount; p.ntiles = B.stiles; }
+  p.n = p.scount;
   return launch_filter(p, st);
+}
+
+// sample positions whose filter value is <= dbound (+ margin) -> dlist / dlcnt, then the exact r-th smallest -> dtau
+int adc_tc_sample_tau(const AdcTcBase& B, const uint8_t* dcodes, int m, const float* dq, int nb, int d,
+                      const float* dbnorms, const float* dlutq, const float* dbound, uint32_t* dlist, int* dlcnt,
+                      int lcap, int r, float* dtau, cudaStream_t st) {
+  AdcFilterParams p;
+  memset(&p, 0, sizeof(p));
+  p.queries = dq; p.img = B.simg.p; p.tau = dbound; p.stats = B.stats.p; p.candidx = dlist; p.ccnt = dlcnt;
+  p.n = B.scount; p.ntiles = B.stiles; p.ccap = lcap; p.nq = nb; p.d = d; p.m = m; p.npass = 2;
+  LSQ_CUDA(cudaMemsetAsync(dlcnt, 0, (size_t)nb * sizeof(int), st));
+  LSQ_TRY(launch_filter(p, st));
+  const size_t smem = (size_t)m * LSQ_H * 4 + (size_t)lcap * 4;
+  LSQ_CUDA(cudaFuncSetAttribute(adc_sample_tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  note_launch();
+  adc_sample_tau_kernel<<<nb, 128, smem, st>>>(dcodes, m, dbnorms, dlutq, dlist, dlcnt, lcap, B.sstride, B.scount, r, dtau);
+  LSQ_CUDA(cudaGetLastError());
+  return LSQ_OK;
 }
 
 int adc_tc_lut_rows(const float* dq, int nb, int d, const float* dcodebooks, int m, float* dlutq, cudaStream_t st) {

@@ -15,9 +15,9 @@ struct AdcStats {
 // per-call image of the base set: bf16 hi/lo UMMA operand tiles of the decoded vectors (norms folded in), maxima;
 // the same for the strided sample the thresholds are estimated on
 struct AdcTcBase {
-  DevBuf<unsigned char> img, simg;
+  DevBuf<unsigned char> img, simg, s1img;
   DevBuf<AdcStats> stats;
-  int64_t ntiles = 0, stiles = 0, scount = 0;
+  int64_t ntiles = 0, stiles = 0, scount = 0, sstride = 1, s1tiles = 0, s1count = 0;
 };
 
 bool adc_tc_shape_ok(int64_t n, int64_t nq, int m, int d);
@@ -27,7 +27,14 @@ bool adc_tc_applicable(const uint8_t* dcodes, int64_t n, int64_t nq, int m, int 
 int adc_tc_prepare(const uint8_t* dcodes, int64_t n, int m, const float* dcodebooks, int d, const float* dbnorms,
                    int64_t scount, int64_t sstride, cudaStream_t st, AdcTcBase& B);
 // filter values of the sample, ordered, in threshold_kernel's layout with 32-query tiles: [(q/32 * scount + t) * 32 + q%32]
-int adc_tc_sample(const AdcTcBase& B, const float* dq, int nb, int d, int m, uint32_t* dsbuf, cudaStream_t st);
+// subsample: the 1/8 sub-sample (B.s1count steps) instead of the sample (B.scount steps)
+int adc_tc_sample(const AdcTcBase& B, bool subsample, const float* dq, int nb, int d, int m, uint32_t* dsbuf,
+                  cudaStream_t st);
+// thresholds without a sample buffer: sample positions with filter value <= dbound[q] (+ margin) -> dlist / dlcnt
+// (lcap per query), scored exactly, r-th smallest -> dtau[q] (+inf if the list overflowed or is shorter than r)
+int adc_tc_sample_tau(const AdcTcBase& B, const uint8_t* dcodes, int m, const float* dq, int nb, int d,
+                      const float* dbnorms, const float* dlutq, const float* dbound, uint32_t* dlist, int* dlcnt,
+                      int lcap, int r, float* dtau, cudaStream_t st);
 // exact LUT rows lutq[q][m*256] (the reference's fp32 chain) for the rescoring
 int adc_tc_lut_rows(const float* dq, int nb, int d, const float* dcodebooks, int m, float* dlutq, cudaStream_t st);
 // filter (-> dcandidx / dccnt) + exact rescoring (-> dcand / dcnt, the buffers the top-k kernels read); dtau[q].

@@ -881,13 +881,28 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
   // survivors (adc_tc.cu); everything around it (LUT, sample pass, thresholds, top-k, re-runs) is unchanged
   const bool use_tc = (lut_kind == LUT_LSQ) && adc_tc_applicable(dcodes, n, nq, m, d, dqueries, dcodebooks, dbnorms);
   AdcTcBase tcbase;
-  DevBuf<uint32_t> dcandidx;
+  DevBuf<uint32_t> dcandidx;   // filter survivors of the main pass; before that, the sample lists of the thresholds
   DevBuf<int> dccnt;
+  DevBuf<float> dbound;
+  bool two_stage = false;
+  int64_t r0 = 0;
+  int lcap = 0;
   if (use_tc) {
     LSQ_TRY(adc_tc_prepare(dcodes, n, m, dcodebooks, d, dbnorms, s, stride, st, tcbase));
     LSQ_CUDA(dcandidx.alloc((size_t)qbatch * cap));
     LSQ_CUDA(dccnt.alloc(qbatch));
     timer.mark("decode");
+    // list-based thresholds: of the r smallest sample values about r/8 fall into the 1/8 sub-sample; its r0-th
+    // smallest (7 sigma + 6 above that) bounds the r-th smallest of the sample except with probability ~1e-10, and
+    // leaves lists of about 8 r0 sample positions per query
+    if (tcbase.s1count > 0 && getenv("LSQ_B200_ADC_SBUF") == nullptr) {
+      const double mu1 = (double)r / 8.0;
+      r0 = (int64_t)ceil(mu1 + 7.0 * sqrt(mu1) + 6.0);
+      lcap = 1024;
+      while (lcap < 3 * 8 * r0) lcap <<= 1;
+      two_stage = (r0 < tcbase.s1count) && (lcap <= 8192) && (lcap <= cap);
+      if (two_stage) LSQ_CUDA(dbound.alloc(qbatch));
+    }
   }
   LSQ_CUDA(dbig.alloc(qbatch + 1));
   LSQ_CUDA(dlut.alloc((size_t)max_tiles * m * LSQ_H * QT));
@@ -906,14 +921,27 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
       // thresholds from the tensor-core values of the sample (any tau is valid: a query whose candidate count
       // ends up < nn or > capacity is re-run), exact LUT rows, filter + exact rescoring of the survivors
       const int tiles32 = (int)ceil_div(nb, 32);
-      LSQ_TRY(adc_tc_sample(tcbase, dq, nb, d, m, dsbuf.p, st));
-      timer.mark("sample");
-      note_launch();
-      threshold_kernel<<<tiles32, 1024, 0, st>>>(dsbuf.p, s, (int)r, dtau.p, 32);
-      LSQ_CUDA(cudaGetLastError());
-      timer.mark("threshold");
       LSQ_TRY(adc_tc_lut_rows(dq, nb, d, dcodebooks, m, dlut.p, st));
       timer.mark("lut");
+      if (two_stage) {
+        // coarse bound from the 1/8 sub-sample (r0-th smallest filter value), then the sample positions below it,
+        // scored exactly: tau = the exact r-th smallest distance of the sample, no 655 MB sample buffer
+        LSQ_TRY(adc_tc_sample(tcbase, true, dq, nb, d, m, dsbuf.p, st));
+        note_launch();
+        threshold_kernel<<<tiles32, 1024, 0, st>>>(dsbuf.p, tcbase.s1count, (int)r0, dbound.p, 32);
+        LSQ_CUDA(cudaGetLastError());
+        timer.mark("bound");
+        LSQ_TRY(adc_tc_sample_tau(tcbase, dcodes, m, dq, nb, d, dbnorms, dlut.p, dbound.p, dcandidx.p, dccnt.p, lcap, (int)r,
+                                  dtau.p, st));
+        timer.mark("threshold");
+      } else {
+        LSQ_TRY(adc_tc_sample(tcbase, false, dq, nb, d, m, dsbuf.p, st));
+        timer.mark("sample");
+        note_launch();
+        threshold_kernel<<<tiles32, 1024, 0, st>>>(dsbuf.p, s, (int)r, dtau.p, 32);
+        LSQ_CUDA(cudaGetLastError());
+        timer.mark("threshold");
+      }
       LSQ_CUDA(cudaMemsetAsync(dbig.p + qbatch, 0, sizeof(int), st));
       LSQ_TRY(adc_tc_main_pass(tcbase, dcodes, n, m, dq, nb, d, dbnorms, dlut.p, dtau.p, dcandidx.p, dccnt.p, cap,
                                nullptr, nullptr, cap, S.id_base, nullptr, 0, st));
