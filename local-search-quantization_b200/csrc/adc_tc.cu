@@ -750,9 +750,10 @@ bool adc_tc_applicable(const uint8_t* dcodes, int64_t n, int64_t nq, int m, int 
       (reinterpret_cast<uintptr_t>(dcodes) & 3))
     return false;
   // above the memory gate the images would crowd out the caller (about 4 d bytes per base vector)
+  const size_t need = (size_t)ceil_div(n, AT_N) * at_tile_bytes(d);
+  if (need <= ((size_t)4 << 30)) return true;   // up to ~8 M vectors: no need to ask the driver (cudaMemGetInfo costs ~0.1 ms)
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
-  const size_t need = (size_t)ceil_div(n, AT_N) * at_tile_bytes(d);
   return need < free_b / 4;
 }
 

@@ -879,7 +879,7 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
   DevBuf<int> dcnt, dstatus, dbig;  // dbig: worklist of the queries the select kernel flags + its length
   // LSQ tables of an inner product: the main pass runs as a tensor-core filter + exact rescoring of the
   // survivors (adc_tc.cu); everything around it (LUT, sample pass, thresholds, top-k, re-runs) is unchanged
-  const bool use_tc = (lut_kind == LUT_LSQ) && adc_tc_applicable(dcodes, n, nq, m, d, dqueries, dcodebooks, dbnorms);
+  bool use_tc = (lut_kind == LUT_LSQ) && adc_tc_applicable(dcodes, n, nq, m, d, dqueries, dcodebooks, dbnorms);
   AdcTcBase tcbase;
   DevBuf<uint32_t> dcandidx;   // filter survivors of the main pass; before that, the sample lists of the thresholds
   DevBuf<int> dccnt;
@@ -887,9 +887,12 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
   bool two_stage = false;
   int64_t r0 = 0;
   int lcap = 0;
+  if (use_tc && (adc_tc_prepare(dcodes, n, m, dcodebooks, d, dbnorms, s, stride, st, tcbase) != LSQ_OK ||
+                 dcandidx.alloc((size_t)qbatch * cap) != cudaSuccess)) {
+    cudaGetLastError();   // no room for the operand images / survivor lists: the lookup scan needs neither
+    use_tc = false;
+  }
   if (use_tc) {
-    LSQ_TRY(adc_tc_prepare(dcodes, n, m, dcodebooks, d, dbnorms, s, stride, st, tcbase));
-    LSQ_CUDA(dcandidx.alloc((size_t)qbatch * cap));
     LSQ_CUDA(dccnt.alloc(qbatch));
     timer.mark("decode");
     // list-based thresholds: of the r smallest sample values about r/8 fall into the 1/8 sub-sample; its r0-th
