@@ -46,7 +46,7 @@ constexpr int SORT_CAP = LINSCAN_MAX_NN;  // keys the shared-memory bitonic sort
 
 enum { MODE_SAMPLE = 0, MODE_MAIN = 1, MODE_ALL = 2 };
 enum { ST_OK = 0, ST_REDO = 1, ST_BIG = 2 };
-constexpr int SEL_CAP = 4096;    // candidate keys the select kernel holds (32 KB of shared memory)
+constexpr int SEL_CAP = 5120;    // candidate keys the select kernel holds (40 KB of shared memory): 5 sigma above the ~3000 expected at nn = 1000, so the 128 KB sorter stays idle
 constexpr int SEL_SORT = 1024;   // survivors it sorts (8 KB)
 
 // Tile geometry.  A lane serves QPL consecutive queries of the tile with ONE vector shared-memory load
