@@ -290,7 +290,7 @@ struct AdcFilterParams {
   float* dbg;                // values mode: [nq][dbg_ld] filter values (tests)
   uint32_t* sbuf;            // sample mode: ordered filter values, threshold_kernel's layout [(q/32 * scount + t) * 32 + q%32]
   int64_t n, ntiles, ccap, dbg_ld, scount;
-  int nq, d, m, exp, npass, nstages;
+  int nq, d, m, npass, nstages;
 };
 
 __device__ __forceinline__ void at_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -564,12 +564,6 @@ __global__ void __launch_bounds__(at_threads(SPLIT), 1) adc_filter_kernel(const 
       uint32_t mask[2 * HPW];
 #pragma unroll
       for (int c = 0; c < 2 * HPW; c++) mask[c] = 0u;
-      if (p.exp == 1) {   // experiment: no drain at all
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_acc_empty[b]);
-        continue;
-      }
 #pragma unroll
       for (int h = 0; h < HPW; h++) {
         uint32_t r0[32], r1[32];
@@ -877,7 +871,6 @@ int adc_tc_main_pass(const AdcTcBase& B, const uint8_t* dcodes, int64_t n, int m
   p.queries = dq; p.img = B.img.p; p.tau = dtau; p.stats = B.stats.p;
   p.candidx = dcandidx; p.ccnt = dccnt; p.dbg = ddbg; p.n = n; p.ntiles = B.ntiles; p.ccap = ccap; p.dbg_ld = dbg_ld;
   p.nq = nb; p.d = d; p.m = m;
-  if (const char* e = getenv("LSQ_B200_ADC_EXP")) p.exp = atoi(e);   // timing experiments only (results invalid)
   // two products hi(q).lo(x) + hi(q).hi(x) by default.  LSQ_B200_ADC_PASSES=1 drops the first (9 instead of 17 MMAs
   // per product, half the TMA bytes) for a margin wider by 2 ||q|| max||lo(x)||: measured 2.9 + 0.8 ms (filter +
   // rescoring of 1.5x the candidates) against 3.05 + 0.5 ms on the 1 M x 10 K benchmark — no gain, so the tighter

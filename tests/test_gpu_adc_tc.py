@@ -85,8 +85,13 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("thresholds", ["lists", "sample_buffer"])
 @pytest.mark.parametrize("n,nq,d,m,nn,kind", CASES)
-def test_linscan_through_the_filter_is_exact(gpu, oracle, n, nq, d, m, nn, kind, monkeypatch):
+def test_linscan_through_the_filter_is_exact(gpu, oracle, n, nq, d, m, nn, kind, thresholds, monkeypatch):
+    if thresholds == "sample_buffer":   # the first design: all sample values written out, r-th smallest selected
+        if (n, nq) not in ((200000, 300), (66000, 129)):
+            pytest.skip("two shapes are enough for the alternative threshold path")
+        monkeypatch.setenv("LSQ_B200_ADC_SBUF", "1")
     mk = gauss_scan_problem if kind == "gauss" else make_scan_problem
     codes, queries, codebooks, norms = mk(7100 + m + nn, n, nq, d, m)
     R = np.eye(d, dtype=np.float32)
