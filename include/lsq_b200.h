@@ -115,7 +115,7 @@ void linscan_aqd_query(float* dists, unsigned int* res, unsigned char* codes, fl
 /* which main pass linscan_lsq runs for n base vectors and nq queries: 1 = tensor-core filter (tcgen05 bf16 GEMM over the
  * decoded base vectors) + exact rescoring of the survivors (csrc/adc_tc.cu; n >= 64 K, nq * m >= 8000, d a multiple
  * of 16 up to 128), 0 = lookup-table scan (csrc/linscan.cu).  Both give the reference's results bit for bit.
- * Environment override: LSQ_B200_ADC=scan|tc. */
+ * linscan_pq / linscan_opq follow the same rule with d = dim1codes * subdim.  Environment override: LSQ_B200_ADC=scan|tc. */
 int lsq_linscan_path(int64_t n, int64_t nq, int m, int d);
 /* Measurement aid: with LSQ_B200_ADC_TIMING set in the environment every linscan call times its phases with CUDA
  * events (and prints them to stderr); this returns the device time (ms) and name of phase i of the calling thread's

@@ -36,6 +36,11 @@
 // exactly as before.  The thresholds tau_q themselves come from the same kernel run on a strided sample of the
 // base set (any tau is valid, see linscan.cu).  tests/: bit-identical ids and distances against the reference's
 // own .so and against the lookup scan (LSQ_B200_ADC=scan).
+//
+// PQ / OPQ tables (linscan_aqd.cpp:37-102: dist = sum_k sum_s sqr(c_k[s] - q[k*subdim + s])) take the same path:
+// dist = ||q||^2 - 2 <q, xhat> + ||xhat||^2 with xhat the CONCATENATION of the sub-codewords, so ||xhat||^2 stands
+// where dbnorm stood and ||q||^2 goes into the threshold term; the reference's sums of squares are good to
+// (subdim + m + 4) u (||q|| + max||xhat||)^2, which replaces the first line of the bound above.
 #include <cuda_bf16.h>
 #include <math.h>
 #include <stdlib.h>
@@ -116,7 +121,7 @@ __global__ void __launch_bounds__(256) adc_cbnorm_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) adc_decode_kernel(const uint8_t* __restrict__ codes, int m,
                                                          const float* __restrict__ C, int d,
                                                          const float* __restrict__ norms, unsigned char* __restrict__ img,
-                                                         AdcStats* stats, int64_t count, int64_t stride) {
+                                                         AdcStats* stats, int64_t count, int64_t stride, int subdim) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int half = lane >> 4, kc = lane & 15;   // which vector of the pair, which K chunk of 8 elements
   const int64_t tile = blockIdx.x;
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(256) adc_decode_kernel(const uint8_t* __restri
         for (int k = 0; k < LSQ_MAXM; k++)
           if (k < m) w[k >> 2] |= (uint32_t)cp[k] << (8 * (k & 3));
       }
-      if (lane_on) {
+      if (lane_on && subdim == 0) {   // LSQ: xhat = sum of m full-dimensional codewords
 #pragma unroll
         for (int k = 0; k < LSQ_MAXM; k++) {
           if (k < m) {
@@ -159,6 +164,12 @@ __global__ void __launch_bounds__(256) adc_decode_kernel(const uint8_t* __restri
             acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
             acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
           }
+        }
+      } else if (lane_on) {           // PQ: xhat = concatenation of m sub-codewords of `subdim` elements
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+          const int i = 8 * kc + e, k = i / subdim, t = i - k * subdim;
+          acc[e] = __ldg(C + ((size_t)k * LSQ_H + cp[k]) * subdim + t);
         }
       }
     }
@@ -190,7 +201,7 @@ __global__ void __launch_bounds__(256) adc_decode_kernel(const uint8_t* __restri
     if (kc == 0) {
       float half_neg = -AT_BIG;   // padding columns of the last tile never pass the filter
       if (valid) {
-        const float nv = norms[v];
+        const float nv = (norms != nullptr) ? norms[v] : n2;   // PQ: the "norm" of the expansion is ||xhat||^2 itself
         half_neg = -0.5f * nv;
         nb = max(nb, __float_as_uint(fabsf(nv)));   // a NaN is the largest pattern: it survives and poisons the margin
         xb = max(xb, __float_as_uint(n2));
@@ -277,6 +288,22 @@ __global__ void __launch_bounds__(256) adc_lut_rows_kernel(const float* __restri
   }
 }
 
+// PQ / OPQ tables: lutq[q][k*256 + r] = sum_s sqr(c[s] - q[k*subdim + s]), s ascending, separate subtract, multiply
+// and add (linscan_aqd.cpp:66-74).  grid (queries, codebooks), thread = table row.
+__global__ void __launch_bounds__(LSQ_H) adc_lut_rows_pq_kernel(const float* __restrict__ queries, int qstride, int subdim,
+                                                                const float* __restrict__ centers, int m,
+                                                                float* __restrict__ lutq) {
+  const int q = blockIdx.x, k = blockIdx.y, r = threadIdx.x;
+  const float* c = centers + ((size_t)k * LSQ_H + r) * subdim;
+  const float* qv = queries + (size_t)q * qstride + k * subdim;
+  float t = 0.0f;
+  for (int s = 0; s < subdim; s++) {
+    const float df = __fsub_rn(__ldg(c + s), __ldg(qv + s));
+    t = __fadd_rn(t, __fmul_rn(df, df));
+  }
+  lutq[((size_t)q * m + k) * LSQ_H + r] = t;
+}
+
 // ------------------------------------------------------------------------------------------------
 // 2. the filter GEMM
 // ------------------------------------------------------------------------------------------------
@@ -290,7 +317,7 @@ struct AdcFilterParams {
   float* dbg;                // values mode: [nq][dbg_ld] filter values (tests)
   uint32_t* sbuf;            // sample mode: ordered filter values, threshold_kernel's layout [(q/32 * scount + t) * 32 + q%32]
   int64_t n, ntiles, ccap, dbg_ld, scount;
-  int nq, d, m, npass, nstages;
+  int nq, d, m, npass, nstages, qstride, pq;
 };
 
 __device__ __forceinline__ void at_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -410,7 +437,7 @@ __global__ void __launch_bounds__(at_threads(SPLIT), 1) adc_filter_kernel(const 
   const bool is_epi = warp < EPI_WARPS && a_mine < na;
   const bool q_valid = is_epi && (q < p.nq);
   if (warp < 8 && a_mine < na) {
-    const float* qrow = p.queries + (size_t)(q_valid ? q : 0) * d;
+    const float* qrow = p.queries + (size_t)(q_valid ? q : 0) * p.qstride;
     const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16) + AT_COL_A + (uint32_t)a_mine * AT_A_STRIDE;
     float qn2 = 0.0f, ql2 = 0.0f;   // ||q||^2 and ||q - hi(q)||^2
     for (int k0 = 0; k0 < d; k0 += 64) {
@@ -441,6 +468,7 @@ __global__ void __launch_bounds__(at_threads(SPLIT), 1) adc_filter_kernel(const 
     }
     // threshold: the filter accumulates <hi(q), x> - dbnorm/2 + half_thr, which is >= 0 iff dist <= tau + margin
     float half_thr = (MODE == AT_FILTER) ? -AT_BIG : 0.0f;   // rows without a query never pass; sample / values: plain values
+    if (MODE != AT_FILTER && p.pq && q_valid) half_thr = -0.5f * qn2;   // PQ: the ||q||^2 term of the expansion
     if (q_valid && MODE == AT_FILTER) {
       const float tau = p.tau[q];
       const float qn = sqrtf(qn2) * 1.00001f, ql = sqrtf(ql2) * 1.00001f;
@@ -451,10 +479,20 @@ __global__ void __launch_bounds__(at_threads(SPLIT), 1) adc_filter_kernel(const 
       const float xlo = (npass == 1) ? sqrtf(__uint_as_float(p.stats->xlo2_bits)) * 1.00001f : 0.0f;
       const float eps_f = 1.0f / 8192.0f;                                   // 2^-13, see the header
       const float eps_r = 2.0f * (float)(d + p.m + 2) * 5.9604645e-8f;      // 2 (d+m+2) u
-      float margin = 2.0f * ql * xmax + 2.0f * qn * xlo + eps_f * 2.0f * qn * xmax +
-                     eps_r * (2.0f * qn * (float)p.m * cmax + nmax);
-      margin += 1.01f * eps_f * (nmax + fabsf(tau) + margin);
-      half_thr = 0.5f * (tau + margin);
+      float margin = 2.0f * ql * xmax + 2.0f * qn * xlo + eps_f * 2.0f * qn * xmax;
+      if (p.pq) {
+        // PQ tables: dist = sum_i (xhat_i - q_i)^2 = ||q||^2 - 2 <q, xhat> + ||xhat||^2; the reference's fp32 sums of
+        // squares are good to (subdim + m + 4) u relative to the distance, which is at most (||q|| + max||xhat||)^2;
+        // ||q||^2 and ||xhat||^2 are fp32 sums here (d u relative each, far inside eps_f)
+        const float span = (qn + xmax) * (qn + xmax);
+        margin += eps_r * span + eps_f * (qn * qn + xmax * xmax);
+        margin += 1.01f * eps_f * (fabsf(tau) + margin);
+        half_thr = 0.5f * (tau + margin - qn2);
+      } else {
+        margin += eps_r * (2.0f * qn * (float)p.m * cmax + nmax);
+        margin += 1.01f * eps_f * (nmax + fabsf(tau) + margin);
+        half_thr = 0.5f * (tau + margin);
+      }
       if (!(fabsf(half_thr) < AT_BIG)) half_thr = __uint_as_float(0x7FC00000u);   // NaN / overflow: poison the row -> exhaustive re-run
     }
     {
@@ -659,7 +697,7 @@ __global__ void __launch_bounds__(256) adc_rescore_kernel(const uint8_t* __restr
 #pragma unroll
     for (int k = 0; k < LSQ_MAXM; k++)
       if (k < m) acc = __fadd_rn(acc, lut[k * LSQ_H + ((w[k >> 2] >> (8 * (k & 3))) & 0xFFu)]);
-    acc = __fadd_rn(acc, norms[v]);
+    if (norms != nullptr) acc = __fadd_rn(acc, norms[v]);   // PQ tables carry no norm term
     if (acc <= tq) {
       const int pos = atomicAdd(&sh_n, 1);
       if (pos < cap) out[pos] = ((unsigned long long)float_to_ordered(acc) << 32) | (uint32_t)(v + (uint32_t)id_base);
@@ -701,7 +739,7 @@ __global__ void __launch_bounds__(128) adc_sample_tau_kernel(const uint8_t* __re
       const uint8_t* cp = codes + (size_t)v * m;
       float acc = 0.0f;
       for (int k = 0; k < m; k++) acc = __fadd_rn(acc, lut[k * LSQ_H + cp[k]]);
-      acc = __fadd_rn(acc, norms[v]);
+      if (norms != nullptr) acc = __fadd_rn(acc, norms[v]);
       key = float_to_ordered(acc);
     }
     dist[i] = key;
@@ -739,7 +777,7 @@ bool adc_tc_shape_ok(int64_t n, int64_t nq, int m, int d) {
 
 bool adc_tc_applicable(const uint8_t* dcodes, int64_t n, int64_t nq, int m, int d, const float* dqueries,
                        const float* dcodebooks, const float* dbnorms) {
-  if (dbnorms == nullptr || !adc_tc_shape_ok(n, nq, m, d)) return false;
+  if (!adc_tc_shape_ok(n, nq, m, d)) return false;
   if ((reinterpret_cast<uintptr_t>(dqueries) & 15) || (reinterpret_cast<uintptr_t>(dcodebooks) & 15) ||
       (reinterpret_cast<uintptr_t>(dcodes) & 3))
     return false;
@@ -752,7 +790,9 @@ bool adc_tc_applicable(const uint8_t* dcodes, int64_t n, int64_t nq, int m, int 
 }
 
 int adc_tc_prepare(const uint8_t* dcodes, int64_t n, int m, const float* dcodebooks, int d, const float* dbnorms,
-                   int64_t scount, int64_t sstride, cudaStream_t st, AdcTcBase& B) {
+                   int64_t scount, int64_t sstride, int subdim, int qstride, cudaStream_t st, AdcTcBase& B) {
+  B.subdim = subdim;      // 0: LSQ (codewords of d elements, summed); > 0: PQ (sub-codewords of subdim elements, d = m * subdim)
+  B.qstride = qstride;
   B.ntiles = ceil_div(n, AT_N);
   B.scount = scount;
   B.stiles = ceil_div(scount, AT_N);
@@ -766,18 +806,18 @@ int adc_tc_prepare(const uint8_t* dcodes, int64_t n, int m, const float* dcodebo
   LSQ_CUDA(B.stats.alloc(1));
   LSQ_CUDA(cudaMemsetAsync(B.stats.p, 0, sizeof(AdcStats), st));
   note_launch();
-  adc_cbnorm_kernel<<<(unsigned)ceil_div((int64_t)m * LSQ_H, 256), 256, 0, st>>>(dcodebooks, m * LSQ_H, d, B.stats.p);
+  adc_cbnorm_kernel<<<(unsigned)ceil_div((int64_t)m * LSQ_H, 256), 256, 0, st>>>(dcodebooks, m * LSQ_H, subdim > 0 ? subdim : d, B.stats.p);
   note_launch();
-  adc_decode_kernel<<<(unsigned)B.ntiles, 256, 0, st>>>(dcodes, m, dcodebooks, d, dbnorms, B.img.p, B.stats.p, n, 1);
+  adc_decode_kernel<<<(unsigned)B.ntiles, 256, 0, st>>>(dcodes, m, dcodebooks, d, dbnorms, B.img.p, B.stats.p, n, 1, subdim);
   if (B.stiles > 0) {
     note_launch();
     adc_decode_kernel<<<(unsigned)B.stiles, 256, 0, st>>>(dcodes, m, dcodebooks, d, dbnorms, B.simg.p, nullptr,
-                                                         scount, sstride);
+                                                         scount, sstride, subdim);
   }
   if (B.s1tiles > 0) {
     note_launch();
     adc_decode_kernel<<<(unsigned)B.s1tiles, 256, 0, st>>>(dcodes, m, dcodebooks, d, dbnorms, B.s1img.p, nullptr,
-                                                          B.s1count, sstride * 8);
+                                                          B.s1count, sstride * 8, subdim);
   }
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
@@ -827,7 +867,7 @@ int adc_tc_sample(const AdcTcBase& B, bool subsample, const float* dq, int nb, i
                   cudaStream_t st) {
   AdcFilterParams p;
   memset(&p, 0, sizeof(p));
-  p.queries = dq; p.sbuf = dsbuf; p.nq = nb; p.d = d; p.m = m; p.npass = 2;
+  p.queries = dq; p.sbuf = dsbuf; p.nq = nb; p.d = d; p.m = m; p.npass = 2; p.qstride = B.qstride; p.pq = B.subdim > 0;
   if (subsample) { p.img = B.s1img.p; p.scount = B.s1count; p.ntiles = B.s1tiles; }
   else { p.img = B.simg.p; p.scount = B.scount; p.ntiles = B.stiles; }
   p.n = p.scount;
@@ -841,7 +881,8 @@ int adc_tc_sample_tau(const AdcTcBase& B, const uint8_t* dcodes, int m, const fl
   AdcFilterParams p;
   memset(&p, 0, sizeof(p));
   p.queries = dq; p.img = B.simg.p; p.tau = dbound; p.stats = B.stats.p; p.candidx = dlist; p.ccnt = dlcnt;
-  p.n = B.scount; p.ntiles = B.stiles; p.ccap = lcap; p.nq = nb; p.d = d; p.m = m; p.npass = 2;
+  p.n = B.scount; p.ntiles = B.stiles; p.ccap = lcap; p.nq = nb; p.d = d; p.m = m; p.npass = 2; p.qstride = B.qstride;
+  p.pq = B.subdim > 0;
   LSQ_CUDA(cudaMemsetAsync(dlcnt, 0, (size_t)nb * sizeof(int), st));
   LSQ_TRY(launch_filter(p, st));
   const size_t smem = (size_t)m * LSQ_H * 4 + (size_t)lcap * 4;
@@ -852,7 +893,14 @@ int adc_tc_sample_tau(const AdcTcBase& B, const uint8_t* dcodes, int m, const fl
   return LSQ_OK;
 }
 
-int adc_tc_lut_rows(const float* dq, int nb, int d, const float* dcodebooks, int m, float* dlutq, cudaStream_t st) {
+int adc_tc_lut_rows(const AdcTcBase& B, const float* dq, int nb, int d, const float* dcodebooks, int m, float* dlutq,
+                    cudaStream_t st) {
+  if (B.subdim > 0) {
+    note_launch();
+    adc_lut_rows_pq_kernel<<<dim3((unsigned)nb, (unsigned)m, 1), LSQ_H, 0, st>>>(dq, B.qstride, B.subdim, dcodebooks, m, dlutq);
+    LSQ_CUDA(cudaGetLastError());
+    return LSQ_OK;
+  }
   const size_t smem = (size_t)d * (LR_Q + LR_J) * sizeof(float);
   LSQ_CUDA(cudaFuncSetAttribute(adc_lut_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   note_launch();
@@ -870,7 +918,7 @@ int adc_tc_main_pass(const AdcTcBase& B, const uint8_t* dcodes, int64_t n, int m
   memset(&p, 0, sizeof(p));
   p.queries = dq; p.img = B.img.p; p.tau = dtau; p.stats = B.stats.p;
   p.candidx = dcandidx; p.ccnt = dccnt; p.dbg = ddbg; p.n = n; p.ntiles = B.ntiles; p.ccap = ccap; p.dbg_ld = dbg_ld;
-  p.nq = nb; p.d = d; p.m = m;
+  p.nq = nb; p.d = d; p.m = m; p.qstride = B.qstride; p.pq = B.subdim > 0;
   // two products hi(q).lo(x) + hi(q).hi(x) by default.  LSQ_B200_ADC_PASSES=1 drops the first (9 instead of 17 MMAs
   // per product, half the TMA bytes) for a margin wider by 2 ||q|| max||lo(x)||: measured 2.9 + 0.8 ms (filter +
   // rescoring of 1.5x the candidates) against 3.05 + 0.5 ms on the 1 M x 10 K benchmark — no gain, so the tighter
@@ -908,7 +956,7 @@ extern "C" int lsq_dev_adc_filter_values(const uint8_t* dcodes, int64_t n, int m
   LSQ_CHECK_ARG(n >= 1 && nq >= 1 && m >= 1 && m <= LSQ_MAXM && d % 16 == 0 && d >= 16 && d <= 128, "adc filter: bad sizes");
   LSQ_CHECK_ARG(ld >= 128 * ceil_div(n, 128), "adc filter: ld too small");
   AdcTcBase B;
-  LSQ_TRY(adc_tc_prepare(dcodes, n, m, dcodebooks, d, dbnorms, 0, 1, st, B));
+  LSQ_TRY(adc_tc_prepare(dcodes, n, m, dcodebooks, d, dbnorms, 0, 1, 0, d, st, B));
   DevBuf<float> dtau;
   DevBuf<int> dccnt;
   LSQ_CUDA(dtau.alloc(nq));

@@ -18,14 +18,17 @@ struct AdcTcBase {
   DevBuf<unsigned char> img, simg, s1img;
   DevBuf<AdcStats> stats;
   int64_t ntiles = 0, stiles = 0, scount = 0, sstride = 1, s1tiles = 0, s1count = 0;
+  int subdim = 0;    // 0: LSQ tables (-2<q,c> + dbnorm); > 0: PQ / OPQ tables (squared differences per sub-space)
+  int qstride = 0;   // floats between query rows
 };
 
 bool adc_tc_shape_ok(int64_t n, int64_t nq, int m, int d);
 bool adc_tc_applicable(const uint8_t* dcodes, int64_t n, int64_t nq, int m, int d, const float* dqueries,
                        const float* dcodebooks, const float* dbnorms);
 // base image + image of the sample {i * sstride : i < scount}
+// PQ / OPQ: subdim > 0, d = m * subdim, dcodebooks = centers [m][256][subdim], dbnorms = nullptr
 int adc_tc_prepare(const uint8_t* dcodes, int64_t n, int m, const float* dcodebooks, int d, const float* dbnorms,
-                   int64_t scount, int64_t sstride, cudaStream_t st, AdcTcBase& B);
+                   int64_t scount, int64_t sstride, int subdim, int qstride, cudaStream_t st, AdcTcBase& B);
 // filter values of the sample, ordered, in threshold_kernel's layout with 32-query tiles: [(q/32 * scount + t) * 32 + q%32]
 // subsample: the 1/8 sub-sample (B.s1count steps) instead of the sample (B.scount steps)
 int adc_tc_sample(const AdcTcBase& B, bool subsample, const float* dq, int nb, int d, int m, uint32_t* dsbuf,
@@ -36,7 +39,8 @@ int adc_tc_sample_tau(const AdcTcBase& B, const uint8_t* dcodes, int m, const fl
                       const float* dbnorms, const float* dlutq, const float* dbound, uint32_t* dlist, int* dlcnt,
                       int lcap, int r, float* dtau, cudaStream_t st);
 // exact LUT rows lutq[q][m*256] (the reference's fp32 chain) for the rescoring
-int adc_tc_lut_rows(const float* dq, int nb, int d, const float* dcodebooks, int m, float* dlutq, cudaStream_t st);
+int adc_tc_lut_rows(const AdcTcBase& B, const float* dq, int nb, int d, const float* dcodebooks, int m, float* dlutq,
+                    cudaStream_t st);
 // filter (-> dcandidx / dccnt) + exact rescoring (-> dcand / dcnt, the buffers the top-k kernels read); dtau[q].
 // dcand == nullptr: filter only.  ddbg (optional): [nb][dbg_ld] filter values.
 int adc_tc_main_pass(const AdcTcBase& B, const uint8_t* dcodes, int64_t n, int m, const float* dq, int nb, int d,

@@ -879,7 +879,10 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
   DevBuf<int> dcnt, dstatus, dbig;  // dbig: worklist of the queries the select kernel flags + its length
   // LSQ tables of an inner product: the main pass runs as a tensor-core filter + exact rescoring of the
   // survivors (adc_tc.cu); everything around it (LUT, sample pass, thresholds, top-k, re-runs) is unchanged
-  bool use_tc = (lut_kind == LUT_LSQ) && adc_tc_applicable(dcodes, n, nq, m, d, dqueries, dcodebooks, dbnorms);
+  // tensor-core dimension: d for the LSQ tables, m * subdim for PQ / OPQ (queries keep their row stride d)
+  const int td = (lut_kind == LUT_LSQ) ? d : m * subdim;
+  bool use_tc = ((lut_kind == LUT_LSQ) ? (dbnorms != nullptr) : (d % 4 == 0)) &&
+                adc_tc_applicable(dcodes, n, nq, m, td, dqueries, dcodebooks, dbnorms);
   AdcTcBase tcbase;
   DevBuf<uint32_t> dcandidx;   // filter survivors of the main pass; before that, the sample lists of the thresholds
   DevBuf<int> dccnt;
@@ -887,7 +890,8 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
   bool two_stage = false;
   int64_t r0 = 0;
   int lcap = 0;
-  if (use_tc && (adc_tc_prepare(dcodes, n, m, dcodebooks, d, dbnorms, s, stride, st, tcbase) != LSQ_OK ||
+  if (use_tc && (adc_tc_prepare(dcodes, n, m, dcodebooks, td, S.dnorms, s, stride, (lut_kind == LUT_LSQ) ? 0 : subdim, d, st,
+                                tcbase) != LSQ_OK ||
                  dcandidx.alloc((size_t)qbatch * cap) != cudaSuccess)) {
     cudaGetLastError();   // no room for the operand images / survivor lists: the lookup scan needs neither
     use_tc = false;
@@ -924,21 +928,21 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
       // thresholds from the tensor-core values of the sample (any tau is valid: a query whose candidate count
       // ends up < nn or > capacity is re-run), exact LUT rows, filter + exact rescoring of the survivors
       const int tiles32 = (int)ceil_div(nb, 32);
-      LSQ_TRY(adc_tc_lut_rows(dq, nb, d, dcodebooks, m, dlut.p, st));
+      LSQ_TRY(adc_tc_lut_rows(tcbase, dq, nb, td, dcodebooks, m, dlut.p, st));
       timer.mark("lut");
       if (two_stage) {
         // coarse bound from the 1/8 sub-sample (r0-th smallest filter value), then the sample positions below it,
         // scored exactly: tau = the exact r-th smallest distance of the sample, no 655 MB sample buffer
-        LSQ_TRY(adc_tc_sample(tcbase, true, dq, nb, d, m, dsbuf.p, st));
+        LSQ_TRY(adc_tc_sample(tcbase, true, dq, nb, td, m, dsbuf.p, st));
         note_launch();
         threshold_kernel<<<tiles32, 1024, 0, st>>>(dsbuf.p, tcbase.s1count, (int)r0, dbound.p, 32);
         LSQ_CUDA(cudaGetLastError());
         timer.mark("bound");
-        LSQ_TRY(adc_tc_sample_tau(tcbase, dcodes, m, dq, nb, d, dbnorms, dlut.p, dbound.p, dcandidx.p, dccnt.p, lcap, (int)r,
+        LSQ_TRY(adc_tc_sample_tau(tcbase, dcodes, m, dq, nb, td, S.dnorms, dlut.p, dbound.p, dcandidx.p, dccnt.p, lcap, (int)r,
                                   dtau.p, st));
         timer.mark("threshold");
       } else {
-        LSQ_TRY(adc_tc_sample(tcbase, false, dq, nb, d, m, dsbuf.p, st));
+        LSQ_TRY(adc_tc_sample(tcbase, false, dq, nb, td, m, dsbuf.p, st));
         timer.mark("sample");
         note_launch();
         threshold_kernel<<<tiles32, 1024, 0, st>>>(dsbuf.p, s, (int)r, dtau.p, 32);
@@ -946,10 +950,10 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
         timer.mark("threshold");
       }
       LSQ_CUDA(cudaMemsetAsync(dbig.p + qbatch, 0, sizeof(int), st));
-      LSQ_TRY(adc_tc_main_pass(tcbase, dcodes, n, m, dq, nb, d, dbnorms, dlut.p, dtau.p, dcandidx.p, dccnt.p, cap,
+      LSQ_TRY(adc_tc_main_pass(tcbase, dcodes, n, m, dq, nb, td, S.dnorms, dlut.p, dtau.p, dcandidx.p, dccnt.p, cap,
                                nullptr, nullptr, cap, S.id_base, nullptr, 0, st));
       timer.mark("filter");
-      LSQ_TRY(adc_tc_rescore(dcodes, n, m, nb, dbnorms, dlut.p, dtau.p, dcandidx.p, dccnt.p, cap, dcand.p, dcnt.p, cap,
+      LSQ_TRY(adc_tc_rescore(dcodes, n, m, nb, S.dnorms, dlut.p, dtau.p, dcandidx.p, dccnt.p, cap, dcand.p, dcnt.p, cap,
                              S.id_base, st));
       timer.mark("rescore");
     } else {

@@ -139,3 +139,35 @@ def test_filter_with_several_query_batches(gpu, oracle, monkeypatch):
     sample = np.r_[0:8, 21840:21856, nq - 8:nq]   # first batch, the batch boundary, the last queries
     dr, ir = _ref(oracle, codes, queries[sample], codebooks, norms, nn)
     assert np.array_equal(it[sample], ir) and np.array_equal(dt[sample], dr)
+
+
+def _ref_pq(oracle, *a):
+    return oracle.ref_linscan_pq(*a) if oracle.ref_available() else oracle.linscan_pq(*a)
+
+
+@pytest.mark.parametrize("n,nq,d,m,nn,kind", [
+    (150000, 50, 128, 8, 1000, "sift"),       # sub-codewords of 16 elements
+    (70000, 300, 64, 16, 200, "gauss"),       # 4 elements: shorter than an 8-element K chunk
+    (66000, 129, 32, 16, 100, "gauss"),       # 2 elements
+    (80000, 40, 64, 4, 50, "gauss"),          # 16 elements, 4 codebooks
+])
+def test_linscan_pq_through_the_filter_is_exact(gpu, oracle, n, nq, d, m, nn, kind, monkeypatch):
+    """PQ / OPQ tables (squared differences per sub-space, linscan_aqd.cpp:37-102) through the tensor-core filter:
+    dist = ||q||^2 - 2<q, xhat> + ||xhat||^2 with xhat the concatenated sub-codewords."""
+    mk = gauss_scan_problem if kind == "gauss" else make_scan_problem
+    subdim = d // m   # Linscan.jl:23
+    codes, queries, codebooks, _ = mk(7500 + m + nn, n, nq, d, m)
+    centers = np.ascontiguousarray(codebooks[:, :subdim].reshape(m, 256, subdim))
+    monkeypatch.setenv("LSQ_B200_ADC", "tc")
+    l0 = gpu.launch_count()
+    dt, it = gpu.linscan_pq(codes, queries, centers, 8 * m, nn)
+    launches_tc = gpu.launch_count() - l0
+    monkeypatch.setenv("LSQ_B200_ADC", "scan")
+    l0 = gpu.launch_count()
+    ds, is_ = gpu.linscan_pq(codes, queries, centers, 8 * m, nn)
+    launches_scan = gpu.launch_count() - l0
+    assert launches_tc > launches_scan, "the tensor-core path did not run"
+    assert np.array_equal(it, is_) and np.array_equal(dt, ds)
+    k = min(nq, 24)
+    dr, ir = _ref_pq(oracle, codes, queries[:k], centers, nn)
+    assert np.array_equal(it[:k].astype(np.int64) - 1, ir.astype(np.int64)) and np.array_equal(dt[:k], dr)
