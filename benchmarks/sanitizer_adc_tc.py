@@ -28,4 +28,16 @@ for passes in ("2", "1"):
         d2, i2 = L.linscan_lsq(codes, q, cb.reshape(m, 256, d), nr, np.eye(d, dtype=np.float32), nn)
         del os.environ["LSQ_B200_ADC"]
         assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+# PQ / OPQ tables through the filter, and the sample-buffer thresholds (the alternative to the list-based ones)
+codes, q, cb, nr = make_scan_problem(9, 20000, 40, 64, 16)
+centers = np.ascontiguousarray(cb[:, :4].reshape(16, 256, 4))
+os.environ["LSQ_B200_ADC"] = "tc"
+d1, i1 = L.linscan_pq(codes, q, centers, 128, 30)
+os.environ["LSQ_B200_ADC_SBUF"] = "1"
+d3, i3 = L.linscan_pq(codes, q, centers, 128, 30)
+del os.environ["LSQ_B200_ADC_SBUF"]
+os.environ["LSQ_B200_ADC"] = "scan"
+d2, i2 = L.linscan_pq(codes, q, centers, 128, 30)
+del os.environ["LSQ_B200_ADC"]
+assert np.array_equal(i1, i2) and np.array_equal(d1, d2) and np.array_equal(i3, i2) and np.array_equal(d3, d2)
 print("done")

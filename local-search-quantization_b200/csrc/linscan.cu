@@ -908,7 +908,7 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
       lcap = 1024;
       while (lcap < 3 * 8 * r0) lcap <<= 1;
       two_stage = (r0 < tcbase.s1count) && (lcap <= 8192) && (lcap <= cap);
-      if (two_stage) LSQ_CUDA(dbound.alloc(qbatch));
+      if (two_stage) LSQ_CUDA(dbound.alloc((size_t)ceil_div(qbatch, 32) * 32));   // threshold_kernel writes whole 32-query tiles
     }
   }
   LSQ_CUDA(dbig.alloc(qbatch + 1));
