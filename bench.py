@@ -272,6 +272,29 @@ def adc_measure(m, n, nq, nn, d=128, reps=5, cpu_queries=64, check_queries=16, r
             del os.environ["LSQ_B200_ADC"]
         out["lookup_scan_ms"] = a.elapsed_time(b)
         out["equal_to_lookup_scan"] = bool(torch.equal(ds, dd) and torch.equal(is_, di))
+        # PQ / OPQ tables (linscan_aqd.cpp) on the same shape: the same filter (||q||^2 - 2<q,xhat> + ||xhat||^2) vs the lookup kernel
+        if d % m == 0:
+            sub = d // m
+            dcen = torch.from_numpy(np.ascontiguousarray(codebooks[:, :sub].reshape(m, 256, sub))).cuda()
+            pq = {}
+            for mode in ("tc", "scan"):
+                os.environ["LSQ_B200_ADC"] = mode
+                try:
+                    dev.linscan(dc, dq, dcen, None, nn, lut_kind=1, subdim=sub)
+                    torch.cuda.synchronize()
+                    ts = []
+                    for _ in range(3):
+                        a.record()
+                        r_pq = dev.linscan(dc, dq, dcen, None, nn, lut_kind=1, subdim=sub)
+                        b.record()
+                        torch.cuda.synchronize()
+                        ts.append(a.elapsed_time(b))
+                finally:
+                    del os.environ["LSQ_B200_ADC"]
+                pq[mode] = (float(np.median(ts)), r_pq)
+            out["pq"] = {"subdim": sub, "ms": pq["tc"][0], "lookup_scan_ms": pq["scan"][0],
+                         "equal_to_lookup_scan": bool(torch.equal(pq["tc"][1][0], pq["scan"][1][0]) and
+                                                      torch.equal(pq["tc"][1][1], pq["scan"][1][1]))}
     else:
         out.update({"lookups_per_s": lookups, "lookup_frac_of_smem_bound": lookups / (world * 148 * 32 * 1.965e9)})
     if cpu_leg and rank == 0:
