@@ -776,7 +776,7 @@ bool adc_tc_shape_ok(int64_t n, int64_t nq, int m, int d) {
 }
 
 bool adc_tc_applicable(const uint8_t* dcodes, int64_t n, int64_t nq, int m, int d, const float* dqueries,
-                       const float* dcodebooks, const float* dbnorms) {
+                       const float* dcodebooks) {
   if (!adc_tc_shape_ok(n, nq, m, d)) return false;
   if ((reinterpret_cast<uintptr_t>(dqueries) & 15) || (reinterpret_cast<uintptr_t>(dcodebooks) & 15) ||
       (reinterpret_cast<uintptr_t>(dcodes) & 3))

@@ -24,7 +24,7 @@ struct AdcTcBase {
 
 bool adc_tc_shape_ok(int64_t n, int64_t nq, int m, int d);
 bool adc_tc_applicable(const uint8_t* dcodes, int64_t n, int64_t nq, int m, int d, const float* dqueries,
-                       const float* dcodebooks, const float* dbnorms);
+                       const float* dcodebooks);
 // base image + image of the sample {i * sstride : i < scount}
 // PQ / OPQ: subdim > 0, d = m * subdim, dcodebooks = centers [m][256][subdim], dbnorms = nullptr
 int adc_tc_prepare(const uint8_t* dcodes, int64_t n, int m, const float* dcodebooks, int d, const float* dbnorms,

@@ -882,7 +882,7 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
   // tensor-core dimension: d for the LSQ tables, m * subdim for PQ / OPQ (queries keep their row stride d)
   const int td = (lut_kind == LUT_LSQ) ? d : m * subdim;
   bool use_tc = ((lut_kind == LUT_LSQ) ? (dbnorms != nullptr) : (d % 4 == 0)) &&
-                adc_tc_applicable(dcodes, n, nq, m, td, dqueries, dcodebooks, dbnorms);
+                adc_tc_applicable(dcodes, n, nq, m, td, dqueries, dcodebooks);
   AdcTcBase tcbase;
   DevBuf<uint32_t> dcandidx;   // filter survivors of the main pass; before that, the sample lists of the thresholds
   DevBuf<int> dccnt;
