@@ -34,7 +34,9 @@
 // A wider margin only lets a few more pairs through to the exact rescoring; it never changes the result.
 // Anything unusual (NaN, candidate overflow, fewer than nn survivors) ends on linscan.cu's exhaustive path,
 // exactly as before.  The thresholds tau_q themselves come from the same kernel run on a strided sample of the
-// base set (any tau is valid, see linscan.cu).  tests/: bit-identical ids and distances against the reference's
+// base set: its values on a 1/8 sub-sample give a coarse bound, the sample positions below that bound are listed
+// (filter mode) and scored exactly, and tau_q is the exact r-th smallest sample distance (adc_sample_tau_kernel; any
+// tau is valid, see linscan.cu).  tests/: bit-identical ids and distances against the reference's
 // own .so and against the lookup scan (LSQ_B200_ADC=scan).
 //
 // PQ / OPQ tables (linscan_aqd.cpp:37-102: dist = sum_k sum_s sqr(c_k[s] - q[k*subdim + s])) take the same path:
