@@ -319,7 +319,9 @@ struct AdcFilterParams {
   float* dbg;                // values mode: [nq][dbg_ld] filter values (tests)
   uint32_t* sbuf;            // sample mode: ordered filter values, threshold_kernel's layout [(q/32 * scount + t) * 32 + q%32]
   int64_t n, ntiles, ccap, dbg_ld, scount;
+  const int* npass_dev;      // optional: number of products chosen on the device (adc_choose_passes_kernel); overrides npass
   int nq, d, m, npass, nstages, qstride, pq;
+  uint32_t stage_stride;     // bytes between ring slots (sized for the larger of the two modes)
 };
 
 __device__ __forceinline__ void at_ld32(uint32_t taddr, uint32_t (&r)[32]) {
@@ -404,7 +406,7 @@ __global__ void __launch_bounds__(at_threads(SPLIT), 1) adc_filter_kernel(const 
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = p.d, ksteps = d / 16;
-  const int npass = p.npass;
+  const int npass = (p.npass_dev != nullptr) ? *p.npass_dev : p.npass;
   const uint32_t hi_bytes = at_hi_bytes(d), tile_bytes = at_tile_bytes(d);
   const uint32_t load_bytes = (npass == 2) ? tile_bytes : hi_bytes;   // one product: the lo image stays in HBM
   const int nstages = p.nstages;
@@ -519,7 +521,7 @@ __global__ void __launch_bounds__(at_threads(SPLIT), 1) adc_filter_kernel(const 
       uint32_t par = 0u;
       for (int64_t t = 0; t < my_tiles; t++) {
         mbar_wait(&bar_empty[s], par ^ 1u);
-        bulk_load_issue(smem_raw + (size_t)s * load_bytes, p.img + (size_t)(t_lo + t) * tile_bytes, load_bytes, &bar_full[s]);
+        bulk_load_issue(smem_raw + (size_t)s * p.stage_stride, p.img + (size_t)(t_lo + t) * tile_bytes, load_bytes, &bar_full[s]);
         if (++s == nstages) { s = 0; par ^= 1u; }
       }
     }
@@ -537,7 +539,7 @@ __global__ void __launch_bounds__(at_threads(SPLIT), 1) adc_filter_kernel(const 
     uint32_t par = 0u;
     for (int64_t t = 0; t < my_tiles; t++) {
       mbar_wait(&bar_full[s], par);
-      const uint32_t stage_u = sB_u + (uint32_t)s * load_bytes;
+      const uint32_t stage_u = sB_u + (uint32_t)s * p.stage_stride;
       const uint32_t lo_hiX = desc_lbo | (stage_u >> 4), lo_loX = desc_lbo | ((stage_u + hi_bytes) >> 4);
       for (int a = 0; a < na; a++) {
         const int b = (int)(j % AT_NACC);
@@ -722,7 +724,12 @@ __global__ void __launch_bounds__(128) adc_sample_tau_kernel(const uint8_t* __re
                                                              const float* __restrict__ norms, const float* __restrict__ lutq,
                                                              const uint32_t* __restrict__ list, const int* __restrict__ lcnt,
                                                              int lcap, int64_t stride, int64_t scount, int r,
-                                                             float* __restrict__ tau) {
+                                                             float* __restrict__ tau, const float* __restrict__ queries,
+                                                             int qstride, int d, const AdcStats* __restrict__ stats,
+                                                             float* __restrict__ infl) {
+  __shared__ float sh_q2[4];
+  __shared__ float sh_tau;
+  __shared__ int sh_c1;
   extern __shared__ __align__(16) unsigned char st_smem[];
   float* lut = reinterpret_cast<float*>(st_smem);                                   // [m * 256]
   uint32_t* dist = reinterpret_cast<uint32_t*>(st_smem + (size_t)m * LSQ_H * 4);    // [lcap] ordered distances
@@ -748,7 +755,7 @@ __global__ void __launch_bounds__(128) adc_sample_tau_kernel(const uint8_t* __re
   }
   __syncthreads();
   if (c_all > lcap || c < r) {
-    if (tid == 0) tau[q] = INFINITY;
+    if (tid == 0) { tau[q] = INFINITY; if (infl != nullptr) infl[q] = 1.0f; }
     return;
   }
   for (int e = tid; e < c; e += 128) {   // rank by counting (ties by position): exactly one element has rank r - 1
@@ -758,7 +765,45 @@ __global__ void __launch_bounds__(128) adc_sample_tau_kernel(const uint8_t* __re
       const uint32_t u = dist[j];
       rk += (u < v) || (u == v && j < e);
     }
-    if (rk == r - 1) tau[q] = ordered_to_float(v);
+    if (rk == r - 1) { tau[q] = ordered_to_float(v); sh_tau = ordered_to_float(v); }
+  }
+  if (infl == nullptr) return;
+  // How many more pairs would a ONE-product filter let through?  Its margin is wider by 2 ||q|| max||lo(xhat)||; the
+  // sample says how many distances lie within that of tau (the list reaches a good deal beyond tau: the coarse bound
+  // sits near the 1 % quantile, tau near 0.3 %; where it does not, the count saturates and the estimate errs high).
+  float q2 = 0.0f;
+  for (int k = tid; k < d; k += 128) { const float x = queries[(size_t)q * qstride + k]; q2 = fmaf(x, x, q2); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q2 += __shfl_xor_sync(0xFFFFFFFFu, q2, o);
+  if ((tid & 31) == 0) sh_q2[tid >> 5] = q2;
+  if (tid == 0) sh_c1 = 0;
+  __syncthreads();
+  const float qn = sqrtf(sh_q2[0] + sh_q2[1] + sh_q2[2] + sh_q2[3]);
+  const float m1 = 2.0f * qn * sqrtf(__uint_as_float(stats->xlo2_bits));
+  const uint32_t lim = float_to_ordered(sh_tau + m1);
+  int mine_c = 0;
+  for (int e = tid; e < c; e += 128) mine_c += (dist[e] <= lim);
+  atomicAdd(&sh_c1, mine_c);
+  __syncthreads();
+  if (tid == 0) infl[q] = (float)sh_c1 / (float)r;
+}
+
+// one product or two?  mean over the queries of the estimated growth of the survivor lists; one product (9 instead of
+// 17 MMAs per tile pair, half the TMA bytes) pays as long as the extra survivors cost less in the rescoring and top-k
+// than the filter saves: measured break-even is beyond 2x, the switch sits at 1.6x
+__global__ void __launch_bounds__(256) adc_choose_passes_kernel(const float* __restrict__ infl, int nq, int* __restrict__ npass) {
+  __shared__ float part[8];
+  float s = 0.0f;
+  for (int i = threadIdx.x; i < nq; i += 256) s += infl[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.0f;
+    for (int w = 0; w < 8; w++) tot += part[w];
+    const float mean = tot / (float)(nq > 0 ? nq : 1);
+    *npass = (mean <= 1.6f) ? 1 : 2;   // a NaN (poisoned statistics) compares false: two products
   }
 }
 
@@ -843,7 +888,8 @@ static int filter_slices(int groups, int64_t ntiles) {
 static int launch_filter(AdcFilterParams& p, cudaStream_t st) {
   const int groups = (int)ceil_div(p.nq, AT_NA * AT_M);
   const int slices = filter_slices(groups, p.ntiles);
-  const size_t stage = (p.npass == 2) ? at_tile_bytes(p.d) : at_hi_bytes(p.d);
+  const size_t stage = (p.npass == 2 || p.npass_dev != nullptr) ? at_tile_bytes(p.d) : at_hi_bytes(p.d);
+  p.stage_stride = (uint32_t)stage;
   p.nstages = (int)std::min<size_t>(AT_STAGES, (size_t)(210 * 1024) / stage);
   const size_t smem = (size_t)p.nstages * stage;
   int split = 2;
@@ -879,7 +925,7 @@ int adc_tc_sample(const AdcTcBase& B, bool subsample, const float* dq, int nb, i
 // sample positions whose filter value is <= dbound (+ margin) -> dlist / dlcnt, then the exact r-th smallest -> dtau
 int adc_tc_sample_tau(const AdcTcBase& B, const uint8_t* dcodes, int m, const float* dq, int nb, int d,
                       const float* dbnorms, const float* dlutq, const float* dbound, uint32_t* dlist, int* dlcnt,
-                      int lcap, int r, float* dtau, cudaStream_t st) {
+                      int lcap, int r, float* dtau, float* dinfl, int* dnpass, cudaStream_t st) {
   AdcFilterParams p;
   memset(&p, 0, sizeof(p));
   p.queries = dq; p.img = B.simg.p; p.tau = dbound; p.stats = B.stats.p; p.candidx = dlist; p.ccnt = dlcnt;
@@ -890,7 +936,12 @@ int adc_tc_sample_tau(const AdcTcBase& B, const uint8_t* dcodes, int m, const fl
   const size_t smem = (size_t)m * LSQ_H * 4 + (size_t)lcap * 4;
   LSQ_CUDA(cudaFuncSetAttribute(adc_sample_tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   note_launch();
-  adc_sample_tau_kernel<<<nb, 128, smem, st>>>(dcodes, m, dbnorms, dlutq, dlist, dlcnt, lcap, B.sstride, B.scount, r, dtau);
+  adc_sample_tau_kernel<<<nb, 128, smem, st>>>(dcodes, m, dbnorms, dlutq, dlist, dlcnt, lcap, B.sstride, B.scount, r, dtau, dq,
+                                               B.qstride, d, B.stats.p, dinfl);
+  if (dinfl != nullptr && dnpass != nullptr) {
+    note_launch();
+    adc_choose_passes_kernel<<<1, 256, 0, st>>>(dinfl, nb, dnpass);
+  }
   LSQ_CUDA(cudaGetLastError());
   return LSQ_OK;
 }
@@ -915,18 +966,19 @@ int adc_tc_lut_rows(const AdcTcBase& B, const float* dq, int nb, int d, const fl
 int adc_tc_main_pass(const AdcTcBase& B, const uint8_t* dcodes, int64_t n, int m, const float* dq, int nb, int d,
                      const float* dbnorms, const float* dlutq, const float* dtau, uint32_t* dcandidx, int* dccnt,
                      int64_t ccap, unsigned long long* dcand, int* dcnt, int64_t cap, int id_base, float* ddbg,
-                     int64_t dbg_ld, cudaStream_t st) {
+                     int64_t dbg_ld, const int* dnpass, cudaStream_t st) {
   AdcFilterParams p;
   memset(&p, 0, sizeof(p));
   p.queries = dq; p.img = B.img.p; p.tau = dtau; p.stats = B.stats.p;
   p.candidx = dcandidx; p.ccnt = dccnt; p.dbg = ddbg; p.n = n; p.ntiles = B.ntiles; p.ccap = ccap; p.dbg_ld = dbg_ld;
   p.nq = nb; p.d = d; p.m = m; p.qstride = B.qstride; p.pq = B.subdim > 0;
-  // two products hi(q).lo(x) + hi(q).hi(x) by default.  LSQ_B200_ADC_PASSES=1 drops the first (9 instead of 17 MMAs
-  // per product, half the TMA bytes) for a margin wider by 2 ||q|| max||lo(x)||: measured 2.9 + 0.8 ms (filter +
-  // rescoring of 1.5x the candidates) against 3.05 + 0.5 ms on the 1 M x 10 K benchmark — no gain, so the tighter
-  // filter is the default.
+  // One product hi(q).hi(x) (9 MMAs per tile pair, margin wider by 2 ||q|| max||lo(x)||) or two, hi(q).lo(x) + hi(q).hi(x)
+  // (17 MMAs)?  On the 1 M x 10 K benchmark: 2.34 + 0.43 ms (filter + rescoring of 1.3x the survivors) against 3.06 +
+  // 0.33 ms.  The choice is made on the device from the sample (adc_choose_passes_kernel) when the caller passes
+  // dnpass; LSQ_B200_ADC_PASSES=1|2 fixes it.  Without either: two products (the tighter filter).
   p.npass = 2;
-  if (const char* e = getenv("LSQ_B200_ADC_PASSES")) p.npass = (atoi(e) == 1) ? 1 : 2;
+  p.npass_dev = dnpass;
+  if (const char* e = getenv("LSQ_B200_ADC_PASSES")) { p.npass = (atoi(e) == 1) ? 1 : 2; p.npass_dev = nullptr; }
   LSQ_CUDA(cudaMemsetAsync(dccnt, 0, (size_t)nb * sizeof(int), st));
   LSQ_TRY(launch_filter(p, st));
   if (dcand != nullptr) LSQ_TRY(adc_tc_rescore(dcodes, n, m, nb, dbnorms, dlutq, dtau, dcandidx, dccnt, ccap, dcand, dcnt, cap, id_base, st));
@@ -965,5 +1017,5 @@ extern "C" int lsq_dev_adc_filter_values(const uint8_t* dcodes, int64_t n, int m
   LSQ_CUDA(dccnt.alloc(nq));
   LSQ_CUDA(cudaMemsetAsync(dtau.p, 0xFF, (size_t)nq * sizeof(float), st));  // NaN thresholds: nothing passes
   return adc_tc_main_pass(B, dcodes, n, m, dqueries, nq, d, dbnorms, nullptr, dtau.p, nullptr, dccnt.p, 0, nullptr,
-                          nullptr, 0, 0, dout, ld, st);
+                          nullptr, 0, 0, dout, ld, nullptr, st);
 }

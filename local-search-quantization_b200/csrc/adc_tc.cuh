@@ -34,10 +34,12 @@ int adc_tc_prepare(const uint8_t* dcodes, int64_t n, int m, const float* dcodebo
 int adc_tc_sample(const AdcTcBase& B, bool subsample, const float* dq, int nb, int d, int m, uint32_t* dsbuf,
                   cudaStream_t st);
 // thresholds without a sample buffer: sample positions with filter value <= dbound[q] (+ margin) -> dlist / dlcnt
-// (lcap per query), scored exactly, r-th smallest -> dtau[q] (+inf if the list overflowed or is shorter than r)
+// (lcap per query), scored exactly, r-th smallest -> dtau[q] (+inf if the list overflowed or is shorter than r);
+// dinfl / dnpass (optional): per-query estimate of how much a one-product filter would lengthen the survivor lists,
+// and the number of products chosen from its mean (1 or 2), read by the main pass on the device
 int adc_tc_sample_tau(const AdcTcBase& B, const uint8_t* dcodes, int m, const float* dq, int nb, int d,
                       const float* dbnorms, const float* dlutq, const float* dbound, uint32_t* dlist, int* dlcnt,
-                      int lcap, int r, float* dtau, cudaStream_t st);
+                      int lcap, int r, float* dtau, float* dinfl, int* dnpass, cudaStream_t st);
 // exact LUT rows lutq[q][m*256] (the reference's fp32 chain) for the rescoring
 int adc_tc_lut_rows(const AdcTcBase& B, const float* dq, int nb, int d, const float* dcodebooks, int m, float* dlutq,
                     cudaStream_t st);
@@ -46,7 +48,7 @@ int adc_tc_lut_rows(const AdcTcBase& B, const float* dq, int nb, int d, const fl
 int adc_tc_main_pass(const AdcTcBase& B, const uint8_t* dcodes, int64_t n, int m, const float* dq, int nb, int d,
                      const float* dbnorms, const float* dlutq, const float* dtau, uint32_t* dcandidx, int* dccnt,
                      int64_t ccap, unsigned long long* dcand, int* dcnt, int64_t cap, int id_base, float* ddbg,
-                     int64_t dbg_ld, cudaStream_t st);
+                     int64_t dbg_ld, const int* dnpass, cudaStream_t st);
 
 // exact rescoring of the filter's survivors: dcandidx / dccnt -> keys in dcand / dcnt (the buffers the top-k kernels read)
 int adc_tc_rescore(const uint8_t* dcodes, int64_t n, int m, int nb, const float* dbnorms, const float* dlutq,

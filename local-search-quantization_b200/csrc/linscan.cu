@@ -886,7 +886,8 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
   AdcTcBase tcbase;
   DevBuf<uint32_t> dcandidx;   // filter survivors of the main pass; before that, the sample lists of the thresholds
   DevBuf<int> dccnt;
-  DevBuf<float> dbound;
+  DevBuf<float> dbound, dinfl;
+  DevBuf<int> dnpass;   // products of the main filter, chosen on the device from the sample
   bool two_stage = false;
   int64_t r0 = 0;
   int lcap = 0;
@@ -908,7 +909,11 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
       lcap = 1024;
       while (lcap < 3 * 8 * r0) lcap <<= 1;
       two_stage = (r0 < tcbase.s1count) && (lcap <= 8192) && (lcap <= cap);
-      if (two_stage) LSQ_CUDA(dbound.alloc((size_t)ceil_div(qbatch, 32) * 32));   // threshold_kernel writes whole 32-query tiles
+      if (two_stage) {
+        LSQ_CUDA(dbound.alloc((size_t)ceil_div(qbatch, 32) * 32));   // threshold_kernel writes whole 32-query tiles
+        LSQ_CUDA(dinfl.alloc(qbatch));
+        LSQ_CUDA(dnpass.alloc(1));
+      }
     }
   }
   LSQ_CUDA(dbig.alloc(qbatch + 1));
@@ -939,7 +944,7 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
         LSQ_CUDA(cudaGetLastError());
         timer.mark("bound");
         LSQ_TRY(adc_tc_sample_tau(tcbase, dcodes, m, dq, nb, td, S.dnorms, dlut.p, dbound.p, dcandidx.p, dccnt.p, lcap, (int)r,
-                                  dtau.p, st));
+                                  dtau.p, dinfl.p, dnpass.p, st));
         timer.mark("threshold");
       } else {
         LSQ_TRY(adc_tc_sample(tcbase, false, dq, nb, td, m, dsbuf.p, st));
@@ -951,7 +956,7 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
       }
       LSQ_CUDA(cudaMemsetAsync(dbig.p + qbatch, 0, sizeof(int), st));
       LSQ_TRY(adc_tc_main_pass(tcbase, dcodes, n, m, dq, nb, td, S.dnorms, dlut.p, dtau.p, dcandidx.p, dccnt.p, cap,
-                               nullptr, nullptr, cap, S.id_base, nullptr, 0, st));
+                               nullptr, nullptr, cap, S.id_base, nullptr, 0, two_stage ? dnpass.p : nullptr, st));
       timer.mark("filter");
       LSQ_TRY(adc_tc_rescore(dcodes, n, m, nb, S.dnorms, dlut.p, dtau.p, dcandidx.p, dccnt.p, cap, dcand.p, dcnt.p, cap,
                              S.id_base, st));

@@ -92,6 +92,17 @@ def test_linscan_through_the_filter_is_exact(gpu, oracle, n, nq, d, m, nn, kind,
         if (n, nq) not in ((200000, 300), (66000, 129)):
             pytest.skip("two shapes are enough for the alternative threshold path")
         monkeypatch.setenv("LSQ_B200_ADC_SBUF", "1")
+    elif (n, nq) in ((150000, 257), (70000, 40)):
+        # by default the number of products is chosen on the device from the sample; force each here
+        for products in ("1", "2"):
+            monkeypatch.setenv("LSQ_B200_ADC", "tc")
+            monkeypatch.setenv("LSQ_B200_ADC_PASSES", products)
+            mk0 = gauss_scan_problem if kind == "gauss" else make_scan_problem
+            c0, q0, cb0, n0 = mk0(7100 + m + nn, n, nq, d, m)
+            df, idf = gpu.linscan_lsq(c0, q0, cb0.reshape(m, 256, d), n0, np.eye(d, dtype=np.float32), nn)
+            dr0, ir0 = _ref(oracle, c0, q0[:8], cb0, n0, nn)
+            assert np.array_equal(idf[:8], ir0) and np.array_equal(df[:8], dr0), products
+        monkeypatch.delenv("LSQ_B200_ADC_PASSES")
     mk = gauss_scan_problem if kind == "gauss" else make_scan_problem
     codes, queries, codebooks, norms = mk(7100 + m + nn, n, nq, d, m)
     R = np.eye(d, dtype=np.float32)
