@@ -254,11 +254,16 @@ def adc_measure(m, n, nq, nn, d=128, reps=5, cpu_queries=64, check_queries=16, r
             ph = lsq_b200.linscan_last_phases()
         finally:
             del os.environ["LSQ_B200_ADC_TIMING"]
+        products = int(ph.pop("_filter_products", 2)) or 2   # 1: hi(q).hi(x) only, 2: + hi(q).lo(x); chosen on the device per call
         out["phases_ms"] = {k: round(v, 3) for k, v in ph.items()}
+        out["filter_products"] = products
+        flops = 2.0 * nq * n * (products * d + 16)
+        out.update({"filter_tflops_whole_call": flops / (ms * 1e-3) / 1e12,
+                    "frac_of_measured_bf16_peak_whole_call": flops / (ms * 1e-3) / 1e12 / bf16_peak / world})
         if ph.get("filter"):
-            ftf = 2.0 * (qhi - qlo) * n * (2 * d + 16) / (ph["filter"] * 1e-3) / 1e12
+            ftf = 2.0 * (qhi - qlo) * n * (products * d + 16) / (ph["filter"] * 1e-3) / 1e12
             out["filter_kernel"] = {"ms": ph["filter"], "tflops": ftf, "frac_of_measured_bf16_peak": ftf / bf16_peak,
-                                    "frac_of_nominal_bf16_peak": ftf / 2250.0, "bound": "tensor (17 tcgen05.mma of 128x128x16 per 128 queries x 128 base vectors)"}
+                                    "frac_of_nominal_bf16_peak": ftf / 2250.0, "bound": f"tensor ({products * (d // 16) + 1} tcgen05.mma of 128x128x16 per 128 queries x 128 base vectors)"}
         # the lookup-table scan on the same problem (the path every shape took before this round's tensor-core filter)
         os.environ["LSQ_B200_ADC"] = "scan"
         try:

@@ -119,7 +119,8 @@ void linscan_aqd_query(float* dists, unsigned int* res, unsigned char* codes, fl
 int lsq_linscan_path(int64_t n, int64_t nq, int m, int d);
 /* Measurement aid: with LSQ_B200_ADC_TIMING set in the environment every linscan call times its phases with CUDA
  * events (and prints them to stderr); this returns the device time (ms) and name of phase i of the calling thread's
- * most recent call, and the number of phases. */
+ * most recent call, and the number of phases; i = -2 returns the number of products the tensor-core filter ran with in
+ * that call (1 or 2; 0 = lookup scan). */
 int lsq_linscan_last_phases(int i, float* ms, const char** name);
 /* status-returning twins of the two above (same arguments) */
 int lsq_linscan_lsq(float* dists, int* idx, const unsigned char* codes, const float* queries,

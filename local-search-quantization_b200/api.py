@@ -144,6 +144,7 @@ def linscan_last_phases():
         ms, name = ct.c_float(0), ct.c_char_p()
         L.lsq_linscan_last_phases(i, ct.byref(ms), ct.byref(name))
         out[name.value.decode()] = ms.value
+    out["_filter_products"] = int(L.lsq_linscan_last_phases(-2, None, None))
     return out
 
 

@@ -10,7 +10,8 @@
 //   1. adc_decode_kernel   xhat_v in fp32, split into bf16 hi + lo, written as ready-made UMMA operand images
 //                          (K-major, no swizzle; one block per 128 base vectors), plus max ||xhat||.  The hi image
 //                          carries 16 extra K elements per vector: the 3-term bf16 split of -dbnorm/2 and three 1s.
-//   2. adc_filter_kernel   tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM): hi(q).lo(x) + hi(q).hi(x).  A CTA
+//   2. adc_filter_kernel   tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM): hi(q).hi(x), preceded by hi(q).lo(x)
+//                          when the sample says the wider one-product margin would cost too many survivors.  A CTA
 //                          keeps 256 queries (two 128-row A tiles) resident in TENSOR MEMORY for its whole life —
 //                          each row extended by three 1s and the 3-term split of (tau_q + margin_q)/2 — and streams
 //                          base tiles through a 3-stage TMA ring.  With the extra K elements the accumulator IS

@@ -745,7 +745,8 @@ static int configure_topk() {
 
 // LSQ_B200_ADC_TIMING=1: device time of every phase of a linscan call (CUDA events on the call's stream), printed
 // to stderr at the end of the call.  Measurement aid; off by default (no events, no extra synchronisation).
-static thread_local std::vector<std::pair<std::string, float>> g_last_phases;   // of the calling thread's last timed call
+static thread_local std::vector<std::pair<std::string, float>> g_last_phases;
+static thread_local int g_last_products = 0;   // products of the tensor-core filter in the last timed call (0: lookup scan)   // of the calling thread's last timed call
 
 struct PhaseTimer {
   bool on;
@@ -992,6 +993,14 @@ int linscan_device(const uint8_t* dcodes, int64_t n, int m, const float* dquerie
                                                                  dstatus.p, 2, dbig.p, dbig.p + qbatch);
     LSQ_CUDA(cudaGetLastError());
     timer.mark("topk");
+    if (timer.on) {   // measurement aid: how many products did the filter run with?
+      g_last_products = 0;
+      if (use_tc) {
+        const char* e = getenv("LSQ_B200_ADC_PASSES");
+        g_last_products = (e != nullptr) ? ((atoi(e) == 1) ? 1 : 2) : 2;
+        if (e == nullptr && two_stage) LSQ_CUDA(cudaMemcpyAsync(&g_last_products, dnpass.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+      }
+    }
     LSQ_CUDA(cudaMemcpyAsync(hstatus.data(), dstatus.p, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, st));
     LSQ_CUDA(cudaStreamSynchronize(st));
     for (int i = 0; i < nb; i++)
@@ -1100,6 +1109,7 @@ void linscan_aqd_query(float* dists, unsigned int* res, unsigned char* codes, fl
 // Measurement aid (with LSQ_B200_ADC_TIMING set): device time of phase i of the calling thread's most recent
 // linscan call; name (may be NULL) receives a pointer valid until the next call.  Returns the number of phases.
 int lsq_linscan_last_phases(int i, float* ms, const char** name) {
+  if (i == -2) return g_last_products;   // products of the tensor-core filter in that call (0: lookup scan)
   if (i >= 0 && i < (int)g_last_phases.size()) {
     if (ms) *ms = g_last_phases[i].second;
     if (name) *name = g_last_phases[i].first.c_str();
